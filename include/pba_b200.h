@@ -1,0 +1,191 @@
+/*
+ * pba_b200.h — C ABI of the B200-native photometric bundle-adjustment inner loop.
+ *
+ * This is the drop-in boundary for ONE path of halismai/photobundle:
+ * PhotometricBundleAdjustment::optimize() (reference src/photobundle.cc:764-876), i.e.
+ * what the reference does between "the window's frames, poses and points are known"
+ * and "ceres::Solve returned".  Everything the reference evaluates per LM iteration —
+ * DescriptorError::operator() (src/photobundle.cc:696-727), the bilinear sampler
+ * (src/sample_eigen.h:33-126), the Jet chain rule (src/jet_extras.h:74-111), the
+ * central-difference gradient planes (src/imgproc.cc:27-106), Ceres' Huber corrector,
+ * Schur elimination, reduced-camera solve and trust-region bookkeeping — runs in
+ * hand-written sm_100a kernels behind these entry points.
+ *
+ * Plain pointers and sizes only; every function returns 0 on success or a negative
+ * pba_status, and pba_last_error() gives the message (the reference throws
+ * std::runtime_error / calls Fatal(); the C++ class in photobundle_b200/host translates
+ * a non-zero status into std::runtime_error).  There is NO CPU fallback: without a
+ * CUDA device every compute entry point fails with PBA_ERR_CUDA.
+ *
+ * Threading: a handle is not thread-safe (neither is the reference object); each
+ * handle owns one CUDA stream; calls return after the stream has drained.
+ */
+#ifndef PBA_B200_H
+#define PBA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBA_MAX_FRAMES 16          /* frames per window (reference default 5; BASELINE 8 / 16) */
+#define PBA_MAX_RADIUS 4           /* patch radius (reference default 2; KITTI cfg 1)           */
+#define PBA_MAX_CHANNELS 8         /* 1 Intensity, 3 IntensityAndGradient, 8 BitPlanes          */
+#define PBA_UNIQUE_ID_BYTES 128    /* sizeof(ncclUniqueId)                                      */
+
+typedef enum {
+  PBA_OK = 0,
+  PBA_ERR_ARGUMENT = -1,
+  PBA_ERR_CUDA = -2,
+  PBA_ERR_NCCL = -3,
+  PBA_ERR_STATE = -4,
+  PBA_ERR_CAPACITY = -5
+} pba_status;
+
+typedef struct pba_handle pba_handle;
+
+/* Replaces: PhotometricBundleAdjustment ctor arguments (Calibration, ImageSize, Options;
+ * src/photobundle.h:148, :26-85) as far as optimize() reads them. */
+typedef struct {
+  int32_t rows, cols;          /* ImageSize (src/types.h:58-77)                                  */
+  int32_t n_channels;          /* DescriptorFrame::numChannels() (src/photobundle.cc:187)        */
+  int32_t patch_radius;        /* Options::patchRadius                                           */
+  int32_t max_frames;          /* Options::slidingWindowSize (capacity)                          */
+  int32_t max_points;          /* capacity of the point arrays                                   */
+  int32_t max_observations;    /* capacity of the observation arrays (<= max_points*max_frames)  */
+  int32_t device;              /* CUDA ordinal; -1 = current device                              */
+  double fx, fy, cx, cy;       /* Calibration (src/calibration.h:22-25)                          */
+  double huber;                /* Options::robustThreshold; <= 0 disables the loss (:797-798)    */
+} pba_config;
+
+/* Replaces: GetSolverOptions (src/photobundle.cc:738-761) + the Ceres defaults the
+ * reference leaves untouched. pba_default_solver_options() fills
+ * exactly those values. */
+typedef struct {
+  int32_t max_num_iterations;          /* 500  */
+  double function_tolerance;           /* 1e-6 */
+  double gradient_tolerance;           /* 1e-6 */
+  double parameter_tolerance;          /* 1e-6 */
+  double initial_trust_region_radius;  /* 1e4  */
+  double max_trust_region_radius;      /* 1e16 */
+  double min_trust_region_radius;      /* 1e-32 */
+  double min_relative_decrease;        /* 1e-3 */
+  double min_lm_diagonal;              /* 1e-6 */
+  double max_lm_diagonal;              /* 1e32 */
+  int32_t max_num_consecutive_invalid_steps; /* 5 */
+  int32_t jacobi_scaling;              /* 1 */
+} pba_solver_options;
+
+/* Same field names as ceres::IterationSummary, which Result::iterationSummary holds
+ * (src/photobundle.h:117; field list src/ceres_cereal.h:12-30). */
+typedef struct {
+  int32_t iteration;
+  int32_t step_is_valid;
+  int32_t step_is_nonmonotonic;
+  int32_t step_is_successful;
+  double cost;
+  double cost_change;
+  double gradient_max_norm;
+  double gradient_norm;
+  double step_norm;
+  double relative_decrease;
+  double trust_region_radius;
+  double eta;
+  double step_size;
+  int32_t line_search_function_evaluations;
+  int32_t line_search_gradient_evaluations;
+  int32_t line_search_iterations;
+  int32_t linear_solver_iterations;
+  double iteration_time_in_seconds;
+  double step_solver_time_in_seconds;
+  double cumulative_time_in_seconds;
+} pba_iteration_summary;
+
+/* Replaces: the ceres::Solver::Summary fields optimize() copies into Result
+ * (src/photobundle.cc:867-874). */
+typedef struct {
+  double initial_cost, final_cost, fixed_cost;
+  int32_t num_successful_steps, num_unsuccessful_steps;
+  int32_t num_residuals, num_residual_blocks;
+  int32_t num_iterations;          /* entries available from pba_get_iterations()            */
+  int32_t termination_type;        /* 0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE             */
+  int32_t num_evaluations;         /* residual+Jacobian passes over all observations (K1)    */
+  int32_t kernel_launches;         /* CUDA kernels launched by this solve                    */
+  int32_t num_collectives;         /* all-reduces issued (0 on one GPU)                      */
+  double total_time_in_seconds;    /* host wall time of the call                             */
+  double device_time_in_seconds;   /* CUDA-event time on the handle's stream                 */
+  char message[256];
+} pba_summary;
+
+/* Output of one residual + Jacobian + block-accumulation pass (K1), unscaled, after the
+ * Huber corrector: what Ceres' evaluator + SchurEliminator would see at the current
+ * poses/points.  Any pointer may be NULL. Layouts are row-major and dense. */
+typedef struct {
+  double cost;              /* sum over observations of 0.5*rho(||r||^2)                     */
+  double* U;                /* [n_frames][6][6]  J_c^T J_c (zero for the fixed frame)        */
+  double* gc;               /* [n_frames][6]     J_c^T r                                     */
+  double* V;                /* [n_points][3][3]  J_p^T J_p                                   */
+  double* gp;               /* [n_points][3]     J_p^T r                                     */
+  double* W;                /* [n_obs][6][3]     J_c^T J_p (zero for the fixed frame)        */
+  double* obs_sqnorm;       /* [n_obs]           ||r||^2 before the loss                     */
+  double* residuals;        /* [n_obs][C*P]      raw residuals w_j*(p0_i - I(u+x, v+y))      */
+  double device_ms;         /* CUDA-event time of the pass                                   */
+} pba_eval_out;
+
+const char* pba_last_error(void);
+const char* pba_version(void);
+void pba_default_solver_options(pba_solver_options* o);
+
+int pba_create(const pba_config* cfg, pba_handle** out);
+void pba_destroy(pba_handle* h);
+
+/* Frames of the window. Replaces DescriptorFrame::Create for the Intensity descriptor
+ * (src/photobundle.cc:225-232: uint8 -> float cast) plus ImageGradient::compute
+ * (:127-135 -> imgradient): the uint8 plane is uploaded as is and the kernel forms the
+ * fp32 intensity and the central-difference gradients (zero-border rule) on the fly.
+ * images[f] is a dense row-major rows x cols plane, borrowed for the call. */
+int pba_set_frames_u8(pba_handle* h, int32_t n_frames, const uint8_t* const* images);
+/* Generic multi-channel descriptors (IntensityAndGradient / BitPlanes): fp32 channel
+ * planes as DescriptorFrame holds them; planes[f*n_channels + k]. */
+int pba_set_frames_f32(pba_handle* h, int32_t n_frames, const float* const* planes);
+/* Sliding window: replace the plane(s) in ring slot `slot` only. */
+int pba_set_frame_u8(pba_handle* h, int32_t slot, const uint8_t* image);
+
+/* Replaces: camera_params (src/photobundle.cc:774-778): per frame [angle-axis(3), t(3)]
+ * of the world->camera transform; fixed_frame = index held constant (:809-816), -1 none. */
+int pba_set_poses(pba_handle* h, int32_t n_frames, const double* cam6, int32_t fixed_frame);
+
+/* Replaces: the residual-block loop (src/photobundle.cc:786-806). xyz [n][3] world points
+ * (ScenePoint::_X), desc [n][C*P] reference descriptors (channel-major, then row-major),
+ * CSR visibility obs_offsets [n+1] / obs_frame [nnz] (window-local frame index), weights
+ * [P] (MakePatchWeights, :617-644). With n_ranks > 1 every rank passes the FULL arrays;
+ * the library keeps its own contiguous shard (balanced by observation count). */
+int pba_set_points(pba_handle* h, int32_t n_points, const double* xyz, const double* desc,
+                   const int32_t* obs_offsets, const int32_t* obs_frame, const double* weights);
+
+/* K1 only, at the current poses/points (BASELINE config 2 and the parity tests). */
+int pba_eval(pba_handle* h, pba_eval_out* out);
+/* K1 launched `iters` times back to back on the handle's stream, CUDA-event timed
+ * (inputs resident in HBM). ms_total = elapsed for all launches. */
+int pba_eval_timed(pba_handle* h, int32_t iters, double* ms_total);
+
+/* Replaces: ceres::Solve(GetSolverOptions(...), &problem, &summary) (src/photobundle.cc:829).
+ * Poses and points are updated on the device; read them with pba_get_*. */
+int pba_solve(pba_handle* h, const pba_solver_options* opt, pba_summary* summary);
+
+int pba_get_poses(pba_handle* h, double* cam6);
+int pba_get_points(pba_handle* h, double* xyz);
+int pba_get_iterations(pba_handle* h, pba_iteration_summary* out, int32_t capacity, int32_t* n);
+
+/* Multi-GPU: one process per GPU; points are sharded, frames/poses replicated, one
+ * all-reduce of the reduced camera system per LM iteration.  Rank 0 calls
+ * pba_comm_unique_id() and distributes the 128 bytes by any means (torch.distributed,
+ * MPI, a file); then every rank calls pba_comm_init(). */
+int pba_comm_unique_id(void* id128);
+int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_ranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBA_B200_H */

@@ -1,0 +1,236 @@
+"""ctypes binding of the C-ABI product library (include/pba_b200.h -> libpba_b200.so).
+
+This is only the Python face of the boundary used by tests/ and bench.py; the host side
+of the product is C++ (photobundle_b200/host) and CUDA (photobundle_b200/csrc).  It fails
+loudly when the CUDA library is missing: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpba_b200.so")
+
+PBA_MAX_FRAMES = 16
+PBA_UNIQUE_ID_BYTES = 128
+
+EXPORTED_SYMBOLS = [
+    "pba_last_error", "pba_version", "pba_default_solver_options", "pba_create", "pba_destroy",
+    "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_poses", "pba_set_points",
+    "pba_eval", "pba_eval_timed", "pba_solve", "pba_get_poses", "pba_get_points", "pba_get_iterations",
+    "pba_comm_unique_id", "pba_comm_init",
+]
+
+
+class PbaError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int32), ("cols", C.c_int32), ("n_channels", C.c_int32), ("patch_radius", C.c_int32),
+        ("max_frames", C.c_int32), ("max_points", C.c_int32), ("max_observations", C.c_int32),
+        ("device", C.c_int32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+        ("huber", C.c_double),
+    ]
+
+
+class SolverOptions(C.Structure):
+    _fields_ = [
+        ("max_num_iterations", C.c_int32), ("function_tolerance", C.c_double),
+        ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+        ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+        ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
+        ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
+        ("max_num_consecutive_invalid_steps", C.c_int32), ("jacobi_scaling", C.c_int32),
+    ]
+
+
+class IterationSummary(C.Structure):
+    _fields_ = [
+        ("iteration", C.c_int32), ("step_is_valid", C.c_int32), ("step_is_nonmonotonic", C.c_int32),
+        ("step_is_successful", C.c_int32), ("cost", C.c_double), ("cost_change", C.c_double),
+        ("gradient_max_norm", C.c_double), ("gradient_norm", C.c_double), ("step_norm", C.c_double),
+        ("relative_decrease", C.c_double), ("trust_region_radius", C.c_double), ("eta", C.c_double),
+        ("step_size", C.c_double), ("line_search_function_evaluations", C.c_int32),
+        ("line_search_gradient_evaluations", C.c_int32), ("line_search_iterations", C.c_int32),
+        ("linear_solver_iterations", C.c_int32), ("iteration_time_in_seconds", C.c_double),
+        ("step_solver_time_in_seconds", C.c_double), ("cumulative_time_in_seconds", C.c_double),
+    ]
+
+
+class Summary(C.Structure):
+    _fields_ = [
+        ("initial_cost", C.c_double), ("final_cost", C.c_double), ("fixed_cost", C.c_double),
+        ("num_successful_steps", C.c_int32), ("num_unsuccessful_steps", C.c_int32),
+        ("num_residuals", C.c_int32), ("num_residual_blocks", C.c_int32), ("num_iterations", C.c_int32),
+        ("termination_type", C.c_int32), ("num_evaluations", C.c_int32), ("kernel_launches", C.c_int32),
+        ("num_collectives", C.c_int32), ("total_time_in_seconds", C.c_double),
+        ("device_time_in_seconds", C.c_double), ("message", C.c_char * 256),
+    ]
+
+
+class EvalOut(C.Structure):
+    _fields_ = [
+        ("cost", C.c_double), ("U", C.c_void_p), ("gc", C.c_void_p), ("V", C.c_void_p), ("gp", C.c_void_p),
+        ("W", C.c_void_p), ("obs_sqnorm", C.c_void_p), ("residuals", C.c_void_p), ("device_ms", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libpba_b200.so; raise (never fall back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PbaError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.pba_last_error.restype = C.c_char_p
+        L.pba_version.restype = C.c_char_p
+        for name in EXPORTED_SYMBOLS:
+            getattr(L, name)  # AttributeError if the ABI and the header drift apart
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise PbaError(f"{what} failed ({rc}): {lib().pba_last_error().decode()}")
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+class Handle:
+    """One window on one GPU (a thin, explicit wrapper: every method is one C call)."""
+
+    def __init__(self, rows, cols, fx, fy, cx, cy, radius=2, n_channels=1, huber=0.05,
+                 max_frames=8, max_points=4096, max_observations=None, device=-1):
+        self.cfg = Config(rows=rows, cols=cols, n_channels=n_channels, patch_radius=radius,
+                          max_frames=max_frames, max_points=max_points,
+                          max_observations=max_observations or max_points * max_frames, device=device,
+                          fx=fx, fy=fy, cx=cx, cy=cy, huber=huber)
+        self._h = C.c_void_p()
+        _check(lib().pba_create(C.byref(self.cfg), C.byref(self._h)), "pba_create")
+        self.n_frames = 0
+        self.n_points = 0
+        self.n_obs = 0
+        self.P = (2 * radius + 1) ** 2
+        self.CP = self.P * n_channels
+
+    @classmethod
+    def for_window(cls, win, device=-1, planes_f32: np.ndarray | None = None):
+        """Create a handle sized for a synthetic.Window and upload it (uint8 Intensity frames
+        unless explicit fp32 channel planes [F, C, rows, cols] are given)."""
+        nch = 1 if planes_f32 is None else int(planes_f32.shape[1])
+        h = cls(win.rows, win.cols, win.fx, win.fy, win.cx, win.cy, radius=win.radius, n_channels=nch,
+                huber=win.huber, max_frames=win.n_frames, max_points=max(1, win.n_points),
+                max_observations=max(1, win.n_obs), device=device)
+        if planes_f32 is None:
+            h.set_frames_u8(win.images)
+        else:
+            h.set_frames_f32(planes_f32)
+        h.set_poses(win.cams_init, win.fixed_frame)
+        h.set_points(win.points_init, win.desc, win.obs_offsets, win.obs_frame, win.weights)
+        return h
+
+    def close(self):
+        if self._h:
+            lib().pba_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_frames_u8(self, images: np.ndarray):
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        F = images.shape[0]
+        arr = (C.c_void_p * F)(*[images[f].ctypes.data for f in range(F)])
+        _check(lib().pba_set_frames_u8(self._h, F, arr), "pba_set_frames_u8")
+        self.n_frames = F
+
+    def set_frame_u8(self, slot: int, image: np.ndarray):
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        _check(lib().pba_set_frame_u8(self._h, slot, _ptr(image)), "pba_set_frame_u8")
+
+    def set_frames_f32(self, planes: np.ndarray):
+        planes = np.ascontiguousarray(planes, dtype=np.float32)  # [F, C, rows, cols]
+        F, Cn = planes.shape[:2]
+        arr = (C.c_void_p * (F * Cn))(*[planes[f, k].ctypes.data for f in range(F) for k in range(Cn)])
+        _check(lib().pba_set_frames_f32(self._h, F, arr), "pba_set_frames_f32")
+        self.n_frames = F
+
+    def set_poses(self, cams: np.ndarray, fixed_frame: int = 0):
+        cams = np.ascontiguousarray(cams, dtype=np.float64)
+        _check(lib().pba_set_poses(self._h, cams.shape[0], _ptr(cams), int(fixed_frame)), "pba_set_poses")
+        self.n_frames = cams.shape[0]
+
+    def set_points(self, xyz, desc, obs_offsets, obs_frame, weights):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        desc = np.ascontiguousarray(desc, dtype=np.float64)
+        obs_offsets = np.ascontiguousarray(obs_offsets, dtype=np.int32)
+        obs_frame = np.ascontiguousarray(obs_frame, dtype=np.int32)
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        n = xyz.shape[0]
+        assert desc.shape == (n, self.CP) and obs_offsets.shape == (n + 1,) and weights.shape == (self.P,)
+        _check(lib().pba_set_points(self._h, n, _ptr(xyz), _ptr(desc), _ptr(obs_offsets), _ptr(obs_frame),
+                                    _ptr(weights)), "pba_set_points")
+        self.n_points = n
+        self.n_obs = int(obs_offsets[-1])
+
+    def eval(self, want_residuals: bool = True) -> dict:
+        F, n, nnz = self.n_frames, self.n_points, self.n_obs
+        out = dict(U=np.zeros((F, 6, 6)), gc=np.zeros((F, 6)), V=np.zeros((n, 3, 3)), gp=np.zeros((n, 3)),
+                   W=np.zeros((nnz, 6, 3)), obs_sqnorm=np.zeros(nnz))
+        if want_residuals:
+            out["residuals"] = np.zeros((nnz, self.CP))
+        eo = EvalOut(U=out["U"].ctypes.data, gc=out["gc"].ctypes.data, V=out["V"].ctypes.data,
+                     gp=out["gp"].ctypes.data, W=out["W"].ctypes.data, obs_sqnorm=out["obs_sqnorm"].ctypes.data,
+                     residuals=out["residuals"].ctypes.data if want_residuals else None)
+        _check(lib().pba_eval(self._h, C.byref(eo)), "pba_eval")
+        out["cost"] = float(eo.cost)
+        out["device_ms"] = float(eo.device_ms)
+        return out
+
+    def eval_timed(self, iters: int) -> float:
+        ms = C.c_double()
+        _check(lib().pba_eval_timed(self._h, int(iters), C.byref(ms)), "pba_eval_timed")
+        return float(ms.value)
+
+    def solve(self, **opt_overrides):
+        opt = SolverOptions()
+        lib().pba_default_solver_options(C.byref(opt))
+        for k, v in opt_overrides.items():
+            setattr(opt, k, v)
+        summ = Summary()
+        _check(lib().pba_solve(self._h, C.byref(opt), C.byref(summ)), "pba_solve")
+        sd = {f[0]: getattr(summ, f[0]) for f in Summary._fields_}
+        sd["message"] = summ.message.decode()
+        return sd
+
+    def get_poses(self) -> np.ndarray:
+        cams = np.zeros((self.n_frames, 6))
+        _check(lib().pba_get_poses(self._h, _ptr(cams)), "pba_get_poses")
+        return cams
+
+    def get_points(self) -> np.ndarray:
+        pts = np.zeros((self.n_points, 3))
+        _check(lib().pba_get_points(self._h, _ptr(pts)), "pba_get_points")
+        return pts
+
+    def get_iterations(self) -> list[dict]:
+        n = C.c_int32()
+        _check(lib().pba_get_iterations(self._h, None, 0, C.byref(n)), "pba_get_iterations")
+        arr = (IterationSummary * max(1, n.value))()
+        _check(lib().pba_get_iterations(self._h, arr, n.value, C.byref(n)), "pba_get_iterations")
+        return [{f[0]: getattr(arr[i], f[0]) for f in IterationSummary._fields_} for i in range(n.value)]

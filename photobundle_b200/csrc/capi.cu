@@ -1,0 +1,537 @@
+// capi.cu — the extern "C" shim (include/pba_b200.h) over the sm_100a kernels.
+// Host side of the drop-in boundary: owns device memory, one CUDA stream per handle, and
+// enqueues the LM loop.  No CPU fallback: every compute entry point needs a CUDA device.
+
+#include "../../include/pba_b200.h"
+#include "pba_device.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pba;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fail(PBA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct pba_handle {
+  pba_config cfg;
+  int device = 0, sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int P = 0, CP = 0, pitch = 0;
+  size_t plane = 0;
+  // device buffers
+  uint8_t* d_u8 = nullptr;
+  float* d_f32 = nullptr;
+  bool frames_are_u8 = false;
+  double *d_cams = nullptr, *d_pts = nullptr, *d_weights = nullptr;
+  float* d_desc = nullptr;
+  int *d_obs_off = nullptr, *d_obs_frame = nullptr;
+  double *d_V = nullptr, *d_gp = nullptr, *d_W = nullptr;
+  double *d_Upart = nullptr, *d_Epart = nullptr, *d_U = nullptr, *d_E = nullptr;
+  double *d_scale_p = nullptr, *d_Vinv = nullptr, *d_Spart = nullptr, *d_S = nullptr, *d_Bpart = nullptr;
+  double *d_obs_sqnorm = nullptr, *d_residuals = nullptr;
+  LmState* d_state = nullptr;
+  IterSummary* d_trace = nullptr;
+  int trace_cap = 0;
+  LmState* h_state = nullptr;  // pinned
+  // problem
+  int n_frames = 0, fixed_frame = -1, n_points = 0, nnz = 0;
+  bool have_frames = false, have_poses = false, have_points = false;
+  std::vector<int> frame_used;
+  std::vector<IterSummary> trace;
+  // multi-GPU
+  int rank = 0, n_ranks = 1;
+};
+
+static void free_all(pba_handle* h) {
+  cudaFree(h->d_u8); cudaFree(h->d_f32); cudaFree(h->d_cams); cudaFree(h->d_pts); cudaFree(h->d_weights);
+  cudaFree(h->d_desc); cudaFree(h->d_obs_off); cudaFree(h->d_obs_frame); cudaFree(h->d_V); cudaFree(h->d_gp);
+  cudaFree(h->d_W); cudaFree(h->d_Upart); cudaFree(h->d_Epart); cudaFree(h->d_U); cudaFree(h->d_E);
+  cudaFree(h->d_scale_p); cudaFree(h->d_Vinv); cudaFree(h->d_Spart); cudaFree(h->d_S); cudaFree(h->d_Bpart);
+  cudaFree(h->d_obs_sqnorm); cudaFree(h->d_residuals); cudaFree(h->d_state); cudaFree(h->d_trace);
+  if (h->h_state) cudaFreeHost(h->h_state);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+extern "C" {
+
+const char* pba_last_error(void) { return g_err; }
+const char* pba_version(void) { return "photobundle_b200 0.1 (sm_100a)"; }
+
+void pba_default_solver_options(pba_solver_options* o) {
+  o->max_num_iterations = 500;          // src/photobundle.cc:751
+  o->function_tolerance = 1e-6;         // :756
+  o->gradient_tolerance = 1e-6;         // :757
+  o->parameter_tolerance = 1e-6;        // :758
+  o->initial_trust_region_radius = 1e4; // Ceres defaults below
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+}
+
+int pba_create(const pba_config* cfg, pba_handle** out) {
+  if (!cfg || !out) return fail(PBA_ERR_ARGUMENT, "pba_create: null argument");
+  if (cfg->rows < 8 || cfg->cols < 8) return fail(PBA_ERR_ARGUMENT, "pba_create: image %dx%d too small", cfg->rows, cfg->cols);
+  if (cfg->patch_radius < 1 || cfg->patch_radius > PBA_MAX_RADIUS)
+    return fail(PBA_ERR_ARGUMENT, "pba_create: patch_radius %d outside [1,%d]", cfg->patch_radius, PBA_MAX_RADIUS);
+  if (cfg->n_channels < 1 || cfg->n_channels > PBA_MAX_CHANNELS)
+    return fail(PBA_ERR_ARGUMENT, "pba_create: n_channels %d outside [1,%d]", cfg->n_channels, PBA_MAX_CHANNELS);
+  if (cfg->max_frames < 1 || cfg->max_frames > PBA_MAX_FRAMES)
+    return fail(PBA_ERR_ARGUMENT, "pba_create: max_frames %d outside [1,%d]", cfg->max_frames, PBA_MAX_FRAMES);
+  if (cfg->max_points < 1 || cfg->max_observations < 1)
+    return fail(PBA_ERR_ARGUMENT, "pba_create: capacities must be positive");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PBA_ERR_CUDA, "pba_create: no CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  pba_handle* h = new pba_handle();
+  h->cfg = *cfg;
+  if (cfg->device >= 0) {
+    if (cfg->device >= ndev) { delete h; return fail(PBA_ERR_ARGUMENT, "pba_create: device %d of %d", cfg->device, ndev); }
+    h->device = cfg->device;
+  } else {
+    cudaGetDevice(&h->device);
+  }
+#define CREATE_TRY(expr)                                                                           \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      free_all(h); delete h;                                                                       \
+      return fail(PBA_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));                  \
+    }                                                                                              \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CREATE_TRY(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10)
+    fprintf(stderr, "[pba_b200] warning: device '%s' is sm_%d%d; this library is built for sm_100a only\n",
+            prop.name, prop.major, prop.minor);
+  h->sm_count = prop.multiProcessorCount;
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaEventCreate(&h->ev0));
+  CREATE_TRY(cudaEventCreate(&h->ev1));
+  const int side = 2 * cfg->patch_radius + 1;
+  h->P = side * side;
+  h->CP = h->P * cfg->n_channels;
+  h->pitch = (cfg->cols + 15) / 16 * 16;
+  h->plane = (size_t)cfg->rows * h->pitch;
+  const size_t F = cfg->max_frames, n = cfg->max_points, nnz = cfg->max_observations;
+  const size_t D = 6 * F;
+  const int k1c = k1_grid((int)n), sc = h->sm_count, bc = back_grid((int)n);
+  CREATE_TRY(cudaMalloc(&h->d_cams, sizeof(double) * 2 * F * 6));
+  CREATE_TRY(cudaMalloc(&h->d_pts, sizeof(double) * 2 * n * 3));
+  CREATE_TRY(cudaMalloc(&h->d_weights, sizeof(double) * h->P));
+  CREATE_TRY(cudaMalloc(&h->d_desc, sizeof(float) * n * h->CP));
+  CREATE_TRY(cudaMalloc(&h->d_obs_off, sizeof(int) * (n + 1)));
+  CREATE_TRY(cudaMalloc(&h->d_obs_frame, sizeof(int) * nnz));
+  CREATE_TRY(cudaMalloc(&h->d_V, sizeof(double) * 2 * n * 6));
+  CREATE_TRY(cudaMalloc(&h->d_gp, sizeof(double) * 2 * n * 3));
+  CREATE_TRY(cudaMalloc(&h->d_W, sizeof(double) * 2 * nnz * 18));
+  CREATE_TRY(cudaMalloc(&h->d_Upart, sizeof(double) * (size_t)k1c * F * kUStride));
+  CREATE_TRY(cudaMalloc(&h->d_Epart, sizeof(double) * (size_t)k1c * 4));
+  CREATE_TRY(cudaMalloc(&h->d_U, sizeof(double) * 2 * F * kUStride));
+  CREATE_TRY(cudaMalloc(&h->d_E, sizeof(double) * 2 * 4));
+  CREATE_TRY(cudaMalloc(&h->d_scale_p, sizeof(double) * n * 3));
+  CREATE_TRY(cudaMalloc(&h->d_Vinv, sizeof(double) * n * 6));
+  CREATE_TRY(cudaMalloc(&h->d_Spart, sizeof(double) * (size_t)sc * (D * D + D)));
+  CREATE_TRY(cudaMalloc(&h->d_S, sizeof(double) * (D * D + D)));
+  CREATE_TRY(cudaMalloc(&h->d_Bpart, sizeof(double) * (size_t)bc * 4));
+  CREATE_TRY(cudaMalloc(&h->d_state, sizeof(LmState)));
+  CREATE_TRY(cudaMallocHost(&h->h_state, sizeof(LmState)));
+  CREATE_TRY(cudaMemset(h->d_Bpart, 0, sizeof(double) * (size_t)bc * 4));
+#undef CREATE_TRY
+  *out = h;
+  return PBA_OK;
+}
+
+void pba_destroy(pba_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_all(h);
+  delete h;
+}
+
+static int upload_plane_u8(pba_handle* h, int slot, const uint8_t* img) {
+  CUDA_TRY(cudaMemcpy2DAsync(h->d_u8 + (size_t)slot * h->plane, h->pitch, img, h->cfg.cols, h->cfg.cols,
+                             h->cfg.rows, cudaMemcpyHostToDevice, h->stream));
+  return PBA_OK;
+}
+
+int pba_set_frames_u8(pba_handle* h, int32_t n_frames, const uint8_t* const* images) {
+  if (!h || !images) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8: null argument");
+  if (h->cfg.n_channels != 1) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8: handle has %d channels; uint8 frames are the 1-channel Intensity descriptor", h->cfg.n_channels);
+  if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(PBA_ERR_CAPACITY, "pba_set_frames_u8: %d frames, capacity %d", n_frames, h->cfg.max_frames);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->d_u8) {
+    CUDA_TRY(cudaMalloc(&h->d_u8, (size_t)h->cfg.max_frames * h->plane));
+    CUDA_TRY(cudaMemsetAsync(h->d_u8, 0, (size_t)h->cfg.max_frames * h->plane, h->stream));
+  }
+  for (int f = 0; f < n_frames; ++f) {
+    if (!images[f]) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8: images[%d] is null", f);
+    int rc = upload_plane_u8(h, f, images[f]);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->frames_are_u8 = true; h->have_frames = true; h->n_frames = n_frames;
+  return PBA_OK;
+}
+
+int pba_set_frame_u8(pba_handle* h, int32_t slot, const uint8_t* image) {
+  if (!h || !image) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8: null argument");
+  if (!h->d_u8 || !h->frames_are_u8) return fail(PBA_ERR_STATE, "pba_set_frame_u8: call pba_set_frames_u8 first");
+  if (slot < 0 || slot >= h->cfg.max_frames) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8: slot %d", slot);
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = upload_plane_u8(h, slot, image);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PBA_OK;
+}
+
+int pba_set_frames_f32(pba_handle* h, int32_t n_frames, const float* const* planes) {
+  if (!h || !planes) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_f32: null argument");
+  if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(PBA_ERR_CAPACITY, "pba_set_frames_f32: %d frames, capacity %d", n_frames, h->cfg.max_frames);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int C = h->cfg.n_channels;
+  if (!h->d_f32) {
+    CUDA_TRY(cudaMalloc(&h->d_f32, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane));
+    CUDA_TRY(cudaMemsetAsync(h->d_f32, 0, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane, h->stream));
+  }
+  for (int i = 0; i < n_frames * C; ++i) {
+    if (!planes[i]) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_f32: planes[%d] is null", i);
+    CUDA_TRY(cudaMemcpy2DAsync(h->d_f32 + (size_t)i * h->plane, sizeof(float) * h->pitch, planes[i],
+                               sizeof(float) * h->cfg.cols, sizeof(float) * h->cfg.cols, h->cfg.rows,
+                               cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->frames_are_u8 = false; h->have_frames = true; h->n_frames = n_frames;
+  return PBA_OK;
+}
+
+int pba_set_poses(pba_handle* h, int32_t n_frames, const double* cam6, int32_t fixed_frame) {
+  if (!h || !cam6) return fail(PBA_ERR_ARGUMENT, "pba_set_poses: null argument");
+  if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(PBA_ERR_CAPACITY, "pba_set_poses: %d frames, capacity %d", n_frames, h->cfg.max_frames);
+  if (fixed_frame < -1 || fixed_frame >= n_frames) return fail(PBA_ERR_ARGUMENT, "pba_set_poses: fixed_frame %d", fixed_frame);
+  if (h->have_frames && n_frames != h->n_frames) return fail(PBA_ERR_ARGUMENT, "pba_set_poses: %d poses for %d frames", n_frames, h->n_frames);
+  CUDA_TRY(cudaSetDevice(h->device));
+  // buffer 0 holds x; buffer 1 starts as a copy (fixed / unused cameras are never rewritten)
+  const size_t stride = (size_t)n_frames * 6;
+  CUDA_TRY(cudaMemcpyAsync(h->d_cams, cam6, sizeof(double) * stride, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_cams + stride, cam6, sizeof(double) * stride, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->n_frames = n_frames; h->fixed_frame = fixed_frame; h->have_poses = true;
+  return PBA_OK;
+}
+
+int pba_set_points(pba_handle* h, int32_t n_points, const double* xyz, const double* desc,
+                   const int32_t* obs_offsets, const int32_t* obs_frame, const double* weights) {
+  if (!h || !xyz || !desc || !obs_offsets || !obs_frame || !weights) return fail(PBA_ERR_ARGUMENT, "pba_set_points: null argument");
+  if (n_points < 0 || n_points > h->cfg.max_points) return fail(PBA_ERR_CAPACITY, "pba_set_points: %d points, capacity %d", n_points, h->cfg.max_points);
+  if (obs_offsets[0] != 0) return fail(PBA_ERR_ARGUMENT, "pba_set_points: obs_offsets[0] must be 0");
+  const int nnz = obs_offsets[n_points];
+  if (nnz < 0 || nnz > h->cfg.max_observations) return fail(PBA_ERR_CAPACITY, "pba_set_points: %d observations, capacity %d", nnz, h->cfg.max_observations);
+  const int F = h->have_poses || h->have_frames ? h->n_frames : h->cfg.max_frames;
+  h->frame_used.assign(h->cfg.max_frames, 0);
+  for (int p = 0; p < n_points; ++p) {
+    if (obs_offsets[p + 1] < obs_offsets[p]) return fail(PBA_ERR_ARGUMENT, "pba_set_points: obs_offsets not monotone at %d", p);
+    for (int o = obs_offsets[p]; o < obs_offsets[p + 1]; ++o) {
+      if (obs_frame[o] < 0 || obs_frame[o] >= F) return fail(PBA_ERR_ARGUMENT, "pba_set_points: obs_frame[%d]=%d outside [0,%d)", o, obs_frame[o], F);
+      h->frame_used[obs_frame[o]] = 1;
+    }
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  std::vector<float> descf((size_t)n_points * h->CP);
+  for (size_t i = 0; i < descf.size(); ++i) descf[i] = (float)desc[i];
+  const size_t pstride = (size_t)n_points * 3;
+  CUDA_TRY(cudaMemcpyAsync(h->d_pts, xyz, sizeof(double) * pstride, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_pts + pstride, xyz, sizeof(double) * pstride, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_desc, descf.data(), sizeof(float) * descf.size(), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_obs_off, obs_offsets, sizeof(int) * (n_points + 1), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_obs_frame, obs_frame, sizeof(int) * nnz, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_weights, weights, sizeof(double) * h->P, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->n_points = n_points; h->nnz = nnz; h->have_points = true;
+  return PBA_OK;
+}
+
+static int check_ready(pba_handle* h, const char* who) {
+  if (!h) return fail(PBA_ERR_ARGUMENT, "%s: null handle", who);
+  if (!h->have_frames) return fail(PBA_ERR_STATE, "%s: frames not set", who);
+  if (!h->have_poses) return fail(PBA_ERR_STATE, "%s: poses not set", who);
+  if (!h->have_points) return fail(PBA_ERR_STATE, "%s: points not set", who);
+  return PBA_OK;
+}
+
+static EvalParams make_eval_params(pba_handle* h, bool with_state) {
+  EvalParams p;
+  memset(&p, 0, sizeof(p));
+  p.fr.u8 = h->frames_are_u8 ? h->d_u8 : nullptr;
+  p.fr.f32 = h->frames_are_u8 ? nullptr : h->d_f32;
+  p.fr.rows = h->cfg.rows; p.fr.cols = h->cfg.cols; p.fr.pitch = h->pitch;
+  p.fr.n_channels = h->cfg.n_channels; p.fr.plane = h->plane;
+  p.n_frames = h->n_frames; p.fixed_frame = h->fixed_frame; p.n_points = h->n_points; p.nnz = h->nnz;
+  p.fx = h->cfg.fx; p.fy = h->cfg.fy; p.cx = h->cfg.cx; p.cy = h->cfg.cy; p.huber = h->cfg.huber;
+  p.st = with_state ? h->d_state : nullptr;
+  p.cams = h->d_cams; p.pts = h->d_pts; p.desc = h->d_desc; p.obs_off = h->d_obs_off;
+  p.obs_frame = h->d_obs_frame; p.weights = h->d_weights;
+  p.V = h->d_V; p.gp = h->d_gp; p.W = h->d_W; p.Upart = h->d_Upart; p.Epart = h->d_Epart;
+  return p;
+}
+
+static LmParams make_lm_params(pba_handle* h) {
+  LmParams lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.st = h->d_state; lp.trace = h->d_trace;
+  lp.n_frames = h->n_frames; lp.n_points = h->n_points; lp.nnz = h->nnz;
+  lp.n_k1_ctas = k1_grid(h->n_points);
+  lp.n_schur_ctas = schur_grid(h->n_points, h->sm_count);
+  lp.n_back_ctas = back_grid(h->n_points);
+  lp.obs_off = h->d_obs_off; lp.obs_frame = h->d_obs_frame;
+  lp.cams = h->d_cams; lp.pts = h->d_pts; lp.V = h->d_V; lp.gp = h->d_gp; lp.W = h->d_W;
+  lp.Upart = h->d_Upart; lp.Epart = h->d_Epart; lp.U = h->d_U; lp.E = h->d_E;
+  lp.scale_p = h->d_scale_p; lp.Vinv = h->d_Vinv; lp.Spart = h->d_Spart; lp.S = h->d_S;
+  lp.rhs = h->d_S + (size_t)36 * h->n_frames * h->n_frames; lp.Bpart = h->d_Bpart;
+  return lp;
+}
+
+static void unpack_sym6(const double* u21, double* out36) {
+  int k = 0;
+  for (int a = 0; a < 6; ++a)
+    for (int b = a; b < 6; ++b, ++k) { out36[a * 6 + b] = u21[k]; out36[b * 6 + a] = u21[k]; }
+}
+
+int pba_eval(pba_handle* h, pba_eval_out* out) {
+  int rc = check_ready(h, "pba_eval");
+  if (rc) return rc;
+  if (!out) return fail(PBA_ERR_ARGUMENT, "pba_eval: null output");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int F = h->n_frames, n = h->n_points, nnz = h->nnz;
+  EvalParams p = make_eval_params(h, false);
+  if (out->obs_sqnorm) {
+    if (!h->d_obs_sqnorm) CUDA_TRY(cudaMalloc(&h->d_obs_sqnorm, sizeof(double) * h->cfg.max_observations));
+    p.obs_sqnorm = h->d_obs_sqnorm;
+  }
+  if (out->residuals) {
+    if (!h->d_residuals) CUDA_TRY(cudaMalloc(&h->d_residuals, sizeof(double) * (size_t)h->cfg.max_observations * h->CP));
+    p.residuals = h->d_residuals;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  CUDA_TRY(launch_k1(p, h->cfg.patch_radius, h->stream));
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  out->device_ms = ms;
+  // host-side reduction of the per-CTA partials (test/inspection path only; pba_solve reduces on the device)
+  const int nb = k1_grid(n);
+  std::vector<double> up((size_t)nb * F * kUStride), ep((size_t)nb * 4);
+  CUDA_TRY(cudaMemcpy(up.data(), h->d_Upart, sizeof(double) * up.size(), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(ep.data(), h->d_Epart, sizeof(double) * ep.size(), cudaMemcpyDeviceToHost));
+  std::vector<double> U((size_t)F * kUStride, 0.0);
+  double cost = 0.0;
+  for (int b = 0; b < nb; ++b) {
+    for (int i = 0; i < F * kUStride; ++i) U[i] += up[(size_t)b * F * kUStride + i];
+    cost += ep[(size_t)b * 4];
+  }
+  out->cost = cost;
+  if (out->U) for (int f = 0; f < F; ++f) unpack_sym6(&U[f * kUStride], out->U + f * 36);
+  if (out->gc) for (int f = 0; f < F; ++f) for (int a = 0; a < 6; ++a) out->gc[f * 6 + a] = U[f * kUStride + 21 + a];
+  if (out->V) {
+    std::vector<double> v((size_t)n * 6);
+    CUDA_TRY(cudaMemcpy(v.data(), h->d_V, sizeof(double) * v.size(), cudaMemcpyDeviceToHost));
+    for (int q = 0; q < n; ++q) {
+      const double* s = &v[(size_t)q * 6];
+      double* o = out->V + (size_t)q * 9;
+      o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[1]; o[4] = s[3]; o[5] = s[4]; o[6] = s[2]; o[7] = s[4]; o[8] = s[5];
+    }
+  }
+  if (out->gp) CUDA_TRY(cudaMemcpy(out->gp, h->d_gp, sizeof(double) * (size_t)n * 3, cudaMemcpyDeviceToHost));
+  if (out->W) CUDA_TRY(cudaMemcpy(out->W, h->d_W, sizeof(double) * (size_t)nnz * 18, cudaMemcpyDeviceToHost));
+  if (out->obs_sqnorm) CUDA_TRY(cudaMemcpy(out->obs_sqnorm, h->d_obs_sqnorm, sizeof(double) * nnz, cudaMemcpyDeviceToHost));
+  if (out->residuals) CUDA_TRY(cudaMemcpy(out->residuals, h->d_residuals, sizeof(double) * (size_t)nnz * h->CP, cudaMemcpyDeviceToHost));
+  return PBA_OK;
+}
+
+int pba_eval_timed(pba_handle* h, int32_t iters, double* ms_total) {
+  int rc = check_ready(h, "pba_eval_timed");
+  if (rc) return rc;
+  if (iters < 1 || !ms_total) return fail(PBA_ERR_ARGUMENT, "pba_eval_timed: bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  EvalParams p = make_eval_params(h, false);
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < iters; ++i) CUDA_TRY(launch_k1(p, h->cfg.patch_radius, h->stream));
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *ms_total = ms;
+  return PBA_OK;
+}
+
+static void format_message(const LmState& s, char* out, size_t cap) {
+  switch (s.msg_code) {
+    case kMsgGradTol: snprintf(out, cap, "Gradient tolerance reached. Gradient max norm: %e <= %e", s.msg_a, s.msg_b); break;
+    case kMsgParamTol: snprintf(out, cap, "Parameter tolerance reached. Relative step_norm: %e <= %e.", s.msg_a, s.msg_b); break;
+    case kMsgFuncTol: snprintf(out, cap, "Function tolerance reached. |cost_change|/cost: %e <= %e", s.msg_a, s.msg_b); break;
+    case kMsgMaxIter: snprintf(out, cap, "Maximum number of iterations reached. Number of iterations: %d.", (int)s.msg_a); break;
+    case kMsgMinRadius: snprintf(out, cap, "Minimum trust region radius reached. Trust region radius: %e <= %e", s.msg_a, s.msg_b); break;
+    case kMsgInvalidSteps: snprintf(out, cap, "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps: %d", (int)s.msg_a); break;
+    default: snprintf(out, cap, "no termination message"); break;
+  }
+}
+
+int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summary) {
+  int rc = check_ready(h, "pba_solve");
+  if (rc) return rc;
+  if (!summary) return fail(PBA_ERR_ARGUMENT, "pba_solve: null summary");
+  const auto t_start = std::chrono::steady_clock::now();
+  pba_solver_options opt;
+  if (opt_in) opt = *opt_in; else pba_default_solver_options(&opt);
+  if (opt.max_num_iterations < 0) return fail(PBA_ERR_ARGUMENT, "pba_solve: max_num_iterations < 0");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int F = h->n_frames;
+  if (h->trace_cap < opt.max_num_iterations + 2) {
+    cudaFree(h->d_trace);
+    h->d_trace = nullptr;
+    h->trace_cap = opt.max_num_iterations + 2;
+    CUDA_TRY(cudaMalloc(&h->d_trace, sizeof(IterSummary) * h->trace_cap));
+  }
+  LmState* s = h->h_state;
+  memset(s, 0, sizeof(*s));
+  s->max_num_iterations = opt.max_num_iterations; s->max_invalid = opt.max_num_consecutive_invalid_steps;
+  s->jacobi_scaling = opt.jacobi_scaling;
+  s->function_tolerance = opt.function_tolerance; s->gradient_tolerance = opt.gradient_tolerance;
+  s->parameter_tolerance = opt.parameter_tolerance; s->initial_radius = opt.initial_trust_region_radius;
+  s->max_radius = opt.max_trust_region_radius; s->min_radius = opt.min_trust_region_radius;
+  s->min_relative_decrease = opt.min_relative_decrease; s->min_diag = opt.min_lm_diagonal; s->max_diag = opt.max_lm_diagonal;
+  s->n_frames = F; s->fixed_frame = h->fixed_frame; s->n_points = h->n_points; s->nnz = h->nnz;
+  s->n_free = 0;
+  for (int f = 0; f < kMaxFrames; ++f) s->free_index[f] = -1;
+  // a camera is a parameter block only if some residual block uses it (src/photobundle.cc:802)
+  for (int f = 0; f < F; ++f)
+    if (h->frame_used[f] && f != h->fixed_frame) s->free_index[f] = s->n_free++;
+  s->cur = 0; s->eval_buf = 0; s->decrease_factor = 2.0; s->radius = opt.initial_trust_region_radius;
+  // x lives in buffer 0 of cams/points; refresh buffer 1 so fixed cameras carry over
+  CUDA_TRY(cudaMemcpyAsync(h->d_cams + (size_t)F * 6, h->d_cams, sizeof(double) * F * 6, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_state, s, sizeof(LmState), cudaMemcpyHostToDevice, h->stream));
+
+  EvalParams ep = make_eval_params(h, true);
+  LmParams lp = make_lm_params(h);
+  int launches = 0;
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  CUDA_TRY(launch_k1(ep, h->cfg.patch_radius, h->stream));
+  CUDA_TRY(launch_reduce_u(lp, h->stream));
+  CUDA_TRY(launch_decide(lp, h->stream));
+  launches += 3;
+  // Enqueue iterations in groups; kernels turn into no-ops once st->done is set.
+  const int group = 4;
+  bool done = false;
+  int enq = 0;
+  while (!done) {
+    for (int g = 0; g < group && enq <= opt.max_num_iterations; ++g, ++enq) {
+      CUDA_TRY(launch_schur(lp, h->stream));
+      CUDA_TRY(launch_reduce_s(lp, h->stream));
+      CUDA_TRY(launch_solve(lp, h->stream));
+      CUDA_TRY(launch_backsub(lp, h->stream));
+      CUDA_TRY(launch_k1(ep, h->cfg.patch_radius, h->stream));
+      CUDA_TRY(launch_reduce_u(lp, h->stream));
+      CUDA_TRY(launch_decide(lp, h->stream));
+      launches += 7;
+    }
+    CUDA_TRY(cudaMemcpyAsync(s, h->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    done = s->done != 0 || enq > opt.max_num_iterations;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  // the accepted x must end up in buffer 0 for pba_get_* and for the next solve
+  if (s->cur != 0) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_cams, h->d_cams + (size_t)F * 6, sizeof(double) * F * 6, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_pts, h->d_pts + (size_t)h->n_points * 3, sizeof(double) * (size_t)h->n_points * 3, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->trace.resize(s->n_trace);
+  if (s->n_trace > 0)
+    CUDA_TRY(cudaMemcpyAsync(h->trace.data(), h->d_trace, sizeof(IterSummary) * s->n_trace, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+
+  memset(summary, 0, sizeof(*summary));
+  summary->initial_cost = s->initial_cost; summary->final_cost = s->x_cost; summary->fixed_cost = 0.0;
+  summary->num_successful_steps = s->num_successful; summary->num_unsuccessful_steps = s->num_unsuccessful;
+  summary->num_residual_blocks = h->nnz; summary->num_residuals = h->nnz * h->CP;
+  summary->num_iterations = s->n_trace; summary->termination_type = s->termination_type;
+  summary->num_evaluations = s->num_evals;
+  summary->kernel_launches = launches; summary->num_collectives = 0;
+  summary->device_time_in_seconds = ms * 1e-3;
+  if (!s->done) { s->msg_code = kMsgMaxIter; s->msg_a = opt.max_num_iterations; summary->termination_type = 1; }
+  format_message(*s, summary->message, sizeof(summary->message));
+  summary->total_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+  return PBA_OK;
+}
+
+int pba_get_poses(pba_handle* h, double* cam6) {
+  if (!h || !cam6) return fail(PBA_ERR_ARGUMENT, "pba_get_poses: null argument");
+  if (!h->have_poses) return fail(PBA_ERR_STATE, "pba_get_poses: poses not set");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpy(cam6, h->d_cams, sizeof(double) * (size_t)h->n_frames * 6, cudaMemcpyDeviceToHost));
+  return PBA_OK;
+}
+
+int pba_get_points(pba_handle* h, double* xyz) {
+  if (!h || !xyz) return fail(PBA_ERR_ARGUMENT, "pba_get_points: null argument");
+  if (!h->have_points) return fail(PBA_ERR_STATE, "pba_get_points: points not set");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpy(xyz, h->d_pts, sizeof(double) * (size_t)h->n_points * 3, cudaMemcpyDeviceToHost));
+  return PBA_OK;
+}
+
+int pba_get_iterations(pba_handle* h, pba_iteration_summary* out, int32_t capacity, int32_t* n) {
+  if (!h || !n) return fail(PBA_ERR_ARGUMENT, "pba_get_iterations: null argument");
+  static_assert(sizeof(pba_iteration_summary) == sizeof(IterSummary), "trace layout mismatch");
+  *n = (int32_t)h->trace.size();
+  if (out) {
+    const int m = std::min<int>(capacity, *n);
+    if (m > 0) memcpy(out, h->trace.data(), sizeof(IterSummary) * m);
+  }
+  return PBA_OK;
+}
+
+int pba_comm_unique_id(void* id128) {
+  (void)id128;
+  return fail(PBA_ERR_NCCL, "pba_comm_unique_id: multi-GPU support not initialised in this build step");
+}
+
+int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_ranks) {
+  (void)h; (void)id128; (void)rank; (void)n_ranks;
+  return fail(PBA_ERR_NCCL, "pba_comm_init: multi-GPU support not initialised in this build step");
+}
+
+}  // extern "C"

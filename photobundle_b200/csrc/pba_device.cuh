@@ -1,0 +1,139 @@
+// pba_device.cuh — device-side data layout shared by the kernels (sm_100a only).
+//
+// HBM layout of one window. "x2" = double-buffered: buffer st->cur holds the
+// accepted point x, buffer st->eval_buf the candidate x+Δ being evaluated.
+//   frames   u8  [F][rows][pitch]            pitch = roundup(cols,16) bytes   (Intensity)
+//         or f32 [F][C][rows][pitch]         pitch = roundup(cols,16) floats  (generic)
+//   cams     f64 x2 [F][6]                   world->camera [angle-axis, t]
+//   points   f64 x2 [n][3]
+//   desc     f32 [n][C*P]                    reference descriptors (exact: the reference
+//                                            widens float channel values to double,
+//                                            src/photobundle.cc:466-479)
+//   obs_off  i32 [n+1], obs_frame i32 [nnz]  CSR visibility, window-local frame index
+//   V,gp,W   f64 x2 [n][6] [n][3] [nnz][18]  point blocks / cross blocks at x
+//   Upart    f64 [k1 CTAs][F][27]            per-CTA partial pose blocks (21 U + 6 g_c)
+//   Epart    f64 [k1 CTAs][4]                per-CTA {cost, Σg_p², max|g_p|, Σ|X|²}
+//   U,E      f64 x2 [F][27], [4]             reduced pose blocks / scalars at x
+//   Spart    f64 [schur CTAs][D*D + D]       per-CTA partial Schur complement, D = 6F
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pba {
+
+constexpr int kMaxFrames = 16;
+constexpr int kMaxD = 6 * kMaxFrames;
+constexpr int kWarpsPerCta = 8;       // K1: one warp per point
+constexpr int kObsBatch = 8;          // observations whose geometry is formed together
+constexpr int kStageSlots = 8;        // (observation, channel) footprints staged together
+constexpr int kPoseConst = 36;        // doubles per frame, see pose_consts()
+constexpr int kUStride = 27;          // 21 upper-tri U + 6 g_c
+constexpr int kSchurThreads = 256;
+constexpr int kSchurChunk = 8;        // points per chunk (one per warp)
+constexpr int kBackThreads = 128;
+
+struct Frames {
+  const uint8_t* u8;   // non-null: Intensity planes, gradients formed in-kernel
+  const float* f32;    // non-null: generic fp32 channel planes
+  int rows, cols, pitch, n_channels;
+  size_t plane;        // elements per plane (rows * pitch)
+};
+
+// Same layout as pba_iteration_summary (include/pba_b200.h).
+struct IterSummary {
+  int32_t iteration, step_is_valid, step_is_nonmonotonic, step_is_successful;
+  double cost, cost_change, gradient_max_norm, gradient_norm, step_norm, relative_decrease,
+      trust_region_radius, eta, step_size;
+  int32_t ls_f, ls_g, ls_it, linear_solver_iterations;
+  double iteration_time_in_seconds, step_solver_time_in_seconds, cumulative_time_in_seconds;
+};
+
+enum MsgCode {
+  kMsgNone = 0, kMsgGradTol = 1, kMsgParamTol = 2, kMsgFuncTol = 3, kMsgMaxIter = 4,
+  kMsgMinRadius = 5, kMsgInvalidSteps = 6
+};
+
+// Levenberg-Marquardt state machine, resident in HBM; every kernel of the loop reads it,
+// only k_decide / k_solve write it (Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy
+// semantics).
+struct LmState {
+  // options
+  int max_num_iterations, max_invalid, jacobi_scaling;
+  double function_tolerance, gradient_tolerance, parameter_tolerance;
+  double initial_radius, max_radius, min_radius, min_relative_decrease, min_diag, max_diag;
+  // problem
+  int n_frames, fixed_frame, n_free, n_points, nnz;
+  int free_index[kMaxFrames];     // frame -> index among optimised frames, -1 otherwise
+  // dynamic
+  int iteration;                  // iteration whose step is being computed / judged
+  int cur, eval_buf;              // buffer of accepted x / buffer the next evaluation writes
+  int done, termination_type, msg_code;
+  double msg_a, msg_b;
+  double radius, decrease_factor;
+  int num_invalid, num_successful, num_unsuccessful, n_trace, num_evals;
+  double x_cost, x_norm, initial_cost;
+  double gmax, gnorm;
+  // step under evaluation (written by k_solve / k_backsub partials)
+  int step_valid;
+  double cam_sg, cam_sHs, cam_step_sq, cam_cand_sq;
+  double scale_c[kMaxD];          // Jacobi column scaling of the pose columns (iteration 0)
+  double step_c[kMaxD];           // trust-region step of the pose columns, scaled space
+};
+
+struct EvalParams {
+  Frames fr;
+  int n_frames, fixed_frame, n_points, nnz;
+  double fx, fy, cx, cy, huber;
+  const LmState* st;         // null: evaluate buffer 0 (pba_eval)
+  const double* cams;        // x2 [F][6]
+  const double* pts;         // x2 [n][3]
+  const float* desc;         // [n][C*P]
+  const int* obs_off;        // [n+1]
+  const int* obs_frame;      // [nnz]
+  const double* weights;     // [P]
+  double* V;                 // x2 [n][6]   upper triangle 00 01 02 11 12 22
+  double* gp;                // x2 [n][3]
+  double* W;                 // x2 [nnz][18] row-major 6x3
+  double* Upart;             // [gridDim.x][F][27]
+  double* Epart;             // [gridDim.x][4]
+  double* obs_sqnorm;        // optional [nnz]
+  double* residuals;         // optional [nnz][C*P]
+};
+
+struct LmParams {
+  LmState* st;
+  IterSummary* trace;
+  int n_frames, n_points, nnz, n_k1_ctas, n_schur_ctas, n_back_ctas;
+  const int* obs_off;
+  const int* obs_frame;
+  double* cams;              // x2
+  double* pts;               // x2
+  const double* V;           // x2
+  const double* gp;          // x2
+  const double* W;           // x2
+  const double* Upart;
+  const double* Epart;
+  double* U;                 // x2 [F][27]
+  double* E;                 // x2 [4]
+  double* scale_p;           // [n][3]
+  double* Vinv;              // [n][6]
+  double* Spart;             // [n_schur_ctas][D*D + D]
+  double* S;                 // [D*D]
+  double* rhs;               // [D]
+  double* Bpart;             // [n_back_ctas][4]
+};
+
+// launchers (k1_eval.cu, lm_kernels.cu)
+int k1_grid(int n_points);
+size_t k1_smem(int radius, int n_frames);
+cudaError_t launch_k1(const EvalParams& prm, int radius, cudaStream_t stream);
+int schur_grid(int n_points, int sm_count);
+int back_grid(int n_points);
+cudaError_t launch_reduce_u(const LmParams& lp, cudaStream_t stream);
+cudaError_t launch_decide(const LmParams& lp, cudaStream_t stream);
+cudaError_t launch_schur(const LmParams& lp, cudaStream_t stream);
+cudaError_t launch_reduce_s(const LmParams& lp, cudaStream_t stream);
+cudaError_t launch_solve(const LmParams& lp, cudaStream_t stream);
+cudaError_t launch_backsub(const LmParams& lp, cudaStream_t stream);
+
+}  // namespace pba

@@ -1,0 +1,199 @@
+"""Parity tests proper (-m gpu): the CUDA path through the C ABI vs the CPU oracle on the
+same seeded inputs.  Tolerances (north-star: final cost within 1e-4 relative, pose
+parameters within 1e-5):
+  residuals        bit-exact for >= 99.9 % of samples, |diff| <= 1e-4 grey levels otherwise
+                   (the only non-identical inputs are device vs glibc sin/cos, <= 1 ulp)
+  block sums       <= 1e-5 relative to the largest entry of the block family (fp32 patch sums)
+  cost             <= 1e-9 relative (fp64 accumulation)
+  LM               same accept/reject sequence; per-iteration cost <= 1e-6 relative;
+                   final cost <= 1e-4 relative; pose parameters <= 1e-5 absolute
+"""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from photobundle_b200 import capi, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_eval(win, planes=None, cams=None, points=None, block_rtol=1e-5, min_exact=0.999):
+    cams = win.cams_init if cams is None else cams
+    points = win.points_init if points is None else points
+    ow = ob.OracleWindow(win, planes=planes)
+    h = capi.Handle.for_window(win, planes_f32=planes)
+    h.set_poses(cams, win.fixed_frame)
+    h.set_points(points, win.desc, win.obs_offsets, win.obs_frame, win.weights)
+    ev = h.eval()
+    ref = ow.evaluate(cams, points, use_autodiff=1)
+    h.close()
+    # T=double residuals of the oracle (cost-only path) for the bit-exactness statement
+    d = np.abs(ev["residuals"] - ref["residuals"])
+    exact = float((d == 0).mean())
+    assert d.max() <= 1e-4, d.max()
+    assert exact >= min_exact, exact
+    np.testing.assert_allclose(ev["obs_sqnorm"], ref["obs_sqnorm"], rtol=1e-6, atol=1e-6)
+    assert abs(ev["cost"] - ref["cost"]) <= 1e-7 * ref["cost"], (ev["cost"], ref["cost"])
+    for k in ("U", "gc", "V", "gp", "W"):
+        scale = np.abs(ref[k]).max()
+        err = np.abs(ev[k] - ref[k]).max()
+        assert err <= block_rtol * scale, (k, err, scale)
+    assert not ev["U"][win.fixed_frame].any() and not ev["gc"][win.fixed_frame].any()
+    return ev, ref
+
+
+def test_k1_small_dense(small_win):
+    _check_eval(small_win)
+
+
+def test_k1_small_ragged(small_ragged_win):
+    _check_eval(small_ragged_win)
+
+
+def test_k1_f32_planes_equal_u8_path(small_win):
+    """Generic fp32 channel planes give the same numbers as the uint8 Intensity fast path."""
+    w = small_win
+    h8 = capi.Handle.for_window(w)
+    hf = capi.Handle.for_window(w, planes_f32=w.planes_f32())
+    a, b = h8.eval(), hf.eval()
+    h8.close(); hf.close()
+    for k in ("residuals", "U", "gc", "V", "gp", "W", "obs_sqnorm"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["cost"] == b["cost"]
+
+
+@pytest.mark.parametrize("radius", [1, 3, 4])
+def test_k1_other_radii(radius):
+    w = synthetic.small_window(seed=5, radius=radius, ragged=True, n_frames=6)
+    _check_eval(w)
+
+
+def test_k1_gaussian_weights():
+    w = synthetic.make_window(n_frames=4, grid=(8, 10), rows=120, cols=160, intrinsics=(200.0, 200.0, 79.7, 60.2),
+                              margin=16, seed=9, gaussian_weights=True)
+    _check_eval(w)
+
+
+def test_k1_multichannel_intensity_and_gradient(small_win):
+    """3-channel IntensityAndGradient descriptor (photobundle.cc:233-240): channels I, Ix, Iy."""
+    import ctypes as C
+    w = small_win
+    I = w.planes_f32()[:, 0]
+    planes = np.zeros((w.n_frames, 3, w.rows, w.cols), dtype=np.float32)
+    planes[:, 0] = I
+    for f in range(w.n_frames):
+        ob.lib().oracle_imgradient(C.c_void_p(I[f].ctypes.data), w.rows, w.cols,
+                                   C.c_void_p(planes[f, 1].ctypes.data), C.c_void_p(planes[f, 2].ctypes.data))
+    import dataclasses
+    desc = np.concatenate([
+        np.stack([synthetic.extract_patch(planes[int(w.obs_frame[w.obs_offsets[p]]), k],
+                                          *_first_px(w, p), w.radius) for p in range(w.n_points)])
+        for k in range(3)], axis=1)
+    w3 = dataclasses.replace(w, desc=desc, n_channels=3)
+    _check_eval(w3, planes=planes)
+
+
+def _first_px(w, p):
+    """integer pixel of point p in its reference frame (re-project the initial point)."""
+    f = int(w.obs_frame[w.obs_offsets[p]])
+    R = synthetic.rodrigues(w.cams_init[f, :3])
+    Xc = R @ w.points_init[p] + w.cams_init[f, 3:]
+    return int(round(w.fx * Xc[0] / Xc[2] + w.cx)), int(round(w.fy * Xc[1] / Xc[2] + w.cy))
+
+
+def test_k1_borders_and_outside(small_win):
+    """Observations on the image border, in the (-1,0) extrapolation band, outside the image
+    and behind the camera take the slow path; it must reproduce the reference's clamp /
+    zero-gradient-border rules (sample_eigen.h:38-46, imgproc.cc:34-43)."""
+    w = small_win
+    pts = w.points_init.copy()
+    rng = np.random.default_rng(1)
+    n = w.n_points
+    # push points so that they project around / beyond each border in frame 0 (identity pose)
+    z = pts[:, 2].copy()
+    targets_u = np.concatenate([rng.uniform(-4, 4, n // 4), rng.uniform(w.cols - 5, w.cols + 3, n // 4),
+                                rng.uniform(0, w.cols, n - 2 * (n // 4))])
+    targets_v = np.concatenate([rng.uniform(0, w.rows, n // 2), rng.uniform(-4, 4, n // 4),
+                                rng.uniform(w.rows - 5, w.rows + 3, n - n // 2 - n // 4)])
+    pts[:, 0] = (targets_u - w.cx) / w.fx * z
+    pts[:, 1] = (targets_v - w.cy) / w.fy * z
+    pts[:5, 2] *= -1.0        # behind the camera
+    pts[5:8] *= 1e-9          # Z ~ 0 -> huge / non-finite projections
+    _check_eval(w, points=pts, min_exact=0.99)
+
+
+def _check_solve(win, pose_tol=1e-5, cost_rtol=1e-4):
+    ow = ob.OracleWindow(win)
+    ocams, opts, osum, otr = ow.solve(win.cams_init, win.points_init)
+    h = capi.Handle.for_window(win)
+    s = h.solve()
+    cams, pts, tr = h.get_poses(), h.get_points(), h.get_iterations()
+    h.close()
+    assert s["termination_type"] == osum["termination_type"]
+    assert [t["step_is_successful"] for t in tr] == [t["step_is_successful"] for t in otr], (s, osum)
+    for a, b in zip(tr, otr):
+        assert abs(a["cost"] - b["cost"]) <= 1e-6 * b["cost"], (a, b)
+        assert abs(a["trust_region_radius"] - b["trust_region_radius"]) <= 1e-3 * b["trust_region_radius"]
+    assert abs(s["initial_cost"] - osum["initial_cost"]) <= 1e-7 * osum["initial_cost"]
+    assert abs(s["final_cost"] - osum["final_cost"]) <= cost_rtol * osum["final_cost"]
+    assert np.abs(cams - ocams).max() <= pose_tol, np.abs(cams - ocams).max()
+    assert np.abs(pts - opts).max() <= 1e-3 * max(1.0, np.abs(opts).max())
+    assert np.array_equal(cams[win.fixed_frame], win.cams_init[win.fixed_frame])
+    assert s["num_residuals"] == win.n_residuals and s["num_residual_blocks"] == win.n_obs
+    assert s["message"].split(".")[0] == osum["message"].split(".")[0]
+    return s, osum
+
+
+def test_lm_small_dense(small_win):
+    _check_solve(small_win)
+
+
+def test_lm_small_ragged(small_ragged_win):
+    _check_solve(small_ragged_win)
+
+
+def test_lm_resolve_is_idempotent(small_win):
+    """Solving again from the optimum terminates immediately without moving (Ceres semantics)."""
+    h = capi.Handle.for_window(small_win)
+    s1 = h.solve()
+    c1 = h.get_poses()
+    s2 = h.solve()
+    c2 = h.get_poses()
+    h.close()
+    assert s2["initial_cost"] == s1["final_cost"]
+    assert s2["final_cost"] <= s1["final_cost"]
+    assert np.abs(c2 - c1).max() <= 1e-4
+
+
+def test_lm_max_iterations_and_no_loss(small_win):
+    import dataclasses
+    h = capi.Handle.for_window(small_win)
+    s = h.solve(max_num_iterations=3)
+    assert s["termination_type"] == 1 and s["num_iterations"] == 4 and "Maximum number of iterations" in s["message"]
+    h.close()
+    w2 = dataclasses.replace(small_win, huber=0.0)     # robustThreshold <= 0 -> no loss (photobundle.cc:797)
+    _check_solve(w2)
+
+
+def test_cfg3_full_size(cfg3_win):
+    """BASELINE cfg2 + cfg3: 8 frames x 4000 points x 5x5 at KITTI size (32 000 observations,
+    800 000 residuals): K1 parity and full-LM parity against the oracle."""
+    w = cfg3_win
+    assert w.n_obs == 32000 and w.n_residuals == 800000
+    _check_eval(w)
+    s, osum = _check_solve(w)
+    assert s["final_cost"] < 0.2 * s["initial_cost"]
+
+
+def test_state_errors(small_win):
+    w = small_win
+    h = capi.Handle(w.rows, w.cols, w.fx, w.fy, w.cx, w.cy, max_frames=w.n_frames, max_points=w.n_points)
+    with pytest.raises(capi.PbaError, match="frames not set"):
+        h.solve()
+    h.set_frames_u8(w.images)
+    with pytest.raises(capi.PbaError, match="poses not set"):
+        h.eval()
+    with pytest.raises(capi.PbaError, match="capacity"):
+        h.set_points(np.zeros((w.n_points + 1, 3)), np.zeros((w.n_points + 1, 25)),
+                     np.zeros(w.n_points + 2, dtype=np.int32), np.zeros(1, dtype=np.int32), w.weights)
+    h.close()
