@@ -174,6 +174,12 @@ int pba_eval_timed(pba_handle* h, int32_t iters, double* ms_total);
  * Poses and points are updated on the device; read them with pba_get_*. */
 int pba_solve(pba_handle* h, const pba_solver_options* opt, pba_summary* summary);
 
+/* Device-resident snapshot of the current poses and points (the x that pba_solve starts from),
+ * and its restoration: lets a caller re-solve the same window without host->device copies
+ * (bench.py's HBM-resident `value` leg; also what a pyramid level-to-level hand-over uses). */
+int pba_save_state(pba_handle* h);
+int pba_restore_state(pba_handle* h);
+
 int pba_get_poses(pba_handle* h, double* cam6);
 int pba_get_points(pba_handle* h, double* xyz);
 int pba_get_iterations(pba_handle* h, pba_iteration_summary* out, int32_t capacity, int32_t* n);

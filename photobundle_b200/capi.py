@@ -20,7 +20,7 @@ PBA_UNIQUE_ID_BYTES = 128
 EXPORTED_SYMBOLS = [
     "pba_last_error", "pba_version", "pba_default_solver_options", "pba_create", "pba_destroy",
     "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_poses", "pba_set_points",
-    "pba_eval", "pba_eval_timed", "pba_solve", "pba_get_poses", "pba_get_points", "pba_get_iterations",
+    "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_get_poses", "pba_get_points", "pba_get_iterations",
     "pba_comm_unique_id", "pba_comm_init",
 ]
 
@@ -217,6 +217,12 @@ class Handle:
         sd = {f[0]: getattr(summ, f[0]) for f in Summary._fields_}
         sd["message"] = summ.message.decode()
         return sd
+
+    def save_state(self):
+        _check(lib().pba_save_state(self._h), "pba_save_state")
+
+    def restore_state(self):
+        _check(lib().pba_restore_state(self._h), "pba_restore_state")
 
     def get_poses(self) -> np.ndarray:
         cams = np.zeros((self.n_frames, 6))

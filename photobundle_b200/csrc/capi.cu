@@ -51,6 +51,8 @@ struct pba_handle {
   double *d_Upart = nullptr, *d_Epart = nullptr, *d_U = nullptr, *d_E = nullptr;
   double *d_scale_p = nullptr, *d_Vinv = nullptr, *d_Spart = nullptr, *d_S = nullptr, *d_Bpart = nullptr;
   double *d_obs_sqnorm = nullptr, *d_residuals = nullptr;
+  double *d_save_cams = nullptr, *d_save_pts = nullptr;
+  bool have_saved = false;
   LmState* d_state = nullptr;
   IterSummary* d_trace = nullptr;
   int trace_cap = 0;
@@ -69,6 +71,7 @@ static void free_all(pba_handle* h) {
   cudaFree(h->d_desc); cudaFree(h->d_obs_off); cudaFree(h->d_obs_frame); cudaFree(h->d_V); cudaFree(h->d_gp);
   cudaFree(h->d_W); cudaFree(h->d_Upart); cudaFree(h->d_Epart); cudaFree(h->d_U); cudaFree(h->d_E);
   cudaFree(h->d_scale_p); cudaFree(h->d_Vinv); cudaFree(h->d_Spart); cudaFree(h->d_S); cudaFree(h->d_Bpart);
+  cudaFree(h->d_save_cams); cudaFree(h->d_save_pts);
   cudaFree(h->d_obs_sqnorm); cudaFree(h->d_residuals); cudaFree(h->d_state); cudaFree(h->d_trace);
   if (h->h_state) cudaFreeHost(h->h_state);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -494,6 +497,31 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   if (!s->done) { s->msg_code = kMsgMaxIter; s->msg_a = opt.max_num_iterations; summary->termination_type = 1; }
   format_message(*s, summary->message, sizeof(summary->message));
   summary->total_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+  return PBA_OK;
+}
+
+int pba_save_state(pba_handle* h) {
+  if (!h) return fail(PBA_ERR_ARGUMENT, "pba_save_state: null handle");
+  if (!h->have_poses || !h->have_points) return fail(PBA_ERR_STATE, "pba_save_state: poses/points not set");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->d_save_cams) {
+    CUDA_TRY(cudaMalloc(&h->d_save_cams, sizeof(double) * (size_t)h->cfg.max_frames * 6));
+    CUDA_TRY(cudaMalloc(&h->d_save_pts, sizeof(double) * (size_t)h->cfg.max_points * 3));
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_save_cams, h->d_cams, sizeof(double) * (size_t)h->n_frames * 6, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_save_pts, h->d_pts, sizeof(double) * (size_t)h->n_points * 3, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->have_saved = true;
+  return PBA_OK;
+}
+
+int pba_restore_state(pba_handle* h) {
+  if (!h) return fail(PBA_ERR_ARGUMENT, "pba_restore_state: null handle");
+  if (!h->have_saved) return fail(PBA_ERR_STATE, "pba_restore_state: nothing saved");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(h->d_cams, h->d_save_cams, sizeof(double) * (size_t)h->n_frames * 6, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_pts, h->d_save_pts, sizeof(double) * (size_t)h->n_points * 3, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
   return PBA_OK;
 }
 

@@ -125,19 +125,26 @@ template <int R> struct Foot {
   static constexpr int FLOATS = ROWS * W;
 };
 
+// Shared memory per CTA:  pose consts [F][36] f64 | per warp: geometry [8][20] f64, pose-block
+// accumulators [F][27] f64, extras [4] f64, per-observation ints [8] int4, footprints [8][ROWS][W] f32
 template <int R>
 __host__ __device__ constexpr size_t k1_smem_bytes(int n_frames) {
   return sizeof(double) * ((size_t)n_frames * kPoseConst) +
          (size_t)kWarpsPerCta * (sizeof(double) * (kObsBatch * 20 + (size_t)n_frames * kUStride + 4) +
+                                 sizeof(int4) * kObsBatch +
                                  sizeof(float) * (size_t)kStageSlots * Foot<R>::FLOATS);
 }
 
-template <int R, bool U8>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams prm) {
+// NCH: compile-time channel count (1 = Intensity, the north-star descriptor); 0 = runtime count.
+template <int R, bool U8, int NCH>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) k1_eval(const EvalParams prm) {
   using FT = Foot<R>;
   constexpr int P = FT::P;
+  constexpr int PR = (P + 31) / 32;             // pixel rounds per lane
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int F = prm.n_frames, C = prm.fr.n_channels, CP = C * P;
+  const int F = prm.n_frames;
+  const int C = NCH ? NCH : prm.fr.n_channels;
+  const int CP = C * P;
 
   if (prm.st && prm.st->done) return;
   const int buf = prm.st ? prm.st->eval_buf : 0;
@@ -150,16 +157,45 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams pr
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_pose = reinterpret_cast<double*>(smem_raw);                       // [F][36]
   double* s_geo = s_pose + (size_t)F * kPoseConst;                            // [warps][8][20]
-  double* s_geo_w = s_geo + (size_t)warp * kObsBatch * 20;
-  double* s_U = s_geo + (size_t)kWarpsPerCta * kObsBatch * 20;                // [warps][F][27]
-  double* s_U_w = s_U + (size_t)warp * F * kUStride;
-  double* s_E = s_U + (size_t)kWarpsPerCta * F * kUStride;                    // [warps][4]
-  float* s_fp = reinterpret_cast<float*>(s_E + kWarpsPerCta * 4);
-  float* s_fp_w = s_fp + (size_t)warp * kStageSlots * FT::FLOATS;             // [8][ROWS][W]
+  double* s_geo_w = s_geo + warp * (kObsBatch * 20);
+  double* s_U = s_geo + kWarpsPerCta * (kObsBatch * 20);                      // [warps][F][27]
+  double* s_U_w = s_U + warp * F * kUStride;
+  double* s_E = s_U + kWarpsPerCta * F * kUStride;                            // [warps][4]
+  int4* s_gi = reinterpret_cast<int4*>(s_E + kWarpsPerCta * 4);               // [warps][8]
+  int4* s_gi_w = s_gi + warp * kObsBatch;
+  float* s_fp = reinterpret_cast<float*>(s_gi + kWarpsPerCta * kObsBatch);
+  float* s_fp_w = s_fp + warp * (kStageSlots * FT::FLOATS);                   // [8][ROWS][W]
 
   if (threadIdx.x < F) pose_consts(cams + 6 * threadIdx.x, s_pose + threadIdx.x * kPoseConst);
   for (int i = lane; i < F * kUStride; i += 32) s_U_w[i] = 0.0;
   __syncthreads();
+
+  // ---- per-lane constants --------------------------------------------------------------
+  double pdx[PR], pdy[PR], wj[PR];
+  float wjf[PR];
+#pragma unroll
+  for (int r = 0; r < PR; ++r) {
+    const int j = lane + 32 * r;
+    const int py = j / FT::SIDE, pxo = j - py * FT::SIDE;
+    pdx[r] = (double)(pxo - R); pdy[r] = (double)(py - R);
+    wj[r] = (j < P) ? prm.weights[j] : 0.0;
+    wjf[r] = (float)wj[r];
+  }
+  // staging: lane (+32*round) <-> aligned 4-element word (row, wd) of the footprint
+  int st_off[FT::ROUNDS];
+#pragma unroll
+  for (int rd = 0; rd < FT::ROUNDS; ++rd) {
+    const int wi = lane + 32 * rd;
+    const int row = wi / FT::NW, wd = wi - row * FT::NW;
+    st_off[rd] = (wi < FT::WORDS) ? row * prm.fr.pitch + 4 * wd : -1;
+  }
+  // block-expansion roles: round 1 (pose block) and round 2 (W | V | g_p)
+  int e1a = 0, e1b = 0, e2a = 0, e2b = 0;
+  if (lane < 21) { e1a = c_pair6[lane][0]; e1b = c_pair6[lane][1]; }
+  else if (lane < 27) { e1a = lane - 21; }
+  if (lane < 18) { e2a = lane / 3; e2b = 6 + lane - 3 * (lane / 3); }
+  else if (lane < 24) { e2a = 6 + c_pair3[lane - 18][0]; e2b = 6 + c_pair3[lane - 18][1]; }
+  else if (lane < 27) { e2a = 6 + lane - 24; }
 
   const int p = blockIdx.x * kWarpsPerCta + warp;
   double cost_w = 0.0, gsq_w = 0.0, gmax_w = 0.0, xsq_w = 0.0;
@@ -168,14 +204,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams pr
     const double X0 = pts[3 * p], X1 = pts[3 * p + 1], X2 = pts[3 * p + 2];
     xsq_w = X0 * X0 + X1 * X1 + X2 * X2;
     double acc_pt = 0.0;  // lanes 18..23: V entries, 24..26: g_p entries (summed over frames)
-    const int obs_per_stage = (C >= kStageSlots) ? 1 : kStageSlots / C;
+    const int obs_per_stage = NCH == 1 ? kStageSlots : ((C >= kStageSlots) ? 1 : kStageSlots / C);
+    // reference descriptor of this point (channel 0 hoisted; further channels read in the loop)
+    double p0c[PR];
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+      const int j = lane + 32 * r;
+      p0c[r] = (j < P) ? (double)prm.desc[(size_t)p * CP + j] : 0.0;
+    }
 
     for (int ob = 0; ob < nobs; ob += kObsBatch) {
       const int nb = min(kObsBatch, nobs - ob);
       // ---- (G) geometry: lane i <-> observation ob+i --------------------------------
-      int g_f = 0, g_c0 = 0, g_r0 = 0, g_fast = 0;
       if (lane < nb) {
-        g_f = prm.obs_frame[o0 + ob + lane];
+        const int g_f = prm.obs_frame[o0 + ob + lane];
         const double* pc = s_pose + g_f * kPoseConst;
         double Xc0, Xc1, Xc2;
         if (pc[8] == 0.0) {  // ceres::AngleAxisRotatePoint, same operation order (no FMA)
@@ -225,18 +267,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams pr
         g[5] = J00; g[6] = 0.0; g[7] = J02;                  // du/dt
         g[14] = 0.0; g[15] = J11; g[16] = J12;               // dv/dt
         // footprint origin and fast-path test (all taps and gradient taps interior)
+        int4 gi = make_int4(g_f, 0, 0, 0);   // {frame, r0, cb (aligned first column), fast | (c0&3)<<1}
         if (fabs(u) < 1.0e8 && fabs(v) < 1.0e8) {
-          g_c0 = (int)floor(u) - R - 1;
-          g_r0 = (int)floor(v) - R - 1;
-          g_fast = (g_c0 >= 0 && g_c0 + FT::ROWS - 1 <= prm.fr.cols - 1 && g_r0 >= 0 &&
-                    g_r0 + FT::ROWS - 1 <= prm.fr.rows - 1) ? 1 : 0;
+          const int c0 = (int)floor(u) - R - 1, r0 = (int)floor(v) - R - 1;
+          const int fast = (c0 >= 0 && c0 + FT::ROWS - 1 <= prm.fr.cols - 1 && r0 >= 0 &&
+                            r0 + FT::ROWS - 1 <= prm.fr.rows - 1) ? 1 : 0;
+          gi.y = r0; gi.z = c0 & ~3; gi.w = fast;
         }
+        s_gi_w[lane] = gi;
       }
       __syncwarp();
 
       for (int sb = 0; sb < nb; sb += obs_per_stage) {
         const int ns_obs = min(obs_per_stage, nb - sb);
-        const int nslots = ns_obs * C;
+        const int nslots = NCH == 1 ? ns_obs : ns_obs * C;
         // ---- (L) stage footprints: all loads first, then the stores ----------------------
         {
           uint32_t t8[kStageSlots][FT::ROUNDS];
@@ -244,25 +288,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams pr
 #pragma unroll
           for (int sl = 0; sl < kStageSlots; ++sl) {
             if (sl < nslots) {
-              const int i = sb + sl / C, k = sl - (sl / C) * C;
-              const int f = __shfl_sync(0xffffffffu, g_f, i);
-              const int c0 = __shfl_sync(0xffffffffu, g_c0, i);
-              const int r0 = __shfl_sync(0xffffffffu, g_r0, i);
-              const int fast = __shfl_sync(0xffffffffu, g_fast, i);
-              if (fast) {
-                const int cb = c0 & ~3;
+              const int i = NCH == 1 ? sb + sl : sb + sl / C;
+              const int k = NCH == 1 ? 0 : sl - (sl / C) * C;
+              const int4 gi = s_gi_w[i];
+              if (gi.w) {
+                const unsigned base = (unsigned)((NCH == 1 ? gi.x : gi.x * C + k) * (int)prm.fr.plane + gi.y * prm.fr.pitch + gi.z);
 #pragma unroll
                 for (int rd = 0; rd < FT::ROUNDS; ++rd) {
-                  const int wi = lane + 32 * rd;
-                  if (wi < FT::WORDS) {
-                    const int row = wi / FT::NW, wd = wi - row * FT::NW;
-                    if (U8) {
-                      const uint8_t* src = prm.fr.u8 + (size_t)f * prm.fr.plane + (size_t)(r0 + row) * prm.fr.pitch + cb + 4 * wd;
-                      t8[sl][rd] = __ldg(reinterpret_cast<const uint32_t*>(src));
-                    } else {
-                      const float* src = prm.fr.f32 + ((size_t)f * C + k) * prm.fr.plane + (size_t)(r0 + row) * prm.fr.pitch + cb + 4 * wd;
-                      t32[U8 ? 0 : sl][U8 ? 0 : rd] = __ldg(reinterpret_cast<const float4*>(src));
-                    }
+                  if (st_off[rd] >= 0) {
+                    if (U8) t8[sl][rd] = __ldg(reinterpret_cast<const uint32_t*>(prm.fr.u8 + (base + (unsigned)st_off[rd])));
+                    else t32[U8 ? 0 : sl][U8 ? 0 : rd] = __ldg(reinterpret_cast<const float4*>(prm.fr.f32 + (base + (unsigned)st_off[rd])));
                   }
                 }
               }
@@ -271,13 +306,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams pr
 #pragma unroll
           for (int sl = 0; sl < kStageSlots; ++sl) {
             if (sl < nslots) {
-              const int i = sb + sl / C;
-              const int fast = __shfl_sync(0xffffffffu, g_fast, i);
-              if (fast) {
+              const int i = NCH == 1 ? sb + sl : sb + sl / C;
+              if (s_gi_w[i].w) {
 #pragma unroll
                 for (int rd = 0; rd < FT::ROUNDS; ++rd) {
-                  const int wi = lane + 32 * rd;
-                  if (wi < FT::WORDS) {
+                  if (st_off[rd] >= 0) {
                     float4 o;
                     if (U8) {
                       const uint32_t q = t8[sl][rd];
@@ -285,7 +318,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams pr
                     } else {
                       o = t32[U8 ? 0 : sl][U8 ? 0 : rd];
                     }
-                    reinterpret_cast<float4*>(s_fp_w + sl * FT::FLOATS)[wi] = o;
+                    reinterpret_cast<float4*>(s_fp_w + sl * FT::FLOATS)[lane + 32 * rd] = o;
                   }
                 }
               }
@@ -298,61 +331,61 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams pr
         for (int si = 0; si < ns_obs; ++si) {
           const int i = sb + si;
           const int o = o0 + ob + i;
-          const int f = __shfl_sync(0xffffffffu, g_f, i);
-          const int c0 = __shfl_sync(0xffffffffu, g_c0, i);
-          const int r0 = __shfl_sync(0xffffffffu, g_r0, i);
-          const int fast = __shfl_sync(0xffffffffu, g_fast, i);
+          const int4 gi = s_gi_w[i];
+          const int f = gi.x, r0 = gi.y, cb = gi.z, fast = gi.w;
           const double* g = s_geo_w + i * 20;
           const double u = g[0], v = g[1];
           double s_sum = 0.0;
           float G11 = 0.f, G12 = 0.f, G22 = 0.f, b1 = 0.f, b2 = 0.f;
           for (int k = 0; k < C; ++k) {
-            const float* fp = s_fp_w + (si * C + k) * FT::FLOATS;
-            for (int j = lane; j < P; j += 32) {
-              const int py = j / FT::SIDE, pxo = j - py * FT::SIDE;
-              const float su = __double2float_rn(__dadd_rn(u, (double)(pxo - R)));
-              const float sv = __double2float_rn(__dadd_rn(v, (double)(py - R)));
-              float I1, gx, gy;
-              if (fast) {
-                const int ix = __float2int_rz(su), iy = __float2int_rz(sv);
-                const float dx = __fsub_rn((float)(ix + 1), su), dy = __fsub_rn((float)(iy + 1), sv);
-                const float* q = fp + (iy - r0) * FT::W + (ix - (c0 & ~3));
-                const float a11 = q[0], a12 = q[1], a21 = q[FT::W], a22 = q[FT::W + 1];
-                const float l1 = q[-1], r1 = q[2], l2 = q[FT::W - 1], r2 = q[FT::W + 2];
-                const float t1 = q[-FT::W], t2 = q[-FT::W + 1], u1 = q[2 * FT::W], u2 = q[2 * FT::W + 1];
-                const double omdx = __dsub_rn(1.0, (double)dx);
-                const float omdy = __fsub_rn(1.0f, dy);
-                I1 = bilerp(dx, dy, omdx, omdy, a11, a12, a21, a22);
-                gx = bilerp(dx, dy, omdx, omdy, __fmul_rn(0.5f, __fsub_rn(a12, l1)), __fmul_rn(0.5f, __fsub_rn(r1, a11)),
-                            __fmul_rn(0.5f, __fsub_rn(a22, l2)), __fmul_rn(0.5f, __fsub_rn(r2, a21)));
-                gy = bilerp(dx, dy, omdx, omdy, __fmul_rn(0.5f, __fsub_rn(a21, t1)), __fmul_rn(0.5f, __fsub_rn(a22, t2)),
-                            __fmul_rn(0.5f, __fsub_rn(u1, a11)), __fmul_rn(0.5f, __fsub_rn(u2, a12)));
-              } else {
-                int x1, x2, y1, y2;
-                float dx, dy;
-                init_axis(sv, prm.fr.rows, y1, y2, dy);
-                init_axis(su, prm.fr.cols, x1, x2, dx);
-                const double omdx = __dsub_rn(1.0, (double)dx);
-                const float omdy = __fsub_rn(1.0f, dy);
-                I1 = bilerp(dx, dy, omdx, omdy, px_at<U8>(prm.fr, f, k, y1, x1), px_at<U8>(prm.fr, f, k, y1, x2),
-                            px_at<U8>(prm.fr, f, k, y2, x1), px_at<U8>(prm.fr, f, k, y2, x2));
-                float gx11, gx12, gx21, gx22, gy11, gy12, gy21, gy22;
-                grad_at<U8>(prm.fr, f, k, y1, x1, gx11, gy11);
-                grad_at<U8>(prm.fr, f, k, y1, x2, gx12, gy12);
-                grad_at<U8>(prm.fr, f, k, y2, x1, gx21, gy21);
-                grad_at<U8>(prm.fr, f, k, y2, x2, gx22, gy22);
-                gx = bilerp(dx, dy, omdx, omdy, gx11, gx12, gx21, gx22);
-                gy = bilerp(dx, dy, omdx, omdy, gy11, gy12, gy21, gy22);
+            const float* fp = s_fp_w + (NCH == 1 ? si : si * C + k) * FT::FLOATS;
+#pragma unroll
+            for (int r = 0; r < PR; ++r) {
+              const int j = lane + 32 * r;
+              if (j < P) {
+                const float su = __double2float_rn(__dadd_rn(u, pdx[r]));
+                const float sv = __double2float_rn(__dadd_rn(v, pdy[r]));
+                float I1, gx, gy;
+                if (fast) {
+                  const int ix = __float2int_rz(su), iy = __float2int_rz(sv);
+                  const float dx = __fsub_rn((float)(ix + 1), su), dy = __fsub_rn((float)(iy + 1), sv);
+                  const float* q = fp + (iy - r0) * FT::W + (ix - cb);
+                  const float a11 = q[0], a12 = q[1], a21 = q[FT::W], a22 = q[FT::W + 1];
+                  const float l1 = q[-1], r1 = q[2], l2 = q[FT::W - 1], r2 = q[FT::W + 2];
+                  const float t1 = q[-FT::W], t2 = q[-FT::W + 1], u1 = q[2 * FT::W], u2 = q[2 * FT::W + 1];
+                  const double omdx = __dsub_rn(1.0, (double)dx);
+                  const float omdy = __fsub_rn(1.0f, dy);
+                  I1 = bilerp(dx, dy, omdx, omdy, a11, a12, a21, a22);
+                  gx = bilerp(dx, dy, omdx, omdy, __fmul_rn(0.5f, __fsub_rn(a12, l1)), __fmul_rn(0.5f, __fsub_rn(r1, a11)),
+                              __fmul_rn(0.5f, __fsub_rn(a22, l2)), __fmul_rn(0.5f, __fsub_rn(r2, a21)));
+                  gy = bilerp(dx, dy, omdx, omdy, __fmul_rn(0.5f, __fsub_rn(a21, t1)), __fmul_rn(0.5f, __fsub_rn(a22, t2)),
+                              __fmul_rn(0.5f, __fsub_rn(u1, a11)), __fmul_rn(0.5f, __fsub_rn(u2, a12)));
+                } else {
+                  int x1, x2, y1, y2;
+                  float dx, dy;
+                  init_axis(sv, prm.fr.rows, y1, y2, dy);
+                  init_axis(su, prm.fr.cols, x1, x2, dx);
+                  const double omdx = __dsub_rn(1.0, (double)dx);
+                  const float omdy = __fsub_rn(1.0f, dy);
+                  I1 = bilerp(dx, dy, omdx, omdy, px_at<U8>(prm.fr, f, k, y1, x1), px_at<U8>(prm.fr, f, k, y1, x2),
+                              px_at<U8>(prm.fr, f, k, y2, x1), px_at<U8>(prm.fr, f, k, y2, x2));
+                  float gx11, gx12, gx21, gx22, gy11, gy12, gy21, gy22;
+                  grad_at<U8>(prm.fr, f, k, y1, x1, gx11, gy11);
+                  grad_at<U8>(prm.fr, f, k, y1, x2, gx12, gy12);
+                  grad_at<U8>(prm.fr, f, k, y2, x1, gx21, gy21);
+                  grad_at<U8>(prm.fr, f, k, y2, x2, gx22, gy22);
+                  gx = bilerp(dx, dy, omdx, omdy, gx11, gx12, gx21, gx22);
+                  gy = bilerp(dx, dy, omdx, omdy, gy11, gy12, gy21, gy22);
+                }
+                const double p0 = (NCH == 1 || k == 0) ? p0c[r] : (double)prm.desc[(size_t)p * CP + k * P + j];
+                const double rr = __dmul_rn(wj[r], __dsub_rn(p0, (double)I1));   // photobundle.cc:720
+                if (prm.residuals) prm.residuals[(size_t)o * CP + k * P + j] = rr;
+                s_sum = fma(rr, rr, s_sum);
+                const float rf = (float)rr;
+                const float hx = wjf[r] * gx, hy = wjf[r] * gy;
+                G11 = fmaf(hx, hx, G11); G12 = fmaf(hx, hy, G12); G22 = fmaf(hy, hy, G22);
+                b1 = fmaf(rf, hx, b1); b2 = fmaf(rf, hy, b2);
               }
-              const double wj = prm.weights[j];
-              const double p0 = (double)prm.desc[(size_t)p * CP + k * P + j];
-              const double r = __dmul_rn(wj, __dsub_rn(p0, (double)I1));   // photobundle.cc:720
-              if (prm.residuals) prm.residuals[(size_t)o * CP + k * P + j] = r;
-              s_sum = fma(r, r, s_sum);
-              const float wf = (float)wj, rf = (float)r;
-              const float hx = wf * gx, hy = wf * gy;
-              G11 = fmaf(hx, hx, G11); G12 = fmaf(hx, hy, G12); G22 = fmaf(hy, hy, G22);
-              b1 = fmaf(rf, hx, b1); b2 = fmaf(rf, hy, b2);
             }
           }
 #pragma unroll
@@ -378,21 +411,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams pr
           const double dG11 = rho1 * (double)G11, dG12 = rho1 * (double)G12, dG22 = rho1 * (double)G22;
           const double db1 = rho1 * (double)b1, db2 = rho1 * (double)b2;
           const bool free_cam = (f != prm.fixed_frame);
-          // round 1: pose block of this observation -> CTA accumulator (each frame at most once per point)
+          const double* A = g + 2;
+          // round 1: pose block of this observation (each frame at most once per point)
           if (free_cam && lane < 27) {
-            double val;
-            if (lane < 21) val = quad(g + 2, c_pair6[lane][0], c_pair6[lane][1], dG11, dG12, dG22);
-            else val = -(g[2 + lane - 21] * db1 + g[11 + lane - 21] * db2);
+            const double val = lane < 21 ? quad(A, e1a, e1b, dG11, dG12, dG22) : -(A[e1a] * db1 + A[9 + e1a] * db2);
             s_U_w[f * kUStride + lane] += val;
           }
           // round 2: W (6x3) out, V / g_p into registers
-          if (lane < 18) {
-            const int a = lane / 3, b = lane - a * 3;
-            outW[(size_t)o * 18 + lane] = free_cam ? quad(g + 2, a, 6 + b, dG11, dG12, dG22) : 0.0;
-          } else if (lane < 24) {
-            acc_pt += quad(g + 2, 6 + c_pair3[lane - 18][0], 6 + c_pair3[lane - 18][1], dG11, dG12, dG22);
-          } else if (lane < 27) {
-            acc_pt += -(g[2 + 6 + lane - 24] * db1 + g[11 + 6 + lane - 24] * db2);
+          if (lane < 27) {
+            const double val = lane < 24 ? quad(A, e2a, e2b, dG11, dG12, dG22) : -(A[e2a] * db1 + A[9 + e2a] * db2);
+            if (lane < 18) outW[(size_t)o * 18 + lane] = free_cam ? val : 0.0;
+            else acc_pt += val;
           }
         }
         __syncwarp();
@@ -403,7 +432,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams pr
     const double gq = (lane >= 24 && lane < 27) ? acc_pt : 0.0;
     double g2 = gq * gq, ga = fabs(gq);
 #pragma unroll
-    for (int m = 1; m <= 4; m <<= 1) {   // lanes 24..27 form an aligned group of four
+    for (int m = 1; m <= 2; m <<= 1) {   // lanes 24..27 form an aligned group of four
       g2 += __shfl_xor_sync(0xffffffffu, g2, m);
       ga = fmax(ga, __shfl_xor_sync(0xffffffffu, ga, m));
     }
@@ -418,7 +447,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams pr
   for (int i = threadIdx.x; i < F * kUStride; i += blockDim.x) {
     double acc = 0.0;
 #pragma unroll
-    for (int w = 0; w < kWarpsPerCta; ++w) acc += s_U[(size_t)w * F * kUStride + i];
+    for (int w = 0; w < kWarpsPerCta; ++w) acc += s_U[w * F * kUStride + i];
     prm.Upart[(size_t)blockIdx.x * F * kUStride + i] = acc;
   }
   if (threadIdx.x == 0) {
@@ -432,20 +461,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k1_eval(const EvalParams pr
 }
 
 // ---- host launcher -----------------------------------------------------------------------
-template <int R, bool U8>
+template <int R, bool U8, int NCH>
 static cudaError_t launch_one(const EvalParams& prm, cudaStream_t stream) {
   const size_t smem = k1_smem_bytes<R>(prm.n_frames);
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k1_eval<R, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k1_eval<R, U8, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     configured[dev & 63] = true;
   }
   const int grid = (prm.n_points + kWarpsPerCta - 1) / kWarpsPerCta;
   if (grid == 0) return cudaSuccess;
-  k1_eval<R, U8><<<grid, kWarpsPerCta * 32, smem, stream>>>(prm);
+  k1_eval<R, U8, NCH><<<grid, kWarpsPerCta * 32, smem, stream>>>(prm);
   return cudaGetLastError();
 }
 
@@ -460,13 +489,19 @@ size_t k1_smem(int radius, int n_frames) {
   }
 }
 
+template <int R>
+static cudaError_t launch_r(const EvalParams& prm, cudaStream_t stream) {
+  if (prm.fr.u8) return launch_one<R, true, 1>(prm, stream);      // uint8 planes are always 1-channel Intensity
+  if (prm.fr.n_channels == 1) return launch_one<R, false, 1>(prm, stream);
+  return launch_one<R, false, 0>(prm, stream);
+}
+
 cudaError_t launch_k1(const EvalParams& prm, int radius, cudaStream_t stream) {
-  const bool u8 = prm.fr.u8 != nullptr;
   switch (radius) {
-    case 1: return u8 ? launch_one<1, true>(prm, stream) : launch_one<1, false>(prm, stream);
-    case 2: return u8 ? launch_one<2, true>(prm, stream) : launch_one<2, false>(prm, stream);
-    case 3: return u8 ? launch_one<3, true>(prm, stream) : launch_one<3, false>(prm, stream);
-    case 4: return u8 ? launch_one<4, true>(prm, stream) : launch_one<4, false>(prm, stream);
+    case 1: return launch_r<1>(prm, stream);
+    case 2: return launch_r<2>(prm, stream);
+    case 3: return launch_r<3>(prm, stream);
+    case 4: return launch_r<4>(prm, stream);
     default: return cudaErrorInvalidValue;
   }
 }
