@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -48,8 +49,10 @@ struct pba_handle {
   float* d_desc = nullptr;
   int *d_obs_off = nullptr, *d_obs_frame = nullptr;
   double *d_V = nullptr, *d_gp = nullptr, *d_W = nullptr;
-  double *d_Upart = nullptr, *d_Epart = nullptr, *d_U = nullptr, *d_E = nullptr;
-  double *d_scale_p = nullptr, *d_Vinv = nullptr, *d_Spart = nullptr, *d_S = nullptr, *d_Bpart = nullptr;
+  double *d_Uacc = nullptr, *d_Eacc = nullptr;
+  double *d_scale_p = nullptr, *d_Vinv = nullptr, *d_S = nullptr;
+  unsigned int* d_ticket = nullptr;
+  unsigned long long* d_dbg = nullptr;   // PBA_DEBUG_TIMELINE=1: per-iteration K_B timeline
   double *d_obs_sqnorm = nullptr, *d_residuals = nullptr;
   double *d_save_cams = nullptr, *d_save_pts = nullptr;
   bool have_saved = false;
@@ -69,8 +72,8 @@ struct pba_handle {
 static void free_all(pba_handle* h) {
   cudaFree(h->d_u8); cudaFree(h->d_f32); cudaFree(h->d_cams); cudaFree(h->d_pts); cudaFree(h->d_weights);
   cudaFree(h->d_desc); cudaFree(h->d_obs_off); cudaFree(h->d_obs_frame); cudaFree(h->d_V); cudaFree(h->d_gp);
-  cudaFree(h->d_W); cudaFree(h->d_Upart); cudaFree(h->d_Epart); cudaFree(h->d_U); cudaFree(h->d_E);
-  cudaFree(h->d_scale_p); cudaFree(h->d_Vinv); cudaFree(h->d_Spart); cudaFree(h->d_S); cudaFree(h->d_Bpart);
+  cudaFree(h->d_W); cudaFree(h->d_Uacc); cudaFree(h->d_Eacc);
+  cudaFree(h->d_scale_p); cudaFree(h->d_Vinv); cudaFree(h->d_S); cudaFree(h->d_ticket); cudaFree(h->d_dbg);
   cudaFree(h->d_save_cams); cudaFree(h->d_save_pts);
   cudaFree(h->d_obs_sqnorm); cudaFree(h->d_residuals); cudaFree(h->d_state); cudaFree(h->d_trace);
   if (h->h_state) cudaFreeHost(h->h_state);
@@ -148,7 +151,6 @@ int pba_create(const pba_config* cfg, pba_handle** out) {
   h->plane = (size_t)cfg->rows * h->pitch;
   const size_t F = cfg->max_frames, n = cfg->max_points, nnz = cfg->max_observations;
   const size_t D = 6 * F;
-  const int k1c = k1_grid((int)n), sc = h->sm_count, bc = back_grid((int)n);
   CREATE_TRY(cudaMalloc(&h->d_cams, sizeof(double) * 2 * F * 6));
   CREATE_TRY(cudaMalloc(&h->d_pts, sizeof(double) * 2 * n * 3));
   CREATE_TRY(cudaMalloc(&h->d_weights, sizeof(double) * h->P));
@@ -158,18 +160,14 @@ int pba_create(const pba_config* cfg, pba_handle** out) {
   CREATE_TRY(cudaMalloc(&h->d_V, sizeof(double) * 2 * n * 6));
   CREATE_TRY(cudaMalloc(&h->d_gp, sizeof(double) * 2 * n * 3));
   CREATE_TRY(cudaMalloc(&h->d_W, sizeof(double) * 2 * nnz * 18));
-  CREATE_TRY(cudaMalloc(&h->d_Upart, sizeof(double) * (size_t)k1c * F * kUStride));
-  CREATE_TRY(cudaMalloc(&h->d_Epart, sizeof(double) * (size_t)k1c * 4));
-  CREATE_TRY(cudaMalloc(&h->d_U, sizeof(double) * 2 * F * kUStride));
-  CREATE_TRY(cudaMalloc(&h->d_E, sizeof(double) * 2 * 4));
+  CREATE_TRY(cudaMalloc(&h->d_Uacc, sizeof(double) * 2 * F * kUStride));
+  CREATE_TRY(cudaMalloc(&h->d_Eacc, sizeof(double) * 2 * kEacc));
   CREATE_TRY(cudaMalloc(&h->d_scale_p, sizeof(double) * n * 3));
   CREATE_TRY(cudaMalloc(&h->d_Vinv, sizeof(double) * n * 6));
-  CREATE_TRY(cudaMalloc(&h->d_Spart, sizeof(double) * (size_t)sc * (D * D + D)));
   CREATE_TRY(cudaMalloc(&h->d_S, sizeof(double) * (D * D + D)));
-  CREATE_TRY(cudaMalloc(&h->d_Bpart, sizeof(double) * (size_t)bc * 4));
-  CREATE_TRY(cudaMalloc(&h->d_state, sizeof(LmState)));
+  CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
+  CREATE_TRY(cudaMalloc(&h->d_state, 2 * sizeof(LmState)));
   CREATE_TRY(cudaMallocHost(&h->h_state, sizeof(LmState)));
-  CREATE_TRY(cudaMemset(h->d_Bpart, 0, sizeof(double) * (size_t)bc * 4));
 #undef CREATE_TRY
   *out = h;
   return PBA_OK;
@@ -293,8 +291,8 @@ static int check_ready(pba_handle* h, const char* who) {
   return PBA_OK;
 }
 
-static EvalParams make_eval_params(pba_handle* h, bool with_state) {
-  EvalParams p;
+static StepParams make_step_params(pba_handle* h, const LmState* st) {
+  StepParams p;
   memset(&p, 0, sizeof(p));
   p.fr.u8 = h->frames_are_u8 ? h->d_u8 : nullptr;
   p.fr.f32 = h->frames_are_u8 ? nullptr : h->d_f32;
@@ -302,27 +300,30 @@ static EvalParams make_eval_params(pba_handle* h, bool with_state) {
   p.fr.n_channels = h->cfg.n_channels; p.fr.plane = h->plane;
   p.n_frames = h->n_frames; p.fixed_frame = h->fixed_frame; p.n_points = h->n_points; p.nnz = h->nnz;
   p.fx = h->cfg.fx; p.fy = h->cfg.fy; p.cx = h->cfg.cx; p.cy = h->cfg.cy; p.huber = h->cfg.huber;
-  p.st = with_state ? h->d_state : nullptr;
+  p.st = st;
   p.cams = h->d_cams; p.pts = h->d_pts; p.desc = h->d_desc; p.obs_off = h->d_obs_off;
   p.obs_frame = h->d_obs_frame; p.weights = h->d_weights;
-  p.V = h->d_V; p.gp = h->d_gp; p.W = h->d_W; p.Upart = h->d_Upart; p.Epart = h->d_Epart;
+  p.V = h->d_V; p.gp = h->d_gp; p.W = h->d_W; p.Uacc = h->d_Uacc; p.Eacc = h->d_Eacc;
+  p.scale_p = h->d_scale_p; p.Vinv = h->d_Vinv;
   return p;
 }
 
 static LmParams make_lm_params(pba_handle* h) {
   LmParams lp;
   memset(&lp, 0, sizeof(lp));
-  lp.st = h->d_state; lp.trace = h->d_trace;
+  lp.trace = h->d_trace; lp.ticket = h->d_ticket;
   lp.n_frames = h->n_frames; lp.n_points = h->n_points; lp.nnz = h->nnz;
-  lp.n_k1_ctas = k1_grid(h->n_points);
-  lp.n_schur_ctas = schur_grid(h->n_points, h->sm_count);
-  lp.n_back_ctas = back_grid(h->n_points);
   lp.obs_off = h->d_obs_off; lp.obs_frame = h->d_obs_frame;
-  lp.cams = h->d_cams; lp.pts = h->d_pts; lp.V = h->d_V; lp.gp = h->d_gp; lp.W = h->d_W;
-  lp.Upart = h->d_Upart; lp.Epart = h->d_Epart; lp.U = h->d_U; lp.E = h->d_E;
-  lp.scale_p = h->d_scale_p; lp.Vinv = h->d_Vinv; lp.Spart = h->d_Spart; lp.S = h->d_S;
-  lp.rhs = h->d_S + (size_t)36 * h->n_frames * h->n_frames; lp.Bpart = h->d_Bpart;
+  lp.cams = h->d_cams; lp.V = h->d_V; lp.gp = h->d_gp; lp.W = h->d_W;
+  lp.Uacc = h->d_Uacc; lp.Eacc = h->d_Eacc;
+  lp.scale_p = h->d_scale_p; lp.Vinv = h->d_Vinv; lp.S = h->d_S;
   return lp;
+}
+
+static int zero_accumulators(pba_handle* h) {
+  CUDA_TRY(cudaMemsetAsync(h->d_Uacc, 0, sizeof(double) * 2 * (size_t)h->cfg.max_frames * kUStride, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_Eacc, 0, sizeof(double) * 2 * kEacc, h->stream));
+  return PBA_OK;
 }
 
 static void unpack_sym6(const double* u21, double* out36) {
@@ -337,7 +338,7 @@ int pba_eval(pba_handle* h, pba_eval_out* out) {
   if (!out) return fail(PBA_ERR_ARGUMENT, "pba_eval: null output");
   CUDA_TRY(cudaSetDevice(h->device));
   const int F = h->n_frames, n = h->n_points, nnz = h->nnz;
-  EvalParams p = make_eval_params(h, false);
+  StepParams p = make_step_params(h, nullptr);
   if (out->obs_sqnorm) {
     if (!h->d_obs_sqnorm) CUDA_TRY(cudaMalloc(&h->d_obs_sqnorm, sizeof(double) * h->cfg.max_observations));
     p.obs_sqnorm = h->d_obs_sqnorm;
@@ -346,24 +347,19 @@ int pba_eval(pba_handle* h, pba_eval_out* out) {
     if (!h->d_residuals) CUDA_TRY(cudaMalloc(&h->d_residuals, sizeof(double) * (size_t)h->cfg.max_observations * h->CP));
     p.residuals = h->d_residuals;
   }
+  rc = zero_accumulators(h);
+  if (rc) return rc;
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-  CUDA_TRY(launch_k1(p, h->cfg.patch_radius, h->stream));
+  CUDA_TRY(launch_k_step(p, h->cfg.patch_radius, h->stream));
   CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   out->device_ms = ms;
-  // host-side reduction of the per-CTA partials (test/inspection path only; pba_solve reduces on the device)
-  const int nb = k1_grid(n);
-  std::vector<double> up((size_t)nb * F * kUStride), ep((size_t)nb * 4);
-  CUDA_TRY(cudaMemcpy(up.data(), h->d_Upart, sizeof(double) * up.size(), cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(ep.data(), h->d_Epart, sizeof(double) * ep.size(), cudaMemcpyDeviceToHost));
-  std::vector<double> U((size_t)F * kUStride, 0.0);
-  double cost = 0.0;
-  for (int b = 0; b < nb; ++b) {
-    for (int i = 0; i < F * kUStride; ++i) U[i] += up[(size_t)b * F * kUStride + i];
-    cost += ep[(size_t)b * 4];
-  }
+  std::vector<double> U((size_t)F * kUStride), E(kEacc);
+  CUDA_TRY(cudaMemcpy(U.data(), h->d_Uacc, sizeof(double) * U.size(), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(E.data(), h->d_Eacc, sizeof(double) * kEacc, cudaMemcpyDeviceToHost));
+  const double cost = E[0];
   out->cost = cost;
   if (out->U) for (int f = 0; f < F; ++f) unpack_sym6(&U[f * kUStride], out->U + f * 36);
   if (out->gc) for (int f = 0; f < F; ++f) for (int a = 0; a < 6; ++a) out->gc[f * 6 + a] = U[f * kUStride + 21 + a];
@@ -388,9 +384,11 @@ int pba_eval_timed(pba_handle* h, int32_t iters, double* ms_total) {
   if (rc) return rc;
   if (iters < 1 || !ms_total) return fail(PBA_ERR_ARGUMENT, "pba_eval_timed: bad argument");
   CUDA_TRY(cudaSetDevice(h->device));
-  EvalParams p = make_eval_params(h, false);
+  StepParams p = make_step_params(h, nullptr);
+  rc = zero_accumulators(h);
+  if (rc) return rc;
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-  for (int i = 0; i < iters; ++i) CUDA_TRY(launch_k1(p, h->cfg.patch_radius, h->stream));
+  for (int i = 0; i < iters; ++i) CUDA_TRY(launch_k_step(p, h->cfg.patch_radius, h->stream));
   CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   float ms = 0.f;
@@ -445,39 +443,54 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   // x lives in buffer 0 of cams/points; refresh buffer 1 so fixed cameras carry over
   CUDA_TRY(cudaMemcpyAsync(h->d_cams + (size_t)F * 6, h->d_cams, sizeof(double) * F * 6, cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->d_state, s, sizeof(LmState), cudaMemcpyHostToDevice, h->stream));
+  rc = zero_accumulators(h);
+  if (rc) return rc;
+  const size_t D = 6 * (size_t)F;
+  CUDA_TRY(cudaMemsetAsync(h->d_S, 0, sizeof(double) * (D * D + D), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
 
-  EvalParams ep = make_eval_params(h, true);
   LmParams lp = make_lm_params(h);
+  const bool timeline = getenv("PBA_DEBUG_TIMELINE") != nullptr;
+  if (timeline && !h->d_dbg) CUDA_TRY(cudaMalloc(&h->d_dbg, sizeof(unsigned long long) * 16 * 1024));
+  const int sgrid = schur_grid(h->n_points, h->sm_count);
   int launches = 0;
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-  CUDA_TRY(launch_k1(ep, h->cfg.patch_radius, h->stream));
-  CUDA_TRY(launch_reduce_u(lp, h->stream));
-  CUDA_TRY(launch_decide(lp, h->stream));
-  launches += 3;
-  // Enqueue iterations in groups; kernels turn into no-ops once st->done is set.
+  // iteration 0: evaluate x.  Then per LM iteration: K_B (decide + Schur + solve), K_A
+  // (back-substitute + evaluate the candidate).  The state ping-pongs between two structs;
+  // kernels turn into no-ops once `done` is set, so iterations are enqueued in groups.
+  CUDA_TRY(launch_k_step(make_step_params(h, h->d_state), h->cfg.patch_radius, h->stream));
+  launches += 1;
   const int group = 4;
   bool done = false;
-  int enq = 0;
+  int k = 0;
   while (!done) {
-    for (int g = 0; g < group && enq <= opt.max_num_iterations; ++g, ++enq) {
-      CUDA_TRY(launch_schur(lp, h->stream));
-      CUDA_TRY(launch_reduce_s(lp, h->stream));
-      CUDA_TRY(launch_solve(lp, h->stream));
-      CUDA_TRY(launch_backsub(lp, h->stream));
-      CUDA_TRY(launch_k1(ep, h->cfg.patch_radius, h->stream));
-      CUDA_TRY(launch_reduce_u(lp, h->stream));
-      CUDA_TRY(launch_decide(lp, h->stream));
-      launches += 7;
+    for (int g = 0; g < group; ++g, ++k) {
+      lp.st_in = h->d_state + (k & 1);
+      lp.st_out = h->d_state + ((k + 1) & 1);
+      lp.dbg = (timeline && k < 1024) ? h->d_dbg + 16 * k : nullptr;
+      CUDA_TRY(launch_schur_solve(lp, sgrid, s->n_free, h->stream));
+      CUDA_TRY(launch_k_step(make_step_params(h, lp.st_out), h->cfg.patch_radius, h->stream));
+      launches += 2;
     }
-    CUDA_TRY(cudaMemcpyAsync(s, h->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(s, h->d_state + (k & 1), sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    done = s->done != 0 || enq > opt.max_num_iterations;
+    done = s->done != 0 || k > opt.max_num_iterations + 2;
   }
   CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   // the accepted x must end up in buffer 0 for pba_get_* and for the next solve
   if (s->cur != 0) {
     CUDA_TRY(cudaMemcpyAsync(h->d_cams, h->d_cams + (size_t)F * 6, sizeof(double) * F * 6, cudaMemcpyDeviceToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_pts, h->d_pts + (size_t)h->n_points * 3, sizeof(double) * (size_t)h->n_points * 3, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (timeline) {
+    std::vector<unsigned long long> t(16 * (size_t)std::min(k, 1024));
+    CUDA_TRY(cudaMemcpy(t.data(), h->d_dbg, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < std::min(k, 16); ++i)
+      fprintf(stderr, "[pba timeline] K_B %2d: decide %6.2f us  schur %6.2f us  solve %6.2f us (assemble %5.2f factor %5.2f subst %5.2f final %5.2f) tail %5.2f us | gap to next K_B start %7.2f us\n", i,
+              (t[16 * i + 1] - t[16 * i]) * 1e-3, (t[16 * i + 2] - t[16 * i + 1]) * 1e-3, (t[16 * i + 3] - t[16 * i + 2]) * 1e-3,
+              (t[16 * i + 5] - t[16 * i + 2]) * 1e-3, (t[16 * i + 6] - t[16 * i + 5]) * 1e-3, (t[16 * i + 7] - t[16 * i + 6]) * 1e-3,
+              (t[16 * i + 3] - t[16 * i + 7]) * 1e-3,
+              (t[16 * i + 4] - t[16 * i + 3]) * 1e-3, i + 1 < k ? (t[16 * (i + 1)] - t[16 * i + 4]) * 1e-3 : 0.0);
   }
   h->trace.resize(s->n_trace);
   if (s->n_trace > 0)

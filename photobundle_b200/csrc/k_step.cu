@@ -1,0 +1,676 @@
+// k_step.cu — K_A: back-substitution + per-(point, frame) photometric residual + analytic
+// Jacobian + block accumulation, one hand-written sm_100a kernel batched over all
+// points x observing frames.
+//
+// Replaces (reference, /root/reference):
+//   DescriptorError::operator()<Jet<double,9>>      src/photobundle.cc:696-727
+//   SampleWithDerivative / SampleLinear             src/sample_eigen.h:33-126
+//   ceres::Chain<float,2,Jet>::Rule                 src/jet_extras.h:74-111
+//   imgradient (central difference, zero borders)   src/imgproc.cc:27-106
+//   Calibration::project                            src/calibration.h:33-38
+//   ceres::AngleAxisRotatePoint, HuberLoss + Corrector, the J^T J / J^T r products Ceres'
+//   SchurEliminator forms per residual block, and SchurEliminator::BackSubstitute.
+//
+// Work decomposition: one warp per scene point.
+//   (B) back-substitution of the point (when a step is pending): Δp = -(V+D²)^-1 (g_p + Wᵀ Δc),
+//       candidate X = X + Δp, and the point's share of the model cost change / step norms;
+//   (G) lane i forms the geometry of observation i in fp64: Xc = R(w)X + t, (u,v) and the
+//       2x9 matrix A = d(u,v)/d[w t X]  (dual numbers are not needed: every one of the
+//       (2r+1)^2 Jacobian rows is -w_j*[gx gy]*A);
+//   (L) the warp stages each observation's (2r+5)x(2r+5) image footprint into shared memory
+//       with ONE coalesced, 4-byte/16-byte aligned load instruction (8 footprints in flight),
+//       converting uint8 -> fp32 on the way (DescriptorFrame::Create's cast);
+//   (S) lane j samples patch pixel j of FOUR observations at a time (independent dependency
+//       chains, ILP 4).  The taps of I come from the footprint, the taps of Gx, Gy are formed in
+//       registers from the same footprint (exactly the 0.5*(a-b) the reference precomputes
+//       into planes), and all three interpolations use the reference's float/double promotion
+//       sequence, so residuals AND sampled gradients are bit-identical to the CPU path given
+//       the same (u,v);
+//   (R) six fp64 patch sums  s=Σr², G=Σ w²ggᵀ (3), b=Σ w r g (2)  per observation are reduced
+//       through a shared-memory transpose (24 sums of a 4-observation group land in 24 lanes),
+//       the Huber corrector of the four observations is evaluated in four lanes at once, and
+//       the whole 9x9 block of each observation,  rho' Aᵀ G A  and  -rho' Aᵀ b, is expanded by
+//       27 lanes in parallel in fp64;
+//   the point's V (3x3) and g_p live in registers across its frames, W (6x3) goes out once
+//   per observation, pose blocks U (6x6) / g_c are summed per CTA in shared memory and added
+//   to the global accumulators with one fp64 atomic per entry per CTA.
+// Out-of-image / border observations, multi-channel descriptors and patches with more than
+// 32 pixels take the generic per-observation path with the reference's clamp and
+// zero-gradient-border rules (src/sample_eigen.h:38-46, src/imgproc.cc:34-43).
+
+#include "pba_device.cuh"
+
+#include <climits>
+#include <cfloat>
+
+#ifndef K_STEP_MIN_CTAS
+#define K_STEP_MIN_CTAS 2
+#endif
+
+namespace pba {
+
+__constant__ signed char c_pair6[21][2] = {
+    {0, 0}, {0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5},
+    {2, 2}, {2, 3}, {2, 4}, {2, 5}, {3, 3}, {3, 4}, {3, 5}, {4, 4}, {4, 5}, {5, 5}};
+__constant__ signed char c_pair3[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+
+// ---- per-frame pose constants (computed once per CTA) ---------------------------------
+//  [0..2] unit axis k (or the raw angle-axis when tiny)   [3..5] t   [6] cos  [7] sin
+//  [8] tiny flag   [9..17] R   [18..26] Rj   [27..35] M,  with
+//  d(Xc)/dw = -Rj [X]x M ;  M = (w wᵀ + (Rᵀ - I)[w]x)/θ² ; tiny angle: Rj = M = I, R = I+[w]x
+__device__ void pose_consts(const double* cam, double* pc) {
+  const double w0 = cam[0], w1 = cam[1], w2 = cam[2];
+  const double theta2 = __dadd_rn(__dadd_rn(__dmul_rn(w0, w0), __dmul_rn(w1, w1)), __dmul_rn(w2, w2));
+  pc[3] = cam[3]; pc[4] = cam[4]; pc[5] = cam[5];
+  if (theta2 > DBL_EPSILON) {
+    const double theta = sqrt(theta2);
+    const double c = cos(theta), s = sin(theta);
+    const double ti = 1.0 / theta;
+    const double k0 = __dmul_rn(w0, ti), k1 = __dmul_rn(w1, ti), k2 = __dmul_rn(w2, ti);
+    pc[0] = k0; pc[1] = k1; pc[2] = k2; pc[6] = c; pc[7] = s; pc[8] = 0.0;
+    const double k[3] = {w0 / theta, w1 / theta, w2 / theta};
+    const double K[9] = {0, -k[2], k[1], k[2], 0, -k[0], -k[1], k[0], 0};
+    double R[9];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) R[a * 3 + b] = (a == b ? c : 0.0) + s * K[a * 3 + b] + (1.0 - c) * k[a] * k[b];
+    const double w[3] = {w0, w1, w2};
+    const double Wx[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        double acc = w[a] * w[b];
+        for (int q = 0; q < 3; ++q) acc += (R[q * 3 + a] - (q == a ? 1.0 : 0.0)) * Wx[q * 3 + b];
+        pc[27 + a * 3 + b] = acc / theta2;
+      }
+    for (int a = 0; a < 9; ++a) { pc[9 + a] = R[a]; pc[18 + a] = R[a]; }
+  } else {
+    pc[0] = w0; pc[1] = w1; pc[2] = w2; pc[6] = 1.0; pc[7] = 0.0; pc[8] = 1.0;
+    const double Wx[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
+    for (int a = 0; a < 9; ++a) {
+      const double id = (a == 0 || a == 4 || a == 8) ? 1.0 : 0.0;
+      pc[9 + a] = id + Wx[a]; pc[18 + a] = id; pc[27 + a] = id;
+    }
+  }
+}
+
+// ---- slow path: reference sampler semantics tap by tap ----------------------------------
+template <bool U8>
+__device__ __forceinline__ float px_at(const Frames& fr, int f, int k, int y, int x) {
+  if (U8) return (float)fr.u8[(size_t)f * fr.plane + (size_t)y * fr.pitch + x];
+  return fr.f32[((size_t)f * fr.n_channels + k) * fr.plane + (size_t)y * fr.pitch + x];
+}
+template <bool U8>
+__device__ __forceinline__ void grad_at(const Frames& fr, int f, int k, int y, int x, float& gx, float& gy) {
+  if (y <= 0 || y >= fr.rows - 1 || x <= 0 || x >= fr.cols - 1) { gx = 0.f; gy = 0.f; return; }
+  gx = __fmul_rn(0.5f, __fsub_rn(px_at<U8>(fr, f, k, y, x + 1), px_at<U8>(fr, f, k, y, x - 1)));
+  gy = __fmul_rn(0.5f, __fsub_rn(px_at<U8>(fr, f, k, y + 1, x), px_at<U8>(fr, f, k, y - 1, x)));
+}
+__device__ __forceinline__ void init_axis(float s, int size, int& i1, int& i2, float& d) {
+  // static_cast<int>(float) of the reference binary = cvttss2si: NaN / out of range -> INT_MIN
+  const int ix = (s > -2147483648.0f && s < 2147483648.0f) ? __float2int_rz(s) : INT_MIN;
+  if (ix < 0) { i1 = 0; i2 = 0; d = 1.0f; }
+  else if (ix > size - 2) { i1 = size - 1; i2 = size - 1; d = 1.0f; }
+  else { i1 = ix; i2 = ix + 1; d = __fsub_rn((float)i2, s); }
+}
+// sample_eigen.h:82-83 with its C++ promotions: dx*a11 in float, (1.0-dx) a double,
+// (1-dy) a float, the sum rounded to float once.
+__device__ __forceinline__ float bilerp(float dx, float dy, double omdx, float omdy,
+                                        float a11, float a12, float a21, float a22) {
+  const double top = __dadd_rn((double)__fmul_rn(dx, a11), __dmul_rn(omdx, (double)a12));
+  const double bot = __dadd_rn((double)__fmul_rn(dx, a21), __dmul_rn(omdx, (double)a22));
+  return __double2float_rn(__dadd_rn(__dmul_rn((double)dy, top), __dmul_rn((double)omdy, bot)));
+}
+
+__device__ __forceinline__ double quad(const double* A, int a, int b, double G11, double G12, double G22) {
+  const double A0a = A[a], A1a = A[9 + a], A0b = A[b], A1b = A[9 + b];
+  return A0a * (G11 * A0b + G12 * A1b) + A1a * (G12 * A0b + G22 * A1b);
+}
+
+template <int R> struct Foot {
+  static constexpr int SIDE = 2 * R + 1;
+  static constexpr int P = SIDE * SIDE;
+  static constexpr int ROWS = 2 * R + 5;                 // taps + gradient halo + rounding slack
+  static constexpr int NW = (2 * R + 11) / 4;            // aligned 4-element words per row
+  static constexpr int W = 4 * NW;                       // floats per staged row
+  static constexpr int WORDS = ROWS * NW;
+  static constexpr int ROUNDS = (WORDS + 31) / 32;
+  static constexpr int FLOATS = ROWS * W;
+};
+
+
+constexpr int kRedStride = 26;   // doubles per lane row of the reduction transpose (24 sums + pad, 16 B aligned)
+
+// ---- shared memory carve-up --------------------------------------------------------------
+// per CTA : pose consts [F][36] f64 | sstep [F][6] f64 (scale_c*step_c) | E [warps][8] f64
+// per warp: geometry [8][20] f64 | pose-block accumulators [F][27] f64 | reduction transpose
+//           [25][26] f64 | scaled sums [24] f64 | ints [8] int4 | frames [16] i32 |
+//           footprints [8][ROWS][W] f32
+template <int R>
+__host__ __device__ constexpr size_t k_step_smem_bytes(int n_frames) {
+  return sizeof(double) * ((size_t)n_frames * (kPoseConst + 6) + kWarpsPerCta * kEacc) +
+         (size_t)kWarpsPerCta * (sizeof(double) * (kObsBatch * 20 + (size_t)n_frames * kUStride + 25 * kRedStride + 24) +
+                                 sizeof(int4) * kObsBatch + sizeof(int) * kMaxFrames +
+                                 sizeof(float) * (size_t)kStageSlots * Foot<R>::FLOATS);
+}
+
+struct Sums { double s, G11, G12, G22, b1, b2; };
+
+__device__ __forceinline__ void warp_reduce(Sums& q) {   // generic path only
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    q.s += __shfl_xor_sync(0xffffffffu, q.s, m);
+    q.G11 += __shfl_xor_sync(0xffffffffu, q.G11, m);
+    q.G12 += __shfl_xor_sync(0xffffffffu, q.G12, m);
+    q.G22 += __shfl_xor_sync(0xffffffffu, q.G22, m);
+    q.b1 += __shfl_xor_sync(0xffffffffu, q.b1, m);
+    q.b2 += __shfl_xor_sync(0xffffffffu, q.b2, m);
+  }
+}
+
+// ceres::HuberLoss (rho'' <= 0 -> the Corrector is a plain sqrt(rho') scaling of r and J).
+// rsqrt-based: a/sqrt(s) and sqrt(s) = s*rsqrt(s) to ~1 ulp (parity tolerance on cost is 1e-9).
+__device__ __forceinline__ void huber_rho(double a, double s, double& rho0, double& rho1) {
+  rho0 = s; rho1 = 1.0;
+  if (a > 0.0 && s > a * a) {
+    const double rs = rsqrt(s);
+    rho0 = 2.0 * a * (s * rs) - a * a;
+    rho1 = fmax(DBL_MIN, a * rs);
+  }
+}
+
+// One patch pixel of one observation from the staged footprint (all taps interior):
+// I, Gx, Gy exactly as SampleLinear returns them.
+template <int R>
+__device__ __forceinline__ void sample_fast(const float* __restrict__ fp, int r0, int cb, double u, double v,
+                                            double pdx, double pdy, float& I1, float& gx, float& gy) {
+  using FT = Foot<R>;
+  const float su = __double2float_rn(__dadd_rn(u, pdx));
+  const float sv = __double2float_rn(__dadd_rn(v, pdy));
+  const int ix = __float2int_rz(su), iy = __float2int_rz(sv);
+  const float dx = __fsub_rn((float)(ix + 1), su), dy = __fsub_rn((float)(iy + 1), sv);
+  const float* q = fp + (iy - r0) * FT::W + (ix - cb);
+  const float a11 = q[0], a12 = q[1], a21 = q[FT::W], a22 = q[FT::W + 1];
+  const float l1 = q[-1], r1 = q[2], l2 = q[FT::W - 1], r2 = q[FT::W + 2];
+  const float t1 = q[-FT::W], t2 = q[-FT::W + 1], u1 = q[2 * FT::W], u2 = q[2 * FT::W + 1];
+  const double omdx = __dsub_rn(1.0, (double)dx);
+  const float omdy = __fsub_rn(1.0f, dy);
+  I1 = bilerp(dx, dy, omdx, omdy, a11, a12, a21, a22);
+  gx = bilerp(dx, dy, omdx, omdy, __fmul_rn(0.5f, __fsub_rn(a12, l1)), __fmul_rn(0.5f, __fsub_rn(r1, a11)),
+              __fmul_rn(0.5f, __fsub_rn(a22, l2)), __fmul_rn(0.5f, __fsub_rn(r2, a21)));
+  gy = bilerp(dx, dy, omdx, omdy, __fmul_rn(0.5f, __fsub_rn(a21, t1)), __fmul_rn(0.5f, __fsub_rn(a22, t2)),
+              __fmul_rn(0.5f, __fsub_rn(u1, a11)), __fmul_rn(0.5f, __fsub_rn(u2, a12)));
+}
+
+// Block expansion of one observation from its loss-scaled patch sums: pose block -> per-warp
+// smem accumulator, W -> HBM, V / g_p -> the caller's register accumulator.
+__device__ __forceinline__ void emit_blocks(double dG11, double dG12, double dG22, double db1, double db2,
+                                            const double* __restrict__ g, int f, bool free_cam, int lane, int e1a, int e1b,
+                                            int e2a, int e2b, double* s_U_w, double* __restrict__ outW_o, double& acc_pt) {
+  const double* A = g + 2;
+  if (lane < 27) {
+    if (free_cam) {
+      const double v1 = lane < 21 ? quad(A, e1a, e1b, dG11, dG12, dG22) : -(A[e1a] * db1 + A[9 + e1a] * db2);
+      s_U_w[f * kUStride + lane] += v1;
+    }
+    const double v2 = lane < 24 ? quad(A, e2a, e2b, dG11, dG12, dG22) : -(A[e2a] * db1 + A[9 + e2a] * db2);
+    if (lane < 18) outW_o[lane] = free_cam ? v2 : 0.0;
+    else acc_pt += v2;
+  }
+}
+
+// NCH: compile-time channel count (1 = Intensity, the north-star descriptor); 0 = runtime count.
+template <int R, bool U8, int NCH>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(const StepParams prm) {
+  using FT = Foot<R>;
+  constexpr int P = FT::P;
+  constexpr int PR = (P + 31) / 32;             // pixel rounds per lane
+  constexpr bool kQuad = (NCH == 1 && PR == 1); // ILP-4 fast path available
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int F = prm.n_frames;
+  const int C = NCH ? NCH : prm.fr.n_channels;
+  const int CP = C * P;
+
+  const LmState* st = prm.st;
+  if (st && st->done) return;
+  const int buf = st ? st->eval_buf : 0;
+  const int cur = st ? st->cur : 0;
+  const bool backsub = st && st->iteration > 0;
+  const double* cams = prm.cams + (size_t)buf * F * 6;
+  double* pts_out = prm.pts + (size_t)buf * prm.n_points * 3;
+  const double* pts_cur = prm.pts + (size_t)cur * prm.n_points * 3;
+  double* outV = prm.V + (size_t)buf * prm.n_points * 6;
+  double* outgp = prm.gp + (size_t)buf * prm.n_points * 3;
+  double* outW = prm.W + (size_t)buf * prm.nnz * 18;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_pose = reinterpret_cast<double*>(smem_raw);                       // [F][36]
+  double* s_sstep = s_pose + F * kPoseConst;                                  // [F][6]
+  double* s_E = s_sstep + F * 6;                                              // [warps][8]
+  double* s_geo = s_E + kWarpsPerCta * kEacc;                                 // [warps][8][20]
+  double* s_geo_w = s_geo + warp * (kObsBatch * 20);
+  double* s_U = s_geo + kWarpsPerCta * (kObsBatch * 20);                      // [warps][F][27]
+  double* s_U_w = s_U + warp * F * kUStride;
+  double* s_red = s_U + kWarpsPerCta * F * kUStride;                          // [warps][25][26]
+  double* s_red_w = s_red + warp * (25 * kRedStride);
+  double* s_tot = s_red + kWarpsPerCta * (25 * kRedStride);                   // [warps][24]
+  double* s_tot_w = s_tot + warp * 24;
+  int4* s_gi = reinterpret_cast<int4*>(s_tot + kWarpsPerCta * 24);            // [warps][8]
+  int4* s_gi_w = s_gi + warp * kObsBatch;
+  int* s_frm = reinterpret_cast<int*>(s_gi + kWarpsPerCta * kObsBatch);       // [warps][16]
+  int* s_frm_w = s_frm + warp * kMaxFrames;
+  float* s_fp = reinterpret_cast<float*>(s_frm + kWarpsPerCta * kMaxFrames);
+  float* s_fp_w = s_fp + warp * (kStageSlots * FT::FLOATS);                   // [8][ROWS][W]
+
+  if (threadIdx.x < F) pose_consts(cams + 6 * threadIdx.x, s_pose + threadIdx.x * kPoseConst);
+  if (backsub)
+    for (int i = threadIdx.x; i < F * 6; i += blockDim.x)
+      s_sstep[i] = (st->free_index[i / 6] >= 0) ? st->scale_c[i] * st->step_c[i] : 0.0;
+  for (int i = lane; i < F * kUStride; i += 32) s_U_w[i] = 0.0;
+  __syncthreads();
+
+  // ---- per-lane constants --------------------------------------------------------------
+  double pdx[PR], pdy[PR], wj[PR];
+#pragma unroll
+  for (int r = 0; r < PR; ++r) {
+    const int j = min(lane + 32 * r, P - 1);      // lanes beyond the patch re-do pixel P-1 with weight 0
+    const int py = j / FT::SIDE, pxo = j - py * FT::SIDE;
+    pdx[r] = (double)(pxo - R); pdy[r] = (double)(py - R);
+    wj[r] = (lane + 32 * r < P) ? prm.weights[j] : 0.0;
+  }
+  int st_off[FT::ROUNDS];
+#pragma unroll
+  for (int rd = 0; rd < FT::ROUNDS; ++rd) {
+    const int wi = lane + 32 * rd;
+    const int row = wi / FT::NW, wd = wi - row * FT::NW;
+    st_off[rd] = (wi < FT::WORDS) ? row * prm.fr.pitch + 4 * wd : -1;
+  }
+  int e1a = 0, e1b = 0, e2a = 0, e2b = 0;
+  if (lane < 21) { e1a = c_pair6[lane][0]; e1b = c_pair6[lane][1]; }
+  else if (lane < 27) { e1a = lane - 21; }
+  if (lane < 18) { e2a = lane / 3; e2b = 6 + lane - 3 * (lane / 3); }
+  else if (lane < 24) { e2a = 6 + c_pair3[lane - 18][0]; e2b = 6 + c_pair3[lane - 18][1]; }
+  else if (lane < 27) { e2a = 6 + lane - 24; }
+
+  const int p = blockIdx.x * kWarpsPerCta + warp;
+  double cost_w = 0.0, gsq_w = 0.0, gmax_w = 0.0, xsq_w = 0.0;
+  double bs_sg = 0.0, bs_sHs = 0.0, bs_step = 0.0, bs_cand = 0.0;
+  if (p < prm.n_points) {
+    const int o0 = prm.obs_off[p], nobs = prm.obs_off[p + 1] - o0;
+    if (lane < nobs) s_frm_w[lane] = prm.obs_frame[o0 + lane];
+    double X0 = pts_cur[3 * p], X1 = pts_cur[3 * p + 1], X2 = pts_cur[3 * p + 2];
+    __syncwarp();
+
+    // ---- (B) back-substitution (SchurEliminator::BackSubstitute + model cost change) -------
+    if (backsub) {
+      // lane = b*8 + a accumulates sum_obs W[a][b] * (scale_c*step_c)[f][a]
+      const int a = lane & 7, b = lane >> 3;
+      const bool act = (a < 6 && b < 3);
+      const double* Wc = prm.W + ((size_t)cur * prm.nnz + o0) * 18;
+      double acc = 0.0;
+      if (act)
+        for (int i = 0; i < nobs; ++i) acc = fma(Wc[i * 18 + a * 3 + b], s_sstep[s_frm_w[i] * 6 + a], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      double wts[3];
+      wts[0] = __shfl_sync(0xffffffffu, acc, 0);
+      wts[1] = __shfl_sync(0xffffffffu, acc, 8);
+      wts[2] = __shfl_sync(0xffffffffu, acc, 16);
+      const double* Vc = prm.V + ((size_t)cur * prm.n_points + p) * 6;
+      const double* gc = prm.gp + ((size_t)cur * prm.n_points + p) * 3;
+      const double sp[3] = {prm.scale_p[(size_t)p * 3], prm.scale_p[(size_t)p * 3 + 1], prm.scale_p[(size_t)p * 3 + 2]};
+      double Vi[6], Vv[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { Vi[k] = prm.Vinv[(size_t)p * 6 + k]; Vv[k] = Vc[k]; }
+      const double gs[3] = {sp[0] * gc[0], sp[1] * gc[1], sp[2] * gc[2]};
+      double t[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { wts[k] *= sp[k]; t[k] = gs[k] + wts[k]; }   // gs - Ws^T y_c, y_c = -step_c
+      const double s0 = -(Vi[0] * t[0] + Vi[1] * t[1] + Vi[2] * t[2]);
+      const double s1 = -(Vi[1] * t[0] + Vi[3] * t[1] + Vi[4] * t[2]);
+      const double s2 = -(Vi[2] * t[0] + Vi[4] * t[1] + Vi[5] * t[2]);
+      const double c0 = X0 + s0 * sp[0], c1 = X1 + s1 * sp[1], c2 = X2 + s2 * sp[2];
+      if (lane == 0) {
+        // s.gs + s^T Vs0 s + 2 step_c^T Ws s   (undamped Vs0 = sp V sp)
+        const double y0 = s0 * sp[0], y1 = s1 * sp[1], y2 = s2 * sp[2];
+        bs_sg = s0 * gs[0] + s1 * gs[1] + s2 * gs[2];
+        bs_sHs = y0 * (Vv[0] * y0 + Vv[1] * y1 + Vv[2] * y2) + y1 * (Vv[1] * y0 + Vv[3] * y1 + Vv[4] * y2) +
+                 y2 * (Vv[2] * y0 + Vv[4] * y1 + Vv[5] * y2) + 2.0 * (wts[0] * s0 + wts[1] * s1 + wts[2] * s2);
+        bs_step = (X0 - c0) * (X0 - c0) + (X1 - c1) * (X1 - c1) + (X2 - c2) * (X2 - c2);
+        bs_cand = c0 * c0 + c1 * c1 + c2 * c2;
+      }
+      X0 = c0; X1 = c1; X2 = c2;
+      if (lane < 3) pts_out[3 * p + lane] = lane == 0 ? c0 : (lane == 1 ? c1 : c2);
+    }
+    xsq_w = X0 * X0 + X1 * X1 + X2 * X2;
+
+    double acc_pt = 0.0;  // lanes 18..23: V entries, 24..26: g_p entries (summed over frames)
+    double p0c[PR];       // reference descriptor of this point, channel 0
+#pragma unroll
+    for (int r = 0; r < PR; ++r) p0c[r] = (double)prm.desc[(size_t)p * CP + min(lane + 32 * r, P - 1)];
+
+    for (int ob = 0; ob < nobs; ob += kObsBatch) {
+      const int nb = min(kObsBatch, nobs - ob);
+      // ---- (G) geometry: lane i <-> observation ob+i --------------------------------
+      if (lane < nb) {
+        const int g_f = s_frm_w[ob + lane];
+        const double* pc = s_pose + g_f * kPoseConst;
+        double Xc0, Xc1, Xc2;
+        if (pc[8] == 0.0) {  // ceres::AngleAxisRotatePoint, same operation order (no FMA)
+          const double k0 = pc[0], k1 = pc[1], k2 = pc[2], c = pc[6], s = pc[7];
+          const double wx0 = __dsub_rn(__dmul_rn(k1, X2), __dmul_rn(k2, X1));
+          const double wx1 = __dsub_rn(__dmul_rn(k2, X0), __dmul_rn(k0, X2));
+          const double wx2 = __dsub_rn(__dmul_rn(k0, X1), __dmul_rn(k1, X0));
+          const double tmp = __dmul_rn(__dadd_rn(__dadd_rn(__dmul_rn(k0, X0), __dmul_rn(k1, X1)), __dmul_rn(k2, X2)),
+                                       __dsub_rn(1.0, c));
+          Xc0 = __dadd_rn(__dadd_rn(__dmul_rn(X0, c), __dmul_rn(wx0, s)), __dmul_rn(k0, tmp));
+          Xc1 = __dadd_rn(__dadd_rn(__dmul_rn(X1, c), __dmul_rn(wx1, s)), __dmul_rn(k1, tmp));
+          Xc2 = __dadd_rn(__dadd_rn(__dmul_rn(X2, c), __dmul_rn(wx2, s)), __dmul_rn(k2, tmp));
+        } else {
+          const double a0 = pc[0], a1 = pc[1], a2 = pc[2];
+          Xc0 = __dadd_rn(X0, __dsub_rn(__dmul_rn(a1, X2), __dmul_rn(a2, X1)));
+          Xc1 = __dadd_rn(X1, __dsub_rn(__dmul_rn(a2, X0), __dmul_rn(a0, X2)));
+          Xc2 = __dadd_rn(X2, __dsub_rn(__dmul_rn(a0, X1), __dmul_rn(a1, X0)));
+        }
+        Xc0 = __dadd_rn(Xc0, pc[3]); Xc1 = __dadd_rn(Xc1, pc[4]); Xc2 = __dadd_rn(Xc2, pc[5]);
+        // Calibration::project: u = ((X*fx)/Z) + cx  (IEEE division, T = double path)
+        const double u = __dadd_rn(__ddiv_rn(__dmul_rn(Xc0, prm.fx), Xc2), prm.cx);
+        const double v = __dadd_rn(__ddiv_rn(__dmul_rn(Xc1, prm.fy), Xc2), prm.cy);
+        double* g = s_geo_w + lane * 20;
+        g[0] = u; g[1] = v;
+        const double iz = 1.0 / Xc2;
+        const double J00 = prm.fx * iz, J02 = -prm.fx * Xc0 * iz * iz;
+        const double J11 = prm.fy * iz, J12 = -prm.fy * Xc1 * iz * iz;
+        const double* Rj = pc + 18;
+        const double* M = pc + 27;
+        double D[9];   // D = -Rj [X]x M
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const double m0 = M[b], m1 = M[3 + b], m2 = M[6 + b];
+          const double t0 = X1 * m2 - X2 * m1, t1 = X2 * m0 - X0 * m2, t2 = X0 * m1 - X1 * m0;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) D[a * 3 + b] = -(Rj[a * 3] * t0 + Rj[a * 3 + 1] * t1 + Rj[a * 3 + 2] * t2);
+        }
+        const double* Rm = pc + 9;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          g[2 + b] = J00 * D[b] + J02 * D[6 + b];            // du/dw
+          g[11 + b] = J11 * D[3 + b] + J12 * D[6 + b];       // dv/dw
+          g[8 + b] = J00 * Rm[b] + J02 * Rm[6 + b];          // du/dX
+          g[17 + b] = J11 * Rm[3 + b] + J12 * Rm[6 + b];     // dv/dX
+        }
+        g[5] = J00; g[6] = 0.0; g[7] = J02;                  // du/dt
+        g[14] = 0.0; g[15] = J11; g[16] = J12;               // dv/dt
+        // footprint origin and fast-path test (all taps and gradient taps interior)
+        int4 gi = make_int4(g_f, 0, 0, 0);   // {frame, r0, cb (aligned first column), fast}
+        if (fabs(u) < 1.0e8 && fabs(v) < 1.0e8) {
+          const int c0 = (int)floor(u) - R - 1, r0 = (int)floor(v) - R - 1;
+          const int fast = (c0 >= 0 && c0 + FT::ROWS - 1 <= prm.fr.cols - 1 && r0 >= 0 &&
+                            r0 + FT::ROWS - 1 <= prm.fr.rows - 1) ? 1 : 0;
+          gi.y = r0; gi.z = c0 & ~3; gi.w = fast;
+        }
+        s_gi_w[lane] = gi;
+      }
+      __syncwarp();
+
+      const int obs_per_stage = NCH == 1 ? kStageSlots : ((C >= kStageSlots) ? 1 : kStageSlots / C);
+      for (int sb = 0; sb < nb; sb += obs_per_stage) {
+        const int ns_obs = min(obs_per_stage, nb - sb);
+        const int nslots = NCH == 1 ? ns_obs : ns_obs * C;
+        // ---- (L) stage footprints: all loads first, then the stores ----------------------
+        {
+          uint32_t t8[kStageSlots][FT::ROUNDS];
+          float4 t32[U8 ? 1 : kStageSlots][U8 ? 1 : FT::ROUNDS];
+#pragma unroll
+          for (int sl = 0; sl < kStageSlots; ++sl) {
+            if (sl < nslots) {
+              const int i = NCH == 1 ? sb + sl : sb + sl / C;
+              const int k = NCH == 1 ? 0 : sl - (sl / C) * C;
+              const int4 gi = s_gi_w[i];
+              if (gi.w) {
+                const unsigned base = (unsigned)((NCH == 1 ? gi.x : gi.x * C + k) * (int)prm.fr.plane + gi.y * prm.fr.pitch + gi.z);
+#pragma unroll
+                for (int rd = 0; rd < FT::ROUNDS; ++rd) {
+                  if (st_off[rd] >= 0) {
+                    if (U8) t8[sl][rd] = __ldg(reinterpret_cast<const uint32_t*>(prm.fr.u8 + (base + (unsigned)st_off[rd])));
+                    else t32[U8 ? 0 : sl][U8 ? 0 : rd] = __ldg(reinterpret_cast<const float4*>(prm.fr.f32 + (base + (unsigned)st_off[rd])));
+                  }
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int sl = 0; sl < kStageSlots; ++sl) {
+            if (sl < nslots) {
+              const int i = NCH == 1 ? sb + sl : sb + sl / C;
+              if (s_gi_w[i].w) {
+#pragma unroll
+                for (int rd = 0; rd < FT::ROUNDS; ++rd) {
+                  if (st_off[rd] >= 0) {
+                    float4 o;
+                    if (U8) {
+                      const uint32_t q = t8[sl][rd];
+                      o = make_float4((float)(q & 0xffu), (float)((q >> 8) & 0xffu), (float)((q >> 16) & 0xffu), (float)(q >> 24));
+                    } else {
+                      o = t32[U8 ? 0 : sl][U8 ? 0 : rd];
+                    }
+                    reinterpret_cast<float4*>(s_fp_w + sl * FT::FLOATS)[lane + 32 * rd] = o;
+                  }
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+
+        // ---- (S)+(R): four observations at a time when every one of them is interior -------
+        for (int qb = 0; qb < ns_obs; qb += 4) {
+          const int nq = min(4, ns_obs - qb);
+          bool all_fast = kQuad;
+          if (kQuad)
+            for (int i = 0; i < nq; ++i) all_fast = all_fast && (s_gi_w[sb + qb + i].w != 0);
+          if (kQuad && all_fast) {
+            double v6[4][6];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int ii = sb + qb + min(i, nq - 1);            // out-of-range slots redo the last one
+              const int4 gi = s_gi_w[ii];
+              const double* g = s_geo_w + ii * 20;
+              float I1, gx, gy;
+              sample_fast<R>(s_fp_w + (ii - sb) * FT::FLOATS, gi.y, gi.z, g[0], g[1], pdx[0], pdy[0], I1, gx, gy);
+              const double rr = __dmul_rn(wj[0], __dsub_rn(p0c[0], (double)I1));   // photobundle.cc:720
+              if (prm.residuals && lane < P && i < nq) prm.residuals[(size_t)(o0 + ob + ii) * CP + lane] = rr;
+              const double hx = wj[0] * (double)gx, hy = wj[0] * (double)gy;
+              v6[i][0] = rr * rr; v6[i][1] = hx * hx; v6[i][2] = hx * hy; v6[i][3] = hy * hy; v6[i][4] = rr * hx; v6[i][5] = rr * hy;
+            }
+            // transpose-reduce the 24 sums of the group through shared memory: lane r <- sum over pixels of value r
+            if (lane < P) {
+              double2* row = reinterpret_cast<double2*>(s_red_w + lane * kRedStride);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) row[i * 3 + k] = make_double2(v6[i][2 * k], v6[i][2 * k + 1]);
+            }
+            __syncwarp();
+            double tot = 0.0;
+            if (lane < 24) {
+#pragma unroll
+              for (int l = 0; l < P; ++l) tot += s_red_w[l * kRedStride + lane];
+            }
+            // Huber corrector of the four observations in parallel: lane 6i+k holds sum k of observation i
+            const int i_l = lane / 6, k_l = lane - 6 * i_l;
+            const double s_i = __shfl_sync(0xffffffffu, tot, min(i_l, 3) * 6);
+            double rho0, rho1;
+            huber_rho(prm.huber, s_i, rho0, rho1);
+            if (lane < 24) {
+              s_tot_w[lane] = k_l == 0 ? s_i : rho1 * tot;
+              if (k_l == 0 && i_l < nq) {
+                cost_w += 0.5 * rho0;
+                if (prm.obs_sqnorm) prm.obs_sqnorm[o0 + ob + sb + qb + i_l] = s_i;
+              }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (i < nq) {
+                const int ii = sb + qb + i;
+                const int o = o0 + ob + ii;
+                const int f = s_gi_w[ii].x;
+                const double* t = s_tot_w + 6 * i;
+                emit_blocks(t[1], t[2], t[3], t[4], t[5], s_geo_w + ii * 20, f, f != prm.fixed_frame, lane, e1a, e1b, e2a, e2b,
+                            s_U_w, outW + (size_t)o * 18, acc_pt);
+              }
+            }
+            __syncwarp();
+          } else {
+            // generic path: any channel count / patch size / border handling, one observation at a time
+            for (int i = 0; i < nq; ++i) {
+              const int ii = sb + qb + i;
+              const int o = o0 + ob + ii;
+              const int4 gi = s_gi_w[ii];
+              const int f = gi.x, r0 = gi.y, cb = gi.z, fast = gi.w;
+              const double* g = s_geo_w + ii * 20;
+              const double u = g[0], v = g[1];
+              Sums q = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+              for (int k = 0; k < C; ++k) {
+                const float* fp = s_fp_w + (NCH == 1 ? ii - sb : (ii - sb) * C + k) * FT::FLOATS;
+#pragma unroll
+                for (int r = 0; r < PR; ++r) {
+                  const int j = lane + 32 * r;
+                  if (j < P) {
+                    const float su = __double2float_rn(__dadd_rn(u, pdx[r]));
+                    const float sv = __double2float_rn(__dadd_rn(v, pdy[r]));
+                    float I1, gx, gy;
+                    if (fast) {
+                      const int ix = __float2int_rz(su), iy = __float2int_rz(sv);
+                      const float dx = __fsub_rn((float)(ix + 1), su), dy = __fsub_rn((float)(iy + 1), sv);
+                      const float* qq = fp + (iy - r0) * FT::W + (ix - cb);
+                      const float a11 = qq[0], a12 = qq[1], a21 = qq[FT::W], a22 = qq[FT::W + 1];
+                      const float l1 = qq[-1], r1 = qq[2], l2 = qq[FT::W - 1], r2 = qq[FT::W + 2];
+                      const float t1 = qq[-FT::W], t2 = qq[-FT::W + 1], u1 = qq[2 * FT::W], u2 = qq[2 * FT::W + 1];
+                      const double omdx = __dsub_rn(1.0, (double)dx);
+                      const float omdy = __fsub_rn(1.0f, dy);
+                      I1 = bilerp(dx, dy, omdx, omdy, a11, a12, a21, a22);
+                      gx = bilerp(dx, dy, omdx, omdy, __fmul_rn(0.5f, __fsub_rn(a12, l1)), __fmul_rn(0.5f, __fsub_rn(r1, a11)),
+                                  __fmul_rn(0.5f, __fsub_rn(a22, l2)), __fmul_rn(0.5f, __fsub_rn(r2, a21)));
+                      gy = bilerp(dx, dy, omdx, omdy, __fmul_rn(0.5f, __fsub_rn(a21, t1)), __fmul_rn(0.5f, __fsub_rn(a22, t2)),
+                                  __fmul_rn(0.5f, __fsub_rn(u1, a11)), __fmul_rn(0.5f, __fsub_rn(u2, a12)));
+                    } else {
+                      int x1, x2, y1, y2;
+                      float dx, dy;
+                      init_axis(sv, prm.fr.rows, y1, y2, dy);
+                      init_axis(su, prm.fr.cols, x1, x2, dx);
+                      const double omdx = __dsub_rn(1.0, (double)dx);
+                      const float omdy = __fsub_rn(1.0f, dy);
+                      I1 = bilerp(dx, dy, omdx, omdy, px_at<U8>(prm.fr, f, k, y1, x1), px_at<U8>(prm.fr, f, k, y1, x2),
+                                  px_at<U8>(prm.fr, f, k, y2, x1), px_at<U8>(prm.fr, f, k, y2, x2));
+                      float gx11, gx12, gx21, gx22, gy11, gy12, gy21, gy22;
+                      grad_at<U8>(prm.fr, f, k, y1, x1, gx11, gy11);
+                      grad_at<U8>(prm.fr, f, k, y1, x2, gx12, gy12);
+                      grad_at<U8>(prm.fr, f, k, y2, x1, gx21, gy21);
+                      grad_at<U8>(prm.fr, f, k, y2, x2, gx22, gy22);
+                      gx = bilerp(dx, dy, omdx, omdy, gx11, gx12, gx21, gx22);
+                      gy = bilerp(dx, dy, omdx, omdy, gy11, gy12, gy21, gy22);
+                    }
+                    const double p0 = (k == 0) ? p0c[r] : (double)prm.desc[(size_t)p * CP + k * P + j];
+                    const double rr = __dmul_rn(wj[r], __dsub_rn(p0, (double)I1));   // photobundle.cc:720
+                    if (prm.residuals) prm.residuals[(size_t)o * CP + k * P + j] = rr;
+                    q.s = fma(rr, rr, q.s);
+                    const double hx = wj[r] * (double)gx, hy = wj[r] * (double)gy;
+                    q.G11 = fma(hx, hx, q.G11); q.G12 = fma(hx, hy, q.G12); q.G22 = fma(hy, hy, q.G22);
+                    q.b1 = fma(rr, hx, q.b1); q.b2 = fma(rr, hy, q.b2);
+                  }
+                }
+              }
+              warp_reduce(q);
+              double rho0, rho1;
+              huber_rho(prm.huber, q.s, rho0, rho1);
+              if (lane == 0) {
+                cost_w += 0.5 * rho0;
+                if (prm.obs_sqnorm) prm.obs_sqnorm[o] = q.s;
+              }
+              emit_blocks(rho1 * q.G11, rho1 * q.G12, rho1 * q.G22, rho1 * q.b1, rho1 * q.b2, g, f, f != prm.fixed_frame, lane,
+                          e1a, e1b, e2a, e2b, s_U_w, outW + (size_t)o * 18, acc_pt);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane >= 18 && lane < 24) outV[(size_t)p * 6 + lane - 18] = acc_pt;
+    else if (lane >= 24 && lane < 27) outgp[(size_t)p * 3 + lane - 24] = acc_pt;
+    const double gq = (lane >= 24 && lane < 27) ? acc_pt : 0.0;
+    double g2 = gq * gq, ga = fabs(gq);
+#pragma unroll
+    for (int m = 1; m <= 2; m <<= 1) {   // lanes 24..27 form an aligned group of four
+      g2 += __shfl_xor_sync(0xffffffffu, g2, m);
+      ga = fmax(ga, __shfl_xor_sync(0xffffffffu, ga, m));
+    }
+    gsq_w = __shfl_sync(0xffffffffu, g2, 24);
+    gmax_w = __shfl_sync(0xffffffffu, ga, 24);
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) cost_w += __shfl_xor_sync(0xffffffffu, cost_w, m);   // lanes 0,6,12,18 hold partial costs
+  if (lane == 0) {
+    double* e = s_E + warp * kEacc;
+    e[0] = cost_w; e[1] = gsq_w; e[2] = gmax_w; e[3] = xsq_w; e[4] = bs_sg; e[5] = bs_sHs; e[6] = bs_step; e[7] = bs_cand;
+  }
+  __syncthreads();
+  // CTA partials (fixed order inside the CTA), then one fp64 atomic per entry per CTA
+  double* Uacc = prm.Uacc + (size_t)buf * F * kUStride;
+  for (int i = threadIdx.x; i < F * kUStride; i += blockDim.x) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerCta; ++w) acc += s_U[w * F * kUStride + i];
+    if (acc != 0.0) atomicAdd(Uacc + i, acc);
+  }
+  if (threadIdx.x < kEacc) {
+    double acc = 0.0;
+    if (threadIdx.x == 2) {
+      for (int w = 0; w < kWarpsPerCta; ++w) acc = fmax(acc, s_E[w * kEacc + 2]);
+      // non-negative doubles order like their bit patterns
+      atomicMax(reinterpret_cast<unsigned long long*>(prm.Eacc + buf * kEacc + 2), (unsigned long long)__double_as_longlong(acc));
+    } else {
+      for (int w = 0; w < kWarpsPerCta; ++w) acc += s_E[w * kEacc + threadIdx.x];
+      if (acc != 0.0) atomicAdd(prm.Eacc + buf * kEacc + threadIdx.x, acc);
+    }
+  }
+}
+
+// ---- host launcher -----------------------------------------------------------------------
+template <int R, bool U8, int NCH>
+static cudaError_t launch_one(const StepParams& prm, cudaStream_t stream) {
+  const size_t smem = k_step_smem_bytes<R>(prm.n_frames);
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k_step<R, U8, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    configured[dev & 63] = true;
+  }
+  const int grid = k_step_grid(prm.n_points);
+  if (grid == 0) return cudaSuccess;
+  k_step<R, U8, NCH><<<grid, kWarpsPerCta * 32, smem, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+int k_step_grid(int n_points) { return (n_points + kWarpsPerCta - 1) / kWarpsPerCta; }
+
+template <int R>
+static cudaError_t launch_r(const StepParams& prm, cudaStream_t stream) {
+  if (prm.fr.u8) return launch_one<R, true, 1>(prm, stream);      // uint8 planes are always 1-channel Intensity
+  if (prm.fr.n_channels == 1) return launch_one<R, false, 1>(prm, stream);
+  return launch_one<R, false, 0>(prm, stream);
+}
+
+cudaError_t launch_k_step(const StepParams& prm, int radius, cudaStream_t stream) {
+  switch (radius) {
+    case 1: return launch_r<1>(prm, stream);
+    case 2: return launch_r<2>(prm, stream);
+    case 3: return launch_r<3>(prm, stream);
+    case 4: return launch_r<4>(prm, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace pba

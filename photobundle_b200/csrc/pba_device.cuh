@@ -1,7 +1,7 @@
 // pba_device.cuh — device-side data layout shared by the kernels (sm_100a only).
 //
-// HBM layout of one window. "x2" = double-buffered: buffer st->cur holds the
-// accepted point x, buffer st->eval_buf the candidate x+Δ being evaluated.
+// HBM layout of one window. "x2" = double-buffered: buffer st.cur holds the
+// accepted point x, buffer st.eval_buf the candidate x+Δ being evaluated.
 //   frames   u8  [F][rows][pitch]            pitch = roundup(cols,16) bytes   (Intensity)
 //         or f32 [F][C][rows][pitch]         pitch = roundup(cols,16) floats  (generic)
 //   cams     f64 x2 [F][6]                   world->camera [angle-axis, t]
@@ -11,10 +11,11 @@
 //                                            src/photobundle.cc:466-479)
 //   obs_off  i32 [n+1], obs_frame i32 [nnz]  CSR visibility, window-local frame index
 //   V,gp,W   f64 x2 [n][6] [n][3] [nnz][18]  point blocks / cross blocks at x
-//   Upart    f64 [k1 CTAs][F][27]            per-CTA partial pose blocks (21 U + 6 g_c)
-//   Epart    f64 [k1 CTAs][4]                per-CTA {cost, Σg_p², max|g_p|, Σ|X|²}
-//   U,E      f64 x2 [F][27], [4]             reduced pose blocks / scalars at x
-//   Spart    f64 [schur CTAs][D*D + D]       per-CTA partial Schur complement, D = 6F
+//   Uacc     f64 x2 [F][27]                  pose blocks (21 upper-tri U + 6 g_c), accumulated
+//                                            by K_A with fp64 atomics (one add per CTA per entry)
+//   Eacc     f64 x2 [8]                      {cost, Σg_p², max|g_p| (bits), Σ|X|², s·g, sᵀHs, |Δ|², |x+Δ|²}
+//   S        f64 [D*D + D]                   Schur complement + rhs accumulators, D = 6F
+//   state    LmState x2                      ping-pong: K_B reads one, writes the other
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -23,14 +24,14 @@ namespace pba {
 
 constexpr int kMaxFrames = 16;
 constexpr int kMaxD = 6 * kMaxFrames;
-constexpr int kWarpsPerCta = 8;       // K1: one warp per point
-constexpr int kObsBatch = 8;          // observations whose geometry is formed together
+constexpr int kWarpsPerCta = 8;       // K_A: one warp per point
+constexpr int kObsBatch = 8;          // observations whose geometry / footprints are staged together
 constexpr int kStageSlots = 8;        // (observation, channel) footprints staged together
 constexpr int kPoseConst = 36;        // doubles per frame, see pose_consts()
 constexpr int kUStride = 27;          // 21 upper-tri U + 6 g_c
 constexpr int kSchurThreads = 256;
 constexpr int kSchurChunk = 8;        // points per chunk (one per warp)
-constexpr int kBackThreads = 128;
+constexpr int kEacc = 8;
 
 struct Frames {
   const uint8_t* u8;   // non-null: Intensity planes, gradients formed in-kernel
@@ -53,9 +54,8 @@ enum MsgCode {
   kMsgMinRadius = 5, kMsgInvalidSteps = 6
 };
 
-// Levenberg-Marquardt state machine, resident in HBM; every kernel of the loop reads it,
-// only k_decide / k_solve write it (Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy
-// semantics).
+// Levenberg-Marquardt state machine, resident in HBM (Ceres TrustRegionMinimizer +
+// LevenbergMarquardtStrategy semantics).
 struct LmState {
   // options
   int max_num_iterations, max_invalid, jacobi_scaling;
@@ -73,20 +73,21 @@ struct LmState {
   int num_invalid, num_successful, num_unsuccessful, n_trace, num_evals;
   double x_cost, x_norm, initial_cost;
   double gmax, gnorm;
-  // step under evaluation (written by k_solve / k_backsub partials)
+  // step under evaluation (written by the solve)
   int step_valid;
   double cam_sg, cam_sHs, cam_step_sq, cam_cand_sq;
   double scale_c[kMaxD];          // Jacobi column scaling of the pose columns (iteration 0)
   double step_c[kMaxD];           // trust-region step of the pose columns, scaled space
 };
 
-struct EvalParams {
+// K_A parameters (k_step.cu)
+struct StepParams {
   Frames fr;
   int n_frames, fixed_frame, n_points, nnz;
   double fx, fy, cx, cy, huber;
-  const LmState* st;         // null: evaluate buffer 0 (pba_eval)
-  const double* cams;        // x2 [F][6]
-  const double* pts;         // x2 [n][3]
+  const LmState* st;         // null: plain evaluation of buffer 0 (pba_eval)
+  double* cams;              // x2 [F][6]
+  double* pts;               // x2 [n][3]
   const float* desc;         // [n][C*P]
   const int* obs_off;        // [n+1]
   const int* obs_frame;      // [nnz]
@@ -94,46 +95,39 @@ struct EvalParams {
   double* V;                 // x2 [n][6]   upper triangle 00 01 02 11 12 22
   double* gp;                // x2 [n][3]
   double* W;                 // x2 [nnz][18] row-major 6x3
-  double* Upart;             // [gridDim.x][F][27]
-  double* Epart;             // [gridDim.x][4]
+  double* Uacc;              // x2 [F][27]
+  double* Eacc;              // x2 [8]
+  const double* scale_p;     // [n][3]   (back-substitution)
+  const double* Vinv;        // [n][6]
   double* obs_sqnorm;        // optional [nnz]
   double* residuals;         // optional [nnz][C*P]
 };
 
+// K_B parameters (k_schur_solve.cu)
 struct LmParams {
-  LmState* st;
+  const LmState* st_in;
+  LmState* st_out;
   IterSummary* trace;
-  int n_frames, n_points, nnz, n_k1_ctas, n_schur_ctas, n_back_ctas;
+  unsigned int* ticket;      // last-CTA detection
+  int n_frames, n_points, nnz;
   const int* obs_off;
   const int* obs_frame;
   double* cams;              // x2
-  double* pts;               // x2
   const double* V;           // x2
   const double* gp;          // x2
   const double* W;           // x2
-  const double* Upart;
-  const double* Epart;
-  double* U;                 // x2 [F][27]
-  double* E;                 // x2 [4]
+  double* Uacc;              // x2 [F][27]
+  double* Eacc;              // x2 [8]
   double* scale_p;           // [n][3]
   double* Vinv;              // [n][6]
-  double* Spart;             // [n_schur_ctas][D*D + D]
-  double* S;                 // [D*D]
-  double* rhs;               // [D]
-  double* Bpart;             // [n_back_ctas][4]
+  double* S;                 // [D*D + D]
+  unsigned long long* dbg;   // optional: globaltimer stamps of the last CTA {start, decided, schur done, solved, end}
 };
 
-// launchers (k1_eval.cu, lm_kernels.cu)
-int k1_grid(int n_points);
-size_t k1_smem(int radius, int n_frames);
-cudaError_t launch_k1(const EvalParams& prm, int radius, cudaStream_t stream);
+// launchers
+int k_step_grid(int n_points);
+cudaError_t launch_k_step(const StepParams& prm, int radius, cudaStream_t stream);
 int schur_grid(int n_points, int sm_count);
-int back_grid(int n_points);
-cudaError_t launch_reduce_u(const LmParams& lp, cudaStream_t stream);
-cudaError_t launch_decide(const LmParams& lp, cudaStream_t stream);
-cudaError_t launch_schur(const LmParams& lp, cudaStream_t stream);
-cudaError_t launch_reduce_s(const LmParams& lp, cudaStream_t stream);
-cudaError_t launch_solve(const LmParams& lp, cudaStream_t stream);
-cudaError_t launch_backsub(const LmParams& lp, cudaStream_t stream);
+cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t stream);
 
 }  // namespace pba

@@ -22,3 +22,15 @@ for rep in range(3):
     t = time.time(); s = h.solve(); dt = time.time() - t
     print(f"solve cfg3: iters {s['num_iterations']} evals {s['num_evaluations']} device {s['device_time_in_seconds']*1e3:.3f} ms wall {dt*1e3:.3f} ms launches {s['kernel_launches']} final {s['final_cost']:.4f} {s['message']}")
 h.close()
+
+# ragged trace / pose diff
+wr = synthetic.small_window(seed=11, ragged=True, n_frames=8, grid=(10, 14))
+owr = ob.OracleWindow(wr)
+oc, op_, osum, otr = owr.solve(wr.cams_init, wr.points_init)
+hr = capi.Handle.for_window(wr)
+sr = hr.solve(); cr = hr.get_poses(); pr = hr.get_points(); trr = hr.get_iterations(); hr.close()
+print("ragged: gpu iters", sr["num_iterations"], sr["final_cost"], "oracle", osum["num_iterations"], osum["final_cost"])
+print(" decisions equal:", [t["step_is_successful"] for t in trr] == [t["step_is_successful"] for t in otr])
+print(" max dpose", np.abs(cr - oc).max(0), "max dpts", np.abs(pr - op_).max())
+for a, b in list(zip(trr, otr))[-6:]:
+    print("  G %d %d %.10f r=%.5e | O %d %d %.10f r=%.5e" % (a["iteration"], a["step_is_successful"], a["cost"], a["trust_region_radius"], b["iteration"], b["step_is_successful"], b["cost"], b["trust_region_radius"]))
