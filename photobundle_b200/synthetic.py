@@ -264,3 +264,56 @@ def small_window(seed: int = 7, ragged: bool = False, radius: int = 2, n_frames:
     return make_window(n_frames=n_frames, grid=grid, rows=rows, cols=cols, radius=radius,
                        intrinsics=(200.0, 200.0, 0.5 * cols - 0.3, 0.5 * rows + 0.2),
                        ragged=ragged, margin=16, seed=seed)
+
+
+# ----------------------------------------------------------------------------------------------
+# Synthetic *sequence* for the sliding-window entry point (addFrame): images, depth maps and the
+# frame-to-frame pose initialisation the reference's apps/run_kitti.cc feeds it (run_kitti.cc:39-51).
+# ----------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class Sequence:
+    images: np.ndarray      # [N, rows, cols] uint8
+    depths: np.ndarray      # [N, rows, cols] float32 (stereo-like noisy depth; <= 0 = invalid)
+    K4: tuple               # fx, fy, cx, cy
+    T_w_gt: np.ndarray      # [N, 4, 4] camera-to-world (the convention of Trajectory)
+    T_rel_gt: np.ndarray    # [N, 4, 4] frame-to-frame poses whose chaining gives T_w_gt
+    T_rel_init: np.ndarray  # [N, 4, 4] perturbed initialisation (what a VO front-end would give)
+
+
+def cam_to_mat(cam: np.ndarray) -> np.ndarray:
+    T = np.eye(4)
+    T[:3, :3] = rodrigues(cam[:3])
+    T[:3, 3] = cam[3:]
+    return T
+
+
+def make_sequence(n_frames: int = 10, rows: int = 120, cols: int = 160, seed: int = 21,
+                  intrinsics=None, rot_sigma: float = 1e-3, trans_sigma: float = 0.01,
+                  depth_noise: float = 0.02) -> Sequence:
+    if intrinsics is None:
+        intrinsics = (200.0, 200.0, 0.5 * cols - 0.3, 0.5 * rows + 0.2)
+    K4 = tuple(float(v) for v in intrinsics)
+    ss = np.random.SeedSequence(seed).spawn(3)
+    rng_tex, rng_depth, rng_pose = (np.random.Generator(np.random.PCG64(s)) for s in ss)
+    scene = PlaneScene(rng_tex, fscale=min(K4[0], K4[1]) / KITTI_FX)
+    cams = np.zeros((n_frames, 6))
+    for i in range(n_frames):
+        w = np.array([0.0, 0.002 * i, 0.0005 * i])
+        C = i * np.array([0.03, 0.005, 0.10])
+        cams[i, :3] = w
+        cams[i, 3:] = -rodrigues(w) @ C
+    images = np.stack([scene.render(cams[i], K4, rows, cols) for i in range(n_frames)])
+    ys, xs = np.meshgrid(np.arange(rows, dtype=np.float64), np.arange(cols, dtype=np.float64), indexing="ij")
+    depths = np.empty((n_frames, rows, cols), dtype=np.float32)
+    for i in range(n_frames):
+        _, z = scene.intersect(cams[i], K4, xs, ys)
+        depths[i] = (z * (1.0 + depth_noise * rng_depth.normal(size=z.shape))).astype(np.float32)
+    T_c = np.stack([cam_to_mat(c) for c in cams])              # world -> camera
+    T_w = np.stack([np.linalg.inv(T) for T in T_c])            # camera -> world
+    # convertPoseToLocal (src/pose_utils.cc:62-74): T_i = inv(T_w[i]) * T_w[i-1], T_0 = inv(T_w[0])
+    T_rel = np.stack([np.linalg.inv(T_w[0])] + [np.linalg.inv(T_w[i]) @ T_w[i - 1] for i in range(1, n_frames)])
+    T_init = T_rel.copy()
+    for i in range(1, n_frames):
+        d = np.concatenate([rng_pose.normal(0, rot_sigma, 3), rng_pose.normal(0, trans_sigma, 3)])
+        T_init[i] = cam_to_mat(d) @ T_rel[i]
+    return Sequence(images=images, depths=depths, K4=K4, T_w_gt=T_w, T_rel_gt=T_rel, T_rel_init=T_init)
