@@ -189,6 +189,9 @@ int pba_get_iterations(pba_handle* h, pba_iteration_summary* out, int32_t capaci
  * pba_comm_unique_id() and distributes the 128 bytes by any means (torch.distributed,
  * MPI, a file); then every rank calls pba_comm_init(). */
 int pba_comm_unique_id(void* id128);
+/* The sharding rule (host arithmetic only, no GPU): points [first, last) belong to `rank`. */
+int pba_shard_range(int32_t n_points, const int32_t* obs_offsets, int32_t rank, int32_t n_ranks,
+                    int32_t* first, int32_t* last);
 int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_ranks);
 
 #ifdef __cplusplus

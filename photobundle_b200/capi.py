@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "pba_last_error", "pba_version", "pba_default_solver_options", "pba_create", "pba_destroy",
     "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_poses", "pba_set_points",
     "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_get_poses", "pba_get_points", "pba_get_iterations",
-    "pba_comm_unique_id", "pba_comm_init",
+    "pba_comm_unique_id", "pba_comm_init", "pba_shard_range",
 ]
 
 
@@ -187,6 +187,9 @@ class Handle:
                                     _ptr(weights)), "pba_set_points")
         self.n_points = n
         self.n_obs = int(obs_offsets[-1])
+        nr, rk = getattr(self, "n_ranks", 1), getattr(self, "rank", 0)
+        a, b = shard_range(obs_offsets, rk, nr)
+        self.n_obs_local = int(obs_offsets[b] - obs_offsets[a])
 
     def eval(self, want_residuals: bool = True) -> dict:
         F, n, nnz = self.n_frames, self.n_points, self.n_obs
@@ -224,13 +227,20 @@ class Handle:
     def restore_state(self):
         _check(lib().pba_restore_state(self._h), "pba_restore_state")
 
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        """One process per GPU: join the window's communicator (before set_points)."""
+        assert len(unique_id) == PBA_UNIQUE_ID_BYTES
+        buf = C.create_string_buffer(unique_id, PBA_UNIQUE_ID_BYTES)
+        _check(lib().pba_comm_init(self._h, buf, int(rank), int(n_ranks)), "pba_comm_init")
+        self.rank, self.n_ranks = rank, n_ranks
+
     def get_poses(self) -> np.ndarray:
         cams = np.zeros((self.n_frames, 6))
         _check(lib().pba_get_poses(self._h, _ptr(cams)), "pba_get_poses")
         return cams
 
     def get_points(self) -> np.ndarray:
-        pts = np.zeros((self.n_points, 3))
+        pts = np.zeros((self.n_points, 3))   # the FULL array on every rank
         _check(lib().pba_get_points(self._h, _ptr(pts)), "pba_get_points")
         return pts
 
@@ -240,3 +250,16 @@ class Handle:
         arr = (IterationSummary * max(1, n.value))()
         _check(lib().pba_get_iterations(self._h, arr, n.value, C.byref(n)), "pba_get_iterations")
         return [{f[0]: getattr(arr[i], f[0]) for f in IterationSummary._fields_} for i in range(n.value)]
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(PBA_UNIQUE_ID_BYTES)
+    _check(lib().pba_comm_unique_id(buf), "pba_comm_unique_id")
+    return buf.raw
+
+
+def shard_range(obs_offsets: np.ndarray, rank: int, n_ranks: int) -> tuple[int, int]:
+    off = np.ascontiguousarray(obs_offsets, dtype=np.int32)
+    a, b = C.c_int32(), C.c_int32()
+    _check(lib().pba_shard_range(off.shape[0] - 1, _ptr(off), rank, n_ranks, C.byref(a), C.byref(b)), "pba_shard_range")
+    return a.value, b.value

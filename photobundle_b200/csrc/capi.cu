@@ -15,7 +15,43 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types/enums only: the library is dlopen'ed when a communicator is requested
+
 using namespace pba;
+
+// ---- NCCL, loaded lazily (single-GPU users never need it) -----------------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static const char* load_nccl() {
+  if (g_nccl.lib) return nullptr;
+  // if the host process (e.g. PyTorch) already carries an NCCL, dlopen returns that same copy
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+  if (!g_nccl.lib) return "libnccl.so.2 not found";
+#define PBA_NCCL_SYM(field, sym) \
+  *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, sym); if (!g_nccl.field) return "missing NCCL symbol " sym;
+  PBA_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  PBA_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  PBA_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  PBA_NCCL_SYM(AllReduce, "ncclAllReduce")
+  PBA_NCCL_SYM(Broadcast, "ncclBroadcast")
+  PBA_NCCL_SYM(GroupStart, "ncclGroupStart")
+  PBA_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+  PBA_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef PBA_NCCL_SYM
+  return nullptr;
+}
 
 static thread_local char g_err[512] = "";
 
@@ -26,6 +62,13 @@ static int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+#define NCCL_TRY(expr)                                                                     \
+  do {                                                                                     \
+    ncclResult_t r__ = (expr);                                                             \
+    if (r__ != ncclSuccess)                                                                \
+      return fail(PBA_ERR_NCCL, "%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(r__), __FILE__, __LINE__); \
+  } while (0)
 
 #define CUDA_TRY(expr)                                                                     \
   do {                                                                                     \
@@ -49,7 +92,7 @@ struct pba_handle {
   float* d_desc = nullptr;
   int *d_obs_off = nullptr, *d_obs_frame = nullptr;
   double *d_V = nullptr, *d_gp = nullptr, *d_W = nullptr;
-  double *d_Uacc = nullptr, *d_Eacc = nullptr;
+  double *d_Xacc = nullptr, *d_Ucur = nullptr;
   double *d_scale_p = nullptr, *d_Vinv = nullptr, *d_S = nullptr;
   unsigned int* d_ticket = nullptr;
   unsigned long long* d_dbg = nullptr;   // PBA_DEBUG_TIMELINE=1: per-iteration K_B timeline
@@ -65,14 +108,18 @@ struct pba_handle {
   bool have_frames = false, have_poses = false, have_points = false;
   std::vector<int> frame_used;
   std::vector<IterSummary> trace;
-  // multi-GPU
+  // multi-GPU: points sharded by contiguous block, frames/poses replicated
   int rank = 0, n_ranks = 1;
+  ncclComm_t comm = nullptr;
+  int n_points_total = 0, nnz_total = 0;
+  std::vector<int> shard_begin;   // [n_ranks+1] first global point of each rank
 };
 
 static void free_all(pba_handle* h) {
   cudaFree(h->d_u8); cudaFree(h->d_f32); cudaFree(h->d_cams); cudaFree(h->d_pts); cudaFree(h->d_weights);
   cudaFree(h->d_desc); cudaFree(h->d_obs_off); cudaFree(h->d_obs_frame); cudaFree(h->d_V); cudaFree(h->d_gp);
-  cudaFree(h->d_W); cudaFree(h->d_Uacc); cudaFree(h->d_Eacc);
+  cudaFree(h->d_W); cudaFree(h->d_Xacc); cudaFree(h->d_Ucur);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->d_scale_p); cudaFree(h->d_Vinv); cudaFree(h->d_S); cudaFree(h->d_ticket); cudaFree(h->d_dbg);
   cudaFree(h->d_save_cams); cudaFree(h->d_save_pts);
   cudaFree(h->d_obs_sqnorm); cudaFree(h->d_residuals); cudaFree(h->d_state); cudaFree(h->d_trace);
@@ -160,8 +207,8 @@ int pba_create(const pba_config* cfg, pba_handle** out) {
   CREATE_TRY(cudaMalloc(&h->d_V, sizeof(double) * 2 * n * 6));
   CREATE_TRY(cudaMalloc(&h->d_gp, sizeof(double) * 2 * n * 3));
   CREATE_TRY(cudaMalloc(&h->d_W, sizeof(double) * 2 * nnz * 18));
-  CREATE_TRY(cudaMalloc(&h->d_Uacc, sizeof(double) * 2 * F * kUStride));
-  CREATE_TRY(cudaMalloc(&h->d_Eacc, sizeof(double) * 2 * kEacc));
+  CREATE_TRY(cudaMalloc(&h->d_Xacc, sizeof(double) * (F * kUStride + kEacc + kMaxRanks)));
+  CREATE_TRY(cudaMalloc(&h->d_Ucur, sizeof(double) * F * kUStride));
   CREATE_TRY(cudaMalloc(&h->d_scale_p, sizeof(double) * n * 3));
   CREATE_TRY(cudaMalloc(&h->d_Vinv, sizeof(double) * n * 6));
   CREATE_TRY(cudaMalloc(&h->d_S, sizeof(double) * (D * D + D)));
@@ -252,6 +299,28 @@ int pba_set_poses(pba_handle* h, int32_t n_frames, const double* cam6, int32_t f
   return PBA_OK;
 }
 
+// Contiguous point blocks balanced by observation count: rank r gets points [begin[r], begin[r+1]).
+static void shard_split(int n_points, const int32_t* obs_offsets, int n_ranks, std::vector<int>& begin) {
+  begin.assign(n_ranks + 1, n_points);
+  begin[0] = 0;
+  const long long nnz = obs_offsets[n_points];
+  int p = 0;
+  for (int r = 1; r < n_ranks; ++r) {
+    const long long target = nnz * r / n_ranks;
+    while (p < n_points && obs_offsets[p] < target) ++p;
+    begin[r] = p;
+  }
+}
+
+int pba_shard_range(int32_t n_points, const int32_t* obs_offsets, int32_t rank, int32_t n_ranks, int32_t* first, int32_t* last) {
+  if (!obs_offsets || !first || !last || n_points < 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+    return fail(PBA_ERR_ARGUMENT, "pba_shard_range: bad argument");
+  std::vector<int> b;
+  shard_split(n_points, obs_offsets, n_ranks, b);
+  *first = b[rank]; *last = b[rank + 1];
+  return PBA_OK;
+}
+
 int pba_set_points(pba_handle* h, int32_t n_points, const double* xyz, const double* desc,
                    const int32_t* obs_offsets, const int32_t* obs_frame, const double* weights) {
   if (!h || !xyz || !desc || !obs_offsets || !obs_frame || !weights) return fail(PBA_ERR_ARGUMENT, "pba_set_points: null argument");
@@ -269,17 +338,23 @@ int pba_set_points(pba_handle* h, int32_t n_points, const double* xyz, const dou
     }
   }
   CUDA_TRY(cudaSetDevice(h->device));
-  std::vector<float> descf((size_t)n_points * h->CP);
-  for (size_t i = 0; i < descf.size(); ++i) descf[i] = (float)desc[i];
-  const size_t pstride = (size_t)n_points * 3;
-  CUDA_TRY(cudaMemcpyAsync(h->d_pts, xyz, sizeof(double) * pstride, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_pts + pstride, xyz, sizeof(double) * pstride, cudaMemcpyHostToDevice, h->stream));
+  // this rank's shard (the whole window on one GPU)
+  shard_split(n_points, obs_offsets, h->n_ranks, h->shard_begin);
+  const int p0 = h->shard_begin[h->rank], p1 = h->shard_begin[h->rank + 1];
+  const int n_loc = p1 - p0, o_base = obs_offsets[p0], nnz_loc = obs_offsets[p1] - o_base;
+  std::vector<float> descf((size_t)n_loc * h->CP);
+  for (size_t i = 0; i < descf.size(); ++i) descf[i] = (float)desc[(size_t)p0 * h->CP + i];
+  std::vector<int32_t> off_loc(n_loc + 1);
+  for (int i = 0; i <= n_loc; ++i) off_loc[i] = obs_offsets[p0 + i] - o_base;
+  const size_t pstride = (size_t)n_loc * 3;
+  CUDA_TRY(cudaMemcpyAsync(h->d_pts, xyz + (size_t)p0 * 3, sizeof(double) * pstride, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_pts + pstride, xyz + (size_t)p0 * 3, sizeof(double) * pstride, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->d_desc, descf.data(), sizeof(float) * descf.size(), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_obs_off, obs_offsets, sizeof(int) * (n_points + 1), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_obs_frame, obs_frame, sizeof(int) * nnz, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_obs_off, off_loc.data(), sizeof(int) * (n_loc + 1), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_obs_frame, obs_frame + o_base, sizeof(int) * nnz_loc, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->d_weights, weights, sizeof(double) * h->P, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  h->n_points = n_points; h->nnz = nnz; h->have_points = true;
+  h->n_points = n_loc; h->nnz = nnz_loc; h->n_points_total = n_points; h->nnz_total = nnz; h->have_points = true;
   return PBA_OK;
 }
 
@@ -303,7 +378,7 @@ static StepParams make_step_params(pba_handle* h, const LmState* st) {
   p.st = st;
   p.cams = h->d_cams; p.pts = h->d_pts; p.desc = h->d_desc; p.obs_off = h->d_obs_off;
   p.obs_frame = h->d_obs_frame; p.weights = h->d_weights;
-  p.V = h->d_V; p.gp = h->d_gp; p.W = h->d_W; p.Uacc = h->d_Uacc; p.Eacc = h->d_Eacc;
+  p.V = h->d_V; p.gp = h->d_gp; p.W = h->d_W; p.Xacc = h->d_Xacc; p.rank = h->rank;
   p.scale_p = h->d_scale_p; p.Vinv = h->d_Vinv;
   return p;
 }
@@ -315,14 +390,13 @@ static LmParams make_lm_params(pba_handle* h) {
   lp.n_frames = h->n_frames; lp.n_points = h->n_points; lp.nnz = h->nnz;
   lp.obs_off = h->d_obs_off; lp.obs_frame = h->d_obs_frame;
   lp.cams = h->d_cams; lp.V = h->d_V; lp.gp = h->d_gp; lp.W = h->d_W;
-  lp.Uacc = h->d_Uacc; lp.Eacc = h->d_Eacc;
+  lp.Xacc = h->d_Xacc; lp.Ucur = h->d_Ucur; lp.split = h->n_ranks > 1 ? 1 : 0;
   lp.scale_p = h->d_scale_p; lp.Vinv = h->d_Vinv; lp.S = h->d_S;
   return lp;
 }
 
 static int zero_accumulators(pba_handle* h) {
-  CUDA_TRY(cudaMemsetAsync(h->d_Uacc, 0, sizeof(double) * 2 * (size_t)h->cfg.max_frames * kUStride, h->stream));
-  CUDA_TRY(cudaMemsetAsync(h->d_Eacc, 0, sizeof(double) * 2 * kEacc, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_Xacc, 0, sizeof(double) * ((size_t)h->cfg.max_frames * kUStride + kEacc + kMaxRanks), h->stream));
   return PBA_OK;
 }
 
@@ -357,8 +431,8 @@ int pba_eval(pba_handle* h, pba_eval_out* out) {
   CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   out->device_ms = ms;
   std::vector<double> U((size_t)F * kUStride), E(kEacc);
-  CUDA_TRY(cudaMemcpy(U.data(), h->d_Uacc, sizeof(double) * U.size(), cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(E.data(), h->d_Eacc, sizeof(double) * kEacc, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(U.data(), h->d_Xacc, sizeof(double) * U.size(), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(E.data(), h->d_Xacc + (size_t)F * kUStride, sizeof(double) * kEacc, cudaMemcpyDeviceToHost));
   const double cost = E[0];
   out->cost = cost;
   if (out->U) for (int f = 0; f < F; ++f) unpack_sym6(&U[f * kUStride], out->U + f * 36);
@@ -458,8 +532,15 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   // iteration 0: evaluate x.  Then per LM iteration: K_B (decide + Schur + solve), K_A
   // (back-substitute + evaluate the candidate).  The state ping-pongs between two structs;
   // kernels turn into no-ops once `done` is set, so iterations are enqueued in groups.
+  const bool multi = h->n_ranks > 1;
+  const size_t xacc_n = (size_t)F * kUStride + kEacc + kMaxRanks;
+  int collectives = 0;
   CUDA_TRY(launch_k_step(make_step_params(h, h->d_state), h->cfg.patch_radius, h->stream));
   launches += 1;
+  if (multi) {   // candidate's pose blocks + cost scalars, summed over the point shards
+    NCCL_TRY(g_nccl.AllReduce(h->d_Xacc, h->d_Xacc, xacc_n, ncclDouble, ncclSum, h->comm, h->stream));
+    ++collectives;
+  }
   const int group = 4;
   bool done = false;
   int k = 0;
@@ -469,8 +550,18 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
       lp.st_out = h->d_state + ((k + 1) & 1);
       lp.dbg = (timeline && k < 1024) ? h->d_dbg + 16 * k : nullptr;
       CUDA_TRY(launch_schur_solve(lp, sgrid, s->n_free, h->stream));
+      launches += 1;
+      if (multi) {   // reduced camera system, summed over the point shards, then the (replicated) solve
+        NCCL_TRY(g_nccl.AllReduce(h->d_S, h->d_S, D * D + D, ncclDouble, ncclSum, h->comm, h->stream));
+        CUDA_TRY(launch_solve_only(lp, h->stream));
+        ++collectives; launches += 1;
+      }
       CUDA_TRY(launch_k_step(make_step_params(h, lp.st_out), h->cfg.patch_radius, h->stream));
-      launches += 2;
+      launches += 1;
+      if (multi) {
+        NCCL_TRY(g_nccl.AllReduce(h->d_Xacc, h->d_Xacc, xacc_n, ncclDouble, ncclSum, h->comm, h->stream));
+        ++collectives;
+      }
     }
     CUDA_TRY(cudaMemcpyAsync(s, h->d_state + (k & 1), sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -502,10 +593,10 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   memset(summary, 0, sizeof(*summary));
   summary->initial_cost = s->initial_cost; summary->final_cost = s->x_cost; summary->fixed_cost = 0.0;
   summary->num_successful_steps = s->num_successful; summary->num_unsuccessful_steps = s->num_unsuccessful;
-  summary->num_residual_blocks = h->nnz; summary->num_residuals = h->nnz * h->CP;
+  summary->num_residual_blocks = h->nnz_total; summary->num_residuals = h->nnz_total * h->CP;
   summary->num_iterations = s->n_trace; summary->termination_type = s->termination_type;
   summary->num_evaluations = s->num_evals;
-  summary->kernel_launches = launches; summary->num_collectives = 0;
+  summary->kernel_launches = launches; summary->num_collectives = collectives;
   summary->device_time_in_seconds = ms * 1e-3;
   if (!s->done) { s->msg_code = kMsgMaxIter; s->msg_a = opt.max_num_iterations; summary->termination_type = 1; }
   format_message(*s, summary->message, sizeof(summary->message));
@@ -550,7 +641,24 @@ int pba_get_points(pba_handle* h, double* xyz) {
   if (!h || !xyz) return fail(PBA_ERR_ARGUMENT, "pba_get_points: null argument");
   if (!h->have_points) return fail(PBA_ERR_STATE, "pba_get_points: points not set");
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(cudaMemcpy(xyz, h->d_pts, sizeof(double) * (size_t)h->n_points * 3, cudaMemcpyDeviceToHost));
+  if (h->n_ranks == 1) {
+    CUDA_TRY(cudaMemcpy(xyz, h->d_pts, sizeof(double) * (size_t)h->n_points * 3, cudaMemcpyDeviceToHost));
+    return PBA_OK;
+  }
+  // gather the shards: every rank broadcasts its block into a full-size device array
+  double* full = nullptr;
+  CUDA_TRY(cudaMalloc(&full, sizeof(double) * (size_t)std::max(1, h->n_points_total) * 3));
+  CUDA_TRY(cudaMemcpyAsync(full + (size_t)h->shard_begin[h->rank] * 3, h->d_pts, sizeof(double) * (size_t)h->n_points * 3,
+                           cudaMemcpyDeviceToDevice, h->stream));
+  NCCL_TRY(g_nccl.GroupStart());
+  for (int r = 0; r < h->n_ranks; ++r) {
+    const size_t cnt = (size_t)(h->shard_begin[r + 1] - h->shard_begin[r]) * 3;
+    if (cnt) NCCL_TRY(g_nccl.Broadcast(full + (size_t)h->shard_begin[r] * 3, full + (size_t)h->shard_begin[r] * 3, cnt, ncclDouble, r, h->comm, h->stream));
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  CUDA_TRY(cudaMemcpyAsync(xyz, full, sizeof(double) * (size_t)h->n_points_total * 3, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  cudaFree(full);
   return PBA_OK;
 }
 
@@ -566,13 +674,31 @@ int pba_get_iterations(pba_handle* h, pba_iteration_summary* out, int32_t capaci
 }
 
 int pba_comm_unique_id(void* id128) {
-  (void)id128;
-  return fail(PBA_ERR_NCCL, "pba_comm_unique_id: multi-GPU support not initialised in this build step");
+  if (!id128) return fail(PBA_ERR_ARGUMENT, "pba_comm_unique_id: null argument");
+  if (const char* e = load_nccl()) return fail(PBA_ERR_NCCL, "pba_comm_unique_id: %s", e);
+  static_assert(sizeof(ncclUniqueId) == PBA_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return PBA_OK;
 }
 
 int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_ranks) {
-  (void)h; (void)id128; (void)rank; (void)n_ranks;
-  return fail(PBA_ERR_NCCL, "pba_comm_init: multi-GPU support not initialised in this build step");
+  if (!h || !id128) return fail(PBA_ERR_ARGUMENT, "pba_comm_init: null argument");
+  if (n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks)
+    return fail(PBA_ERR_ARGUMENT, "pba_comm_init: rank %d of %d (at most %d ranks)", rank, n_ranks, kMaxRanks);
+  if (h->have_points) return fail(PBA_ERR_STATE, "pba_comm_init: call before pba_set_points (points are sharded at upload)");
+  if (const char* e = load_nccl()) return fail(PBA_ERR_NCCL, "pba_comm_init: %s", e);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+  h->rank = 0; h->n_ranks = 1;
+  if (n_ranks > 1) {
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NCCL_TRY(g_nccl.CommInitRank(&h->comm, n_ranks, id, rank));
+    h->rank = rank; h->n_ranks = n_ranks;
+  }
+  return PBA_OK;
 }
 
 }  // extern "C"

@@ -44,6 +44,7 @@ __device__ __forceinline__ void finish(LmState& st, int type, int code, double a
 __device__ bool decide(LmState& st, const double* E, double gm, double g2, double csq, const double* Ubuf, int F,
                        IterSummary& it) {
   st.num_evals++;
+  st.took_step = 0;
   const int buf = st.eval_buf;
   const double cost_e = E[0];
   const double gmax_e = fmax(gm, E[2]), gnorm_e = sqrt(g2 + E[1]);
@@ -57,7 +58,7 @@ __device__ bool decide(LmState& st, const double* E, double gm, double g2, doubl
         st.scale_c[f * 6 + a] = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(Ubuf[f * kUStride + utri6(a, a)])) : 1.0;
     st.gmax = gmax_e; st.gnorm = gnorm_e;
     st.radius = st.initial_radius; st.decrease_factor = 2.0;
-    st.cur = buf; st.eval_buf = 1 - buf;
+    st.cur = buf; st.eval_buf = 1 - buf; st.took_step = 1;
     it.iteration = 0; it.cost = cost_e; it.gradient_max_norm = gmax_e; it.gradient_norm = gnorm_e;
   } else {
     it.iteration = st.iteration;
@@ -87,7 +88,7 @@ __device__ bool decide(LmState& st, const double* E, double gm, double g2, doubl
       it.relative_decrease = it.cost_change / mcc;
       if (it.relative_decrease > st.min_relative_decrease) {
         // HandleSuccessfulStep: the candidate's blocks are already in buffer `buf`
-        st.cur = buf; st.eval_buf = 1 - buf;
+        st.cur = buf; st.eval_buf = 1 - buf; st.took_step = 1;
         st.x_cost = cost_e; st.x_norm = sqrt(st.cam_cand_sq + E[7]);
         st.gmax = gmax_e; st.gnorm = gnorm_e;
         it.gradient_max_norm = gmax_e; it.gradient_norm = gnorm_e;
@@ -152,7 +153,7 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
     s_ok = 1;
     for (int f = 0; f < F; ++f) if (st.free_index[f] >= 0) s_fr[st.free_index[f]] = f;
   }
-  for (int i = tid; i < F * kUStride; i += nthr) Us[i] = __ldcg(lp.Uacc + (size_t)cur * F * kUStride + i);
+  for (int i = tid; i < F * kUStride; i += nthr) Us[i] = lp.Ucur[i];
   __syncthreads();
   // assemble S + Us + Dc² (lower triangle) and rhs + gs_c
   for (int r = ty; r < N; r += 16) {
@@ -500,6 +501,23 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
   }
 }
 
+// Tail of an LM iteration (one CTA): adopt the candidate's pose blocks if the step was taken, solve
+// the reduced camera system, re-zero the accumulators K_A fills next, publish the new state.
+__device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, int F) {
+  const int tid = threadIdx.x;
+  if (st.took_step)
+    for (int i = tid; i < F * kUStride; i += blockDim.x) lp.Ucur[i] = __ldcg(lp.Xacc + i);
+  __syncthreads();
+  solve_reduced(lp, st, sm, F);
+  if (lp.dbg && tid == 0) lp.dbg[3] = gtime();
+  for (int i = tid; i < F * kUStride + kEacc + kMaxRanks; i += blockDim.x) lp.Xacc[i] = 0.0;
+  if (tid == 0) *lp.ticket = 0u;
+  __syncthreads();
+  for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+    reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&st)[i];
+  if (lp.dbg && tid == 0) lp.dbg[4] = gtime();
+}
+
 // MODE 0: pairs fast path (<= 7 optimised cameras, <= 8 frames); MODE k>0: generic 3x3-tile path, k tiles/thread
 template <int MODE>
 __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp) {
@@ -531,23 +549,26 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
     for (int i = lane; i < F * 6; i += 32) {
       const int f = i / 6, a = i - f * 6;
       if (s_st.free_index[f] >= 0) {
-        const double g = __ldcg(lp.Uacc + ((size_t)buf * F + f) * kUStride + 21 + a);
+        const double g = __ldcg(lp.Xacc + f * kUStride + 21 + a);
         gm = fmax(gm, fabs(g)); g2 += g * g;
         const double c = lp.cams[((size_t)buf * F + f) * 6 + a];
         csq += c * c;
       }
     }
-    double e = lane < kEacc ? __ldcg(lp.Eacc + buf * kEacc + lane) : 0.0;
+    double e = lane < kEacc ? __ldcg(lp.Xacc + F * kUStride + lane) : 0.0;
+    double gpm = lane < kMaxRanks ? __ldcg(lp.Xacc + F * kUStride + kEacc + lane) : 0.0;   // per-rank max|g_p|
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
       gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, m));
       g2 += __shfl_xor_sync(0xffffffffu, g2, m);
       csq += __shfl_xor_sync(0xffffffffu, csq, m);
+      gpm = fmax(gpm, __shfl_xor_sync(0xffffffffu, gpm, m));
     }
     double E[kEacc];
 #pragma unroll
     for (int k = 0; k < kEacc; ++k) E[k] = __shfl_sync(0xffffffffu, e, k);
-    if (lane == 0) s_push = decide(s_st, E, gm, g2, csq, lp.Uacc + (size_t)buf * F * kUStride, F, s_it) ? 1 : 0;
+    E[2] = gpm;
+    if (lane == 0) s_push = decide(s_st, E, gm, g2, csq, lp.Xacc, F, s_it) ? 1 : 0;
   }
   __syncthreads();
   if (blockIdx.x == 0 && tid == 0 && s_push) lp.trace[s_st.n_trace - 1] = s_it;
@@ -711,17 +732,26 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
   __syncthreads();
   if (lp.dbg && tid == 0 && s_last) { lp.dbg[0] = t_start; lp.dbg[1] = t_dec; lp.dbg[2] = gtime(); }
   if (!s_last) return;
-  solve_reduced(lp, s_st, sm, F);
-  if (lp.dbg && tid == 0) lp.dbg[3] = gtime();
-  // accumulators of the buffer K_A evaluates next start from zero
-  const int eb = s_st.eval_buf;
-  for (int i = tid; i < F * kUStride; i += blockDim.x) lp.Uacc[(size_t)eb * F * kUStride + i] = 0.0;
-  if (tid < kEacc) lp.Eacc[eb * kEacc + tid] = 0.0;
-  if (tid == 0) *lp.ticket = 0u;
-  __syncthreads();
+  if (lp.split) {
+    // multi-GPU: the reduced system is summed across ranks first; k_solve_only finishes the iteration
+    if (tid == 0) *lp.ticket = 0u;
+    for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+      reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
+    return;
+  }
+  finish_iteration(lp, s_st, sm, F);
+}
+
+// split mode: one CTA, after the all-reduce of S
+__global__ void __launch_bounds__(kSchurThreads) k_solve_only(const LmParams lp) {
+  __shared__ LmState s_st;
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
   for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
-    reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
-  if (lp.dbg && tid == 0) lp.dbg[4] = gtime();
+    reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_out)[i];
+  __syncthreads();
+  if (s_st.done) return;
+  finish_iteration(lp, s_st, sm, lp.n_frames);
 }
 
 // ---- launchers ----------------------------------------------------------------------------
@@ -758,6 +788,21 @@ cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStr
   if (need <= 1) return launch_mode<1>(lp, grid, smem, s);
   if (need <= 2) return launch_mode<2>(lp, grid, smem, s);
   return launch_mode<3>(lp, grid, smem, s);
+}
+
+cudaError_t launch_solve_only(const LmParams& lp, cudaStream_t s) {
+  const int F = lp.n_frames, N = 6 * F;
+  const size_t solve_b = sizeof(double) * ((size_t)N * (N + 1) + (size_t)F * 36 + N + (size_t)F * kUStride);
+  static bool cfg[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!cfg[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k_solve_only, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    cfg[dev & 63] = true;
+  }
+  k_solve_only<<<1, kSchurThreads, solve_b, s>>>(lp);
+  return cudaGetLastError();
 }
 
 }  // namespace pba

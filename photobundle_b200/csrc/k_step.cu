@@ -616,22 +616,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
   }
   __syncthreads();
   // CTA partials (fixed order inside the CTA), then one fp64 atomic per entry per CTA
-  double* Uacc = prm.Uacc + (size_t)buf * F * kUStride;
   for (int i = threadIdx.x; i < F * kUStride; i += blockDim.x) {
     double acc = 0.0;
 #pragma unroll
     for (int w = 0; w < kWarpsPerCta; ++w) acc += s_U[w * F * kUStride + i];
-    if (acc != 0.0) atomicAdd(Uacc + i, acc);
+    if (acc != 0.0) atomicAdd(prm.Xacc + i, acc);
   }
   if (threadIdx.x < kEacc) {
     double acc = 0.0;
     if (threadIdx.x == 2) {
       for (int w = 0; w < kWarpsPerCta; ++w) acc = fmax(acc, s_E[w * kEacc + 2]);
-      // non-negative doubles order like their bit patterns
-      atomicMax(reinterpret_cast<unsigned long long*>(prm.Eacc + buf * kEacc + 2), (unsigned long long)__double_as_longlong(acc));
+      // non-negative doubles order like their bit patterns; one slot per rank (summed by the all-reduce)
+      atomicMax(reinterpret_cast<unsigned long long*>(prm.Xacc + F * kUStride + kEacc + prm.rank),
+                (unsigned long long)__double_as_longlong(acc));
     } else {
       for (int w = 0; w < kWarpsPerCta; ++w) acc += s_E[w * kEacc + threadIdx.x];
-      if (acc != 0.0) atomicAdd(prm.Eacc + buf * kEacc + threadIdx.x, acc);
+      if (acc != 0.0) atomicAdd(prm.Xacc + F * kUStride + threadIdx.x, acc);
     }
   }
 }

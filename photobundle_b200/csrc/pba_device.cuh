@@ -11,9 +11,12 @@
 //                                            src/photobundle.cc:466-479)
 //   obs_off  i32 [n+1], obs_frame i32 [nnz]  CSR visibility, window-local frame index
 //   V,gp,W   f64 x2 [n][6] [n][3] [nnz][18]  point blocks / cross blocks at x
-//   Uacc     f64 x2 [F][27]                  pose blocks (21 upper-tri U + 6 g_c), accumulated
-//                                            by K_A with fp64 atomics (one add per CTA per entry)
-//   Eacc     f64 x2 [8]                      {cost, Σg_p², max|g_p| (bits), Σ|X|², s·g, sᵀHs, |Δ|², |x+Δ|²}
+//   Xacc     f64 [F][27] + [8] + [8]         candidate's pose blocks (21 upper-tri U + 6 g_c),
+//                                            scalars {cost, Σg_p², -, Σ|X|², s·g, sᵀHs, |Δ|², |x+Δ|²}
+//                                            and one max|g_p| slot per rank; accumulated by K_A with
+//                                            fp64 atomics (one per CTA per entry); this is the buffer
+//                                            that is all-reduced when a window spans several GPUs
+//   Ucur     f64 [F][27]                     pose blocks of the accepted point
 //   S        f64 [D*D + D]                   Schur complement + rhs accumulators, D = 6F
 //   state    LmState x2                      ping-pong: K_B reads one, writes the other
 #pragma once
@@ -32,6 +35,7 @@ constexpr int kUStride = 27;          // 21 upper-tri U + 6 g_c
 constexpr int kSchurThreads = 256;
 constexpr int kSchurChunk = 8;        // points per chunk (one per warp)
 constexpr int kEacc = 8;
+constexpr int kMaxRanks = 8;         // max|g_p| slots in Xacc (one per rank)
 
 struct Frames {
   const uint8_t* u8;   // non-null: Intensity planes, gradients formed in-kernel
@@ -68,6 +72,7 @@ struct LmState {
   int iteration;                  // iteration whose step is being computed / judged
   int cur, eval_buf;              // buffer of accepted x / buffer the next evaluation writes
   int done, termination_type, msg_code;
+  int took_step;                  // the last decision accepted a candidate (or was iteration 0)
   double msg_a, msg_b;
   double radius, decrease_factor;
   int num_invalid, num_successful, num_unsuccessful, n_trace, num_evals;
@@ -95,8 +100,8 @@ struct StepParams {
   double* V;                 // x2 [n][6]   upper triangle 00 01 02 11 12 22
   double* gp;                // x2 [n][3]
   double* W;                 // x2 [nnz][18] row-major 6x3
-  double* Uacc;              // x2 [F][27]
-  double* Eacc;              // x2 [8]
+  double* Xacc;              // [F][27] + [8] + [kMaxRanks]
+  int rank;                  // which max|g_p| slot this process owns
   const double* scale_p;     // [n][3]   (back-substitution)
   const double* Vinv;        // [n][6]
   double* obs_sqnorm;        // optional [nnz]
@@ -116,8 +121,9 @@ struct LmParams {
   const double* V;           // x2
   const double* gp;          // x2
   const double* W;           // x2
-  double* Uacc;              // x2 [F][27]
-  double* Eacc;              // x2 [8]
+  double* Xacc;              // [F][27] + [8] + [kMaxRanks]  (candidate)
+  double* Ucur;              // [F][27]                       (accepted point)
+  int split;                 // 1: multi-GPU — the reduced system is all-reduced before a separate solve kernel
   double* scale_p;           // [n][3]
   double* Vinv;              // [n][6]
   double* S;                 // [D*D + D]
@@ -129,5 +135,6 @@ int k_step_grid(int n_points);
 cudaError_t launch_k_step(const StepParams& prm, int radius, cudaStream_t stream);
 int schur_grid(int n_points, int sm_count);
 cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t stream);
+cudaError_t launch_solve_only(const LmParams& lp, cudaStream_t stream);   // split mode, after the all-reduce of S
 
 }  // namespace pba
