@@ -155,18 +155,38 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
   }
   for (int i = tid; i < F * kUStride; i += nthr) Us[i] = lp.Ucur[i];
   __syncthreads();
-  // assemble S + Us + Dc² (lower triangle) and rhs + gs_c
-  for (int r = ty; r < N; r += 16) {
-    const int fi = r / 6, a = r - fi * 6, f = s_fr[fi];
-    for (int c = tx; c <= r; c += 16) {
-      const int fj = c / 6, b = c - fj * 6, g = s_fr[fj];
-      double val = __ldcg(lp.S + (6 * g + b) * D + 6 * f + a);    // upper block (g <= f), transposed
-      if (fi == fj) {
-        const double u = st.scale_c[6 * f + a] * usym6(Us + f * kUStride, a, b) * st.scale_c[6 * f + b];
-        val += u;
-        if (a == b) val += fmin(fmax(u, st.min_diag), st.max_diag) / radius;
-      }
-      A[r * ld + c] = val;
+  // assemble S + Us + Dc² (lower triangle) and rhs + gs_c; a 3x3 batch of loads is in flight per thread
+  for (int r0 = ty; r0 < N; r0 += 48) {
+    for (int c0 = tx; c0 < N && c0 <= r0 + 32; c0 += 48) {
+      double v[3][3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int r = r0 + 16 * u, c = c0 + 16 * q;
+          v[u][q] = 0.0;
+          if (r < N && c <= r) {
+            const int f = s_fr[r / 6], a = r % 6, g = s_fr[c / 6], b = c % 6;
+            v[u][q] = __ldcg(lp.S + (6 * g + b) * D + 6 * f + a);    // upper block (g <= f), transposed
+          }
+        }
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int r = r0 + 16 * u, c = c0 + 16 * q;
+          if (r < N && c <= r) {
+            double val = v[u][q];
+            const int fi = r / 6, a = r - fi * 6, fj = c / 6, b = c - fj * 6;
+            if (fi == fj) {
+              const int f = s_fr[fi];
+              const double uu = st.scale_c[6 * f + a] * usym6(Us + f * kUStride, a, b) * st.scale_c[6 * f + b];
+              val += uu;
+              if (a == b) val += fmin(fmax(uu, st.min_diag), st.max_diag) / radius;
+            }
+            A[r * ld + c] = val;
+          }
+        }
     }
   }
   for (int r = tid; r < N; r += nthr) {
@@ -371,7 +391,7 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
   const bool first = (st.iteration == 1);
   double* Zw = sm + warp * (D * 4);                 // [D][3] + rh [D]
   double* rhw = Zw + D * 3;
-  double* Scta = sm + (kSchurThreads / 32) * (D * 4);
+  double* Scta = sm + 4 * (32 * 36 + 64);          // after the merge buffers (which alias Z/rh)
   __shared__ int s_fr2[kMaxFrames];
   if (tid == 0)
     for (int f = 0; f < F; ++f) if (st.free_index[f] >= 0) s_fr2[st.free_index[f]] = f;
@@ -392,15 +412,18 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
   for (int e = 0; e < 36; ++e) acc[e] = 0.0;
   double racc0 = 0.0, racc1 = 0.0;
 
-  for (int p = blockIdx.x * (kSchurThreads / 32) + warp; p < n; p += gridDim.x * (kSchurThreads / 32)) {
-    const int o0 = __ldg(lp.obs_off + p), nobs = __ldg(lp.obs_off + p + 1) - o0;
-    double V[6];
+  // Per-point inputs are loaded one point ahead: the loads of point p+stride are issued right
+  // after point p's phase A has consumed its registers, so their latency hides behind phase B.
+  const int pstride = gridDim.x * (kSchurThreads / 32);
+  double V[6], g0 = 0, g1 = 0, g2 = 0, sp0 = 1, sp1 = 1, sp2 = 1, w[2][3];
+  int rf[2], ra[2];
+  auto load_point = [&](int q) {
+    const int o0 = __ldg(lp.obs_off + q), nobs = __ldg(lp.obs_off + q + 1) - o0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) V[k] = __ldg(Vb + (size_t)p * 6 + k);
-    const double g0 = __ldg(gb + (size_t)p * 3), g1 = __ldg(gb + (size_t)p * 3 + 1), g2 = __ldg(gb + (size_t)p * 3 + 2);
+    for (int k = 0; k < 6; ++k) V[k] = __ldg(Vb + (size_t)q * 6 + k);
+    g0 = __ldg(gb + (size_t)q * 3); g1 = __ldg(gb + (size_t)q * 3 + 1); g2 = __ldg(gb + (size_t)q * 3 + 2);
+    if (!first) { sp0 = lp.scale_p[(size_t)q * 3]; sp1 = lp.scale_p[(size_t)q * 3 + 1]; sp2 = lp.scale_p[(size_t)q * 3 + 2]; }
     // rows (observation i, pose parameter a): lane + 32k  (nobs <= 8 on this path -> 2 rounds)
-    double w[2][3];
-    int rf[2], ra[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int row = lane + 32 * k;
@@ -415,14 +438,15 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
         w[k][0] = __ldg(wp); w[k][1] = __ldg(wp + 1); w[k][2] = __ldg(wp + 2);
       }
     }
-    double sp0, sp1, sp2;
+  };
+  const int p_first = blockIdx.x * (kSchurThreads / 32) + warp;
+  if (p_first < n) load_point(p_first);
+  for (int p = p_first; p < n; p += pstride) {
     if (first) {
       sp0 = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[0])) : 1.0;
       sp1 = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[3])) : 1.0;
       sp2 = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[5])) : 1.0;
       if (lane == 0) { lp.scale_p[(size_t)p * 3] = sp0; lp.scale_p[(size_t)p * 3 + 1] = sp1; lp.scale_p[(size_t)p * 3 + 2] = sp2; }
-    } else {
-      sp0 = lp.scale_p[(size_t)p * 3]; sp1 = lp.scale_p[(size_t)p * 3 + 1]; sp2 = lp.scale_p[(size_t)p * 3 + 2];
     }
     double a00 = sp0 * V[0] * sp0, a01 = sp0 * V[1] * sp1, a02 = sp0 * V[2] * sp2;
     double a11 = sp1 * V[3] * sp1, a12 = sp1 * V[4] * sp2, a22 = sp2 * V[5] * sp2;
@@ -458,6 +482,7 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
     }
     mask = __reduce_or_sync(0xffffffffu, mask);
     __syncwarp();
+    if (p + pstride < n) load_point(p + pstride);     // prefetch (registers of point p are dead now)
     if (lane < npairs && ((mask >> pa) & 1u) && ((mask >> pb) & 1u)) {
       const double* za = Zw + 18 * pa;
       const double* zb = Zw + 18 * pb;
@@ -475,18 +500,35 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
     if (lane + 32 < 6 * nf && ((mask >> ((lane + 32) / 6)) & 1u)) racc1 += rhw[lane + 32];
     __syncwarp();
   }
-  // merge the warps (turn-taking keeps it deterministic inside the CTA), then one atomic per entry
-  for (int w = 0; w < kSchurThreads / 32; ++w) {
-    if (warp == w) {
-      if (lane < npairs) {
+  // merge the warps pairwise through shared memory (fixed tree: deterministic inside the CTA), then
+  // one atomic per entry.  Buffers: warp w writes into slot w of Smerge [warps/2][32*36 + 64].
+  double* Smerge = sm;   // the Z / rh staging area is dead now
+  __syncthreads();
+  for (int half = (kSchurThreads / 32) / 2; half >= 1; half >>= 1) {
+    if (warp >= half && warp < 2 * half) {
+      double* dst = Smerge + (size_t)(warp - half) * (32 * 36 + 64);
 #pragma unroll
-        for (int e = 0; e < 36; ++e) Scta[lane * 36 + e] += acc[e];
-      }
-      if (lane < 6 * nf) Scta[32 * 36 + lane] += racc0;
-      if (lane + 32 < 6 * nf) Scta[32 * 36 + lane + 32] += racc1;
+      for (int e = 0; e < 36; ++e) dst[e * 32 + lane] = acc[e];
+      dst[32 * 36 + lane] = racc0; dst[32 * 36 + 32 + lane] = racc1;
+    }
+    __syncthreads();
+    if (warp < half) {
+      const double* src = Smerge + (size_t)warp * (32 * 36 + 64);
+#pragma unroll
+      for (int e = 0; e < 36; ++e) acc[e] += src[e * 32 + lane];
+      racc0 += src[32 * 36 + lane]; racc1 += src[32 * 36 + 32 + lane];
     }
     __syncthreads();
   }
+  if (warp == 0) {
+    if (lane < npairs) {
+#pragma unroll
+      for (int e = 0; e < 36; ++e) Scta[lane * 36 + e] = acc[e];
+    }
+    if (lane < 6 * nf) Scta[32 * 36 + lane] = racc0;
+    if (lane + 32 < 6 * nf) Scta[32 * 36 + lane + 32] = racc1;
+  }
+  __syncthreads();
   for (int t = tid; t < npairs * 36; t += blockDim.x) {
     const int pr = t / 36, e = t - pr * 36, i = e / 6, j = e - i * 6;
     int qa = 0, rem = pr;
@@ -779,7 +821,8 @@ cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStr
   const int F = lp.n_frames, D = 6 * F, N = D;
   const size_t solve_b = sizeof(double) * ((size_t)N * (N + 1) + (size_t)F * 36 + N + (size_t)F * kUStride);
   if (F <= 8 && n_free <= 7) {
-    const size_t pairs_b = sizeof(double) * ((size_t)(kSchurThreads / 32) * D * 4 + 32 * 36 + D);
+    const size_t stage = (size_t)(kSchurThreads / 32) * D * 4, merge = 4 * (32 * 36 + 64);
+    const size_t pairs_b = sizeof(double) * ((stage > merge ? stage : merge) + 32 * 36 + D);
     return launch_mode<0>(lp, grid, pairs_b > solve_b ? pairs_b : solve_b, s);
   }
   const size_t schur_b = sizeof(double) * (size_t)kSchurChunk * (D * 3 * 2 + D);

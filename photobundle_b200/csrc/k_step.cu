@@ -46,6 +46,9 @@
 #ifndef K_STEP_MIN_CTAS
 #define K_STEP_MIN_CTAS 2
 #endif
+#ifndef K_STEP_GROUP
+#define K_STEP_GROUP 4      // observations sampled together per warp (ILP)
+#endif
 
 namespace pba {
 
@@ -137,17 +140,18 @@ template <int R> struct Foot {
 };
 
 
-constexpr int kRedStride = 26;   // doubles per lane row of the reduction transpose (24 sums + pad, 16 B aligned)
+constexpr int kG = K_STEP_GROUP;
+constexpr int kRedStride = 6 * kG + 2;   // doubles per lane row of the reduction transpose (6 sums x group + pad, 16 B aligned)
 
 // ---- shared memory carve-up --------------------------------------------------------------
-// per CTA : pose consts [F][36] f64 | sstep [F][6] f64 (scale_c*step_c) | E [warps][8] f64
-// per warp: geometry [8][20] f64 | pose-block accumulators [F][27] f64 | reduction transpose
-//           [25][26] f64 | scaled sums [24] f64 | ints [8] int4 | frames [16] i32 |
-//           footprints [8][ROWS][W] f32
+// per CTA : pose consts [F][36] f64 | sstep [F][6] f64 (scale_c*step_c) | pose-block accumulators
+//           [F][27] f64 | E [warps][8] f64
+// per warp: geometry [8][20] f64 | reduction transpose [25][6G+2] f64 | scaled sums [6G] f64 |
+//           ints [8] int4 | frames [16] i32 | footprints [8][ROWS][W] f32
 template <int R>
 __host__ __device__ constexpr size_t k_step_smem_bytes(int n_frames) {
-  return sizeof(double) * ((size_t)n_frames * (kPoseConst + 6) + kWarpsPerCta * kEacc) +
-         (size_t)kWarpsPerCta * (sizeof(double) * (kObsBatch * 20 + (size_t)n_frames * kUStride + 25 * kRedStride + 24) +
+  return sizeof(double) * ((size_t)n_frames * (kPoseConst + 6 + kUStride) + (n_frames & 1) + kWarpsPerCta * kEacc) +
+         (size_t)kWarpsPerCta * (sizeof(double) * (kObsBatch * 20 + 25 * kRedStride + 6 * kG) +
                                  sizeof(int4) * kObsBatch + sizeof(int) * kMaxFrames +
                                  sizeof(float) * (size_t)kStageSlots * Foot<R>::FLOATS);
 }
@@ -204,12 +208,12 @@ __device__ __forceinline__ void sample_fast(const float* __restrict__ fp, int r0
 // smem accumulator, W -> HBM, V / g_p -> the caller's register accumulator.
 __device__ __forceinline__ void emit_blocks(double dG11, double dG12, double dG22, double db1, double db2,
                                             const double* __restrict__ g, int f, bool free_cam, int lane, int e1a, int e1b,
-                                            int e2a, int e2b, double* s_U_w, double* __restrict__ outW_o, double& acc_pt) {
+                                            int e2a, int e2b, double* s_Ucta, double* __restrict__ outW_o, double& acc_pt) {
   const double* A = g + 2;
   if (lane < 27) {
     if (free_cam) {
       const double v1 = lane < 21 ? quad(A, e1a, e1b, dG11, dG12, dG22) : -(A[e1a] * db1 + A[9 + e1a] * db2);
-      s_U_w[f * kUStride + lane] += v1;
+      atomicAdd(s_Ucta + f * kUStride + lane, v1);   // 8 warps share the CTA accumulator
     }
     const double v2 = lane < 24 ? quad(A, e2a, e2b, dG11, dG12, dG22) : -(A[e2a] * db1 + A[9 + e2a] * db2);
     if (lane < 18) outW_o[lane] = free_cam ? v2 : 0.0;
@@ -228,6 +232,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
   const int F = prm.n_frames;
   const int C = NCH ? NCH : prm.fr.n_channels;
   const int CP = C * P;
+  const bool want_res = prm.residuals != nullptr;
 
   const LmState* st = prm.st;
   if (st && st->done) return;
@@ -244,16 +249,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_pose = reinterpret_cast<double*>(smem_raw);                       // [F][36]
   double* s_sstep = s_pose + F * kPoseConst;                                  // [F][6]
-  double* s_E = s_sstep + F * 6;                                              // [warps][8]
+  double* s_Ucta = s_sstep + F * 6;                                           // [F][27]
+  double* s_E = s_Ucta + F * kUStride + (F & 1);                              // [warps][8] (even offset: 16 B alignment below)
   double* s_geo = s_E + kWarpsPerCta * kEacc;                                 // [warps][8][20]
   double* s_geo_w = s_geo + warp * (kObsBatch * 20);
-  double* s_U = s_geo + kWarpsPerCta * (kObsBatch * 20);                      // [warps][F][27]
-  double* s_U_w = s_U + warp * F * kUStride;
-  double* s_red = s_U + kWarpsPerCta * F * kUStride;                          // [warps][25][26]
+  double* s_red = s_geo + kWarpsPerCta * (kObsBatch * 20);                    // [warps][25][6G+2]
   double* s_red_w = s_red + warp * (25 * kRedStride);
-  double* s_tot = s_red + kWarpsPerCta * (25 * kRedStride);                   // [warps][24]
-  double* s_tot_w = s_tot + warp * 24;
-  int4* s_gi = reinterpret_cast<int4*>(s_tot + kWarpsPerCta * 24);            // [warps][8]
+  double* s_tot = s_red + kWarpsPerCta * (25 * kRedStride);                   // [warps][6G]
+  double* s_tot_w = s_tot + warp * (6 * kG);
+  int4* s_gi = reinterpret_cast<int4*>(s_tot + kWarpsPerCta * (6 * kG));      // [warps][8]
   int4* s_gi_w = s_gi + warp * kObsBatch;
   int* s_frm = reinterpret_cast<int*>(s_gi + kWarpsPerCta * kObsBatch);       // [warps][16]
   int* s_frm_w = s_frm + warp * kMaxFrames;
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
   if (backsub)
     for (int i = threadIdx.x; i < F * 6; i += blockDim.x)
       s_sstep[i] = (st->free_index[i / 6] >= 0) ? st->scale_c[i] * st->step_c[i] : 0.0;
-  for (int i = lane; i < F * kUStride; i += 32) s_U_w[i] = 0.0;
+  for (int i = threadIdx.x; i < F * kUStride; i += blockDim.x) s_Ucta[i] = 0.0;
   __syncthreads();
 
   // ---- per-lane constants --------------------------------------------------------------
@@ -351,6 +355,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
     for (int ob = 0; ob < nobs; ob += kObsBatch) {
       const int nb = min(kObsBatch, nobs - ob);
       // ---- (G) geometry: lane i <-> observation ob+i --------------------------------
+      int g_fast_l = 0;
       if (lane < nb) {
         const int g_f = s_frm_w[ob + lane];
         const double* pc = s_pose + g_f * kPoseConst;
@@ -409,7 +414,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
           gi.y = r0; gi.z = c0 & ~3; gi.w = fast;
         }
         s_gi_w[lane] = gi;
+        g_fast_l = gi.w;
       }
+      const unsigned fastmask = __ballot_sync(0xffffffffu, g_fast_l != 0);
       __syncwarp();
 
       const int obs_per_stage = NCH == 1 ? kStageSlots : ((C >= kStageSlots) ? 1 : kStageSlots / C);
@@ -463,22 +470,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
         __syncwarp();
 
         // ---- (S)+(R): four observations at a time when every one of them is interior -------
-        for (int qb = 0; qb < ns_obs; qb += 4) {
-          const int nq = min(4, ns_obs - qb);
-          bool all_fast = kQuad;
-          if (kQuad)
-            for (int i = 0; i < nq; ++i) all_fast = all_fast && (s_gi_w[sb + qb + i].w != 0);
+        for (int qb = 0; qb < ns_obs; qb += kG) {
+          const int nq = min(kG, ns_obs - qb);
+          const bool all_fast = kQuad && (((fastmask >> (sb + qb)) & ((1u << nq) - 1u)) == ((1u << nq) - 1u));
           if (kQuad && all_fast) {
-            double v6[4][6];
+            double v6[kG][6];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kG; ++i) {
               const int ii = sb + qb + min(i, nq - 1);            // out-of-range slots redo the last one
               const int4 gi = s_gi_w[ii];
               const double* g = s_geo_w + ii * 20;
               float I1, gx, gy;
               sample_fast<R>(s_fp_w + (ii - sb) * FT::FLOATS, gi.y, gi.z, g[0], g[1], pdx[0], pdy[0], I1, gx, gy);
               const double rr = __dmul_rn(wj[0], __dsub_rn(p0c[0], (double)I1));   // photobundle.cc:720
-              if (prm.residuals && lane < P && i < nq) prm.residuals[(size_t)(o0 + ob + ii) * CP + lane] = rr;
+              if (want_res && lane < P && i < nq) prm.residuals[(size_t)(o0 + ob + ii) * CP + lane] = rr;
               const double hx = wj[0] * (double)gx, hy = wj[0] * (double)gy;
               v6[i][0] = rr * rr; v6[i][1] = hx * hx; v6[i][2] = hx * hy; v6[i][3] = hy * hy; v6[i][4] = rr * hx; v6[i][5] = rr * hy;
             }
@@ -486,22 +491,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
             if (lane < P) {
               double2* row = reinterpret_cast<double2*>(s_red_w + lane * kRedStride);
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
+              for (int i = 0; i < kG; ++i)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) row[i * 3 + k] = make_double2(v6[i][2 * k], v6[i][2 * k + 1]);
             }
             __syncwarp();
             double tot = 0.0;
-            if (lane < 24) {
+            if (lane < 6 * kG) {
 #pragma unroll
               for (int l = 0; l < P; ++l) tot += s_red_w[l * kRedStride + lane];
             }
             // Huber corrector of the four observations in parallel: lane 6i+k holds sum k of observation i
             const int i_l = lane / 6, k_l = lane - 6 * i_l;
-            const double s_i = __shfl_sync(0xffffffffu, tot, min(i_l, 3) * 6);
+            const double s_i = __shfl_sync(0xffffffffu, tot, min(i_l, kG - 1) * 6);
             double rho0, rho1;
             huber_rho(prm.huber, s_i, rho0, rho1);
-            if (lane < 24) {
+            if (lane < 6 * kG) {
               s_tot_w[lane] = k_l == 0 ? s_i : rho1 * tot;
               if (k_l == 0 && i_l < nq) {
                 cost_w += 0.5 * rho0;
@@ -510,14 +515,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
             }
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kG; ++i) {
               if (i < nq) {
                 const int ii = sb + qb + i;
                 const int o = o0 + ob + ii;
                 const int f = s_gi_w[ii].x;
                 const double* t = s_tot_w + 6 * i;
                 emit_blocks(t[1], t[2], t[3], t[4], t[5], s_geo_w + ii * 20, f, f != prm.fixed_frame, lane, e1a, e1b, e2a, e2b,
-                            s_U_w, outW + (size_t)o * 18, acc_pt);
+                            s_Ucta, outW + (size_t)o * 18, acc_pt);
               }
             }
             __syncwarp();
@@ -573,7 +578,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
                     }
                     const double p0 = (k == 0) ? p0c[r] : (double)prm.desc[(size_t)p * CP + k * P + j];
                     const double rr = __dmul_rn(wj[r], __dsub_rn(p0, (double)I1));   // photobundle.cc:720
-                    if (prm.residuals) prm.residuals[(size_t)o * CP + k * P + j] = rr;
+                    if (want_res) prm.residuals[(size_t)o * CP + k * P + j] = rr;
                     q.s = fma(rr, rr, q.s);
                     const double hx = wj[r] * (double)gx, hy = wj[r] * (double)gy;
                     q.G11 = fma(hx, hx, q.G11); q.G12 = fma(hx, hy, q.G12); q.G22 = fma(hy, hy, q.G22);
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
                 if (prm.obs_sqnorm) prm.obs_sqnorm[o] = q.s;
               }
               emit_blocks(rho1 * q.G11, rho1 * q.G12, rho1 * q.G22, rho1 * q.b1, rho1 * q.b2, g, f, f != prm.fixed_frame, lane,
-                          e1a, e1b, e2a, e2b, s_U_w, outW + (size_t)o * 18, acc_pt);
+                          e1a, e1b, e2a, e2b, s_Ucta, outW + (size_t)o * 18, acc_pt);
             }
           }
         }
@@ -617,9 +622,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
   __syncthreads();
   // CTA partials (fixed order inside the CTA), then one fp64 atomic per entry per CTA
   for (int i = threadIdx.x; i < F * kUStride; i += blockDim.x) {
-    double acc = 0.0;
-#pragma unroll
-    for (int w = 0; w < kWarpsPerCta; ++w) acc += s_U[w * F * kUStride + i];
+    const double acc = s_Ucta[i];
     if (acc != 0.0) atomicAdd(prm.Xacc + i, acc);
   }
   if (threadIdx.x < kEacc) {

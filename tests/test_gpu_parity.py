@@ -168,8 +168,8 @@ def test_lm_resolve_is_idempotent(small_win):
     s2 = h.solve()
     c2 = h.get_poses()
     h.close()
-    assert abs(s2["initial_cost"] - s1["final_cost"]) <= 1e-12 * s1["final_cost"]   # fp64 atomics: order varies
-    assert s2["final_cost"] <= s1["final_cost"]
+    assert abs(s2["initial_cost"] - s1["final_cost"]) <= 1e-10 * s1["final_cost"]   # fp64 atomics: order varies
+    assert s2["final_cost"] <= s1["final_cost"] * (1 + 1e-9)
     assert np.abs(c2 - c1).max() <= 1e-4
 
 
