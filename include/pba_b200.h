@@ -149,6 +149,16 @@ int pba_set_frames_u8(pba_handle* h, int32_t n_frames, const uint8_t* const* ima
 /* Generic multi-channel descriptors (IntensityAndGradient / BitPlanes): fp32 channel
  * planes as DescriptorFrame holds them; planes[f*n_channels + k]. */
 int pba_set_frames_f32(pba_handle* h, int32_t n_frames, const float* const* planes);
+/* Pyramid level l of a window (BASELINE config 4): `images` are the LEVEL-0 frames of size
+ * src_rows x src_cols; they are uploaded once and reduced `levels_down` times on the device with
+ * the cv::pyrDown rule the reference intends at src/photobundle_pyramid.cc:46 (separable
+ * [1 4 6 4 1]/16, reflect-101 borders, even samples, size (n+1)/2 per src/types.h:70-73).  The
+ * handle must have been created with the level's rows/cols and the level's intrinsics
+ * (Calibration::pyrDown, src/calibration.h:72-78). */
+int pba_set_frames_u8_pyr(pba_handle* h, int32_t n_frames, const uint8_t* const* images, int32_t src_rows,
+                          int32_t src_cols, int32_t levels_down);
+/* The same reduction for one image, host to host (rows x cols -> (rows+1)/2 x (cols+1)/2). */
+int pba_pyrdown_u8(const uint8_t* src, int32_t rows, int32_t cols, uint8_t* dst, int32_t device);
 /* Sliding window: replace the plane(s) in ring slot `slot` only. */
 int pba_set_frame_u8(pba_handle* h, int32_t slot, const uint8_t* image);
 

@@ -19,7 +19,7 @@ PBA_UNIQUE_ID_BYTES = 128
 
 EXPORTED_SYMBOLS = [
     "pba_last_error", "pba_version", "pba_default_solver_options", "pba_create", "pba_destroy",
-    "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_poses", "pba_set_points",
+    "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_frames_u8_pyr", "pba_pyrdown_u8", "pba_set_poses", "pba_set_points",
     "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_get_poses", "pba_get_points", "pba_get_iterations",
     "pba_comm_unique_id", "pba_comm_init", "pba_shard_range",
 ]
@@ -159,6 +159,14 @@ class Handle:
         _check(lib().pba_set_frames_u8(self._h, F, arr), "pba_set_frames_u8")
         self.n_frames = F
 
+    def set_frames_u8_pyr(self, images: np.ndarray, levels_down: int):
+        """Upload LEVEL-0 frames and reduce them `levels_down` times on the device (cv::pyrDown rule)."""
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        F, r, c = images.shape
+        arr = (C.c_void_p * F)(*[images[f].ctypes.data for f in range(F)])
+        _check(lib().pba_set_frames_u8_pyr(self._h, F, arr, r, c, int(levels_down)), "pba_set_frames_u8_pyr")
+        self.n_frames = F
+
     def set_frame_u8(self, slot: int, image: np.ndarray):
         image = np.ascontiguousarray(image, dtype=np.uint8)
         _check(lib().pba_set_frame_u8(self._h, slot, _ptr(image)), "pba_set_frame_u8")
@@ -263,3 +271,11 @@ def shard_range(obs_offsets: np.ndarray, rank: int, n_ranks: int) -> tuple[int, 
     a, b = C.c_int32(), C.c_int32()
     _check(lib().pba_shard_range(off.shape[0] - 1, _ptr(off), rank, n_ranks, C.byref(a), C.byref(b)), "pba_shard_range")
     return a.value, b.value
+
+
+def pyrdown_u8(img: np.ndarray, device: int = -1) -> np.ndarray:
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    r, c = img.shape
+    out = np.zeros(((r + 1) // 2, (c + 1) // 2), dtype=np.uint8)
+    _check(lib().pba_pyrdown_u8(_ptr(img), r, c, _ptr(out), device), "pba_pyrdown_u8")
+    return out

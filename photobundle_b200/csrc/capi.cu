@@ -253,6 +253,64 @@ int pba_set_frames_u8(pba_handle* h, int32_t n_frames, const uint8_t* const* ima
   return PBA_OK;
 }
 
+int pba_set_frames_u8_pyr(pba_handle* h, int32_t n_frames, const uint8_t* const* images, int32_t src_rows,
+                          int32_t src_cols, int32_t levels_down) {
+  if (!h || !images) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8_pyr: null argument");
+  if (levels_down == 0 && src_rows == h->cfg.rows && src_cols == h->cfg.cols) return pba_set_frames_u8(h, n_frames, images);
+  if (h->cfg.n_channels != 1) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8_pyr: uint8 frames are the 1-channel Intensity descriptor");
+  if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(PBA_ERR_CAPACITY, "pba_set_frames_u8_pyr: %d frames, capacity %d", n_frames, h->cfg.max_frames);
+  int r = src_rows, c = src_cols;
+  for (int l = 0; l < levels_down; ++l) { r = (r + 1) / 2; c = (c + 1) / 2; }
+  if (levels_down < 0 || r != h->cfg.rows || c != h->cfg.cols)
+    return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8_pyr: %dx%d reduced %d times is %dx%d, handle is %dx%d", src_rows, src_cols,
+                levels_down, r, c, h->cfg.rows, h->cfg.cols);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->d_u8) {
+    CUDA_TRY(cudaMalloc(&h->d_u8, (size_t)h->cfg.max_frames * h->plane));
+    CUDA_TRY(cudaMemsetAsync(h->d_u8, 0, (size_t)h->cfg.max_frames * h->plane, h->stream));
+  }
+  // two ping-pong scratch planes at level-0 size
+  const int p0 = (src_cols + 15) / 16 * 16;
+  uint8_t* scratch = nullptr;
+  CUDA_TRY(cudaMalloc(&scratch, 2 * (size_t)src_rows * p0));
+  for (int f = 0; f < n_frames; ++f) {
+    if (!images[f]) { cudaFree(scratch); return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8_pyr: images[%d] is null", f); }
+    uint8_t* a = scratch;
+    uint8_t* b = scratch + (size_t)src_rows * p0;
+    CUDA_TRY(cudaMemcpy2DAsync(a, p0, images[f], src_cols, src_cols, src_rows, cudaMemcpyHostToDevice, h->stream));
+    int rr = src_rows, cc = src_cols, pa = p0;
+    for (int l = 0; l < levels_down; ++l) {
+      const bool last = (l == levels_down - 1);
+      uint8_t* dst = last ? h->d_u8 + (size_t)f * h->plane : b;
+      const int pd = last ? h->pitch : p0;
+      CUDA_TRY(launch_pyrdown_u8(a, rr, cc, pa, dst, pd, h->stream));
+      rr = (rr + 1) / 2; cc = (cc + 1) / 2; pa = pd;
+      std::swap(a, b);
+      if (!last) { /* a now holds the reduced image */ }
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  cudaFree(scratch);
+  h->frames_are_u8 = true; h->have_frames = true; h->n_frames = n_frames;
+  return PBA_OK;
+}
+
+int pba_pyrdown_u8(const uint8_t* src, int32_t rows, int32_t cols, uint8_t* dst, int32_t device) {
+  if (!src || !dst || rows < 1 || cols < 1) return fail(PBA_ERR_ARGUMENT, "pba_pyrdown_u8: bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PBA_ERR_CUDA, "pba_pyrdown_u8: no CUDA device; no CPU fallback");
+  if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+  const int drows = (rows + 1) / 2, dcols = (cols + 1) / 2;
+  uint8_t *ds = nullptr, *dd = nullptr;
+  CUDA_TRY(cudaMalloc(&ds, (size_t)rows * cols));
+  CUDA_TRY(cudaMalloc(&dd, (size_t)drows * dcols));
+  CUDA_TRY(cudaMemcpy(ds, src, (size_t)rows * cols, cudaMemcpyHostToDevice));
+  CUDA_TRY(launch_pyrdown_u8(ds, rows, cols, cols, dd, dcols, 0));
+  CUDA_TRY(cudaMemcpy(dst, dd, (size_t)drows * dcols, cudaMemcpyDeviceToHost));
+  cudaFree(ds); cudaFree(dd);
+  return PBA_OK;
+}
+
 int pba_set_frame_u8(pba_handle* h, int32_t slot, const uint8_t* image) {
   if (!h || !image) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8: null argument");
   if (!h->d_u8 || !h->frames_are_u8) return fail(PBA_ERR_STATE, "pba_set_frame_u8: call pba_set_frames_u8 first");

@@ -137,4 +137,7 @@ int schur_grid(int n_points, int sm_count);
 cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t stream);
 cudaError_t launch_solve_only(const LmParams& lp, cudaStream_t stream);   // split mode, after the all-reduce of S
 
+cudaError_t launch_pyrdown_u8(const uint8_t* src, int srows, int scols, int spitch, uint8_t* dst, int dpitch,
+                              cudaStream_t stream);
+
 }  // namespace pba

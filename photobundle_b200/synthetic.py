@@ -317,3 +317,71 @@ def make_sequence(n_frames: int = 10, rows: int = 120, cols: int = 160, seed: in
         d = np.concatenate([rng_pose.normal(0, rot_sigma, 3), rng_pose.normal(0, trans_sigma, 3)])
         T_init[i] = cam_to_mat(d) @ T_rel[i]
     return Sequence(images=images, depths=depths, K4=K4, T_w_gt=T_w, T_rel_gt=T_rel, T_rel_init=T_init)
+
+
+# ----------------------------------------------------------------------------------------------
+# Pyramid (BASELINE config 4).  The reference's pyramid class is unfinished, so
+# the level semantics are defined here: same window and same world points at every level; level l
+# uses frames reduced l times with the cv::pyrDown rule (what src/photobundle_pyramid.cc:46 intends),
+# intrinsics per Calibration::pyrDown (src/calibration.h:72-78: K *= 0.5), and descriptors
+# re-extracted per level as the bilinear 5x5 patch of the level-l reference frame at the point's
+# level-0 pixel divided by 2^l (so that descriptor location and projection stay consistent).
+# ----------------------------------------------------------------------------------------------
+def _reflect101(i: np.ndarray, n: int) -> np.ndarray:
+    i = np.asarray(i).copy()
+    if n == 1:
+        return np.zeros_like(i)
+    for _ in range(4):
+        i = np.where(i < 0, -i, i)
+        i = np.where(i >= n, 2 * n - 2 - i, i)
+    return i
+
+
+def pyr_down_u8(img: np.ndarray) -> np.ndarray:
+    """cv::pyrDown for CV_8U: separable [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8."""
+    rows, cols = img.shape
+    drows, dcols = (rows + 1) // 2, (cols + 1) // 2
+    w = (1, 4, 6, 4, 1)
+    src = img.astype(np.int32)
+    h = sum(w[i] * src[:, _reflect101(2 * np.arange(dcols) + i - 2, cols)] for i in range(5))
+    v = sum(w[j] * h[_reflect101(2 * np.arange(drows) + j - 2, rows), :] for j in range(5))
+    return ((v + 128) >> 8).astype(np.uint8)
+
+
+def _bilinear_patch(img: np.ndarray, x: float, y: float, radius: int) -> np.ndarray:
+    rows, cols = img.shape
+    out = np.empty((2 * radius + 1) ** 2)
+    k = 0
+    for dy in range(-radius, radius + 1):
+        for dx in range(-radius, radius + 1):
+            xx = min(max(x + dx, 0.0), cols - 1.0)
+            yy = min(max(y + dy, 0.0), rows - 1.0)
+            x0, y0 = min(int(xx), cols - 2), min(int(yy), rows - 2)
+            ax, ay = xx - x0, yy - y0
+            out[k] = ((1 - ay) * ((1 - ax) * img[y0, x0] + ax * img[y0, x0 + 1]) +
+                      ay * ((1 - ax) * img[y0 + 1, x0] + ax * img[y0 + 1, x0 + 1]))
+            k += 1
+    return out.astype(np.float32).astype(np.float64)   # descriptors are float channel values widened to double
+
+
+def pyramid_level(win: Window, level: int, images_l: np.ndarray, ref_px: np.ndarray, ref_frame: np.ndarray) -> Window:
+    """The level-`level` window of `win`; images_l are win.images reduced `level` times."""
+    s = float(2 ** level)
+    img_f = images_l.astype(np.float64)
+    desc = np.stack([_bilinear_patch(img_f[int(ref_frame[k])], ref_px[k, 0] / s, ref_px[k, 1] / s, win.radius)
+                     for k in range(win.n_points)]) if level > 0 else win.desc
+    return dataclasses.replace(win, images=images_l, fx=win.fx / s, fy=win.fy / s, cx=win.cx / s, cy=win.cy / s, desc=desc)
+
+
+def reference_pixels(win: Window) -> tuple[np.ndarray, np.ndarray]:
+    """(integer pixel of each point in its reference frame, reference frame index), recovered by
+    projecting the initial point with the initial pose it was lifted with."""
+    ref = win.obs_frame[win.obs_offsets[:-1]]
+    px = np.empty((win.n_points, 2))
+    for f in np.unique(ref):
+        sel = np.nonzero(ref == f)[0]
+        R = rodrigues(win.cams_init[f, :3])
+        Xc = win.points_init[sel] @ R.T + win.cams_init[f, 3:]
+        px[sel, 0] = np.rint(win.fx * Xc[:, 0] / Xc[:, 2] + win.cx)
+        px[sel, 1] = np.rint(win.fy * Xc[:, 1] / Xc[:, 2] + win.cy)
+    return px, ref
