@@ -42,15 +42,33 @@
 
 #include <climits>
 #include <cfloat>
+#include <type_traits>
 
-#ifndef K_STEP_MIN_CTAS
-#define K_STEP_MIN_CTAS 2
+// CTA geometry.  The bench window is 4000 points = 4000 warps of work; two 14-warp CTAs per SM
+// (<= 72 registers, uint8 footprints in shared memory) keep EVERY point resident in a single wave
+// on 148 SMs, which matters more than per-warp ILP: with 16 warps/SM the kernel ran 1.7 waves and
+// the half-empty second wave cost a full per-point latency (profiles/r01e_kstep_trace.txt).
+#ifndef K_STEP_WARPS_U8
+#define K_STEP_WARPS_U8 14
+#endif
+#ifndef K_STEP_WARPS_F32
+#define K_STEP_WARPS_F32 8
 #endif
 #ifndef K_STEP_GROUP
-#define K_STEP_GROUP 4      // observations sampled together per warp (ILP)
+#define K_STEP_GROUP 2      // observations sampled together per warp (ILP)
 #endif
 
 namespace pba {
+
+template <bool U8> struct Geo { static constexpr int WARPS = U8 ? K_STEP_WARPS_U8 : K_STEP_WARPS_F32; };
+
+// K_STEP_TRACE: per-warp clock64 stamps at the phase boundaries (scratch builds only).
+#ifdef K_STEP_TRACE
+__device__ long long g_kstep_trace[4096 * 16];
+#define KTRACE(slot) do { if (lane == 0 && p < 4096) g_kstep_trace[p * 16 + (slot)] = clock64(); } while (0)
+#else
+#define KTRACE(slot) do {} while (0)
+#endif
 
 __constant__ signed char c_pair6[21][2] = {
     {0, 0}, {0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5},
@@ -144,16 +162,18 @@ constexpr int kG = K_STEP_GROUP;
 constexpr int kRedStride = 6 * kG + 2;   // doubles per lane row of the reduction transpose (6 sums x group + pad, 16 B aligned)
 
 // ---- shared memory carve-up --------------------------------------------------------------
-// per CTA : pose consts [F][36] f64 | sstep [F][6] f64 (scale_c*step_c) | pose-block accumulators
-//           [F][27] f64 | E [warps][8] f64
+// per CTA : pose consts [F][36] f64 | sstep [F][6] f64 (scale_c*step_c) | E [warps][8] f64
 // per warp: geometry [8][20] f64 | reduction transpose [25][6G+2] f64 | scaled sums [6G] f64 |
-//           ints [8] int4 | frames [16] i32 | footprints [8][ROWS][W] f32
-template <int R>
+//           pose-block accumulators [F][27] f64 | ints [8] int4 | frames [16] i32 |
+//           footprints [8][ROWS][W] f32
+template <int R, bool U8>
 __host__ __device__ constexpr size_t k_step_smem_bytes(int n_frames) {
-  return sizeof(double) * ((size_t)n_frames * (kPoseConst + 6 + kUStride) + (n_frames & 1) + kWarpsPerCta * kEacc) +
-         (size_t)kWarpsPerCta * (sizeof(double) * (kObsBatch * 20 + 25 * kRedStride + 6 * kG) +
-                                 sizeof(int4) * kObsBatch + sizeof(int) * kMaxFrames +
-                                 sizeof(float) * (size_t)kStageSlots * Foot<R>::FLOATS);
+  constexpr int WARPS = Geo<U8>::WARPS;
+  // footprints: raw uint8 (ROWS x W bytes) on the Intensity path, fp32 otherwise
+  constexpr size_t fp_bytes = (size_t)kStageSlots * Foot<R>::FLOATS * (U8 ? 1 : 4);
+  return sizeof(double) * ((size_t)n_frames * (kPoseConst + 6) + WARPS * kEacc) +
+         (size_t)WARPS * (sizeof(double) * (kObsBatch * 20 + 25 * kRedStride + 6 * kG + (size_t)n_frames * kUStride + (n_frames & 1)) +
+                          sizeof(int4) * kObsBatch + sizeof(int) * kMaxFrames + ((fp_bytes + 15) / 16) * 16);
 }
 
 struct Sums { double s, G11, G12, G22, b1, b2; };
@@ -183,18 +203,18 @@ __device__ __forceinline__ void huber_rho(double a, double s, double& rho0, doub
 
 // One patch pixel of one observation from the staged footprint (all taps interior):
 // I, Gx, Gy exactly as SampleLinear returns them.
-template <int R>
-__device__ __forceinline__ void sample_fast(const float* __restrict__ fp, int r0, int cb, double u, double v,
+template <int R, class T>
+__device__ __forceinline__ void sample_fast(const T* __restrict__ fp, int r0, int cb, double u, double v,
                                             double pdx, double pdy, float& I1, float& gx, float& gy) {
   using FT = Foot<R>;
   const float su = __double2float_rn(__dadd_rn(u, pdx));
   const float sv = __double2float_rn(__dadd_rn(v, pdy));
   const int ix = __float2int_rz(su), iy = __float2int_rz(sv);
   const float dx = __fsub_rn((float)(ix + 1), su), dy = __fsub_rn((float)(iy + 1), sv);
-  const float* q = fp + (iy - r0) * FT::W + (ix - cb);
-  const float a11 = q[0], a12 = q[1], a21 = q[FT::W], a22 = q[FT::W + 1];
-  const float l1 = q[-1], r1 = q[2], l2 = q[FT::W - 1], r2 = q[FT::W + 2];
-  const float t1 = q[-FT::W], t2 = q[-FT::W + 1], u1 = q[2 * FT::W], u2 = q[2 * FT::W + 1];
+  const T* q = fp + (iy - r0) * FT::W + (ix - cb);
+  const float a11 = (float)q[0], a12 = (float)q[1], a21 = (float)q[FT::W], a22 = (float)q[FT::W + 1];
+  const float l1 = (float)q[-1], r1 = (float)q[2], l2 = (float)q[FT::W - 1], r2 = (float)q[FT::W + 2];
+  const float t1 = (float)q[-FT::W], t2 = (float)q[-FT::W + 1], u1 = (float)q[2 * FT::W], u2 = (float)q[2 * FT::W + 1];
   const double omdx = __dsub_rn(1.0, (double)dx);
   const float omdy = __fsub_rn(1.0f, dy);
   I1 = bilerp(dx, dy, omdx, omdy, a11, a12, a21, a22);
@@ -208,12 +228,12 @@ __device__ __forceinline__ void sample_fast(const float* __restrict__ fp, int r0
 // smem accumulator, W -> HBM, V / g_p -> the caller's register accumulator.
 __device__ __forceinline__ void emit_blocks(double dG11, double dG12, double dG22, double db1, double db2,
                                             const double* __restrict__ g, int f, bool free_cam, int lane, int e1a, int e1b,
-                                            int e2a, int e2b, double* s_Ucta, double* __restrict__ outW_o, double& acc_pt) {
+                                            int e2a, int e2b, double* s_U_w, double* __restrict__ outW_o, double& acc_pt) {
   const double* A = g + 2;
   if (lane < 27) {
     if (free_cam) {
       const double v1 = lane < 21 ? quad(A, e1a, e1b, dG11, dG12, dG22) : -(A[e1a] * db1 + A[9 + e1a] * db2);
-      atomicAdd(s_Ucta + f * kUStride + lane, v1);   // 8 warps share the CTA accumulator
+      s_U_w[f * kUStride + lane] += v1;   // warp-private: no atomics
     }
     const double v2 = lane < 24 ? quad(A, e2a, e2b, dG11, dG12, dG22) : -(A[e2a] * db1 + A[9 + e2a] * db2);
     if (lane < 18) outW_o[lane] = free_cam ? v2 : 0.0;
@@ -223,8 +243,10 @@ __device__ __forceinline__ void emit_blocks(double dG11, double dG12, double dG2
 
 // NCH: compile-time channel count (1 = Intensity, the north-star descriptor); 0 = runtime count.
 template <int R, bool U8, int NCH>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(const StepParams prm) {
+__global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParams prm) {
   using FT = Foot<R>;
+  using FPT = typename std::conditional<U8, uint8_t, float>::type;   // footprint element in shared memory
+  constexpr int WARPS = Geo<U8>::WARPS;
   constexpr int P = FT::P;
   constexpr int PR = (P + 31) / 32;             // pixel rounds per lane
   constexpr bool kQuad = (NCH == 1 && PR == 1); // ILP-4 fast path available
@@ -235,6 +257,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
   const bool want_res = prm.residuals != nullptr;
 
   const LmState* st = prm.st;
+#ifdef K_STEP_TRACE
+  { const int p = blockIdx.x * WARPS + warp; KTRACE(0); }
+#endif
   if (st && st->done) return;
   const int buf = st ? st->eval_buf : 0;
   const int cur = st ? st->cur : 0;
@@ -249,26 +274,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_pose = reinterpret_cast<double*>(smem_raw);                       // [F][36]
   double* s_sstep = s_pose + F * kPoseConst;                                  // [F][6]
-  double* s_Ucta = s_sstep + F * 6;                                           // [F][27]
-  double* s_E = s_Ucta + F * kUStride + (F & 1);                              // [warps][8] (even offset: 16 B alignment below)
-  double* s_geo = s_E + kWarpsPerCta * kEacc;                                 // [warps][8][20]
+  double* s_E = s_sstep + F * 6;                                              // [warps][8] (all offsets even: 16 B alignment)
+  double* s_geo = s_E + WARPS * kEacc;                                 // [warps][8][20]
   double* s_geo_w = s_geo + warp * (kObsBatch * 20);
-  double* s_red = s_geo + kWarpsPerCta * (kObsBatch * 20);                    // [warps][25][6G+2]
+  double* s_red = s_geo + WARPS * (kObsBatch * 20);                    // [warps][25][6G+2]
   double* s_red_w = s_red + warp * (25 * kRedStride);
-  double* s_tot = s_red + kWarpsPerCta * (25 * kRedStride);                   // [warps][6G]
+  double* s_tot = s_red + WARPS * (25 * kRedStride);                   // [warps][6G]
   double* s_tot_w = s_tot + warp * (6 * kG);
-  int4* s_gi = reinterpret_cast<int4*>(s_tot + kWarpsPerCta * (6 * kG));      // [warps][8]
+  const int ustride = F * kUStride + (F & 1);
+  double* s_U = s_tot + WARPS * (6 * kG);                              // [warps][F][27]: this warp's pose blocks
+  double* s_U_w = s_U + warp * ustride;
+  int4* s_gi = reinterpret_cast<int4*>(s_U + WARPS * ustride);         // [warps][8]
   int4* s_gi_w = s_gi + warp * kObsBatch;
-  int* s_frm = reinterpret_cast<int*>(s_gi + kWarpsPerCta * kObsBatch);       // [warps][16]
+  int* s_frm = reinterpret_cast<int*>(s_gi + WARPS * kObsBatch);       // [warps][16]
   int* s_frm_w = s_frm + warp * kMaxFrames;
-  float* s_fp = reinterpret_cast<float*>(s_frm + kWarpsPerCta * kMaxFrames);
-  float* s_fp_w = s_fp + warp * (kStageSlots * FT::FLOATS);                   // [8][ROWS][W]
+  constexpr int kFpStride = ((kStageSlots * FT::FLOATS * (int)sizeof(FPT) + 15) / 16) * 16 / (int)sizeof(FPT);
+  FPT* s_fp = reinterpret_cast<FPT*>(s_frm + WARPS * kMaxFrames);
+  FPT* s_fp_w = s_fp + warp * kFpStride;                                       // [8][ROWS][W]
 
   if (threadIdx.x < F) pose_consts(cams + 6 * threadIdx.x, s_pose + threadIdx.x * kPoseConst);
   if (backsub)
     for (int i = threadIdx.x; i < F * 6; i += blockDim.x)
       s_sstep[i] = (st->free_index[i / 6] >= 0) ? st->scale_c[i] * st->step_c[i] : 0.0;
-  for (int i = threadIdx.x; i < F * kUStride; i += blockDim.x) s_Ucta[i] = 0.0;
+  for (int i = lane; i < F * kUStride; i += 32) s_U_w[i] = 0.0;
   __syncthreads();
 
   // ---- per-lane constants --------------------------------------------------------------
@@ -294,11 +322,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
   else if (lane < 24) { e2a = 6 + c_pair3[lane - 18][0]; e2b = 6 + c_pair3[lane - 18][1]; }
   else if (lane < 27) { e2a = 6 + lane - 24; }
 
-  const int p = blockIdx.x * kWarpsPerCta + warp;
   double cost_w = 0.0, gsq_w = 0.0, gmax_w = 0.0, xsq_w = 0.0;
   double bs_sg = 0.0, bs_sHs = 0.0, bs_step = 0.0, bs_cand = 0.0;
-  if (p < prm.n_points) {
+  for (int p = blockIdx.x * WARPS + warp; p < prm.n_points; p += gridDim.x * WARPS) {
+    KTRACE(1);
     const int o0 = prm.obs_off[p], nobs = prm.obs_off[p + 1] - o0;
+    __syncwarp();
     if (lane < nobs) s_frm_w[lane] = prm.obs_frame[o0 + lane];
     double X0 = pts_cur[3 * p], X1 = pts_cur[3 * p + 1], X2 = pts_cur[3 * p + 2];
     __syncwarp();
@@ -336,16 +365,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
       if (lane == 0) {
         // s.gs + s^T Vs0 s + 2 step_c^T Ws s   (undamped Vs0 = sp V sp)
         const double y0 = s0 * sp[0], y1 = s1 * sp[1], y2 = s2 * sp[2];
-        bs_sg = s0 * gs[0] + s1 * gs[1] + s2 * gs[2];
-        bs_sHs = y0 * (Vv[0] * y0 + Vv[1] * y1 + Vv[2] * y2) + y1 * (Vv[1] * y0 + Vv[3] * y1 + Vv[4] * y2) +
+        bs_sg += s0 * gs[0] + s1 * gs[1] + s2 * gs[2];
+        bs_sHs += y0 * (Vv[0] * y0 + Vv[1] * y1 + Vv[2] * y2) + y1 * (Vv[1] * y0 + Vv[3] * y1 + Vv[4] * y2) +
                  y2 * (Vv[2] * y0 + Vv[4] * y1 + Vv[5] * y2) + 2.0 * (wts[0] * s0 + wts[1] * s1 + wts[2] * s2);
-        bs_step = (X0 - c0) * (X0 - c0) + (X1 - c1) * (X1 - c1) + (X2 - c2) * (X2 - c2);
-        bs_cand = c0 * c0 + c1 * c1 + c2 * c2;
+        bs_step += (X0 - c0) * (X0 - c0) + (X1 - c1) * (X1 - c1) + (X2 - c2) * (X2 - c2);
+        bs_cand += c0 * c0 + c1 * c1 + c2 * c2;
       }
       X0 = c0; X1 = c1; X2 = c2;
       if (lane < 3) pts_out[3 * p + lane] = lane == 0 ? c0 : (lane == 1 ? c1 : c2);
     }
-    xsq_w = X0 * X0 + X1 * X1 + X2 * X2;
+    xsq_w += X0 * X0 + X1 * X1 + X2 * X2;
+    KTRACE(2);
 
     double acc_pt = 0.0;  // lanes 18..23: V entries, 24..26: g_p entries (summed over frames)
     double p0c[PR];       // reference descriptor of this point, channel 0
@@ -418,6 +448,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
       }
       const unsigned fastmask = __ballot_sync(0xffffffffu, g_fast_l != 0);
       __syncwarp();
+      KTRACE(3);
 
       const int obs_per_stage = NCH == 1 ? kStageSlots : ((C >= kStageSlots) ? 1 : kStageSlots / C);
       for (int sb = 0; sb < nb; sb += obs_per_stage) {
@@ -453,14 +484,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
 #pragma unroll
                 for (int rd = 0; rd < FT::ROUNDS; ++rd) {
                   if (st_off[rd] >= 0) {
-                    float4 o;
-                    if (U8) {
-                      const uint32_t q = t8[sl][rd];
-                      o = make_float4((float)(q & 0xffu), (float)((q >> 8) & 0xffu), (float)((q >> 16) & 0xffu), (float)(q >> 24));
-                    } else {
-                      o = t32[U8 ? 0 : sl][U8 ? 0 : rd];
-                    }
-                    reinterpret_cast<float4*>(s_fp_w + sl * FT::FLOATS)[lane + 32 * rd] = o;
+                    if (U8) reinterpret_cast<uint32_t*>(s_fp_w + sl * FT::FLOATS)[lane + 32 * rd] = t8[sl][rd];
+                    else reinterpret_cast<float4*>(s_fp_w + sl * FT::FLOATS)[lane + 32 * rd] = t32[U8 ? 0 : sl][U8 ? 0 : rd];
                   }
                 }
               }
@@ -469,6 +494,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
         }
         __syncwarp();
 
+        KTRACE(4);
         // ---- (S)+(R): four observations at a time when every one of them is interior -------
         for (int qb = 0; qb < ns_obs; qb += kG) {
           const int nq = min(kG, ns_obs - qb);
@@ -481,12 +507,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
               const int4 gi = s_gi_w[ii];
               const double* g = s_geo_w + ii * 20;
               float I1, gx, gy;
-              sample_fast<R>(s_fp_w + (ii - sb) * FT::FLOATS, gi.y, gi.z, g[0], g[1], pdx[0], pdy[0], I1, gx, gy);
+              sample_fast<R, FPT>(s_fp_w + (ii - sb) * FT::FLOATS, gi.y, gi.z, g[0], g[1], pdx[0], pdy[0], I1, gx, gy);
               const double rr = __dmul_rn(wj[0], __dsub_rn(p0c[0], (double)I1));   // photobundle.cc:720
               if (want_res && lane < P && i < nq) prm.residuals[(size_t)(o0 + ob + ii) * CP + lane] = rr;
               const double hx = wj[0] * (double)gx, hy = wj[0] * (double)gy;
               v6[i][0] = rr * rr; v6[i][1] = hx * hx; v6[i][2] = hx * hy; v6[i][3] = hy * hy; v6[i][4] = rr * hx; v6[i][5] = rr * hy;
             }
+            KTRACE(5 + (qb ? 4 : 0));
             // transpose-reduce the 24 sums of the group through shared memory: lane r <- sum over pixels of value r
             if (lane < P) {
               double2* row = reinterpret_cast<double2*>(s_red_w + lane * kRedStride);
@@ -501,6 +528,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
 #pragma unroll
               for (int l = 0; l < P; ++l) tot += s_red_w[l * kRedStride + lane];
             }
+            KTRACE(6 + (qb ? 4 : 0));
             // Huber corrector of the four observations in parallel: lane 6i+k holds sum k of observation i
             const int i_l = lane / 6, k_l = lane - 6 * i_l;
             const double s_i = __shfl_sync(0xffffffffu, tot, min(i_l, kG - 1) * 6);
@@ -514,6 +542,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
               }
             }
             __syncwarp();
+            KTRACE(7 + (qb ? 4 : 0));
 #pragma unroll
             for (int i = 0; i < kG; ++i) {
               if (i < nq) {
@@ -522,10 +551,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
                 const int f = s_gi_w[ii].x;
                 const double* t = s_tot_w + 6 * i;
                 emit_blocks(t[1], t[2], t[3], t[4], t[5], s_geo_w + ii * 20, f, f != prm.fixed_frame, lane, e1a, e1b, e2a, e2b,
-                            s_Ucta, outW + (size_t)o * 18, acc_pt);
+                            s_U_w, outW + (size_t)o * 18, acc_pt);
               }
             }
             __syncwarp();
+            KTRACE(8 + (qb ? 4 : 0));
           } else {
             // generic path: any channel count / patch size / border handling, one observation at a time
             for (int i = 0; i < nq; ++i) {
@@ -537,7 +567,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
               const double u = g[0], v = g[1];
               Sums q = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
               for (int k = 0; k < C; ++k) {
-                const float* fp = s_fp_w + (NCH == 1 ? ii - sb : (ii - sb) * C + k) * FT::FLOATS;
+                const FPT* fp = s_fp_w + (NCH == 1 ? ii - sb : (ii - sb) * C + k) * FT::FLOATS;
 #pragma unroll
                 for (int r = 0; r < PR; ++r) {
                   const int j = lane + 32 * r;
@@ -548,10 +578,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
                     if (fast) {
                       const int ix = __float2int_rz(su), iy = __float2int_rz(sv);
                       const float dx = __fsub_rn((float)(ix + 1), su), dy = __fsub_rn((float)(iy + 1), sv);
-                      const float* qq = fp + (iy - r0) * FT::W + (ix - cb);
-                      const float a11 = qq[0], a12 = qq[1], a21 = qq[FT::W], a22 = qq[FT::W + 1];
-                      const float l1 = qq[-1], r1 = qq[2], l2 = qq[FT::W - 1], r2 = qq[FT::W + 2];
-                      const float t1 = qq[-FT::W], t2 = qq[-FT::W + 1], u1 = qq[2 * FT::W], u2 = qq[2 * FT::W + 1];
+                      const FPT* qq = fp + (iy - r0) * FT::W + (ix - cb);
+                      const float a11 = (float)qq[0], a12 = (float)qq[1], a21 = (float)qq[FT::W], a22 = (float)qq[FT::W + 1];
+                      const float l1 = (float)qq[-1], r1 = (float)qq[2], l2 = (float)qq[FT::W - 1], r2 = (float)qq[FT::W + 2];
+                      const float t1 = (float)qq[-FT::W], t2 = (float)qq[-FT::W + 1], u1 = (float)qq[2 * FT::W], u2 = (float)qq[2 * FT::W + 1];
                       const double omdx = __dsub_rn(1.0, (double)dx);
                       const float omdy = __fsub_rn(1.0f, dy);
                       I1 = bilerp(dx, dy, omdx, omdy, a11, a12, a21, a22);
@@ -594,13 +624,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
                 if (prm.obs_sqnorm) prm.obs_sqnorm[o] = q.s;
               }
               emit_blocks(rho1 * q.G11, rho1 * q.G12, rho1 * q.G22, rho1 * q.b1, rho1 * q.b2, g, f, f != prm.fixed_frame, lane,
-                          e1a, e1b, e2a, e2b, s_Ucta, outW + (size_t)o * 18, acc_pt);
+                          e1a, e1b, e2a, e2b, s_U_w, outW + (size_t)o * 18, acc_pt);
             }
           }
         }
         __syncwarp();
       }
     }
+    KTRACE(13);
     if (lane >= 18 && lane < 24) outV[(size_t)p * 6 + lane - 18] = acc_pt;
     else if (lane >= 24 && lane < 27) outgp[(size_t)p * 3 + lane - 24] = acc_pt;
     const double gq = (lane >= 24 && lane < 27) ? acc_pt : 0.0;
@@ -610,8 +641,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
       g2 += __shfl_xor_sync(0xffffffffu, g2, m);
       ga = fmax(ga, __shfl_xor_sync(0xffffffffu, ga, m));
     }
-    gsq_w = __shfl_sync(0xffffffffu, g2, 24);
-    gmax_w = __shfl_sync(0xffffffffu, ga, 24);
+    gsq_w += __shfl_sync(0xffffffffu, g2, 24);
+    gmax_w = fmax(gmax_w, __shfl_sync(0xffffffffu, ga, 24));
   }
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) cost_w += __shfl_xor_sync(0xffffffffu, cost_w, m);   // lanes 0,6,12,18 hold partial costs
@@ -620,44 +651,61 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, K_STEP_MIN_CTAS) k_step(con
     e[0] = cost_w; e[1] = gsq_w; e[2] = gmax_w; e[3] = xsq_w; e[4] = bs_sg; e[5] = bs_sHs; e[6] = bs_step; e[7] = bs_cand;
   }
   __syncthreads();
+  KTRACE(14);
   // CTA partials (fixed order inside the CTA), then one fp64 atomic per entry per CTA
   for (int i = threadIdx.x; i < F * kUStride; i += blockDim.x) {
-    const double acc = s_Ucta[i];
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) acc += s_U[w * ustride + i];
     if (acc != 0.0) atomicAdd(prm.Xacc + i, acc);
   }
   if (threadIdx.x < kEacc) {
     double acc = 0.0;
     if (threadIdx.x == 2) {
-      for (int w = 0; w < kWarpsPerCta; ++w) acc = fmax(acc, s_E[w * kEacc + 2]);
+      for (int w = 0; w < WARPS; ++w) acc = fmax(acc, s_E[w * kEacc + 2]);
       // non-negative doubles order like their bit patterns; one slot per rank (summed by the all-reduce)
       atomicMax(reinterpret_cast<unsigned long long*>(prm.Xacc + F * kUStride + kEacc + prm.rank),
                 (unsigned long long)__double_as_longlong(acc));
     } else {
-      for (int w = 0; w < kWarpsPerCta; ++w) acc += s_E[w * kEacc + threadIdx.x];
+      for (int w = 0; w < WARPS; ++w) acc += s_E[w * kEacc + threadIdx.x];
       if (acc != 0.0) atomicAdd(prm.Xacc + F * kUStride + threadIdx.x, acc);
     }
   }
+  KTRACE(15);
 }
+
+#ifdef K_STEP_TRACE
+extern "C" void pba_debug_kstep_trace(long long* out, int n) {
+  cudaMemcpyFromSymbol(out, g_kstep_trace, sizeof(long long) * n);
+}
+#endif
 
 // ---- host launcher -----------------------------------------------------------------------
 template <int R, bool U8, int NCH>
 static cudaError_t launch_one(const StepParams& prm, cudaStream_t stream) {
-  const size_t smem = k_step_smem_bytes<R>(prm.n_frames);
+  constexpr int WARPS = Geo<U8>::WARPS;
+  const size_t smem = k_step_smem_bytes<R, U8>(prm.n_frames);
   static bool configured[64] = {};
+  static int sm_count[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k_step<R, U8, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_step<R, U8, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
+    // two CTAs per SM need the large shared-memory carve-out
+    cudaFuncSetAttribute(k_step<R, U8, NCH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
-  const int grid = k_step_grid(prm.n_points);
+  // persistent: at most two CTAs per SM, every warp strides over the points
+  const int want = (prm.n_points + WARPS - 1) / WARPS, cap = 2 * sm_count[dev & 63];
+  const int grid = want < cap ? want : cap;
   if (grid == 0) return cudaSuccess;
-  k_step<R, U8, NCH><<<grid, kWarpsPerCta * 32, smem, stream>>>(prm);
+  k_step<R, U8, NCH><<<grid, WARPS * 32, smem, stream>>>(prm);
   return cudaGetLastError();
 }
 
-int k_step_grid(int n_points) { return (n_points + kWarpsPerCta - 1) / kWarpsPerCta; }
+int k_step_grid(int n_points) { return (n_points + K_STEP_WARPS_U8 - 1) / K_STEP_WARPS_U8; }
 
 template <int R>
 static cudaError_t launch_r(const StepParams& prm, cudaStream_t stream) {
