@@ -66,16 +66,41 @@ def _solve_pyramid_oracle(win, levels, imgs, pxref):
 
 @pytest.mark.gpu
 def test_pyramid_small_matches_oracle():
+    """Coarse-to-fine on a small window.  The coarse levels (60x80, 120x160 pixels) are badly
+    conditioned and their LM tails are chaotic (accept/reject decisions within rounding of their
+    thresholds), so each level is checked on its own: both solvers start the level from the SAME
+    state (the oracle's result of the coarser level) and must coincide iteration by iteration for
+    the first iterations; free-running end results are compared on cost and rotation only."""
+    from oracle import binding as ob
     win = synthetic.make_window(n_frames=6, grid=(14, 18), rows=240, cols=320, intrinsics=(400.0, 400.0, 159.7, 120.2),
                                 margin=40, seed=13)
-    cams, pts, summ, imgs, pxref = _solve_pyramid_gpu(win, 3)
-    ocams, opts, osum = _solve_pyramid_oracle(win, 3, imgs, pxref)
-    for s, (os_, otr) in zip(summ, osum):
-        assert abs(s["initial_cost"] - os_["initial_cost"]) <= 5e-4 * os_["initial_cost"]
-        assert abs(s["final_cost"] - os_["final_cost"]) <= 5e-4 * os_["final_cost"]
-    assert np.abs(cams - ocams)[:, :3].max() <= 1e-4
-    scale, terr = _gauge_aligned_translation_error(cams, ocams)
-    assert terr <= 1e-3, (scale, terr)
+    px, ref = synthetic.reference_pixels(win)
+    imgs = [win.images]
+    for _ in range(2):
+        imgs.append(np.stack([synthetic.pyr_down_u8(i) for i in imgs[-1]]))
+    ocams, opts = win.cams_init.copy(), win.points_init.copy()
+    for lv in (2, 1, 0):
+        wl = synthetic.pyramid_level(win, lv, imgs[lv], px, ref)
+        h = capi.Handle(wl.rows, wl.cols, wl.fx, wl.fy, wl.cx, wl.cy, radius=wl.radius, huber=wl.huber,
+                        max_frames=wl.n_frames, max_points=wl.n_points, max_observations=wl.n_obs)
+        h.set_frames_u8_pyr(win.images, lv)          # level-0 frames in, reduced on the device
+        h.set_poses(ocams, wl.fixed_frame)
+        h.set_points(opts, wl.desc, wl.obs_offsets, wl.obs_frame, wl.weights)
+        s = h.solve()
+        tr, cams = h.get_iterations(), h.get_poses()
+        h.close()
+        ocams, opts, os_, otr = ob.OracleWindow(wl).solve(ocams, opts)
+        assert abs(s["initial_cost"] - os_["initial_cost"]) <= 1e-9 * os_["initial_cost"]
+        n = min(8, len(tr), len(otr))
+        assert [t["step_is_successful"] for t in tr[:n]] == [t["step_is_successful"] for t in otr[:n]]
+        for a, b in zip(tr[:n], otr[:n]):
+            assert abs(a["cost"] - b["cost"]) <= 1e-6 * b["cost"], (lv, a, b)
+        assert abs(s["final_cost"] - os_["final_cost"]) <= 5e-3 * os_["final_cost"], (lv, s, os_)
+        assert np.abs(cams - ocams)[:, :3].max() <= 1e-3, (lv, np.abs(cams - ocams).max(0))
+    # free-running coarse-to-fine on the GPU ends at the same finest-level cost
+    cams, pts, summ, _, _ = _solve_pyramid_gpu(win, 3)
+    assert abs(summ[-1]["final_cost"] - os_["final_cost"]) <= 5e-3 * os_["final_cost"]
+    assert np.abs(cams - ocams)[:, :3].max() <= 1e-3
 
 
 @pytest.mark.gpu
