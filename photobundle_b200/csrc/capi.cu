@@ -113,9 +113,21 @@ struct pba_handle {
   ncclComm_t comm = nullptr;
   int n_points_total = 0, nnz_total = 0;
   std::vector<int> shard_begin;   // [n_ranks+1] first global point of each rank
+  // single-GPU LM loop as one CUDA graph: a WHILE conditional node whose body is two LM iterations
+  // (K_B, K_A, K_B, K_A); K_B clears the condition when the minimizer terminates
+  cudaGraph_t lm_graph = nullptr;
+  cudaGraphExec_t lm_exec = nullptr;
+  std::vector<unsigned char> lm_key;   // kernel parameters the instantiated graph was built from
 };
 
+static void drop_lm_graph(pba_handle* h) {
+  if (h->lm_exec) cudaGraphExecDestroy(h->lm_exec);
+  if (h->lm_graph) cudaGraphDestroy(h->lm_graph);
+  h->lm_exec = nullptr; h->lm_graph = nullptr; h->lm_key.clear();
+}
+
 static void free_all(pba_handle* h) {
+  drop_lm_graph(h);
   cudaFree(h->d_u8); cudaFree(h->d_f32); cudaFree(h->d_cams); cudaFree(h->d_pts); cudaFree(h->d_weights);
   cudaFree(h->d_desc); cudaFree(h->d_obs_off); cudaFree(h->d_obs_frame); cudaFree(h->d_V); cudaFree(h->d_gp);
   cudaFree(h->d_W); cudaFree(h->d_Xacc); cudaFree(h->d_Ucur);
@@ -541,6 +553,51 @@ static void format_message(const LmState& s, char* out, size_t cap) {
   }
 }
 
+// (Re)build the device-side LM loop when the kernel parameters changed since the last solve.
+static int ensure_lm_graph(pba_handle* h, const LmParams& lp0, int sgrid, int n_free) {
+  StepParams sp[2] = {make_step_params(h, h->d_state + 1), make_step_params(h, h->d_state)};
+  std::vector<unsigned char> key(sizeof(sp) + sizeof(LmParams) + 3 * sizeof(int));
+  {
+    LmParams k = lp0;
+    k.cond = 0; k.st_in = nullptr; k.st_out = nullptr; k.dbg = nullptr;
+    const int extra[3] = {sgrid, n_free, h->cfg.patch_radius};
+    memcpy(key.data(), sp, sizeof(sp));
+    memcpy(key.data() + sizeof(sp), &k, sizeof(k));
+    memcpy(key.data() + sizeof(sp) + sizeof(k), extra, sizeof(extra));
+  }
+  if (h->lm_exec && key == h->lm_key) return PBA_OK;
+  drop_lm_graph(h);
+  CUDA_TRY(cudaGraphCreate(&h->lm_graph, 0));
+  cudaGraphConditionalHandle cond;
+  CUDA_TRY(cudaGraphConditionalHandleCreate(&cond, h->lm_graph, 1, cudaGraphCondAssignDefault));
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = cond;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t node;
+  CUDA_TRY(cudaGraphAddNode(&node, h->lm_graph, nullptr, 0, &np));
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  CUDA_TRY(cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+  cudaError_t e = cudaSuccess;
+  for (int half = 0; half < 2 && e == cudaSuccess; ++half) {
+    LmParams lp = lp0;
+    lp.st_in = h->d_state + half; lp.st_out = h->d_state + (1 - half);
+    lp.dbg = nullptr; lp.cond = (unsigned long long)cond;
+    e = launch_schur_solve(lp, sgrid, n_free, h->stream);
+    if (e == cudaSuccess) e = launch_k_step(sp[half], h->cfg.patch_radius, h->stream);
+  }
+  cudaGraph_t captured = nullptr;
+  cudaError_t e2 = cudaStreamEndCapture(h->stream, &captured);
+  if (e != cudaSuccess || e2 != cudaSuccess) {
+    drop_lm_graph(h);
+    return fail(PBA_ERR_CUDA, "pba_solve: capturing the LM loop failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+  }
+  CUDA_TRY(cudaGraphInstantiate(&h->lm_exec, h->lm_graph, 0));
+  h->lm_key.swap(key);
+  return PBA_OK;
+}
+
 int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summary) {
   int rc = check_ready(h, "pba_solve");
   if (rc) return rc;
@@ -602,6 +659,19 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   const int group = 4;
   bool done = false;
   int k = 0;
+  // one GPU: the whole loop runs on the device (WHILE node); PBA_NO_GRAPH=1 keeps the stream loop
+  const bool use_graph = !multi && !timeline && getenv("PBA_NO_GRAPH") == nullptr;
+  if (use_graph) {
+    rc = ensure_lm_graph(h, lp, sgrid, s->n_free);
+    if (rc) return rc;
+    CUDA_TRY(cudaGraphLaunch(h->lm_exec, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(s, h->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!s->done) return fail(PBA_ERR_CUDA, "pba_solve: the LM graph returned before the minimizer terminated");
+    launches += 4 * ((s->num_evals + 1) / 2);   // the body (two iterations, four kernels) ran ceil(decisions / 2) times
+    done = true;
+  }
   while (!done) {
     for (int g = 0; g < group; ++g, ++k) {
       lp.st_in = h->d_state + (k & 1);
@@ -625,7 +695,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     done = s->done != 0 || k > opt.max_num_iterations + 2;
   }
-  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  if (!use_graph) CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   // the accepted x must end up in buffer 0 for pba_get_* and for the next solve
   if (s->cur != 0) {
     CUDA_TRY(cudaMemcpyAsync(h->d_cams, h->d_cams + (size_t)F * 6, sizeof(double) * F * 6, cudaMemcpyDeviceToDevice, h->stream));

@@ -580,9 +580,11 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
     reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_in)[i];
   __syncthreads();
   if (s_st.done) {
-    if (blockIdx.x == 0)
+    if (blockIdx.x == 0) {
       for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
         reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
+      if (lp.cond && tid == 0) cudaGraphSetConditional(lp.cond, 0u);   // leave the while node of the solve graph
+    }
     return;
   }
   if (warp == 0) {
@@ -615,9 +617,11 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
   __syncthreads();
   if (blockIdx.x == 0 && tid == 0 && s_push) lp.trace[s_st.n_trace - 1] = s_it;
   if (s_st.done) {
-    if (blockIdx.x == 0)
+    if (blockIdx.x == 0) {
       for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
         reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
+      if (lp.cond && tid == 0) cudaGraphSetConditional(lp.cond, 0u);   // leave the while node of the solve graph
+    }
     return;
   }
 

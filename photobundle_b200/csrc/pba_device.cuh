@@ -128,6 +128,7 @@ struct LmParams {
   double* Vinv;              // [n][6]
   double* S;                 // [D*D + D]
   unsigned long long* dbg;   // optional: globaltimer stamps of the last CTA {start, decided, schur done, solved, end}
+  unsigned long long cond;   // non-zero: cudaGraphConditionalHandle of the device-side LM loop, cleared when done
 };
 
 // launchers
