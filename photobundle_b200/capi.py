@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpba_b200.so")
+# PBA_B200_LIB: developer override to A/B-test scratch builds of the same library (scripts/)
+LIB_PATH = os.environ.get("PBA_B200_LIB") or os.path.join(_HERE, "libpba_b200.so")
 
 PBA_MAX_FRAMES = 16
 PBA_UNIQUE_ID_BYTES = 128

@@ -651,6 +651,9 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
     e[0] = cost_w; e[1] = gsq_w; e[2] = gmax_w; e[3] = xsq_w; e[4] = bs_sg; e[5] = bs_sHs; e[6] = bs_step; e[7] = bs_cand;
   }
   __syncthreads();
+#ifdef K_STEP_TRACE
+  const int p = blockIdx.x * WARPS + warp;   // single-wave geometry: one point per warp
+#endif
   KTRACE(14);
   // CTA partials (fixed order inside the CTA), then one fp64 atomic per entry per CTA
   for (int i = threadIdx.x; i < F * kUStride; i += blockDim.x) {
