@@ -79,36 +79,40 @@ __constant__ signed char c_pair3[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}
 //  [0..2] unit axis k (or the raw angle-axis when tiny)   [3..5] t   [6] cos  [7] sin
 //  [8] tiny flag   [9..17] R   [18..26] Rj   [27..35] M,  with
 //  d(Xc)/dw = -Rj [X]x M ;  M = (w wᵀ + (Rᵀ - I)[w]x)/θ² ; tiny angle: Rj = M = I, R = I+[w]x
-__device__ void pose_consts(const double* cam, double* pc) {
+// One thread per (frame, matrix element e = 3a+b): the nine threads of a frame evaluate the angle,
+// its sine/cosine and the axis redundantly (the latency of that chain is what costs, not its
+// throughput) and then one element each of R, Rj and M; thread e = 0 also writes the vector part.
+__device__ void pose_consts(const double* cam, double* pc, int e) {
   const double w0 = cam[0], w1 = cam[1], w2 = cam[2];
   const double theta2 = __dadd_rn(__dadd_rn(__dmul_rn(w0, w0), __dmul_rn(w1, w1)), __dmul_rn(w2, w2));
-  pc[3] = cam[3]; pc[4] = cam[4]; pc[5] = cam[5];
+  const int a = e / 3, b = e - 3 * a;
+  const double w[3] = {w0, w1, w2};
+  const double Wx[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
   if (theta2 > DBL_EPSILON) {
     const double theta = sqrt(theta2);
-    const double c = cos(theta), s = sin(theta);
-    const double ti = 1.0 / theta;
-    const double k0 = __dmul_rn(w0, ti), k1 = __dmul_rn(w1, ti), k2 = __dmul_rn(w2, ti);
-    pc[0] = k0; pc[1] = k1; pc[2] = k2; pc[6] = c; pc[7] = s; pc[8] = 0.0;
+    double s, c;
+    sincos(theta, &s, &c);
     const double k[3] = {w0 / theta, w1 / theta, w2 / theta};
     const double K[9] = {0, -k[2], k[1], k[2], 0, -k[0], -k[1], k[0], 0};
-    double R[9];
-    for (int a = 0; a < 3; ++a)
-      for (int b = 0; b < 3; ++b) R[a * 3 + b] = (a == b ? c : 0.0) + s * K[a * 3 + b] + (1.0 - c) * k[a] * k[b];
-    const double w[3] = {w0, w1, w2};
-    const double Wx[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
-    for (int a = 0; a < 3; ++a)
-      for (int b = 0; b < 3; ++b) {
-        double acc = w[a] * w[b];
-        for (int q = 0; q < 3; ++q) acc += (R[q * 3 + a] - (q == a ? 1.0 : 0.0)) * Wx[q * 3 + b];
-        pc[27 + a * 3 + b] = acc / theta2;
-      }
-    for (int a = 0; a < 9; ++a) { pc[9 + a] = R[a]; pc[18 + a] = R[a]; }
+    double Rcol[3];   // column a of R
+#pragma unroll
+    for (int q = 0; q < 3; ++q) Rcol[q] = (q == a ? c : 0.0) + s * K[q * 3 + a] + (1.0 - c) * k[q] * k[a];
+    const double Rab = (a == b ? c : 0.0) + s * K[a * 3 + b] + (1.0 - c) * k[a] * k[b];
+    double acc = w[a] * w[b];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) acc += (Rcol[q] - (q == a ? 1.0 : 0.0)) * Wx[q * 3 + b];
+    pc[9 + e] = Rab; pc[18 + e] = Rab; pc[27 + e] = acc / theta2;
+    if (e == 0) {
+      const double ti = 1.0 / theta;
+      pc[0] = __dmul_rn(w0, ti); pc[1] = __dmul_rn(w1, ti); pc[2] = __dmul_rn(w2, ti);
+      pc[3] = cam[3]; pc[4] = cam[4]; pc[5] = cam[5]; pc[6] = c; pc[7] = s; pc[8] = 0.0;
+    }
   } else {
-    pc[0] = w0; pc[1] = w1; pc[2] = w2; pc[6] = 1.0; pc[7] = 0.0; pc[8] = 1.0;
-    const double Wx[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
-    for (int a = 0; a < 9; ++a) {
-      const double id = (a == 0 || a == 4 || a == 8) ? 1.0 : 0.0;
-      pc[9 + a] = id + Wx[a]; pc[18 + a] = id; pc[27 + a] = id;
+    const double id = (a == b) ? 1.0 : 0.0;
+    pc[9 + e] = id + Wx[e]; pc[18 + e] = id; pc[27 + e] = id;
+    if (e == 0) {
+      pc[0] = w0; pc[1] = w1; pc[2] = w2; pc[3] = cam[3]; pc[4] = cam[4]; pc[5] = cam[5];
+      pc[6] = 1.0; pc[7] = 0.0; pc[8] = 1.0;
     }
   }
 }
@@ -224,6 +228,61 @@ __device__ __forceinline__ void sample_fast(const T* __restrict__ fp, int r0, in
               __fmul_rn(0.5f, __fsub_rn(u1, a11)), __fmul_rn(0.5f, __fsub_rn(u2, a12)));
 }
 
+// ---- exact small-integer -> float/double conversions on the FMA / FP64 pipes --------------------
+// The F2F/I2F conversion instructions run on the quarter-rate XU pipe, which is what bounds the
+// sampling phase; for the 8-bit taps of an Intensity frame the same values are produced exactly by
+// the classic magic-number constructions (no rounding anywhere, so parity is unaffected).
+__device__ __forceinline__ float u8_to_f32(int b) {            // b in [0, 255]
+  return __fsub_rn(__int_as_float(0x4B000000 | b), 8388608.0f);
+}
+__device__ __forceinline__ double u8_to_f64(int b) {           // b in [0, 255]
+  return __dsub_rn(__hiloint2double(0x43300000, b), 4503599627370496.0);
+}
+__device__ __forceinline__ float half_diff_f32(int d) {        // 0.5f * d, d in [-255, 255]
+  return __fmaf_rn(__int_as_float(0x4B400000 + d), 0.5f, -6291456.0f);
+}
+__device__ __forceinline__ double diff_f64(int d) {            // (double)d, d in [-255, 255]
+  return __dsub_rn(__hiloint2double(0x43300000, d ^ (int)0x80000000), 4503599627370496.0 + 2147483648.0);
+}
+// bilerp() with the two right-hand taps already in double and the 1-dx weight pre-scaled by the
+// caller (wd*da12 == (1-dx)*(double)a12 bit for bit: power-of-two scalings commute with rounding).
+__device__ __forceinline__ float bilerp_m(float dx, double dyd, double omdyd, double wd, float fa11, double da12,
+                                          float fa21, double da22) {
+  const double top = __dadd_rn((double)__fmul_rn(dx, fa11), __dmul_rn(wd, da12));
+  const double bot = __dadd_rn((double)__fmul_rn(dx, fa21), __dmul_rn(wd, da22));
+  return __double2float_rn(__dadd_rn(__dmul_rn(dyd, top), __dmul_rn(omdyd, bot)));
+}
+// sample_fast for uint8 footprints: identical results, 8-bit taps kept as integers.
+template <int R>
+__device__ __forceinline__ void sample_fast_u8(const uint8_t* __restrict__ fp, int r0, int cb, double u, double v,
+                                               double pdx, double pdy, float& I1, float& gx, float& gy) {
+  using FT = Foot<R>;
+  const float su = __double2float_rn(__dadd_rn(u, pdx));
+  const float sv = __double2float_rn(__dadd_rn(v, pdy));
+  const int ix = __float2int_rz(su), iy = __float2int_rz(sv);
+  const float dx = __fsub_rn((float)(ix + 1), su), dy = __fsub_rn((float)(iy + 1), sv);
+  const uint8_t* q = fp + (iy - r0) * FT::W + (ix - cb);
+  const int a11 = q[0], a12 = q[1], a21 = q[FT::W], a22 = q[FT::W + 1];
+  const int l1 = q[-1], r1 = q[2], l2 = q[FT::W - 1], r2 = q[FT::W + 2];
+  const int t1 = q[-FT::W], t2 = q[-FT::W + 1], u1 = q[2 * FT::W], u2 = q[2 * FT::W + 1];
+  const double omdx = __dsub_rn(1.0, (double)dx);
+  const double homdx = __dmul_rn(0.5, omdx);
+  const double dyd = (double)dy, omdyd = (double)__fsub_rn(1.0f, dy);
+  I1 = bilerp_m(dx, dyd, omdyd, omdx, u8_to_f32(a11), u8_to_f64(a12), u8_to_f32(a21), u8_to_f64(a22));
+  gx = bilerp_m(dx, dyd, omdyd, homdx, half_diff_f32(a12 - l1), diff_f64(r1 - a11), half_diff_f32(a22 - l2), diff_f64(r2 - a21));
+  gy = bilerp_m(dx, dyd, omdyd, homdx, half_diff_f32(a21 - t1), diff_f64(a22 - t2), half_diff_f32(u1 - a11), diff_f64(u2 - a12));
+}
+
+// ---- asynchronous global -> shared copies (LDGSTS) -----------------------------------------------
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Block expansion of one observation from its loss-scaled patch sums: pose block -> per-warp
 // smem accumulator, W -> HBM, V / g_p -> the caller's register accumulator.
 __device__ __forceinline__ void emit_blocks(double dG11, double dG12, double dG22, double db1, double db2,
@@ -250,6 +309,7 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
   constexpr int P = FT::P;
   constexpr int PR = (P + 31) / 32;             // pixel rounds per lane
   constexpr bool kQuad = (NCH == 1 && PR == 1); // ILP-4 fast path available
+  constexpr bool kAsyncStage = (NCH == 1);      // footprints staged with cp.async ahead of (G2)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int F = prm.n_frames;
   const int C = NCH ? NCH : prm.fr.n_channels;
@@ -292,7 +352,7 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
   FPT* s_fp = reinterpret_cast<FPT*>(s_frm + WARPS * kMaxFrames);
   FPT* s_fp_w = s_fp + warp * kFpStride;                                       // [8][ROWS][W]
 
-  if (threadIdx.x < F) pose_consts(cams + 6 * threadIdx.x, s_pose + threadIdx.x * kPoseConst);
+  if (threadIdx.x < 9 * F) pose_consts(cams + 6 * (threadIdx.x / 9), s_pose + (threadIdx.x / 9) * kPoseConst, threadIdx.x % 9);
   if (backsub)
     for (int i = threadIdx.x; i < F * 6; i += blockDim.x)
       s_sstep[i] = (st->free_index[i / 6] >= 0) ? st->scale_c[i] * st->step_c[i] : 0.0;
@@ -306,7 +366,7 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
     const int j = min(lane + 32 * r, P - 1);      // lanes beyond the patch re-do pixel P-1 with weight 0
     const int py = j / FT::SIDE, pxo = j - py * FT::SIDE;
     pdx[r] = (double)(pxo - R); pdy[r] = (double)(py - R);
-    wj[r] = (lane + 32 * r < P) ? prm.weights[j] : 0.0;
+    wj[r] = (lane + 32 * r < P) ? __ldg(prm.weights + j) : 0.0;
   }
   int st_off[FT::ROUNDS];
 #pragma unroll
@@ -330,6 +390,9 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
     __syncwarp();
     if (lane < nobs) s_frm_w[lane] = prm.obs_frame[o0 + lane];
     double X0 = pts_cur[3 * p], X1 = pts_cur[3 * p + 1], X2 = pts_cur[3 * p + 2];
+    double p0c[PR];       // reference descriptor of this point, channel 0 (first use: sampling)
+#pragma unroll
+    for (int r = 0; r < PR; ++r) p0c[r] = (double)__ldg(prm.desc + (size_t)p * CP + min(lane + 32 * r, P - 1));
     __syncwarp();
 
     // ---- (B) back-substitution (SchurEliminator::BackSubstitute + model cost change) -------
@@ -338,9 +401,23 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
       const int a = lane & 7, b = lane >> 3;
       const bool act = (a < 6 && b < 3);
       const double* Wc = prm.W + ((size_t)cur * prm.nnz + o0) * 18;
+      // all of the point's W loads are issued before the first use (one L2 round trip, not nobs)
+      const double* Vc = prm.V + ((size_t)cur * prm.n_points + p) * 6;
+      const double* gc = prm.gp + ((size_t)cur * prm.n_points + p) * 3;
+      double sp[3], Vi[6], Vv[6], gcv[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { sp[k] = __ldg(prm.scale_p + (size_t)p * 3 + k); gcv[k] = __ldg(gc + k); }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { Vi[k] = __ldg(prm.Vinv + (size_t)p * 6 + k); Vv[k] = __ldg(Vc + k); }
       double acc = 0.0;
-      if (act)
-        for (int i = 0; i < nobs; ++i) acc = fma(Wc[i * 18 + a * 3 + b], s_sstep[s_frm_w[i] * 6 + a], acc);
+      for (int i0 = 0; i0 < nobs; i0 += 8) {
+        double wv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wv[k] = (act && i0 + k < nobs) ? __ldg(Wc + (i0 + k) * 18 + a * 3 + b) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (act && i0 + k < nobs) acc = fma(wv[k], s_sstep[s_frm_w[i0 + k] * 6 + a], acc);
+      }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       acc += __shfl_xor_sync(0xffffffffu, acc, 4);
@@ -348,13 +425,7 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
       wts[0] = __shfl_sync(0xffffffffu, acc, 0);
       wts[1] = __shfl_sync(0xffffffffu, acc, 8);
       wts[2] = __shfl_sync(0xffffffffu, acc, 16);
-      const double* Vc = prm.V + ((size_t)cur * prm.n_points + p) * 6;
-      const double* gc = prm.gp + ((size_t)cur * prm.n_points + p) * 3;
-      const double sp[3] = {prm.scale_p[(size_t)p * 3], prm.scale_p[(size_t)p * 3 + 1], prm.scale_p[(size_t)p * 3 + 2]};
-      double Vi[6], Vv[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) { Vi[k] = prm.Vinv[(size_t)p * 6 + k]; Vv[k] = Vc[k]; }
-      const double gs[3] = {sp[0] * gc[0], sp[1] * gc[1], sp[2] * gc[2]};
+      const double gs[3] = {sp[0] * gcv[0], sp[1] * gcv[1], sp[2] * gcv[2]};
       double t[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) { wts[k] *= sp[k]; t[k] = gs[k] + wts[k]; }   // gs - Ws^T y_c, y_c = -step_c
@@ -378,18 +449,15 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
     KTRACE(2);
 
     double acc_pt = 0.0;  // lanes 18..23: V entries, 24..26: g_p entries (summed over frames)
-    double p0c[PR];       // reference descriptor of this point, channel 0
-#pragma unroll
-    for (int r = 0; r < PR; ++r) p0c[r] = (double)prm.desc[(size_t)p * CP + min(lane + 32 * r, P - 1)];
-
     for (int ob = 0; ob < nobs; ob += kObsBatch) {
       const int nb = min(kObsBatch, nobs - ob);
-      // ---- (G) geometry: lane i <-> observation ob+i --------------------------------
+      // ---- (G1) warp + project: lane i <-> observation ob+i ---------------------------
       int g_fast_l = 0;
+      double Xc0 = 0.0, Xc1 = 0.0, Xc2 = 1.0;
+      const double* pc = s_pose;
       if (lane < nb) {
         const int g_f = s_frm_w[ob + lane];
-        const double* pc = s_pose + g_f * kPoseConst;
-        double Xc0, Xc1, Xc2;
+        pc = s_pose + g_f * kPoseConst;
         if (pc[8] == 0.0) {  // ceres::AngleAxisRotatePoint, same operation order (no FMA)
           const double k0 = pc[0], k1 = pc[1], k2 = pc[2], c = pc[6], s = pc[7];
           const double wx0 = __dsub_rn(__dmul_rn(k1, X2), __dmul_rn(k2, X1));
@@ -412,6 +480,45 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
         const double v = __dadd_rn(__ddiv_rn(__dmul_rn(Xc1, prm.fy), Xc2), prm.cy);
         double* g = s_geo_w + lane * 20;
         g[0] = u; g[1] = v;
+        // footprint origin and fast-path test (all taps and gradient taps interior)
+        int4 gi = make_int4(g_f, 0, 0, 0);   // {frame, r0, cb (aligned first column), fast}
+        if (fabs(u) < 1.0e8 && fabs(v) < 1.0e8) {
+          const int c0 = (int)floor(u) - R - 1, r0 = (int)floor(v) - R - 1;
+          const int fast = (c0 >= 0 && c0 + FT::ROWS - 1 <= prm.fr.cols - 1 && r0 >= 0 &&
+                            r0 + FT::ROWS - 1 <= prm.fr.rows - 1) ? 1 : 0;
+          gi.y = r0; gi.z = c0 & ~3; gi.w = fast;
+        }
+        s_gi_w[lane] = gi;
+        g_fast_l = gi.w;
+      }
+      const unsigned fastmask = __ballot_sync(0xffffffffu, g_fast_l != 0);
+      __syncwarp();
+      // ---- (L) 1-channel frames: every footprint of the batch is requested NOW with asynchronous
+      // copies (global -> shared, no registers held), so the L2 round trips overlap with (G2) ------
+      if (kAsyncStage) {
+#pragma unroll
+        for (int sl = 0; sl < kStageSlots; ++sl) {
+          if (sl < nb) {
+            const int4 gi = s_gi_w[sl];
+            if (gi.w) {
+              const unsigned base = (unsigned)(gi.x * (int)prm.fr.plane + gi.y * prm.fr.pitch + gi.z);
+#pragma unroll
+              for (int rd = 0; rd < FT::ROUNDS; ++rd) {
+                if (st_off[rd] >= 0) {
+                  if (U8) cp_async_4(reinterpret_cast<uint32_t*>(s_fp_w + sl * FT::FLOATS) + lane + 32 * rd,
+                                     prm.fr.u8 + (base + (unsigned)st_off[rd]));
+                  else cp_async_16(reinterpret_cast<float4*>(s_fp_w + sl * FT::FLOATS) + lane + 32 * rd,
+                                   prm.fr.f32 + (base + (unsigned)st_off[rd]));
+                }
+              }
+            }
+          }
+        }
+        cp_async_commit();
+      }
+      // ---- (G2) the 2x9 matrix A = d(u,v)/d[w t X] of each observation -------------------------
+      if (lane < nb) {
+        double* g = s_geo_w + lane * 20;
         const double iz = 1.0 / Xc2;
         const double J00 = prm.fx * iz, J02 = -prm.fx * Xc0 * iz * iz;
         const double J11 = prm.fy * iz, J12 = -prm.fy * Xc1 * iz * iz;
@@ -435,18 +542,8 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
         }
         g[5] = J00; g[6] = 0.0; g[7] = J02;                  // du/dt
         g[14] = 0.0; g[15] = J11; g[16] = J12;               // dv/dt
-        // footprint origin and fast-path test (all taps and gradient taps interior)
-        int4 gi = make_int4(g_f, 0, 0, 0);   // {frame, r0, cb (aligned first column), fast}
-        if (fabs(u) < 1.0e8 && fabs(v) < 1.0e8) {
-          const int c0 = (int)floor(u) - R - 1, r0 = (int)floor(v) - R - 1;
-          const int fast = (c0 >= 0 && c0 + FT::ROWS - 1 <= prm.fr.cols - 1 && r0 >= 0 &&
-                            r0 + FT::ROWS - 1 <= prm.fr.rows - 1) ? 1 : 0;
-          gi.y = r0; gi.z = c0 & ~3; gi.w = fast;
-        }
-        s_gi_w[lane] = gi;
-        g_fast_l = gi.w;
       }
-      const unsigned fastmask = __ballot_sync(0xffffffffu, g_fast_l != 0);
+      if (kAsyncStage) cp_async_wait_all();
       __syncwarp();
       KTRACE(3);
 
@@ -454,45 +551,36 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
       for (int sb = 0; sb < nb; sb += obs_per_stage) {
         const int ns_obs = min(obs_per_stage, nb - sb);
         const int nslots = NCH == 1 ? ns_obs : ns_obs * C;
-        // ---- (L) stage footprints: all loads first, then the stores ----------------------
-        {
-          uint32_t t8[kStageSlots][FT::ROUNDS];
-          float4 t32[U8 ? 1 : kStageSlots][U8 ? 1 : FT::ROUNDS];
+        // ---- (L) multi-channel frames: stage (observation, channel) footprints through registers ----
+        if (!kAsyncStage) {
+          float4 t32[kStageSlots][FT::ROUNDS];
 #pragma unroll
           for (int sl = 0; sl < kStageSlots; ++sl) {
             if (sl < nslots) {
-              const int i = NCH == 1 ? sb + sl : sb + sl / C;
-              const int k = NCH == 1 ? 0 : sl - (sl / C) * C;
+              const int i = sb + sl / C;
+              const int k = sl - (sl / C) * C;
               const int4 gi = s_gi_w[i];
               if (gi.w) {
-                const unsigned base = (unsigned)((NCH == 1 ? gi.x : gi.x * C + k) * (int)prm.fr.plane + gi.y * prm.fr.pitch + gi.z);
+                const unsigned base = (unsigned)((gi.x * C + k) * (int)prm.fr.plane + gi.y * prm.fr.pitch + gi.z);
 #pragma unroll
-                for (int rd = 0; rd < FT::ROUNDS; ++rd) {
-                  if (st_off[rd] >= 0) {
-                    if (U8) t8[sl][rd] = __ldg(reinterpret_cast<const uint32_t*>(prm.fr.u8 + (base + (unsigned)st_off[rd])));
-                    else t32[U8 ? 0 : sl][U8 ? 0 : rd] = __ldg(reinterpret_cast<const float4*>(prm.fr.f32 + (base + (unsigned)st_off[rd])));
-                  }
-                }
+                for (int rd = 0; rd < FT::ROUNDS; ++rd)
+                  if (st_off[rd] >= 0) t32[sl][rd] = __ldg(reinterpret_cast<const float4*>(prm.fr.f32 + (base + (unsigned)st_off[rd])));
               }
             }
           }
 #pragma unroll
           for (int sl = 0; sl < kStageSlots; ++sl) {
             if (sl < nslots) {
-              const int i = NCH == 1 ? sb + sl : sb + sl / C;
+              const int i = sb + sl / C;
               if (s_gi_w[i].w) {
 #pragma unroll
-                for (int rd = 0; rd < FT::ROUNDS; ++rd) {
-                  if (st_off[rd] >= 0) {
-                    if (U8) reinterpret_cast<uint32_t*>(s_fp_w + sl * FT::FLOATS)[lane + 32 * rd] = t8[sl][rd];
-                    else reinterpret_cast<float4*>(s_fp_w + sl * FT::FLOATS)[lane + 32 * rd] = t32[U8 ? 0 : sl][U8 ? 0 : rd];
-                  }
-                }
+                for (int rd = 0; rd < FT::ROUNDS; ++rd)
+                  if (st_off[rd] >= 0) reinterpret_cast<float4*>(s_fp_w + sl * FT::FLOATS)[lane + 32 * rd] = t32[sl][rd];
               }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
 
         KTRACE(4);
         // ---- (S)+(R): four observations at a time when every one of them is interior -------
@@ -507,7 +595,8 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
               const int4 gi = s_gi_w[ii];
               const double* g = s_geo_w + ii * 20;
               float I1, gx, gy;
-              sample_fast<R, FPT>(s_fp_w + (ii - sb) * FT::FLOATS, gi.y, gi.z, g[0], g[1], pdx[0], pdy[0], I1, gx, gy);
+              if constexpr (U8) sample_fast_u8<R>(s_fp_w + (ii - sb) * FT::FLOATS, gi.y, gi.z, g[0], g[1], pdx[0], pdy[0], I1, gx, gy);
+              else sample_fast<R, FPT>(s_fp_w + (ii - sb) * FT::FLOATS, gi.y, gi.z, g[0], g[1], pdx[0], pdy[0], I1, gx, gy);
               const double rr = __dmul_rn(wj[0], __dsub_rn(p0c[0], (double)I1));   // photobundle.cc:720
               if (want_res && lane < P && i < nq) prm.residuals[(size_t)(o0 + ob + ii) * CP + lane] = rr;
               const double hx = wj[0] * (double)gx, hy = wj[0] * (double)gy;
