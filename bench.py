@@ -340,8 +340,9 @@ def main():
             "timing": "sum of per-step CUDA-event intervals recorded by the library on its own stream; "
                       "L2 flushed (256 MiB write) between steps outside the intervals",
             "parallelism": "1 window on 1 GPU" if world == 1 else
-                           f"1 window, points sharded over {world} GPUs (frames/poses replicated); NCCL all-reduce of the pose "
-                           f"blocks+cost and of the reduced camera system per LM iteration ({last['num_collectives']} collectives/solve)",
+                           f"1 window, points sharded over {world} GPUs (frames/poses replicated); per LM iteration the pose "
+                           f"blocks+cost and the reduced camera system are exchanged by {h.exchange_kind()} "
+                           f"({last['num_collectives']} NCCL collectives/solve)",
         },
         "k1": {"us_per_launch_cold_l2": 1e3 * k1_ms, "us_per_launch_warm_l2": 1e3 * k1_ms_warm,
                "observations_per_launch": n_obs_local,

@@ -195,7 +195,7 @@ int pba_get_points(pba_handle* h, double* xyz);
 int pba_get_iterations(pba_handle* h, pba_iteration_summary* out, int32_t capacity, int32_t* n);
 
 /* Multi-GPU: one process per GPU; points are sharded, frames/poses replicated, one
- * all-reduce of the reduced camera system per LM iteration.  Rank 0 calls
+ * exchange of the pose blocks and of the reduced camera system per LM iteration.  Rank 0 calls
  * pba_comm_unique_id() and distributes the 128 bytes by any means (torch.distributed,
  * MPI, a file); then every rank calls pba_comm_init(). */
 int pba_comm_unique_id(void* id128);
@@ -203,6 +203,15 @@ int pba_comm_unique_id(void* id128);
 int pba_shard_range(int32_t n_points, const int32_t* obs_offsets, int32_t rank, int32_t n_ranks,
                     int32_t* first, int32_t* last);
 int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_ranks);
+/* How the per-iteration sums travel between the GPUs of a window: PBA_EXCHANGE_NONE (one GPU),
+ * PBA_EXCHANGE_PEER (default: every rank stores its pose blocks / reduced-system contribution
+ * straight into all peers' memory over NVLink from inside the kernels and the consumers sum the
+ * slots in rank order - no collective call, no extra launch), or PBA_EXCHANGE_NCCL (all-reduce
+ * fallback when peer mappings are unavailable or PBA_MGPU_EXCHANGE=nccl). */
+#define PBA_EXCHANGE_NONE 0
+#define PBA_EXCHANGE_PEER 1
+#define PBA_EXCHANGE_NCCL 2
+int pba_comm_exchange_kind(const pba_handle* h);
 
 #ifdef __cplusplus
 }

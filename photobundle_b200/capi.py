@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "pba_last_error", "pba_version", "pba_default_solver_options", "pba_create", "pba_destroy",
     "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_frames_u8_pyr", "pba_pyrdown_u8", "pba_set_poses", "pba_set_points",
     "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_get_poses", "pba_get_points", "pba_get_iterations",
-    "pba_comm_unique_id", "pba_comm_init", "pba_shard_range",
+    "pba_comm_unique_id", "pba_comm_init", "pba_shard_range", "pba_comm_exchange_kind",
 ]
 
 
@@ -242,6 +242,9 @@ class Handle:
         buf = C.create_string_buffer(unique_id, PBA_UNIQUE_ID_BYTES)
         _check(lib().pba_comm_init(self._h, buf, int(rank), int(n_ranks)), "pba_comm_init")
         self.rank, self.n_ranks = rank, n_ranks
+
+    def exchange_kind(self) -> str:
+        return {0: "none", 1: "peer-memory", 2: "nccl"}[int(lib().pba_comm_exchange_kind(self._h))]
 
     def get_poses(self) -> np.ndarray:
         cams = np.zeros((self.n_frames, 6))

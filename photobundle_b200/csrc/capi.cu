@@ -28,6 +28,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -46,6 +47,7 @@ static const char* load_nccl() {
   PBA_NCCL_SYM(CommDestroy, "ncclCommDestroy")
   PBA_NCCL_SYM(AllReduce, "ncclAllReduce")
   PBA_NCCL_SYM(Broadcast, "ncclBroadcast")
+  PBA_NCCL_SYM(AllGather, "ncclAllGather")
   PBA_NCCL_SYM(GroupStart, "ncclGroupStart")
   PBA_NCCL_SYM(GroupEnd, "ncclGroupEnd")
   PBA_NCCL_SYM(GetErrorString, "ncclGetErrorString")
@@ -113,6 +115,13 @@ struct pba_handle {
   ncclComm_t comm = nullptr;
   int n_points_total = 0, nnz_total = 0;
   std::vector<int> shard_begin;   // [n_ranks+1] first global point of each rank
+  // per-iteration exchange over NVLink peer memory (CUDA IPC), see pba_device.cuh `Xchg`; when it cannot
+  // be set up (no peer access, PBA_MGPU_EXCHANGE=nccl) the NCCL all-reduce path is used instead
+  bool use_xchg = false;
+  void* d_xchg = nullptr;                       // this rank's exchange buffer
+  void* peer_xchg[kMaxRanks] = {};              // every rank's buffer as mapped here ([rank] = d_xchg)
+  Xchg xc = {};
+  unsigned long long epoch_next = 1;
   // single-GPU LM loop as one CUDA graph: a WHILE conditional node whose body is two LM iterations
   // (K_B, K_A, K_B, K_A); K_B clears the condition when the minimizer terminates
   cudaGraph_t lm_graph = nullptr;
@@ -131,6 +140,9 @@ static void free_all(pba_handle* h) {
   cudaFree(h->d_u8); cudaFree(h->d_f32); cudaFree(h->d_cams); cudaFree(h->d_pts); cudaFree(h->d_weights);
   cudaFree(h->d_desc); cudaFree(h->d_obs_off); cudaFree(h->d_obs_frame); cudaFree(h->d_V); cudaFree(h->d_gp);
   cudaFree(h->d_W); cudaFree(h->d_Xacc); cudaFree(h->d_Ucur);
+  for (int q = 0; q < kMaxRanks; ++q)
+    if (h->peer_xchg[q] && h->peer_xchg[q] != h->d_xchg) cudaIpcCloseMemHandle(h->peer_xchg[q]);
+  cudaFree(h->d_xchg);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->d_scale_p); cudaFree(h->d_Vinv); cudaFree(h->d_S); cudaFree(h->d_ticket); cudaFree(h->d_dbg);
   cudaFree(h->d_save_cams); cudaFree(h->d_save_pts);
@@ -139,6 +151,79 @@ static void free_all(pba_handle* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+
+// Peer-memory exchange buffers: allocate, export through CUDA IPC, all-gather the handles with NCCL, map
+// every peer.  All ranks agree (all-reduce of a success flag) on whether the exchange is usable; when
+// it is not, the NCCL all-reduce path stays in place.
+static int setup_xchg(pba_handle* h) {
+  h->use_xchg = false;
+  const int n = h->n_ranks;
+  const char* mode = getenv("PBA_MGPU_EXCHANGE");
+  int want = !(mode && strcmp(mode, "nccl") == 0);
+  const size_t F = h->cfg.max_frames, D = 6 * F;
+  const size_t xa_n = F * kUStride + kEacc + kMaxRanks, s_n = D * D + D;
+  const size_t n_cells = 2 * n * (xa_n + s_n);   // 16-byte LL cells
+  const size_t bytes = sizeof(ulonglong2) * n_cells + sizeof(unsigned long long) * n + 64;
+  if (h->d_xchg) { cudaFree(h->d_xchg); h->d_xchg = nullptr; }
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  int ok = want;
+  if (ok && cudaMalloc(&h->d_xchg, bytes) != cudaSuccess) { ok = 0; h->d_xchg = nullptr; }
+  if (ok && cudaMemsetAsync(h->d_xchg, 0, bytes, h->stream) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, h->d_xchg) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  // gather {ok, handle} of every rank
+  struct Rec { int ok; int pad[3]; cudaIpcMemHandle_t hnd; };
+  static_assert(sizeof(Rec) == 16 + sizeof(cudaIpcMemHandle_t), "Rec layout");
+  Rec* d_rec = nullptr;
+  CUDA_TRY(cudaMalloc(&d_rec, sizeof(Rec) * n));
+  Rec me; memset(&me, 0, sizeof(me)); me.ok = ok; me.hnd = mine;
+  CUDA_TRY(cudaMemcpyAsync(d_rec + h->rank, &me, sizeof(Rec), cudaMemcpyHostToDevice, h->stream));
+  NCCL_TRY(g_nccl.AllGather(d_rec + h->rank, d_rec, sizeof(Rec), ncclChar, h->comm, h->stream));
+  std::vector<Rec> all(n);
+  CUDA_TRY(cudaMemcpyAsync(all.data(), d_rec, sizeof(Rec) * n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  for (int q = 0; q < n; ++q) ok = ok && all[q].ok;
+  for (int q = 0; q < kMaxRanks; ++q) h->peer_xchg[q] = nullptr;
+  if (ok) {
+    for (int q = 0; q < n && ok; ++q) {
+      if (q == h->rank) { h->peer_xchg[q] = h->d_xchg; continue; }
+      if (cudaIpcOpenMemHandle(&h->peer_xchg[q], all[q].hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        h->peer_xchg[q] = nullptr; ok = 0; cudaGetLastError();
+      }
+    }
+  }
+  // second agreement round: did every rank map every peer?
+  me.ok = ok;
+  CUDA_TRY(cudaMemcpyAsync(d_rec + h->rank, &me, sizeof(Rec), cudaMemcpyHostToDevice, h->stream));
+  NCCL_TRY(g_nccl.AllGather(d_rec + h->rank, d_rec, sizeof(Rec), ncclChar, h->comm, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(all.data(), d_rec, sizeof(Rec) * n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  cudaFree(d_rec);
+  for (int q = 0; q < n; ++q) ok = ok && all[q].ok;
+  if (!ok) {
+    for (int q = 0; q < n; ++q)
+      if (h->peer_xchg[q] && h->peer_xchg[q] != h->d_xchg) { cudaIpcCloseMemHandle(h->peer_xchg[q]); h->peer_xchg[q] = nullptr; }
+    if (want) fprintf(stderr, "[pba_b200] rank %d: peer-memory exchange unavailable, using NCCL all-reduce\n", h->rank);
+    return PBA_OK;
+  }
+  Xchg& x = h->xc;
+  memset(&x, 0, sizeof(x));
+  x.n_ranks = n; x.rank = h->rank; x.xa_n = (int)xa_n; x.s_n = (int)s_n;
+  for (int q = 0; q < n; ++q) {
+    ulonglong2* base = static_cast<ulonglong2*>(h->peer_xchg[q]);
+    x.xa[q] = base;
+    x.s[q] = base + 2 * n * xa_n;
+    x.fr[q] = reinterpret_cast<unsigned long long*>(base + n_cells);
+  }
+  unsigned long long* fl_own = reinterpret_cast<unsigned long long*>(static_cast<ulonglong2*>(h->d_xchg) + n_cells);
+  x.ticket_a = reinterpret_cast<unsigned int*>(fl_own + n);
+  x.error = reinterpret_cast<int*>(fl_own + n) + 2;
+  h->use_xchg = true;
+  h->epoch_next = 1;
+  return PBA_OK;
 }
 
 extern "C" {
@@ -450,6 +535,7 @@ static StepParams make_step_params(pba_handle* h, const LmState* st) {
   p.obs_frame = h->d_obs_frame; p.weights = h->d_weights;
   p.V = h->d_V; p.gp = h->d_gp; p.W = h->d_W; p.Xacc = h->d_Xacc; p.rank = h->rank;
   p.scale_p = h->d_scale_p; p.Vinv = h->d_Vinv;
+  if (h->use_xchg) p.xc = h->xc;
   return p;
 }
 
@@ -460,7 +546,8 @@ static LmParams make_lm_params(pba_handle* h) {
   lp.n_frames = h->n_frames; lp.n_points = h->n_points; lp.nnz = h->nnz;
   lp.obs_off = h->d_obs_off; lp.obs_frame = h->d_obs_frame;
   lp.cams = h->d_cams; lp.V = h->d_V; lp.gp = h->d_gp; lp.W = h->d_W;
-  lp.Xacc = h->d_Xacc; lp.Ucur = h->d_Ucur; lp.split = h->n_ranks > 1 ? 1 : 0;
+  lp.Xacc = h->d_Xacc; lp.Ucur = h->d_Ucur; lp.split = (h->n_ranks > 1 && !h->use_xchg) ? 1 : 0;
+  if (h->use_xchg) lp.xc = h->xc;
   lp.scale_p = h->d_scale_p; lp.Vinv = h->d_Vinv; lp.S = h->d_S;
   return lp;
 }
@@ -549,6 +636,7 @@ static void format_message(const LmState& s, char* out, size_t cap) {
     case kMsgMaxIter: snprintf(out, cap, "Maximum number of iterations reached. Number of iterations: %d.", (int)s.msg_a); break;
     case kMsgMinRadius: snprintf(out, cap, "Minimum trust region radius reached. Trust region radius: %e <= %e", s.msg_a, s.msg_b); break;
     case kMsgInvalidSteps: snprintf(out, cap, "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps: %d", (int)s.msg_a); break;
+    case kMsgXchgTimeout: snprintf(out, cap, "Multi-GPU exchange timed out waiting for a peer (epoch %.0f, %s).", s.msg_a, s.msg_b ? "reduced system" : "pose blocks"); break;
     default: snprintf(out, cap, "no termination message"); break;
   }
 }
@@ -629,6 +717,10 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   for (int f = 0; f < F; ++f)
     if (h->frame_used[f] && f != h->fixed_frame) s->free_index[f] = s->n_free++;
   s->cur = 0; s->eval_buf = 0; s->decrease_factor = 2.0; s->radius = opt.initial_trust_region_radius;
+  if (h->use_xchg) {   // every rank advances by the same amount per solve: flags never need a reset
+    s->xepoch = h->epoch_next;
+    h->epoch_next += (unsigned long long)opt.max_num_iterations + 16ull;
+  }
   // x lives in buffer 0 of cams/points; refresh buffer 1 so fixed cameras carry over
   CUDA_TRY(cudaMemcpyAsync(h->d_cams + (size_t)F * 6, h->d_cams, sizeof(double) * F * 6, cudaMemcpyDeviceToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->d_state, s, sizeof(LmState), cudaMemcpyHostToDevice, h->stream));
@@ -643,11 +735,15 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   if (timeline && !h->d_dbg) CUDA_TRY(cudaMalloc(&h->d_dbg, sizeof(unsigned long long) * 16 * 1024));
   const int sgrid = schur_grid(h->n_points, h->sm_count);
   int launches = 0;
+  if (h->use_xchg) {   // align the ranks before the clock starts (device-side barrier over peer memory)
+    CUDA_TRY(launch_rendezvous(h->xc, s->xepoch, h->stream));
+    launches += 1;
+  }
   CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
   // iteration 0: evaluate x.  Then per LM iteration: K_B (decide + Schur + solve), K_A
   // (back-substitute + evaluate the candidate).  The state ping-pongs between two structs;
   // kernels turn into no-ops once `done` is set, so iterations are enqueued in groups.
-  const bool multi = h->n_ranks > 1;
+  const bool multi = h->n_ranks > 1 && !h->use_xchg;   // NCCL all-reduce path; the peer-memory exchange needs no host-side calls
   const size_t xacc_n = (size_t)F * kUStride + kEacc + kMaxRanks;
   int collectives = 0;
   CUDA_TRY(launch_k_step(make_step_params(h, h->d_state), h->cfg.patch_radius, h->stream));
@@ -710,6 +806,11 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
               (t[16 * i + 5] - t[16 * i + 2]) * 1e-3, (t[16 * i + 6] - t[16 * i + 5]) * 1e-3, (t[16 * i + 7] - t[16 * i + 6]) * 1e-3,
               (t[16 * i + 3] - t[16 * i + 7]) * 1e-3,
               (t[16 * i + 4] - t[16 * i + 3]) * 1e-3, i + 1 < k ? (t[16 * (i + 1)] - t[16 * i + 4]) * 1e-3 : 0.0);
+    if (h->use_xchg)
+      for (int i = 0; i < std::min(k, 6); ++i)
+        fprintf(stderr, "[pba timeline] rank %d K_B %2d S exchange: push %5.2f us  fence+flags %5.2f us  wait %5.2f us  sum %5.2f us\n", h->rank, i,
+                (t[16 * i + 8] - t[16 * i + 2]) * 1e-3, (t[16 * i + 9] - t[16 * i + 8]) * 1e-3, (t[16 * i + 10] - t[16 * i + 9]) * 1e-3,
+                (t[16 * i + 11] - t[16 * i + 10]) * 1e-3);
   }
   h->trace.resize(s->n_trace);
   if (s->n_trace > 0)
@@ -726,6 +827,14 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   summary->num_evaluations = s->num_evals;
   summary->kernel_launches = launches; summary->num_collectives = collectives;
   summary->device_time_in_seconds = ms * 1e-3;
+  if (h->use_xchg) {
+    int xerr = 0;
+    CUDA_TRY(cudaMemcpy(&xerr, h->xc.error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (xerr) {
+      CUDA_TRY(cudaMemset(h->xc.error, 0, sizeof(int)));
+      return fail(PBA_ERR_NCCL, "pba_solve: the peer-memory exchange timed out (a rank did not reach the same LM iteration)");
+    }
+  }
   if (!s->done) { s->msg_code = kMsgMaxIter; s->msg_a = opt.max_num_iterations; summary->termination_type = 1; }
   format_message(*s, summary->message, sizeof(summary->message));
   summary->total_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
@@ -811,6 +920,11 @@ int pba_comm_unique_id(void* id128) {
   return PBA_OK;
 }
 
+int pba_comm_exchange_kind(const pba_handle* h) {
+  if (!h || h->n_ranks <= 1) return PBA_EXCHANGE_NONE;
+  return h->use_xchg ? PBA_EXCHANGE_PEER : PBA_EXCHANGE_NCCL;
+}
+
 int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_ranks) {
   if (!h || !id128) return fail(PBA_ERR_ARGUMENT, "pba_comm_init: null argument");
   if (n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks)
@@ -825,6 +939,8 @@ int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_rank
     memcpy(&id, id128, sizeof(id));
     NCCL_TRY(g_nccl.CommInitRank(&h->comm, n_ranks, id, rank));
     h->rank = rank; h->n_ranks = n_ranks;
+    int rc = setup_xchg(h);
+    if (rc) return rc;
   }
   return PBA_OK;
 }

@@ -545,10 +545,10 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
 
 // Tail of an LM iteration (one CTA): adopt the candidate's pose blocks if the step was taken, solve
 // the reduced camera system, re-zero the accumulators K_A fills next, publish the new state.
-__device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, int F) {
+__device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, int F, const double* xs) {
   const int tid = threadIdx.x;
   if (st.took_step)
-    for (int i = tid; i < F * kUStride; i += blockDim.x) lp.Ucur[i] = __ldcg(lp.Xacc + i);
+    for (int i = tid; i < F * kUStride; i += blockDim.x) lp.Ucur[i] = xs ? xs[i] : __ldcg(lp.Xacc + i);
   __syncthreads();
   solve_reduced(lp, st, sm, F);
   if (lp.dbg && tid == 0) lp.dbg[3] = gtime();
@@ -569,6 +569,8 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
   __shared__ int s_push, s_last;
   __shared__ unsigned s_mask[kSchurChunk];
   __shared__ unsigned char s_pair[kMaxFrames * (kMaxFrames + 1) / 2][2];   // upper block pairs (g <= f)
+  __shared__ double s_xs[kMaxFrames * kUStride + kEacc + kMaxRanks];        // the evaluation's pose blocks + scalars (summed over ranks)
+  __shared__ int s_xok;
   extern __shared__ double sm[];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -587,20 +589,52 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
     }
     return;
   }
+  // the evaluation's accumulators: local (one GPU / NCCL path: already all-reduced) or the sum of every
+  // rank's slot in rank order (peer-memory exchange: wait for the flags first)
+  const int xn = F * kUStride + kEacc + kMaxRanks;
+  const bool xmode = lp.xc.n_ranks > 1;
+  if (xmode) {
+    if (tid == 0) s_xok = 1;
+    __syncthreads();
+    const ulonglong2* xb = lp.xc.xa[lp.xc.rank] + (size_t)(s_st.xepoch & 1ull) * lp.xc.n_ranks * lp.xc.xa_n;
+    for (int i = tid; i < xn; i += blockDim.x) {
+      double acc = 0.0;
+      for (int q = 0; q < lp.xc.n_ranks; ++q) {
+        double v;
+        if (!ll_load(xb + (size_t)q * lp.xc.xa_n + i, s_st.xepoch, v)) s_xok = 0;
+        acc += v;
+      }
+      s_xs[i] = acc;
+    }
+    __syncthreads();
+    if (!s_xok) {   // a peer never arrived: fail the solve instead of hanging the GPU
+      if (blockIdx.x == 0) {
+        if (tid == 0) { finish(s_st, 2, kMsgXchgTimeout, (double)s_st.xepoch, 0.0); *lp.xc.error = 1; }
+        __syncthreads();
+        for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+          reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
+        if (lp.cond && tid == 0) cudaGraphSetConditional(lp.cond, 0u);
+      }
+      return;
+    }
+  } else {
+    for (int i = tid; i < xn; i += blockDim.x) s_xs[i] = __ldcg(lp.Xacc + i);
+  }
+  __syncthreads();
   if (warp == 0) {
     const int buf = s_st.eval_buf;
     double gm = 0.0, g2 = 0.0, csq = 0.0;
     for (int i = lane; i < F * 6; i += 32) {
       const int f = i / 6, a = i - f * 6;
       if (s_st.free_index[f] >= 0) {
-        const double g = __ldcg(lp.Xacc + f * kUStride + 21 + a);
+        const double g = s_xs[f * kUStride + 21 + a];
         gm = fmax(gm, fabs(g)); g2 += g * g;
         const double c = lp.cams[((size_t)buf * F + f) * 6 + a];
         csq += c * c;
       }
     }
-    double e = lane < kEacc ? __ldcg(lp.Xacc + F * kUStride + lane) : 0.0;
-    double gpm = lane < kMaxRanks ? __ldcg(lp.Xacc + F * kUStride + kEacc + lane) : 0.0;   // per-rank max|g_p|
+    double e = lane < kEacc ? s_xs[F * kUStride + lane] : 0.0;
+    double gpm = lane < kMaxRanks ? s_xs[F * kUStride + kEacc + lane] : 0.0;   // per-rank max|g_p|
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
       gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, m));
@@ -612,7 +646,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
 #pragma unroll
     for (int k = 0; k < kEacc; ++k) E[k] = __shfl_sync(0xffffffffu, e, k);
     E[2] = gpm;
-    if (lane == 0) s_push = decide(s_st, E, gm, g2, csq, lp.Xacc, F, s_it) ? 1 : 0;
+    if (lane == 0) s_push = decide(s_st, E, gm, g2, csq, s_xs, F, s_it) ? 1 : 0;
   }
   __syncthreads();
   if (blockIdx.x == 0 && tid == 0 && s_push) lp.trace[s_st.n_trace - 1] = s_it;
@@ -785,7 +819,77 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
       reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
     return;
   }
-  finish_iteration(lp, s_st, sm, F);
+  if (xmode) {
+    // publish this rank's reduced-system contribution (upper block triangle + rhs) to every rank as LL
+    // cells, then sum everybody's in rank order straight out of the cells (polling replaces flag + fence)
+    const unsigned long long e = s_st.xepoch;
+    const int sn = D * D + D;
+    const size_t off = ((size_t)(e & 1ull) * lp.xc.n_ranks + lp.xc.rank) * lp.xc.s_n;
+    constexpr int kB = 4;                    // elements per thread in flight
+    for (int i0 = tid; i0 < sn; i0 += kB * blockDim.x) {
+      double v[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int i = i0 + u * blockDim.x;
+        v[u] = (i < sn) ? __ldcg(lp.S + i) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int i = i0 + u * blockDim.x;
+        const bool need = i < sn && (i >= D * D || (i / D) / 6 <= (i % D) / 6);
+        if (need)
+          for (int q = 0; q < lp.xc.n_ranks; ++q) ll_store(lp.xc.s[q] + off + i, v[u], e);
+      }
+    }
+    if (lp.dbg && tid == 0) lp.dbg[8] = gtime();
+    const ulonglong2* sb = lp.xc.s[lp.xc.rank] + (size_t)(e & 1ull) * lp.xc.n_ranks * lp.xc.s_n;
+    for (int i0 = tid; i0 < sn; i0 += kB * blockDim.x) {
+      double acc[kB];
+      bool need[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int i = i0 + u * blockDim.x;
+        need[u] = i < sn && (i >= D * D || (i / D) / 6 <= (i % D) / 6);
+        acc[u] = 0.0;
+      }
+      for (int q = 0; q < lp.xc.n_ranks; ++q) {
+        double v[kB];
+        bool got[kB];
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {     // first try: all loads in flight
+          const int i = i0 + u * blockDim.x;
+          v[u] = 0.0;
+          got[u] = !need[u] || ll_try_load(sb + (size_t)q * lp.xc.s_n + i, e, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {
+          const int i = i0 + u * blockDim.x;
+          if (!got[u] && !ll_load(sb + (size_t)q * lp.xc.s_n + i, e, v[u])) s_xok = 0;
+          acc[u] += v[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (need[u]) lp.S[i] = acc[u];
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (lp.dbg && tid == 0) { lp.dbg[9] = lp.dbg[8]; lp.dbg[10] = lp.dbg[8]; }
+    if (!s_xok) {
+      if (tid == 0) { finish(s_st, 2, kMsgXchgTimeout, (double)e, 1.0); *lp.xc.error = 1; *lp.ticket = 0u; }
+      __syncthreads();
+      for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+        reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
+      if (lp.cond && tid == 0) cudaGraphSetConditional(lp.cond, 0u);
+      return;
+    }
+    if (tid == 0) s_st.xepoch = e + 1;
+    __syncthreads();
+    if (lp.dbg && tid == 0) lp.dbg[11] = gtime();
+  }
+  finish_iteration(lp, s_st, sm, F, s_xs);
 }
 
 // split mode: one CTA, after the all-reduce of S
@@ -797,7 +901,23 @@ __global__ void __launch_bounds__(kSchurThreads) k_solve_only(const LmParams lp)
     reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_out)[i];
   __syncthreads();
   if (s_st.done) return;
-  finish_iteration(lp, s_st, sm, lp.n_frames);
+  finish_iteration(lp, s_st, sm, lp.n_frames, nullptr);
+}
+
+// Device-side barrier across the ranks of a window (start of a solve): raise my flag in every rank's
+// buffer, wait for everybody's.  Keeps the ranks' timelines aligned so that a rank that was called a
+// little earlier does not spend its first iteration waiting inside the LM loop.
+__global__ void k_rendezvous(const Xchg xc, unsigned long long epoch) {
+  const int q = threadIdx.x;
+  if (q < xc.n_ranks) {
+    st_release_sys(xc.fr[q] + xc.rank, epoch);
+    if (!xchg_wait(xc.fr[xc.rank] + q, epoch)) *xc.error = 1;
+  }
+}
+
+cudaError_t launch_rendezvous(const Xchg& xc, unsigned long long epoch, cudaStream_t stream) {
+  k_rendezvous<<<1, 32, 0, stream>>>(xc, epoch);
+  return cudaGetLastError();
 }
 
 // ---- launchers ----------------------------------------------------------------------------

@@ -55,7 +55,7 @@ struct IterSummary {
 
 enum MsgCode {
   kMsgNone = 0, kMsgGradTol = 1, kMsgParamTol = 2, kMsgFuncTol = 3, kMsgMaxIter = 4,
-  kMsgMinRadius = 5, kMsgInvalidSteps = 6
+  kMsgMinRadius = 5, kMsgInvalidSteps = 6, kMsgXchgTimeout = 7
 };
 
 // Levenberg-Marquardt state machine, resident in HBM (Ceres TrustRegionMinimizer +
@@ -83,6 +83,28 @@ struct LmState {
   double cam_sg, cam_sHs, cam_step_sq, cam_cand_sq;
   double scale_c[kMaxD];          // Jacobi column scaling of the pose columns (iteration 0)
   double step_c[kMaxD];           // trust-region step of the pose columns, scaled space
+  unsigned long long xepoch;      // multi-GPU: epoch of the exchange this state waits for / publishes (monotone across solves)
+};
+
+// Multi-GPU exchange over NVLink peer memory.  Every rank owns one exchange buffer
+// (cudaMalloc + CUDA IPC) that all peers map:
+//   xa  [2 parity][n_ranks][xa_n] cells   rank q's pose blocks + cost scalars of the evaluation (K_A pushes)
+//   s   [2 parity][n_ranks][s_n]  cells   rank q's reduced-system contribution               (K_B pushes)
+// A cell is 16 bytes = two self-validating 8-byte packets {32 data bits, 32-bit epoch tag} (the "LL"
+// idea: an aligned 8-byte store is single-copy atomic, so a packet whose tag matches carries valid data
+// and neither a fence nor a separate flag round trip is needed).  A rank writes its vector into slot
+// [own rank] of EVERY rank's buffer with plain peer stores; consumers poll the cells and sum the slots in
+// rank order, so every rank obtains bit-identical sums (identical LM decisions) without any collective
+// call.  Slots alternate by epoch parity; the tag tells a fresh cell from the one written two epochs ago.
+//   fr  u64 [n_ranks]                     rendezvous flags (start of a solve)
+struct Xchg {
+  int n_ranks, rank;              // n_ranks <= 1: single GPU, everything below unused
+  int xa_n, s_n;                  // doubles per slot
+  ulonglong2* xa[kMaxRanks];      // rank q's xa region (peer mapping; [rank] = local)
+  ulonglong2* s[kMaxRanks];
+  unsigned long long* fr[kMaxRanks];   // rendezvous flags (start of a solve)
+  unsigned int* ticket_a;         // K_A last-CTA detection (local)
+  int* error;                     // local: set when a wait timed out
 };
 
 // K_A parameters (k_step.cu)
@@ -106,6 +128,7 @@ struct StepParams {
   const double* Vinv;        // [n][6]
   double* obs_sqnorm;        // optional [nnz]
   double* residuals;         // optional [nnz][C*P]
+  Xchg xc;                   // multi-GPU exchange (n_ranks > 1 and st != null: the last CTA publishes Xacc)
 };
 
 // K_B parameters (k_schur_solve.cu)
@@ -129,7 +152,54 @@ struct LmParams {
   double* S;                 // [D*D + D]
   unsigned long long* dbg;   // optional: globaltimer stamps of the last CTA {start, decided, schur done, solved, end}
   unsigned long long cond;   // non-zero: cudaGraphConditionalHandle of the device-side LM loop, cleared when done
+  Xchg xc;                   // multi-GPU exchange over peer memory (xc.n_ranks > 1), else split/NCCL or single GPU
 };
+
+// ---- system-scope flag helpers for the peer-memory exchange ---------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kXchgTimeoutNs = 4000000000ull;   // a peer that never arrives must not hang the GPU
+// LL cells: store / try-load one double tagged with the low 32 bits of the epoch
+__device__ __forceinline__ void ll_store(ulonglong2* cell, double v, unsigned long long epoch) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = epoch << 32;
+  const unsigned long long p0 = t | (b & 0xffffffffull), p1 = t | (b >> 32);
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(cell), "l"(p0), "l"(p1) : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const ulonglong2* cell, unsigned long long epoch, double& v) {
+  unsigned long long p0, p1;
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(p0), "=l"(p1) : "l"(cell) : "memory");
+  const unsigned long long t = epoch & 0xffffffffull;
+  v = __longlong_as_double((long long)((p0 & 0xffffffffull) | (p1 << 32)));
+  return (p0 >> 32) == t && (p1 >> 32) == t;
+}
+// Blocking load of one cell; returns false on timeout.
+__device__ __forceinline__ bool ll_load(const ulonglong2* cell, unsigned long long epoch, double& v) {
+  if (ll_try_load(cell, epoch, v)) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  while (!ll_try_load(cell, epoch, v))
+    if (globaltimer_ns() - t0 > kXchgTimeoutNs) return false;
+  return true;
+}
+// Thread q < n waits until flags[q] >= epoch; returns false on timeout.  Call from >= n threads, then barrier.
+__device__ __forceinline__ bool xchg_wait(const unsigned long long* flag, unsigned long long epoch) {
+  const unsigned long long t0 = globaltimer_ns();
+  while (ld_acquire_sys(flag) < epoch) {
+    if (globaltimer_ns() - t0 > kXchgTimeoutNs) return false;
+    __nanosleep(64);
+  }
+  return true;
+}
 
 // launchers
 int k_step_grid(int n_points);
@@ -137,6 +207,7 @@ cudaError_t launch_k_step(const StepParams& prm, int radius, cudaStream_t stream
 int schur_grid(int n_points, int sm_count);
 cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t stream);
 cudaError_t launch_solve_only(const LmParams& lp, cudaStream_t stream);   // split mode, after the all-reduce of S
+cudaError_t launch_rendezvous(const Xchg& xc, unsigned long long epoch, cudaStream_t stream);   // device-side barrier across the ranks
 
 cudaError_t launch_pyrdown_u8(const uint8_t* src, int srows, int scols, int spitch, uint8_t* dst, int dpitch,
                               cudaStream_t stream);

@@ -68,10 +68,14 @@ def test_sharded_blocks_sum_to_global_gloo():
     assert q.get(timeout=5) <= 1e-13
 
 
-def _run_workers(n, kind):
+def _run_workers(n, kind, exchange=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(29700 + n), os.path.join(ROOT, "tests", "mgpu_worker.py"), kind]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    env.pop("PBA_MGPU_EXCHANGE", None)
+    if exchange:
+        env["PBA_MGPU_EXCHANGE"] = exchange
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1]
     return json.loads(line[len("MGPU_RESULT "):])
@@ -82,10 +86,32 @@ def test_two_gpus_equal_one_gpu():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
-    one, two = _run_workers(1, "small"), _run_workers(2, "small")
-    assert two["ranks_agree"] and two["collectives"] > 0 and one["collectives"] == 0
-    assert two["accepts"] == one["accepts"]
+    one = _run_workers(1, "small")
+    assert one["collectives"] == 0 and one["exchange"] == "none"
+    # default: in-kernel exchange over NVLink peer memory (no collective calls); fallback: NCCL all-reduce
+    for exchange in (None, "nccl"):
+        two = _run_workers(2, "small", exchange)
+        if exchange == "nccl":
+            assert two["exchange"] == "nccl" and two["collectives"] > 0
+        else:
+            assert two["exchange"] in ("peer-memory", "nccl")   # nccl only where peer mappings are unavailable
+            assert (two["collectives"] == 0) == (two["exchange"] == "peer-memory")
+        assert two["ranks_agree"]
+        assert two["accepts"] == one["accepts"]
+        assert abs(two["final_cost"] - one["final_cost"]) <= 1e-9 * one["final_cost"]
+        np.testing.assert_allclose(np.array(two["cams"]), np.array(one["cams"]), atol=1e-8)
+        np.testing.assert_allclose(np.array(two["pts_tail"]), np.array(one["pts_tail"]), atol=1e-6)
+        assert two["n_pts"] == one["n_pts"]
+
+
+@pytest.mark.gpu
+def test_two_gpus_bench_window_repeated_solves():
+    """cfg3 window on 2 GPUs, solved twice on the same handle (epochs keep counting across solves)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    one, two = _run_workers(1, "cfg3"), _run_workers(2, "cfg3")
+    assert two["ranks_agree"] and two["accepts"] == one["accepts"]
     assert abs(two["final_cost"] - one["final_cost"]) <= 1e-9 * one["final_cost"]
     np.testing.assert_allclose(np.array(two["cams"]), np.array(one["cams"]), atol=1e-8)
-    np.testing.assert_allclose(np.array(two["pts_tail"]), np.array(one["pts_tail"]), atol=1e-6)
-    assert two["n_pts"] == one["n_pts"]
+    assert abs(two["second_final_cost"] - two["final_cost"]) <= 1e-12 * two["final_cost"]
