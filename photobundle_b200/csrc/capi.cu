@@ -88,7 +88,10 @@ struct pba_handle {
   size_t plane = 0;
   // device buffers
   uint8_t* d_u8 = nullptr;
+  uint8_t* d_stage_u8 = nullptr;   // dense [F][rows][cols] landing zone of the host->device copies (re-pitched on the device)
   float* d_f32 = nullptr;
+  float* p_desc = nullptr;         // pinned staging of pba_set_points (descriptors as float, local offsets)
+  int32_t* p_off = nullptr;
   bool frames_are_u8 = false;
   double *d_cams = nullptr, *d_pts = nullptr, *d_weights = nullptr;
   float* d_desc = nullptr;
@@ -137,7 +140,9 @@ static void drop_lm_graph(pba_handle* h) {
 
 static void free_all(pba_handle* h) {
   drop_lm_graph(h);
-  cudaFree(h->d_u8); cudaFree(h->d_f32); cudaFree(h->d_cams); cudaFree(h->d_pts); cudaFree(h->d_weights);
+  cudaFree(h->d_u8); cudaFree(h->d_stage_u8); cudaFree(h->d_f32);
+  if (h->p_desc) cudaFreeHost(h->p_desc);
+  if (h->p_off) cudaFreeHost(h->p_off); cudaFree(h->d_cams); cudaFree(h->d_pts); cudaFree(h->d_weights);
   cudaFree(h->d_desc); cudaFree(h->d_obs_off); cudaFree(h->d_obs_frame); cudaFree(h->d_V); cudaFree(h->d_gp);
   cudaFree(h->d_W); cudaFree(h->d_Xacc); cudaFree(h->d_Ucur);
   for (int q = 0; q < kMaxRanks; ++q)
@@ -325,9 +330,20 @@ void pba_destroy(pba_handle* h) {
   delete h;
 }
 
+// One dense host->device copy per frame (a pitched 2-D copy straight from host memory moves odd-width
+// rows one by one: 8 GB/s instead of the link rate), then the rows are spread to the 16-byte pitch on
+// the device.
 static int upload_plane_u8(pba_handle* h, int slot, const uint8_t* img) {
-  CUDA_TRY(cudaMemcpy2DAsync(h->d_u8 + (size_t)slot * h->plane, h->pitch, img, h->cfg.cols, h->cfg.cols,
-                             h->cfg.rows, cudaMemcpyHostToDevice, h->stream));
+  const size_t dense = (size_t)h->cfg.rows * h->cfg.cols;
+  if (h->pitch == h->cfg.cols) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_u8 + (size_t)slot * h->plane, img, dense, cudaMemcpyHostToDevice, h->stream));
+    return PBA_OK;
+  }
+  if (!h->d_stage_u8) CUDA_TRY(cudaMalloc(&h->d_stage_u8, (size_t)h->cfg.max_frames * dense));
+  uint8_t* st = h->d_stage_u8 + (size_t)slot * dense;
+  CUDA_TRY(cudaMemcpyAsync(st, img, dense, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpy2DAsync(h->d_u8 + (size_t)slot * h->plane, h->pitch, st, h->cfg.cols, h->cfg.cols, h->cfg.rows,
+                             cudaMemcpyDeviceToDevice, h->stream));
   return PBA_OK;
 }
 
@@ -374,8 +390,8 @@ int pba_set_frames_u8_pyr(pba_handle* h, int32_t n_frames, const uint8_t* const*
     if (!images[f]) { cudaFree(scratch); return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8_pyr: images[%d] is null", f); }
     uint8_t* a = scratch;
     uint8_t* b = scratch + (size_t)src_rows * p0;
-    CUDA_TRY(cudaMemcpy2DAsync(a, p0, images[f], src_cols, src_cols, src_rows, cudaMemcpyHostToDevice, h->stream));
-    int rr = src_rows, cc = src_cols, pa = p0;
+    CUDA_TRY(cudaMemcpyAsync(a, images[f], (size_t)src_rows * src_cols, cudaMemcpyHostToDevice, h->stream));   // dense: pitch = cols
+    int rr = src_rows, cc = src_cols, pa = src_cols;
     for (int l = 0; l < levels_down; ++l) {
       const bool last = (l == levels_down - 1);
       uint8_t* dst = last ? h->d_u8 + (size_t)f * h->plane : b;
@@ -497,15 +513,21 @@ int pba_set_points(pba_handle* h, int32_t n_points, const double* xyz, const dou
   shard_split(n_points, obs_offsets, h->n_ranks, h->shard_begin);
   const int p0 = h->shard_begin[h->rank], p1 = h->shard_begin[h->rank + 1];
   const int n_loc = p1 - p0, o_base = obs_offsets[p0], nnz_loc = obs_offsets[p1] - o_base;
-  std::vector<float> descf((size_t)n_loc * h->CP);
-  for (size_t i = 0; i < descf.size(); ++i) descf[i] = (float)desc[(size_t)p0 * h->CP + i];
-  std::vector<int32_t> off_loc(n_loc + 1);
+  if (!h->p_desc) {   // pinned staging, sized for the handle's capacity
+    CUDA_TRY(cudaMallocHost(&h->p_desc, sizeof(float) * (size_t)h->cfg.max_points * h->CP));
+    CUDA_TRY(cudaMallocHost(&h->p_off, sizeof(int32_t) * ((size_t)h->cfg.max_points + 1)));
+  }
+  float* descf = h->p_desc;
+  const size_t n_desc = (size_t)n_loc * h->CP;
+  const double* dsrc = desc + (size_t)p0 * h->CP;
+  for (size_t i = 0; i < n_desc; ++i) descf[i] = (float)dsrc[i];
+  int32_t* off_loc = h->p_off;
   for (int i = 0; i <= n_loc; ++i) off_loc[i] = obs_offsets[p0 + i] - o_base;
   const size_t pstride = (size_t)n_loc * 3;
   CUDA_TRY(cudaMemcpyAsync(h->d_pts, xyz + (size_t)p0 * 3, sizeof(double) * pstride, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_pts + pstride, xyz + (size_t)p0 * 3, sizeof(double) * pstride, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_desc, descf.data(), sizeof(float) * descf.size(), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(h->d_obs_off, off_loc.data(), sizeof(int) * (n_loc + 1), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_pts + pstride, h->d_pts, sizeof(double) * pstride, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_desc, descf, sizeof(float) * n_desc, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_obs_off, off_loc, sizeof(int) * (n_loc + 1), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->d_obs_frame, obs_frame + o_base, sizeof(int) * nnz_loc, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->d_weights, weights, sizeof(double) * h->P, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
