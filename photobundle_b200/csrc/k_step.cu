@@ -167,7 +167,7 @@ constexpr int kRedStride = 6 * kG + 2;   // doubles per lane row of the reductio
 
 // ---- shared memory carve-up --------------------------------------------------------------
 // per CTA : pose consts [F][36] f64 | sstep [F][6] f64 (scale_c*step_c) | E [warps][8] f64
-// per warp: geometry [8][20] f64 | reduction transpose [25][6G+2] f64 | scaled sums [6G] f64 |
+// per warp: geometry [8][20] f64 | reduction transpose [25][6G+2] f64 | patch sums [8][6] f64 |
 //           pose-block accumulators [F][27] f64 | ints [8] int4 | frames [16] i32 |
 //           footprints [8][ROWS][W] f32
 template <int R, bool U8>
@@ -176,7 +176,7 @@ __host__ __device__ constexpr size_t k_step_smem_bytes(int n_frames) {
   // footprints: raw uint8 (ROWS x W bytes) on the Intensity path, fp32 otherwise
   constexpr size_t fp_bytes = (size_t)kStageSlots * Foot<R>::FLOATS * (U8 ? 1 : 4);
   return sizeof(double) * ((size_t)n_frames * (kPoseConst + 6) + WARPS * kEacc) +
-         (size_t)WARPS * (sizeof(double) * (kObsBatch * 20 + 25 * kRedStride + 6 * kG + (size_t)n_frames * kUStride + (n_frames & 1)) +
+         (size_t)WARPS * (sizeof(double) * (kObsBatch * 20 + 25 * kRedStride + 6 * kObsBatch + (size_t)n_frames * kUStride + (n_frames & 1)) +
                           sizeof(int4) * kObsBatch + sizeof(int) * kMaxFrames + ((fp_bytes + 15) / 16) * 16);
 }
 
@@ -339,10 +339,10 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
   double* s_geo_w = s_geo + warp * (kObsBatch * 20);
   double* s_red = s_geo + WARPS * (kObsBatch * 20);                    // [warps][25][6G+2]
   double* s_red_w = s_red + warp * (25 * kRedStride);
-  double* s_tot = s_red + WARPS * (25 * kRedStride);                   // [warps][6G]
-  double* s_tot_w = s_tot + warp * (6 * kG);
+  double* s_tot = s_red + WARPS * (25 * kRedStride);                   // [warps][8][6]: patch sums of the batch's observations
+  double* s_tot_w = s_tot + warp * (6 * kObsBatch);
   const int ustride = F * kUStride + (F & 1);
-  double* s_U = s_tot + WARPS * (6 * kG);                              // [warps][F][27]: this warp's pose blocks
+  double* s_U = s_tot + WARPS * (6 * kObsBatch);                            // [warps][F][27]: this warp's pose blocks
   double* s_U_w = s_U + warp * ustride;
   int4* s_gi = reinterpret_cast<int4*>(s_U + WARPS * ustride);         // [warps][8]
   int4* s_gi_w = s_gi + warp * kObsBatch;
@@ -548,6 +548,7 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
       KTRACE(3);
 
       const int obs_per_stage = NCH == 1 ? kStageSlots : ((C >= kStageSlots) ? 1 : kStageSlots / C);
+      unsigned defmask = 0;   // observations of this batch whose corrector + block expansion are deferred
       for (int sb = 0; sb < nb; sb += obs_per_stage) {
         const int ns_obs = min(obs_per_stage, nb - sb);
         const int nslots = NCH == 1 ? ns_obs : ns_obs * C;
@@ -618,33 +619,12 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
               for (int l = 0; l < P; ++l) tot += s_red_w[l * kRedStride + lane];
             }
             KTRACE(6 + (qb ? 4 : 0));
-            // Huber corrector of the four observations in parallel: lane 6i+k holds sum k of observation i
-            const int i_l = lane / 6, k_l = lane - 6 * i_l;
-            const double s_i = __shfl_sync(0xffffffffu, tot, min(i_l, kG - 1) * 6);
-            double rho0, rho1;
-            huber_rho(prm.huber, s_i, rho0, rho1);
-            if (lane < 6 * kG) {
-              s_tot_w[lane] = k_l == 0 ? s_i : rho1 * tot;
-              if (k_l == 0 && i_l < nq) {
-                cost_w += 0.5 * rho0;
-                if (prm.obs_sqnorm) prm.obs_sqnorm[o0 + ob + sb + qb + i_l] = s_i;
-              }
-            }
+            // lane 6i+k holds sum k of observation i: park the raw sums; the loss corrector and the block
+            // expansion of the whole batch follow the sampling loop (one latency chain per batch, not per group)
+            if (lane < 6 * nq) s_tot_w[(sb + qb) * 6 + lane] = tot;
+            defmask |= ((1u << nq) - 1u) << (sb + qb);
             __syncwarp();
             KTRACE(7 + (qb ? 4 : 0));
-#pragma unroll
-            for (int i = 0; i < kG; ++i) {
-              if (i < nq) {
-                const int ii = sb + qb + i;
-                const int o = o0 + ob + ii;
-                const int f = s_gi_w[ii].x;
-                const double* t = s_tot_w + 6 * i;
-                emit_blocks(t[1], t[2], t[3], t[4], t[5], s_geo_w + ii * 20, f, f != prm.fixed_frame, lane, e1a, e1b, e2a, e2b,
-                            s_U_w, outW + (size_t)o * 18, acc_pt);
-              }
-            }
-            __syncwarp();
-            KTRACE(8 + (qb ? 4 : 0));
           } else {
             // generic path: any channel count / patch size / border handling, one observation at a time
             for (int i = 0; i < nq; ++i) {
@@ -715,6 +695,37 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
               emit_blocks(rho1 * q.G11, rho1 * q.G12, rho1 * q.G22, rho1 * q.b1, rho1 * q.b2, g, f, f != prm.fixed_frame, lane,
                           e1a, e1b, e2a, e2b, s_U_w, outW + (size_t)o * 18, acc_pt);
             }
+          }
+        }
+        __syncwarp();
+      }
+      if (kQuad && defmask) {
+        // ---- (H) Huber corrector of every deferred observation at once: lane 6i+k <-> sum k of observation i
+#pragma unroll
+        for (int r = 0; r < (6 * kObsBatch + 31) / 32; ++r) {
+          const int idx = lane + 32 * r;
+          const int i_l = idx / 6, k_l = idx - 6 * i_l;
+          if (idx < 6 * nb && ((defmask >> i_l) & 1u)) {
+            const double s_i = s_tot_w[6 * i_l], raw = s_tot_w[idx];
+            double rho0, rho1;
+            huber_rho(prm.huber, s_i, rho0, rho1);
+            if (k_l == 0) {
+              cost_w += 0.5 * rho0;
+              if (prm.obs_sqnorm) prm.obs_sqnorm[o0 + ob + i_l] = s_i;
+            } else {
+              s_tot_w[idx] = rho1 * raw;
+            }
+          }
+        }
+        __syncwarp();
+        // ---- (E) block expansion, the batch's observations back to back (independent chains)
+#pragma unroll
+        for (int i = 0; i < kObsBatch; ++i) {
+          if (i < nb && ((defmask >> i) & 1u)) {
+            const int f = s_gi_w[i].x;
+            const double* t = s_tot_w + 6 * i;
+            emit_blocks(t[1], t[2], t[3], t[4], t[5], s_geo_w + i * 20, f, f != prm.fixed_frame, lane, e1a, e1b, e2a, e2b,
+                        s_U_w, outW + (size_t)(o0 + ob + i) * 18, acc_pt);
           }
         }
         __syncwarp();
