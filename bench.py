@@ -75,6 +75,8 @@ class ClockSampler(threading.Thread):
         self.stop_flag = threading.Event()
 
     def run(self):
+        if self._run_nvml():
+            return
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
@@ -84,6 +86,28 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
+
+    def _run_nvml(self):
+        """NVML in-process (a query takes ~0.1 ms, so a 20 ms timed region gets real samples); False -> nvidia-smi."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            dev = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = nv.nvmlDeviceGetMaxClockInfo(dev, nv.NVML_CLOCK_SM)
+            bits = [("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)]
+        except Exception:
+            return False
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(dev, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(dev)
+                pw = nv.nvmlDeviceGetPowerUsage(dev) / 1000.0
+                self.samples.append([str(self.gpu), str(sm), str(mx), str(pw), hex(r)] + ["Active" if r & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.002)
+        return True
 
     def summary(self):
         if not self.samples:
@@ -347,6 +371,10 @@ def main():
         "k1": {"us_per_launch_cold_l2": 1e3 * k1_ms, "us_per_launch_warm_l2": 1e3 * k1_ms_warm,
                "observations_per_launch": n_obs_local,
                "residuals_per_sec": 25 * n_obs_local / (k1_ms * 1e-3), "observations_per_sec": n_obs_local / (k1_ms * 1e-3)},
+        "k_b": {"us_per_launch_incl_launch_gaps": (1e3 * dev_s / steps - last["num_evaluations"] * 1e3 * k1_ms_warm) / max(1, last["num_iterations"] - 1),
+                "what": "decision + Schur elimination + reduced solve (k_schur_solve); latency-bound single-CTA tail, see DESIGN.md §4; "
+                        "derived as (solve time - K_A launches x warm K_A time) / LM iterations",
+                "algorithmic_bytes_per_launch": n_obs_local * 112 + (win.n_points // world) * 12},
         "roofline": {"bound": "hbm", "kernel": "k_step<2,u8,1> (K_A)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": k1_traffic_from_profile(),
                      "algorithmic_bytes_per_launch": n_obs_local * ALGO_BYTES_PER_OBS_K1, "peak_source": peak_src,

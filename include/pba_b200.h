@@ -194,6 +194,28 @@ int pba_get_poses(pba_handle* h, double* cam6);
 int pba_get_points(pba_handle* h, double* xyz);
 int pba_get_iterations(pba_handle* h, pba_iteration_summary* out, int32_t capacity, int32_t* n);
 
+/* ---- multi-channel descriptors, built on the device --------------------------------
+ * DescriptorFrame::Create (src/photobundle.cc:220-248): Intensity = the uint8 image cast to float (1
+ * channel, pba_set_frames_u8); IntensityAndGradient = {I, Ix, Iy} (imgradient, src/imgproc.cc:27-106);
+ * BitPlanes = 8 blurred bit planes of the census transform of the pre-blurred image (computeBitPlanes,
+ * src/imgproc.cc:222-245).  The handle must have been created with pba_descriptor_channels(type)
+ * channels. */
+#define PBA_DESC_INTENSITY 0
+#define PBA_DESC_INTENSITY_AND_GRADIENT 1
+#define PBA_DESC_BITPLANES 2
+int pba_descriptor_channels(int32_t descriptor_type);   /* 1, 3, 8; -1 for an unknown type */
+/* Upload the window's uint8 images and build every frame's channel planes on the device. */
+int pba_set_frames_u8_descriptor(pba_handle* h, int32_t n_frames, const uint8_t* const* images, int32_t descriptor_type);
+/* One channel plane of a window frame, dense rows x cols floats (tests / inspection). */
+int pba_get_channel_plane(pba_handle* h, int32_t frame, int32_t channel, float* out);
+/* The caller side of the path (addFrame, src/photobundle.cc:482-615) needs, for the NEW frame only, the
+ * saliency map (DescriptorFrame::computeSaliencyMap, :212-220: sum over channels of |Ix| + |Iy|) and the
+ * reference descriptors of the points it selects (ExtractPatch, :466-479).  pba_prepare_frame_u8 builds
+ * the channels of one image in a scratch area of the handle; the two calls below read from it. */
+int pba_prepare_frame_u8(pba_handle* h, const uint8_t* image, int32_t descriptor_type);
+int pba_saliency_map(pba_handle* h, float* out /* rows x cols */);
+int pba_extract_descriptors(pba_handle* h, int32_t n, const int32_t* xy /* n x {x, y} */, double* desc /* n x C*P */);
+
 /* Multi-GPU: one process per GPU; points are sharded, frames/poses replicated, one
  * exchange of the pose blocks and of the reduced camera system per LM iteration.  Rank 0 calls
  * pba_comm_unique_id() and distributes the 128 bytes by any means (torch.distributed,

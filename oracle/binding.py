@@ -105,6 +105,37 @@ def _p(a: np.ndarray) -> int:
     return a.ctypes.data
 
 
+DESCRIPTOR_TYPES = {"intensity": 0, "intensity_and_gradient": 1, "bitplanes": 2}
+
+
+def build_channels(image_u8: np.ndarray, descriptor: str) -> np.ndarray:
+    """DescriptorFrame::Create restated: uint8 image -> fp32 channel planes [C, rows, cols]."""
+    L = lib()
+    img = np.ascontiguousarray(image_u8, dtype=np.uint8)
+    t = DESCRIPTOR_TYPES[descriptor]
+    Cn = int(L.oracle_descriptor_channels(t))
+    out = np.zeros((Cn,) + img.shape, dtype=np.float32)
+    L.oracle_build_channels(t, C.c_void_p(_p(img)), img.shape[0], img.shape[1], C.c_void_p(_p(out)))
+    return out
+
+
+def saliency_map(planes: np.ndarray) -> np.ndarray:
+    planes = np.ascontiguousarray(planes, dtype=np.float32)
+    out = np.zeros(planes.shape[1:], dtype=np.float32)
+    lib().oracle_saliency_map(C.c_void_p(_p(planes)), planes.shape[0], planes.shape[1], planes.shape[2], C.c_void_p(_p(out)))
+    return out
+
+
+def extract_patches(planes: np.ndarray, xy: np.ndarray, radius: int) -> np.ndarray:
+    planes = np.ascontiguousarray(planes, dtype=np.float32)
+    xy = np.ascontiguousarray(xy, dtype=np.int32).reshape(-1, 2)
+    P = (2 * radius + 1) ** 2
+    out = np.zeros((xy.shape[0], planes.shape[0] * P), dtype=np.float64)
+    lib().oracle_extract_patches(C.c_void_p(_p(planes)), planes.shape[0], planes.shape[1], planes.shape[2], int(radius),
+                                 xy.shape[0], C.c_void_p(_p(xy)), C.c_void_p(_p(out)))
+    return out
+
+
 class OracleWindow:
     """Holds a synthetic.Window in the layout oracle_problem wants and keeps arrays alive."""
 

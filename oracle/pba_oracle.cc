@@ -788,6 +788,127 @@ void oracle_imgradient(const float* I, int32_t rows, int32_t cols, float* gx, fl
   imgradient(I, rows, cols, gx, gy);
 }
 
+// ---- descriptor channels (DescriptorFrame::Create, src/photobundle.cc:220-248) ----------------------
+static inline int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+  return i;
+}
+
+int32_t oracle_descriptor_channels(int32_t type) { return type == 0 ? 1 : type == 1 ? 3 : type == 2 ? 8 : -1; }
+
+// the uint8 stages of computeBitPlanes: pre-blur and census transform (exposed for the golden-vector test)
+void oracle_bitplanes_stages(const uint8_t* img, int32_t rows, int32_t cols, uint8_t* blur_out, uint8_t* census_out) {
+  const size_t n = (size_t)rows * cols;
+  uint8_t* blurp = blur_out;
+  std::memset(census_out, 0, n);
+  const int w3[3] = {70, 116, 70};
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x) {
+      int acc = 0;
+      for (int j = 0; j < 3; ++j) {
+        const uint8_t* row = img + (size_t)reflect101(y + j - 1, rows) * cols;
+        int h = 0;
+        for (int i = 0; i < 3; ++i) h += w3[i] * (int)row[reflect101(x + i - 1, cols)];
+        acc += w3[j] * h;
+      }
+      blurp[(size_t)y * cols + x] = (uint8_t)((acc + 32768) >> 16);
+    }
+  // (2) censusTransform (src/imgproc.cc:140-220): bit k set when neighbour k >= centre (unsigned), neighbours in
+  //     row-major order skipping the centre; first/last row and column are 0
+  for (int y = 1; y < rows - 1; ++y)
+    for (int x = 1; x < cols - 1; ++x) {
+      const uint8_t* s = blurp + (size_t)y * cols + x;
+      const unsigned c = s[0];
+      census_out[(size_t)y * cols + x] = (uint8_t)((s[-cols - 1] >= c ? 0x01 : 0) | (s[-cols] >= c ? 0x02 : 0) | (s[-cols + 1] >= c ? 0x04 : 0) |
+                                               (s[-1] >= c ? 0x08 : 0) | (s[1] >= c ? 0x10 : 0) | (s[cols - 1] >= c ? 0x20 : 0) |
+                                               (s[cols] >= c ? 0x40 : 0) | (s[cols + 1] >= c ? 0x80 : 0));
+    }
+}
+
+// planes: dense [C][rows][cols]
+void oracle_build_channels(int32_t type, const uint8_t* img, int32_t rows, int32_t cols, float* planes) {
+  const size_t n = (size_t)rows * cols;
+  if (type == 0 || type == 1) {
+    // image.cast<float>() (:226, :229)
+    for (size_t i = 0; i < n; ++i) planes[i] = (float)img[i];
+    if (type == 1) {
+      // imgradient(uint8) (src/imgproc.cc:27-106): S * (float(a) - float(b)), S = 0.5f, zero first/last row and column
+      float* gx = planes + n;
+      float* gy = planes + 2 * n;
+      std::memset(gx, 0, sizeof(float) * n);
+      std::memset(gy, 0, sizeof(float) * n);
+      for (int y = 1; y < rows - 1; ++y)
+        for (int x = 1; x < cols - 1; ++x) {
+          const uint8_t* s = img + (size_t)y * cols + x;
+          gx[(size_t)y * cols + x] = 0.5f * ((float)s[1] - (float)s[-1]);
+          gy[(size_t)y * cols + x] = 0.5f * ((float)s[cols] - (float)s[-cols]);
+        }
+    }
+    return;
+  }
+  // BitPlanes: computeBitPlanes(image, sigma_ct = 1, sigma_bp = 1.5) (src/imgproc.cc:222-245, src/imgproc.h:45-46)
+  // (1) cv::GaussianBlur(uint8, 3x3, sigma 1): fixed-point kernel {70,116,70}/256 per axis, (sum + 2^15) >> 16,
+  //     BORDER_REFLECT_101 (pinned against cv2 in tests/golden/make_bitplanes_golden.py)
+  std::vector<uint8_t> blur(n), census(n, 0);
+  oracle_bitplanes_stages(img, rows, cols, blur.data(), census.data());
+  // (3) ExtractBitPlanesChannel: bit b as 0/1 float, cv::GaussianBlur(float, 5x5, sigma 1.5): separable fp32,
+  //     kernel = float(getGaussianKernel(5, 1.5)), BORDER_REFLECT_101
+  const float k0 = 0x1.2b1778p-2f, k1 = 0x1.defcep-3f, k2 = 0x1.ebd75p-4f;
+  std::vector<float> bit(n), rowp(n);
+  for (int b = 0; b < 8; ++b) {
+    for (size_t i = 0; i < n; ++i) bit[i] = (float)((census[i] & (1 << b)) >> b);
+    for (int y = 0; y < rows; ++y) {
+      const float* r = bit.data() + (size_t)y * cols;
+      for (int x = 0; x < cols; ++x) {
+        const float a0 = r[reflect101(x - 2, cols)], a1 = r[reflect101(x - 1, cols)], a2 = r[x], a3 = r[reflect101(x + 1, cols)],
+                    a4 = r[reflect101(x + 2, cols)];
+        rowp[(size_t)y * cols + x] = (k0 * a2 + k1 * (a1 + a3)) + k2 * (a0 + a4);
+      }
+    }
+    float* dst = planes + (size_t)b * n;
+    for (int y = 0; y < rows; ++y)
+      for (int x = 0; x < cols; ++x) {
+        const float r0 = rowp[(size_t)reflect101(y - 2, rows) * cols + x], r1 = rowp[(size_t)reflect101(y - 1, rows) * cols + x],
+                    r2 = rowp[(size_t)y * cols + x], r3 = rowp[(size_t)reflect101(y + 1, rows) * cols + x],
+                    r4 = rowp[(size_t)reflect101(y + 2, rows) * cols + x];
+        dst[(size_t)y * cols + x] = (k0 * r2 + k1 * (r1 + r3)) + k2 * (r0 + r4);
+      }
+  }
+}
+
+// DescriptorFrame::computeSaliencyMap (src/photobundle.cc:212-220): sum over channels of |Ix| + |Iy|
+void oracle_saliency_map(const float* planes, int32_t n_channels, int32_t rows, int32_t cols, float* out) {
+  const size_t n = (size_t)rows * cols;
+  std::vector<float> gx(n), gy(n);
+  for (int k = 0; k < n_channels; ++k) {
+    imgradient(planes + (size_t)k * n, rows, cols, gx.data(), gy.data());
+    for (size_t i = 0; i < n; ++i) {
+      const float m = std::fabs(gx[i]) + std::fabs(gy[i]);
+      out[i] = k == 0 ? m : out[i] + m;
+    }
+  }
+}
+
+// ExtractPatch (src/photobundle.cc:466-479) for every channel, channel-major
+void oracle_extract_patches(const float* planes, int32_t n_channels, int32_t rows, int32_t cols, int32_t radius, int32_t n,
+                            const int32_t* xy, double* desc) {
+  const int side = 2 * radius + 1, P = side * side;
+  const int max_cols = cols - radius - 1, max_rows = rows - radius - 1;
+  for (int p = 0; p < n; ++p)
+    for (int k = 0; k < n_channels; ++k) {
+      const float* I = planes + (size_t)k * rows * cols;
+      int i = 0;
+      for (int r = -radius; r <= radius; ++r) {
+        const int r_i = std::max(radius, std::min(xy[2 * p + 1] + r, max_rows));
+        for (int c = -radius; c <= radius; ++c, ++i) {
+          const int c_i = std::max(radius, std::min(xy[2 * p] + c, max_cols));
+          desc[((size_t)p * n_channels + k) * P + i] = (double)I[(size_t)r_i * cols + c_i];
+        }
+      }
+    }
+}
+
 void oracle_sample_linear(const float* I, const float* Gx, const float* Gy, int32_t rows,
                           int32_t cols, float y, float x, float* out3) {
   PlaneSet ps{I, Gx, Gy, rows, cols};

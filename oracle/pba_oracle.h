@@ -122,6 +122,18 @@ void oracle_default_options(oracle_solver_options* o);
 /* src/imgproc.cc:27-106 (central difference * 0.5, zero on all four borders). */
 void oracle_imgradient(const float* I, int32_t rows, int32_t cols, float* gx, float* gy);
 
+/* Descriptor channels (DescriptorFrame::Create, src/photobundle.cc:220-248): type 0 Intensity (1 plane),
+ * 1 IntensityAndGradient (3), 2 BitPlanes (8; computeBitPlanes src/imgproc.cc:222-245 with the two
+ * cv::GaussianBlur calls restated, pinned against OpenCV by tests/golden/bitplanes_ref.npz).
+ * planes: dense [C][rows][cols]. */
+int32_t oracle_descriptor_channels(int32_t type);
+void oracle_build_channels(int32_t type, const uint8_t* img, int32_t rows, int32_t cols, float* planes);
+void oracle_bitplanes_stages(const uint8_t* img, int32_t rows, int32_t cols, uint8_t* blur_out, uint8_t* census_out);
+/* DescriptorFrame::computeSaliencyMap (src/photobundle.cc:212-220) and ExtractPatch (:466-479). */
+void oracle_saliency_map(const float* planes, int32_t n_channels, int32_t rows, int32_t cols, float* out);
+void oracle_extract_patches(const float* planes, int32_t n_channels, int32_t rows, int32_t cols, int32_t radius, int32_t n,
+                            const int32_t* xy, double* desc);
+
 /* src/sample_eigen.h:33-102. out = {I, Gx, Gy} at (x, y). */
 void oracle_sample_linear(const float* I, const float* Gx, const float* Gy,
                           int32_t rows, int32_t cols, float y, float x, float* out3);

@@ -23,6 +23,8 @@ EXPORTED_SYMBOLS = [
     "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_frames_u8_pyr", "pba_pyrdown_u8", "pba_set_poses", "pba_set_points",
     "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_get_poses", "pba_get_points", "pba_get_iterations",
     "pba_comm_unique_id", "pba_comm_init", "pba_shard_range", "pba_comm_exchange_kind",
+    "pba_descriptor_channels", "pba_set_frames_u8_descriptor", "pba_get_channel_plane", "pba_prepare_frame_u8",
+    "pba_saliency_map", "pba_extract_descriptors",
 ]
 
 
@@ -123,6 +125,7 @@ class Handle:
         self.n_frames = 0
         self.n_points = 0
         self.n_obs = 0
+        self.rows, self.cols = rows, cols
         self.P = (2 * radius + 1) ** 2
         self.CP = self.P * n_channels
 
@@ -178,6 +181,38 @@ class Handle:
         arr = (C.c_void_p * (F * Cn))(*[planes[f, k].ctypes.data for f in range(F) for k in range(Cn)])
         _check(lib().pba_set_frames_f32(self._h, F, arr), "pba_set_frames_f32")
         self.n_frames = F
+
+    DESCRIPTOR_TYPES = {"intensity": 0, "intensity_and_gradient": 1, "bitplanes": 2}
+
+    def set_frames_u8_descriptor(self, images: np.ndarray, descriptor: str):
+        """Upload uint8 frames and build the descriptor's channel planes on the device (DescriptorFrame::Create)."""
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        F = images.shape[0]
+        arr = (C.c_void_p * F)(*[images[f].ctypes.data for f in range(F)])
+        _check(lib().pba_set_frames_u8_descriptor(self._h, F, arr, self.DESCRIPTOR_TYPES[descriptor]), "pba_set_frames_u8_descriptor")
+        self.n_frames = F
+
+    def get_channel_plane(self, frame: int, channel: int) -> np.ndarray:
+        out = np.zeros((self.rows, self.cols), dtype=np.float32)
+        _check(lib().pba_get_channel_plane(self._h, int(frame), int(channel), _ptr(out)), "pba_get_channel_plane")
+        return out
+
+    def prepare_frame_u8(self, image: np.ndarray, descriptor: str):
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        assert image.shape == (self.rows, self.cols)
+        _check(lib().pba_prepare_frame_u8(self._h, _ptr(image), self.DESCRIPTOR_TYPES[descriptor]), "pba_prepare_frame_u8")
+        self._prepared_channels = int(lib().pba_descriptor_channels(self.DESCRIPTOR_TYPES[descriptor]))
+
+    def saliency_map(self) -> np.ndarray:
+        out = np.zeros((self.rows, self.cols), dtype=np.float32)
+        _check(lib().pba_saliency_map(self._h, _ptr(out)), "pba_saliency_map")
+        return out
+
+    def extract_descriptors(self, xy: np.ndarray) -> np.ndarray:
+        xy = np.ascontiguousarray(xy, dtype=np.int32).reshape(-1, 2)
+        out = np.zeros((xy.shape[0], self._prepared_channels * self.P), dtype=np.float64)
+        _check(lib().pba_extract_descriptors(self._h, xy.shape[0], _ptr(xy), _ptr(out)), "pba_extract_descriptors")
+        return out
 
     def set_poses(self, cams: np.ndarray, fixed_frame: int = 0):
         cams = np.ascontiguousarray(cams, dtype=np.float64)

@@ -90,6 +90,13 @@ struct pba_handle {
   uint8_t* d_u8 = nullptr;
   uint8_t* d_stage_u8 = nullptr;   // dense [F][rows][cols] landing zone of the host->device copies (re-pitched on the device)
   float* d_f32 = nullptr;
+  // descriptor construction (pba_set_frames_u8_descriptor / pba_prepare_frame_u8)
+  uint8_t *d_scr_a = nullptr, *d_scr_b = nullptr;   // pitched uint8 scratch planes (pre-blur, census)
+  uint8_t* d_new_u8 = nullptr;     // the new frame of pba_prepare_frame_u8 (pitched) ...
+  float* d_new_planes = nullptr;   // ... and its channel planes [C][rows][pitch]
+  int new_channels = 0, new_active = 0;   // planes allocated / channels of the prepared frame
+  float* d_sal = nullptr;          // saliency map, dense
+  int* d_xy = nullptr;  double* d_desc_out = nullptr;  int xy_cap = 0;
   float* p_desc = nullptr;         // pinned staging of pba_set_points (descriptors as float, local offsets)
   int32_t* p_off = nullptr;
   bool frames_are_u8 = false;
@@ -141,6 +148,8 @@ static void drop_lm_graph(pba_handle* h) {
 static void free_all(pba_handle* h) {
   drop_lm_graph(h);
   cudaFree(h->d_u8); cudaFree(h->d_stage_u8); cudaFree(h->d_f32);
+  cudaFree(h->d_scr_a); cudaFree(h->d_scr_b); cudaFree(h->d_new_u8); cudaFree(h->d_new_planes); cudaFree(h->d_sal);
+  cudaFree(h->d_xy); cudaFree(h->d_desc_out);
   if (h->p_desc) cudaFreeHost(h->p_desc);
   if (h->p_off) cudaFreeHost(h->p_off); cudaFree(h->d_cams); cudaFree(h->d_pts); cudaFree(h->d_weights);
   cudaFree(h->d_desc); cudaFree(h->d_obs_off); cudaFree(h->d_obs_frame); cudaFree(h->d_V); cudaFree(h->d_gp);
@@ -452,6 +461,120 @@ int pba_set_frames_f32(pba_handle* h, int32_t n_frames, const float* const* plan
   }
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->frames_are_u8 = false; h->have_frames = true; h->n_frames = n_frames;
+  return PBA_OK;
+}
+
+int pba_descriptor_channels(int32_t t) {
+  return t == PBA_DESC_INTENSITY ? 1 : t == PBA_DESC_INTENSITY_AND_GRADIENT ? 3 : t == PBA_DESC_BITPLANES ? 8 : -1;
+}
+
+static int ensure_descriptor_scratch(pba_handle* h) {
+  if (!h->d_scr_a) {
+    CUDA_TRY(cudaMalloc(&h->d_scr_a, h->plane));
+    CUDA_TRY(cudaMalloc(&h->d_scr_b, h->plane));
+  }
+  return PBA_OK;
+}
+
+int pba_set_frames_u8_descriptor(pba_handle* h, int32_t n_frames, const uint8_t* const* images, int32_t type) {
+  if (!h || !images) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8_descriptor: null argument");
+  if (type == PBA_DESC_INTENSITY) return pba_set_frames_u8(h, n_frames, images);
+  const int C = pba_descriptor_channels(type);
+  if (C < 0) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8_descriptor: unknown descriptor type %d", type);
+  if (h->cfg.n_channels != C) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8_descriptor: descriptor type %d has %d channels, the handle %d", type, C, h->cfg.n_channels);
+  if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(PBA_ERR_CAPACITY, "pba_set_frames_u8_descriptor: %d frames, capacity %d", n_frames, h->cfg.max_frames);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->d_u8) {
+    CUDA_TRY(cudaMalloc(&h->d_u8, (size_t)h->cfg.max_frames * h->plane));
+    CUDA_TRY(cudaMemsetAsync(h->d_u8, 0, (size_t)h->cfg.max_frames * h->plane, h->stream));
+  }
+  if (!h->d_f32) {
+    CUDA_TRY(cudaMalloc(&h->d_f32, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane));
+    CUDA_TRY(cudaMemsetAsync(h->d_f32, 0, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane, h->stream));
+  }
+  int rc = ensure_descriptor_scratch(h);
+  if (rc) return rc;
+  for (int f = 0; f < n_frames; ++f) {
+    if (!images[f]) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8_descriptor: images[%d] is null", f);
+    rc = upload_plane_u8(h, f, images[f]);
+    if (rc) return rc;
+    CUDA_TRY(launch_channels(type, h->d_u8 + (size_t)f * h->plane, h->cfg.rows, h->cfg.cols, h->pitch, h->d_scr_a, h->d_scr_b,
+                             h->d_f32 + (size_t)f * C * h->plane, h->pitch, h->plane, h->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->frames_are_u8 = false; h->have_frames = true; h->n_frames = n_frames;
+  return PBA_OK;
+}
+
+int pba_get_channel_plane(pba_handle* h, int32_t frame, int32_t channel, float* out) {
+  if (!h || !out) return fail(PBA_ERR_ARGUMENT, "pba_get_channel_plane: null argument");
+  if (!h->have_frames || h->frames_are_u8 || !h->d_f32) return fail(PBA_ERR_STATE, "pba_get_channel_plane: no fp32 channel planes on the device");
+  if (frame < 0 || frame >= h->n_frames || channel < 0 || channel >= h->cfg.n_channels)
+    return fail(PBA_ERR_ARGUMENT, "pba_get_channel_plane: frame %d / channel %d", frame, channel);
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpy2D(out, sizeof(float) * h->cfg.cols, h->d_f32 + ((size_t)frame * h->cfg.n_channels + channel) * h->plane,
+                        sizeof(float) * h->pitch, sizeof(float) * h->cfg.cols, h->cfg.rows, cudaMemcpyDeviceToHost));
+  return PBA_OK;
+}
+
+int pba_prepare_frame_u8(pba_handle* h, const uint8_t* image, int32_t type) {
+  if (!h || !image) return fail(PBA_ERR_ARGUMENT, "pba_prepare_frame_u8: null argument");
+  const int C = pba_descriptor_channels(type);
+  if (C < 0) return fail(PBA_ERR_ARGUMENT, "pba_prepare_frame_u8: unknown descriptor type %d", type);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t dense = (size_t)h->cfg.rows * h->cfg.cols;
+  const int c_alloc = C < 3 ? 3 : C;   // Intensity is built as {I, Ix, Iy} and uses plane 0 only
+  if (!h->d_new_u8) {
+    CUDA_TRY(cudaMalloc(&h->d_new_u8, h->plane));
+    CUDA_TRY(cudaMemsetAsync(h->d_new_u8, 0, h->plane, h->stream));
+    CUDA_TRY(cudaMalloc(&h->d_sal, sizeof(float) * dense));
+  }
+  if (h->new_channels < c_alloc) {
+    cudaFree(h->d_new_planes); h->d_new_planes = nullptr; h->new_channels = 0;
+    CUDA_TRY(cudaMalloc(&h->d_new_planes, sizeof(float) * (size_t)c_alloc * h->plane));
+    CUDA_TRY(cudaMemsetAsync(h->d_new_planes, 0, sizeof(float) * (size_t)c_alloc * h->plane, h->stream));
+    h->new_channels = c_alloc;
+  }
+  int rc = ensure_descriptor_scratch(h);
+  if (rc) return rc;
+  if (!h->d_stage_u8) CUDA_TRY(cudaMalloc(&h->d_stage_u8, (size_t)h->cfg.max_frames * dense));
+  CUDA_TRY(cudaMemcpyAsync(h->d_stage_u8, image, dense, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpy2DAsync(h->d_new_u8, h->pitch, h->d_stage_u8, h->cfg.cols, h->cfg.cols, h->cfg.rows, cudaMemcpyDeviceToDevice, h->stream));
+  CUDA_TRY(launch_channels(type == PBA_DESC_BITPLANES ? PBA_DESC_BITPLANES : PBA_DESC_INTENSITY_AND_GRADIENT, h->d_new_u8, h->cfg.rows,
+                           h->cfg.cols, h->pitch, h->d_scr_a, h->d_scr_b, h->d_new_planes, h->pitch, h->plane, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));   // `image` is only borrowed for the duration of the call
+  h->new_active = C;
+  return PBA_OK;
+}
+
+int pba_saliency_map(pba_handle* h, float* out) {
+  if (!h || !out) return fail(PBA_ERR_ARGUMENT, "pba_saliency_map: null argument");
+  if (h->new_active <= 0) return fail(PBA_ERR_STATE, "pba_saliency_map: call pba_prepare_frame_u8 first");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(launch_saliency(h->d_new_planes, h->new_active, h->cfg.rows, h->cfg.cols, h->pitch, h->plane, h->d_sal, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(out, h->d_sal, sizeof(float) * (size_t)h->cfg.rows * h->cfg.cols, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PBA_OK;
+}
+
+int pba_extract_descriptors(pba_handle* h, int32_t n, const int32_t* xy, double* desc) {
+  if (!h || (n > 0 && (!xy || !desc))) return fail(PBA_ERR_ARGUMENT, "pba_extract_descriptors: null argument");
+  if (h->new_active <= 0) return fail(PBA_ERR_STATE, "pba_extract_descriptors: call pba_prepare_frame_u8 first");
+  if (n < 0) return fail(PBA_ERR_ARGUMENT, "pba_extract_descriptors: n < 0");
+  if (n == 0) return PBA_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int CP = h->new_active * h->P;
+  if (h->xy_cap < n) {
+    cudaFree(h->d_xy); cudaFree(h->d_desc_out); h->d_xy = nullptr; h->d_desc_out = nullptr; h->xy_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->d_xy, sizeof(int) * 2 * (size_t)n));
+    CUDA_TRY(cudaMalloc(&h->d_desc_out, sizeof(double) * (size_t)n * PBA_MAX_CHANNELS * h->P));
+    h->xy_cap = n;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_xy, xy, sizeof(int) * 2 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(launch_extract_patches(h->d_new_planes, h->new_active, h->cfg.rows, h->cfg.cols, h->pitch, h->plane, h->cfg.patch_radius, n,
+                                  h->d_xy, h->d_desc_out, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(desc, h->d_desc_out, sizeof(double) * (size_t)n * CP, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
   return PBA_OK;
 }
 

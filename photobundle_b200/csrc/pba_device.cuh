@@ -209,6 +209,13 @@ cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStr
 cudaError_t launch_solve_only(const LmParams& lp, cudaStream_t stream);   // split mode, after the all-reduce of S
 cudaError_t launch_rendezvous(const Xchg& xc, unsigned long long epoch, cudaStream_t stream);   // device-side barrier across the ranks
 
+// descriptor channels (k_prep.cu): type 1 = IntensityAndGradient (3 planes), 2 = BitPlanes (8 planes)
+cudaError_t launch_channels(int descriptor_type, const uint8_t* src, int rows, int cols, int spitch, uint8_t* scratch_a,
+                            uint8_t* scratch_b, float* dst, int dpitch, size_t dplane, cudaStream_t stream);
+cudaError_t launch_saliency(const float* planes, int n_channels, int rows, int cols, int pitch, size_t plane, float* out,
+                            cudaStream_t stream);
+cudaError_t launch_extract_patches(const float* planes, int n_channels, int rows, int cols, int pitch, size_t plane, int radius,
+                                   int n, const int* xy, double* desc, cudaStream_t stream);
 cudaError_t launch_pyrdown_u8(const uint8_t* src, int srows, int scols, int spitch, uint8_t* dst, int dpitch,
                               cudaStream_t stream);
 

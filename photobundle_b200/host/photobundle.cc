@@ -307,9 +307,11 @@ PhotometricBundleAdjustment::PhotometricBundleAdjustment(const Calibration& cali
     : _calib(calib), _image_size(image_size), _options(options) {
   if (_options.slidingWindowSize < 1 || _options.slidingWindowSize > PBA_MAX_FRAMES)
     throw std::runtime_error("slidingWindowSize outside [1, " + std::to_string(PBA_MAX_FRAMES) + "]");
-  if (_options.descriptorType != Options::DescriptorType::Intensity)
-    throw std::runtime_error("only the Intensity descriptor is wired to the GPU path in this build "
-                             "(the kernels take C-channel planes through pba_set_frames_f32)");
+  // DescriptorFrame::Create (src/photobundle.cc:220-248): the channel planes are built on the device
+  _desc_type = _options.descriptorType == Options::DescriptorType::Intensity ? PBA_DESC_INTENSITY
+             : _options.descriptorType == Options::DescriptorType::IntensityAndGradient ? PBA_DESC_INTENSITY_AND_GRADIENT
+                                                                                         : PBA_DESC_BITPLANES;
+  _n_channels = pba_descriptor_channels(_desc_type);
   _mask.resize((size_t)_image_size.rows * _image_size.cols);
   _saliency_map.resize((size_t)_image_size.rows * _image_size.cols);
   _K_inv = calib.K().inverse();
@@ -324,7 +326,7 @@ void PhotometricBundleAdjustment::ensureGpu(int n_points, int n_obs) {
   if (_gpu) { pba_destroy(_gpu); _gpu = nullptr; }
   pba_config cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.rows = _image_size.rows; cfg.cols = _image_size.cols; cfg.n_channels = 1;
+  cfg.rows = _image_size.rows; cfg.cols = _image_size.cols; cfg.n_channels = _n_channels;
   cfg.patch_radius = _options.patchRadius; cfg.max_frames = _options.slidingWindowSize;
   _gpu_max_points = std::max(n_points, _options.maxNumPoints * _options.slidingWindowSize);
   _gpu_max_obs = std::max(n_obs, _gpu_max_points * std::min(_options.slidingWindowSize, 4));
@@ -362,7 +364,7 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
 
   const int B = std::max(_options.maskBlockRadius, std::max(2, _options.patchRadius));
   const int max_rows = rows - B - 1, max_cols = cols - B - 1, radius = _options.patchRadius,
-            patch_length = PatchSizeFromRadius(radius), descriptor_dim = patch_length /* 1 channel */,
+            patch_length = PatchSizeFromRadius(radius), descriptor_dim = patch_length * _n_channels,
             mask_radius = _options.maskBlockRadius;
 
   // ---- visibility of the existing points in the new frame (src/photobundle.cc:508-542)
@@ -389,7 +391,16 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
     }
   }
 
-  // ---- new points: saliency = |Ix| + |Iy| (imgradient, zero borders), local maxima with valid depth
+  // ---- new points: saliency = sum over channels of |Ix| + |Iy| (imgradient, zero borders), local maxima
+  // with valid depth.  Multi-channel descriptors: the new frame's channels, their saliency and (below) the
+  // reference descriptors come from the device (pba_prepare_frame_u8 / pba_saliency_map / pba_extract_descriptors).
+  const bool multi = _desc_type != PBA_DESC_INTENSITY;
+  auto check = [&](int rc, const char* what) { if (rc != PBA_OK) throw std::runtime_error(std::string(what) + ": " + pba_last_error()); };
+  if (multi) {
+    ensureGpu(0, 0);
+    check(pba_prepare_frame_u8(_gpu, I_ptr, _desc_type), "pba_prepare_frame_u8");
+    check(pba_saliency_map(_gpu, _saliency_map.data()), "pba_saliency_map");
+  } else {
   std::fill(_saliency_map.begin(), _saliency_map.end(), 0.0f);
   for (int y = 1; y < rows - 1; ++y)
     for (int x = 1; x < cols - 1; ++x) {
@@ -397,6 +408,7 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
       const float iy = 0.5f * ((float)I_ptr[(size_t)(y + 1) * cols + x] - (float)I_ptr[(size_t)(y - 1) * cols + x]);
       _saliency_map[(size_t)y * cols + x] = std::fabs(ix) + std::fabs(iy);
     }
+  }
   const int nms = _options.nonMaxSuppRadius;
   auto is_local_max = [&](int row, int col) -> bool {   // IsLocalMax_, src/imgproc.h:175-212
     if (nms > 0) {
@@ -439,7 +451,18 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
   if (_options.verbose)
     printf("updated %d [%0.2f%%] max %d new %d\n", num_updated, 100.0 * num_updated / _scene_points.size(),
            max_num_to_update, (int)new_scene_points.size());
-  for (auto& p : new_scene_points) ExtractPatch(p->descriptor.data(), I_ptr, rows, cols, p->x, p->y, radius);
+  if (multi) {
+    // ExtractPatch of every channel (src/photobundle.cc:466-479, :601-606) on the device
+    const int n_new = (int)new_scene_points.size();
+    std::vector<int32_t> xy((size_t)2 * n_new);
+    for (int i = 0; i < n_new; ++i) { xy[2 * i] = new_scene_points[i]->x; xy[2 * i + 1] = new_scene_points[i]->y; }
+    std::vector<double> dsc((size_t)n_new * descriptor_dim);
+    check(pba_extract_descriptors(_gpu, n_new, xy.data(), dsc.data()), "pba_extract_descriptors");
+    for (int i = 0; i < n_new; ++i)
+      std::copy(dsc.begin() + (size_t)i * descriptor_dim, dsc.begin() + (size_t)(i + 1) * descriptor_dim, new_scene_points[i]->descriptor.begin());
+  } else {
+    for (auto& p : new_scene_points) ExtractPatch(p->descriptor.data(), I_ptr, rows, cols, p->x, p->y, radius);
+  }
   _scene_points.reserve(_scene_points.size() + new_scene_points.size());
   std::move(new_scene_points.begin(), new_scene_points.end(), std::back_inserter(_scene_points));
 
@@ -491,7 +514,7 @@ void PhotometricBundleAdjustment::optimize(Result* result) {
     std::vector<const uint8_t*> imgs(F);
     for (int f = 0; f < F; ++f) imgs[f] = _frame_buffer[f].image.data();
     auto check = [&](int rc, const char* what) { if (rc != PBA_OK) throw std::runtime_error(std::string(what) + ": " + pba_last_error()); };
-    check(pba_set_frames_u8(_gpu, F, imgs.data()), "pba_set_frames_u8");
+    check(pba_set_frames_u8_descriptor(_gpu, F, imgs.data(), _desc_type), "pba_set_frames_u8_descriptor");
     check(pba_set_poses(_gpu, F, cams.data(), 0 /* first camera constant, :809-816 */), "pba_set_poses");
     check(pba_set_points(_gpu, n_sel, xyz.data(), desc.data(), obs_off.data(), obs_frame.data(), patch_weights.data()), "pba_set_points");
     pba_solver_options opt;

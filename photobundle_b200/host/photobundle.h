@@ -90,6 +90,7 @@ class PhotometricBundleAdjustment {
   Mat33 _K_inv;
   pba_handle* _gpu = nullptr;
   int _gpu_max_points = 0, _gpu_max_obs = 0;
+  int _desc_type = 0, _n_channels = 1;   // PBA_DESC_* / channels per pixel of the descriptor
   void ensureGpu(int n_points, int n_obs);
 };
 

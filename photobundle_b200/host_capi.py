@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpba_host.so")
 class Options(C.Structure):
     _fields_ = [("maxNumPoints", C.c_int32), ("slidingWindowSize", C.c_int32), ("patchRadius", C.c_int32),
                 ("maskBlockRadius", C.c_int32), ("maxFrameDistance", C.c_int32), ("nonMaxSuppRadius", C.c_int32),
-                ("doGaussianWeighting", C.c_int32), ("verbose", C.c_int32), ("device", C.c_int32),
+                ("doGaussianWeighting", C.c_int32), ("verbose", C.c_int32), ("device", C.c_int32), ("descriptorType", C.c_int32),
                 ("minScore", C.c_double), ("robustThreshold", C.c_double), ("minValidDepth", C.c_double),
                 ("maxValidDepth", C.c_double)]
 
@@ -101,7 +101,7 @@ class BundleAdjuster:
         for i in range(n):
             nv = L.pbah_scene_point(self._h, i, C.c_void_p(X.ctypes.data), C.c_void_p(xy.ctypes.data),
                                     C.c_void_p(vis.ctypes.data), 64, C.c_void_p(desc.ctypes.data), desc.size)
-            P = (2 * self.opts.patchRadius + 1) ** 2
+            P = (2 * self.opts.patchRadius + 1) ** 2 * {0: 1, 1: 3, 2: 8}[int(self.opts.descriptorType)]
             out.append(dict(X=X.copy(), x=int(xy[0]), y=int(xy[1]), vis=vis[:nv].tolist(), desc=desc[:P].copy()))
         return out
 

@@ -134,3 +134,33 @@ def test_run_sequence_driver(seq, tmp_path):
     assert out.shape == (n, 12)
     T = np.tile(np.eye(4), (n, 1, 1)); T[:, :3, :] = out.reshape(n, 3, 4)
     _check_refined(T, seq)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("descriptor_type,channels", [(1, 3), (2, 8)])
+def test_sliding_window_multichannel_descriptors(seq, descriptor_type, channels):
+    """Options::descriptorType = IntensityAndGradient / BitPlanes (src/photobundle.cc:233-245): the channel
+    planes, the saliency map and the reference descriptors are built on the device (k_prep.cu); the
+    descriptors the class stores equal the oracle's restatement and the window solve reduces the cost."""
+    from oracle import binding as ob
+    rows, cols = seq.images.shape[1:]
+    n = 7
+    ba = host_capi.BundleAdjuster(rows, cols, *seq.K4, slidingWindowSize=5, maxNumPoints=1024, verbose=0, minScore=0.65,
+                                  descriptorType=descriptor_type)
+    ran = []
+    for i in range(n):
+        ran.append(ba.add_frame(seq.images[i], seq.depths[i], seq.T_rel_init[i]))
+        if i == 0:
+            pts = ba.scene_points()
+            name = {1: "intensity_and_gradient", 2: "bitplanes"}[descriptor_type]
+            planes = ob.build_channels(seq.images[0], name)
+            assert len(pts) > 100
+            for p in pts[:50]:
+                assert len(p["desc"]) == channels * 25
+                xy = np.array([[p["x"], p["y"]]], dtype=np.int32)
+                assert np.array_equal(np.asarray(p["desc"]), ob.extract_patches(planes, xy, 2)[0])
+    assert ran == [False] * 4 + [True] * (n - 4)
+    res = ba.result()
+    assert res["finalCost"] < res["initialCost"] and res["numResiduals"] > 1000 * channels // 2
+    assert np.isfinite(res["poses"]).all()
+    ba.close()
