@@ -239,3 +239,32 @@ def test_state_errors(small_win):
         h.set_points(np.zeros((w.n_points + 1, 3)), np.zeros((w.n_points + 1, 25)),
                      np.zeros(w.n_points + 2, dtype=np.int32), np.zeros(1, dtype=np.int32), w.weights)
     h.close()
+
+
+def test_empty_window(small_win):
+    """No residual blocks: nothing to evaluate, the solve terminates at once with zero cost (no hang, no launch of an empty grid)."""
+    w = small_win
+    h = capi.Handle(w.rows, w.cols, w.fx, w.fy, w.cx, w.cy, radius=2, max_frames=w.n_frames, max_points=16, max_observations=64)
+    h.set_frames_u8(w.images)
+    h.set_poses(w.cams_init, 0)
+    h.set_points(np.zeros((0, 3)), np.zeros((0, 25)), np.zeros(1, dtype=np.int32), np.zeros(0, dtype=np.int32), w.weights)
+    assert h.eval()["cost"] == 0.0
+    s = h.solve()
+    assert s["initial_cost"] == 0.0 and s["final_cost"] == 0.0 and s["termination_type"] == 0 and s["num_iterations"] == 1
+    assert np.array_equal(h.get_poses(), w.cams_init)
+    h.close()
+
+
+def test_sixteen_free_cameras_full_reduced_system():
+    """Largest reduced system the boundary admits: 16 frames, no fixed camera (96 x 96), points seen in up to 16 frames."""
+    import dataclasses
+    w = dataclasses.replace(synthetic.small_window(seed=5, n_frames=16, grid=(8, 10)), fixed_frame=-1)
+    ocams, opts, osum, otr = ob.OracleWindow(w, num_threads=1).solve(w.cams_init, w.points_init, max_num_iterations=6)
+    h = capi.Handle.for_window(w)
+    s = h.solve(max_num_iterations=6)
+    tr = h.get_iterations()
+    h.close()
+    assert [t["step_is_successful"] for t in tr] == [t["step_is_successful"] for t in otr]
+    for a, b in zip(tr, otr):
+        assert abs(a["cost"] - b["cost"]) <= 1e-6 * b["cost"]
+    assert s["final_cost"] < 0.6 * s["initial_cost"]
