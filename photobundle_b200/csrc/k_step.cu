@@ -82,25 +82,33 @@ __constant__ signed char c_pair3[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}
 // One thread per (frame, matrix element e = 3a+b): the nine threads of a frame evaluate the angle,
 // its sine/cosine and the axis redundantly (the latency of that chain is what costs, not its
 // throughput) and then one element each of R, Rj and M; thread e = 0 also writes the vector part.
+__device__ __forceinline__ double sel3(double x0, double x1, double x2, int i) { return i == 0 ? x0 : (i == 1 ? x1 : x2); }
+// element (r, c) of the cross-product matrix [v]x  (selects instead of indexed local arrays: local memory
+// means L2 here, the shared-memory carve-out leaves almost no L1)
+__device__ __forceinline__ double skew_el(double v0, double v1, double v2, int r, int c) {
+  if (r == c) return 0.0;
+  const double m = sel3(v0, v1, v2, 3 - r - c);
+  return ((c - r + 3) % 3 == 1) ? -m : m;
+}
 __device__ void pose_consts(const double* cam, double* pc, int e) {
   const double w0 = cam[0], w1 = cam[1], w2 = cam[2];
   const double theta2 = __dadd_rn(__dadd_rn(__dmul_rn(w0, w0), __dmul_rn(w1, w1)), __dmul_rn(w2, w2));
   const int a = e / 3, b = e - 3 * a;
-  const double w[3] = {w0, w1, w2};
-  const double Wx[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
   if (theta2 > DBL_EPSILON) {
     const double theta = sqrt(theta2);
     double s, c;
     sincos(theta, &s, &c);
-    const double k[3] = {w0 / theta, w1 / theta, w2 / theta};
-    const double K[9] = {0, -k[2], k[1], k[2], 0, -k[0], -k[1], k[0], 0};
-    double Rcol[3];   // column a of R
-#pragma unroll
-    for (int q = 0; q < 3; ++q) Rcol[q] = (q == a ? c : 0.0) + s * K[q * 3 + a] + (1.0 - c) * k[q] * k[a];
-    const double Rab = (a == b ? c : 0.0) + s * K[a * 3 + b] + (1.0 - c) * k[a] * k[b];
-    double acc = w[a] * w[b];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) acc += (Rcol[q] - (q == a ? 1.0 : 0.0)) * Wx[q * 3 + b];
+    const double k0 = w0 / theta, k1 = w1 / theta, k2 = w2 / theta;
+    const double ka = sel3(k0, k1, k2, a), kb = sel3(k0, k1, k2, b);
+    // column a of R, and R[a][b]:  R = c I + s [k]x + (1 - c) k k^T
+    const double R0a = (a == 0 ? c : 0.0) + s * skew_el(k0, k1, k2, 0, a) + (1.0 - c) * k0 * ka;
+    const double R1a = (a == 1 ? c : 0.0) + s * skew_el(k0, k1, k2, 1, a) + (1.0 - c) * k1 * ka;
+    const double R2a = (a == 2 ? c : 0.0) + s * skew_el(k0, k1, k2, 2, a) + (1.0 - c) * k2 * ka;
+    const double Rab = (a == b ? c : 0.0) + s * skew_el(k0, k1, k2, a, b) + (1.0 - c) * ka * kb;
+    double acc = sel3(w0, w1, w2, a) * sel3(w0, w1, w2, b);
+    acc += (R0a - (a == 0 ? 1.0 : 0.0)) * skew_el(w0, w1, w2, 0, b);
+    acc += (R1a - (a == 1 ? 1.0 : 0.0)) * skew_el(w0, w1, w2, 1, b);
+    acc += (R2a - (a == 2 ? 1.0 : 0.0)) * skew_el(w0, w1, w2, 2, b);
     pc[9 + e] = Rab; pc[18 + e] = Rab; pc[27 + e] = acc / theta2;
     if (e == 0) {
       const double ti = 1.0 / theta;
@@ -109,7 +117,7 @@ __device__ void pose_consts(const double* cam, double* pc, int e) {
     }
   } else {
     const double id = (a == b) ? 1.0 : 0.0;
-    pc[9 + e] = id + Wx[e]; pc[18 + e] = id; pc[27 + e] = id;
+    pc[9 + e] = id + skew_el(w0, w1, w2, a, b); pc[18 + e] = id; pc[27 + e] = id;
     if (e == 0) {
       pc[0] = w0; pc[1] = w1; pc[2] = w2; pc[3] = cam[3]; pc[4] = cam[4]; pc[5] = cam[5];
       pc[6] = 1.0; pc[7] = 0.0; pc[8] = 1.0;
@@ -335,55 +343,40 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
   double* s_pose = reinterpret_cast<double*>(smem_raw);                       // [F][36]
   double* s_sstep = s_pose + F * kPoseConst;                                  // [F][6]
   double* s_E = s_sstep + F * 6;                                              // [warps][8] (all offsets even: 16 B alignment)
-  double* s_geo = s_E + WARPS * kEacc;                                 // [warps][8][20]
-  double* s_geo_w = s_geo + warp * (kObsBatch * 20);
-  double* s_red = s_geo + WARPS * (kObsBatch * 20);                    // [warps][25][6G+2]
-  double* s_red_w = s_red + warp * (25 * kRedStride);
-  double* s_tot = s_red + WARPS * (25 * kRedStride);                   // [warps][8][6]: patch sums of the batch's observations
-  double* s_tot_w = s_tot + warp * (6 * kObsBatch);
+  // one contiguous block per warp, every region but the last at a compile-time offset of its base: a single
+  // live address register instead of one per region (the kernel sits at the 72-register ceiling)
+  constexpr int kFpBytes = ((kStageSlots * FT::FLOATS * (int)sizeof(FPT) + 15) / 16) * 16;
+  constexpr int kOffGeo = 0;                                                  // [8][20] f64
+  constexpr int kOffRed = kOffGeo + 8 * kObsBatch * 20;                       // [25][6G+2] f64
+  constexpr int kOffTot = kOffRed + 8 * 25 * kRedStride;                      // [8][6] f64: patch sums of the batch's observations
+  constexpr int kOffGi = kOffTot + 8 * 6 * kObsBatch;                         // [8] int4
+  constexpr int kOffFrm = kOffGi + 16 * kObsBatch;                            // [16] i32
+  constexpr int kOffFp = kOffFrm + 4 * kMaxFrames;                            // [8][ROWS][W] footprints
+  constexpr int kOffU = kOffFp + kFpBytes;                                    // [F][27] f64: this warp's pose blocks
+  static_assert(kOffGi % 16 == 0 && kOffFp % 16 == 0 && kOffU % 8 == 0, "per-warp shared-memory layout alignment");
   const int ustride = F * kUStride + (F & 1);
-  double* s_U = s_tot + WARPS * (6 * kObsBatch);                            // [warps][F][27]: this warp's pose blocks
-  double* s_U_w = s_U + warp * ustride;
-  int4* s_gi = reinterpret_cast<int4*>(s_U + WARPS * ustride);         // [warps][8]
-  int4* s_gi_w = s_gi + warp * kObsBatch;
-  int* s_frm = reinterpret_cast<int*>(s_gi + WARPS * kObsBatch);       // [warps][16]
-  int* s_frm_w = s_frm + warp * kMaxFrames;
-  constexpr int kFpStride = ((kStageSlots * FT::FLOATS * (int)sizeof(FPT) + 15) / 16) * 16 / (int)sizeof(FPT);
-  FPT* s_fp = reinterpret_cast<FPT*>(s_frm + WARPS * kMaxFrames);
-  FPT* s_fp_w = s_fp + warp * kFpStride;                                       // [8][ROWS][W]
+  const int warp_bytes = kOffU + 8 * ustride;
+  unsigned char* s_warp0 = reinterpret_cast<unsigned char*>(s_E + WARPS * kEacc);
+  unsigned char* wbase = s_warp0 + warp * warp_bytes;
+  double* s_geo_w = reinterpret_cast<double*>(wbase + kOffGeo);
+  double* s_red_w = reinterpret_cast<double*>(wbase + kOffRed);
+  double* s_tot_w = reinterpret_cast<double*>(wbase + kOffTot);
+  int4* s_gi_w = reinterpret_cast<int4*>(wbase + kOffGi);
+  int* s_frm_w = reinterpret_cast<int*>(wbase + kOffFrm);
+  FPT* s_fp_w = reinterpret_cast<FPT*>(wbase + kOffFp);
+  double* s_U_w = reinterpret_cast<double*>(wbase + kOffU);
 
   if (threadIdx.x < 9 * F) pose_consts(cams + 6 * (threadIdx.x / 9), s_pose + (threadIdx.x / 9) * kPoseConst, threadIdx.x % 9);
   if (backsub)
     for (int i = threadIdx.x; i < F * 6; i += blockDim.x)
       s_sstep[i] = (st->free_index[i / 6] >= 0) ? st->scale_c[i] * st->step_c[i] : 0.0;
   for (int i = lane; i < F * kUStride; i += 32) s_U_w[i] = 0.0;
+  if (lane < kEacc) s_E[warp * kEacc + lane] = 0.0;
   __syncthreads();
 
-  // ---- per-lane constants --------------------------------------------------------------
-  double pdx[PR], pdy[PR], wj[PR];
-#pragma unroll
-  for (int r = 0; r < PR; ++r) {
-    const int j = min(lane + 32 * r, P - 1);      // lanes beyond the patch re-do pixel P-1 with weight 0
-    const int py = j / FT::SIDE, pxo = j - py * FT::SIDE;
-    pdx[r] = (double)(pxo - R); pdy[r] = (double)(py - R);
-    wj[r] = (lane + 32 * r < P) ? __ldg(prm.weights + j) : 0.0;
-  }
-  int st_off[FT::ROUNDS];
-#pragma unroll
-  for (int rd = 0; rd < FT::ROUNDS; ++rd) {
-    const int wi = lane + 32 * rd;
-    const int row = wi / FT::NW, wd = wi - row * FT::NW;
-    st_off[rd] = (wi < FT::WORDS) ? row * prm.fr.pitch + 4 * wd : -1;
-  }
-  int e1a = 0, e1b = 0, e2a = 0, e2b = 0;
-  if (lane < 21) { e1a = c_pair6[lane][0]; e1b = c_pair6[lane][1]; }
-  else if (lane < 27) { e1a = lane - 21; }
-  if (lane < 18) { e2a = lane / 3; e2b = 6 + lane - 3 * (lane / 3); }
-  else if (lane < 24) { e2a = 6 + c_pair3[lane - 18][0]; e2b = 6 + c_pair3[lane - 18][1]; }
-  else if (lane < 27) { e2a = 6 + lane - 24; }
-
-  double cost_w = 0.0, gsq_w = 0.0, gmax_w = 0.0, xsq_w = 0.0;
-  double bs_sg = 0.0, bs_sHs = 0.0, bs_step = 0.0, bs_cand = 0.0;
+  // per-warp scalars {cost, sum g_p^2, max|g_p|, sum|X|^2, s.g, s'Hs, |step|^2, |x+step|^2} accumulate in shared
+  // memory (s_E, zeroed before the prologue barrier), not in registers that would stay live across every phase
+  double* s_E_w = s_E + warp * kEacc;
   for (int p = blockIdx.x * WARPS + warp; p < prm.n_points; p += gridDim.x * WARPS) {
     KTRACE(1);
     const int o0 = prm.obs_off[p], nobs = prm.obs_off[p + 1] - o0;
@@ -436,17 +429,46 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
       if (lane == 0) {
         // s.gs + s^T Vs0 s + 2 step_c^T Ws s   (undamped Vs0 = sp V sp)
         const double y0 = s0 * sp[0], y1 = s1 * sp[1], y2 = s2 * sp[2];
-        bs_sg += s0 * gs[0] + s1 * gs[1] + s2 * gs[2];
-        bs_sHs += y0 * (Vv[0] * y0 + Vv[1] * y1 + Vv[2] * y2) + y1 * (Vv[1] * y0 + Vv[3] * y1 + Vv[4] * y2) +
-                 y2 * (Vv[2] * y0 + Vv[4] * y1 + Vv[5] * y2) + 2.0 * (wts[0] * s0 + wts[1] * s1 + wts[2] * s2);
-        bs_step += (X0 - c0) * (X0 - c0) + (X1 - c1) * (X1 - c1) + (X2 - c2) * (X2 - c2);
-        bs_cand += c0 * c0 + c1 * c1 + c2 * c2;
+        s_E_w[4] += s0 * gs[0] + s1 * gs[1] + s2 * gs[2];
+        s_E_w[5] += y0 * (Vv[0] * y0 + Vv[1] * y1 + Vv[2] * y2) + y1 * (Vv[1] * y0 + Vv[3] * y1 + Vv[4] * y2) +
+                    y2 * (Vv[2] * y0 + Vv[4] * y1 + Vv[5] * y2) + 2.0 * (wts[0] * s0 + wts[1] * s1 + wts[2] * s2);
+        s_E_w[6] += (X0 - c0) * (X0 - c0) + (X1 - c1) * (X1 - c1) + (X2 - c2) * (X2 - c2);
+        s_E_w[7] += c0 * c0 + c1 * c1 + c2 * c2;
       }
       X0 = c0; X1 = c1; X2 = c2;
       if (lane < 3) pts_out[3 * p + lane] = lane == 0 ? c0 : (lane == 1 ? c1 : c2);
     }
-    xsq_w += X0 * X0 + X1 * X1 + X2 * X2;
+    if (lane == 0) s_E_w[3] += X0 * X0 + X1 * X1 + X2 * X2;
+    double cost_p = 0.0;   // this lane's share of the point's cost
     KTRACE(2);
+
+    // ---- per-lane constants.  Formed HERE, per point, from an opaque copy of the lane id: as loop invariants
+    // they were kept live across the back-substitution, pushed it over the 72-register ceiling and came back
+    // from local memory - which, with the shared-memory carve-out at its maximum, means from L2.
+    int lane_l = lane;
+    asm volatile("" : "+r"(lane_l));
+    double pdx[PR], pdy[PR], wj[PR];
+  #pragma unroll
+    for (int r = 0; r < PR; ++r) {
+      const int j = min(lane_l + 32 * r, P - 1);      // lanes beyond the patch re-do pixel P-1 with weight 0
+      const int py = j / FT::SIDE, pxo = j - py * FT::SIDE;
+      pdx[r] = (double)(pxo - R); pdy[r] = (double)(py - R);
+      wj[r] = (lane_l + 32 * r < P) ? __ldg(prm.weights + j) : 0.0;
+    }
+    int st_off[FT::ROUNDS];
+  #pragma unroll
+    for (int rd = 0; rd < FT::ROUNDS; ++rd) {
+      const int wi = lane_l + 32 * rd;
+      const int row = wi / FT::NW, wd = wi - row * FT::NW;
+      st_off[rd] = (wi < FT::WORDS) ? row * prm.fr.pitch + 4 * wd : -1;
+    }
+    int e1a = 0, e1b = 0, e2a = 0, e2b = 0;
+    if (lane_l < 21) { e1a = c_pair6[lane_l][0]; e1b = c_pair6[lane_l][1]; }
+    else if (lane_l < 27) { e1a = lane_l - 21; }
+    if (lane_l < 18) { e2a = lane_l / 3; e2b = 6 + lane_l - 3 * (lane_l / 3); }
+    else if (lane_l < 24) { e2a = 6 + c_pair3[lane_l - 18][0]; e2b = 6 + c_pair3[lane_l - 18][1]; }
+    else if (lane_l < 27) { e2a = 6 + lane_l - 24; }
+
 
     double acc_pt = 0.0;  // lanes 18..23: V entries, 24..26: g_p entries (summed over frames)
     for (int ob = 0; ob < nobs; ob += kObsBatch) {
@@ -689,7 +711,7 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
               double rho0, rho1;
               huber_rho(prm.huber, q.s, rho0, rho1);
               if (lane == 0) {
-                cost_w += 0.5 * rho0;
+                cost_p += 0.5 * rho0;
                 if (prm.obs_sqnorm) prm.obs_sqnorm[o] = q.s;
               }
               emit_blocks(rho1 * q.G11, rho1 * q.G12, rho1 * q.G22, rho1 * q.b1, rho1 * q.b2, g, f, f != prm.fixed_frame, lane,
@@ -710,7 +732,7 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
             double rho0, rho1;
             huber_rho(prm.huber, s_i, rho0, rho1);
             if (k_l == 0) {
-              cost_w += 0.5 * rho0;
+              cost_p += 0.5 * rho0;
               if (prm.obs_sqnorm) prm.obs_sqnorm[o0 + ob + i_l] = s_i;
             } else {
               s_tot_w[idx] = rho1 * raw;
@@ -741,14 +763,13 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
       g2 += __shfl_xor_sync(0xffffffffu, g2, m);
       ga = fmax(ga, __shfl_xor_sync(0xffffffffu, ga, m));
     }
-    gsq_w += __shfl_sync(0xffffffffu, g2, 24);
-    gmax_w = fmax(gmax_w, __shfl_sync(0xffffffffu, ga, 24));
-  }
 #pragma unroll
-  for (int m = 16; m > 0; m >>= 1) cost_w += __shfl_xor_sync(0xffffffffu, cost_w, m);   // lanes 0,6,12,18 hold partial costs
-  if (lane == 0) {
-    double* e = s_E + warp * kEacc;
-    e[0] = cost_w; e[1] = gsq_w; e[2] = gmax_w; e[3] = xsq_w; e[4] = bs_sg; e[5] = bs_sHs; e[6] = bs_step; e[7] = bs_cand;
+    for (int m = 16; m > 0; m >>= 1) cost_p += __shfl_xor_sync(0xffffffffu, cost_p, m);
+    if (lane == 24) {   // lane 24 holds the reduced g_p sums
+      s_E_w[0] += cost_p;
+      s_E_w[1] += g2;
+      s_E_w[2] = fmax(s_E_w[2], ga);
+    }
   }
   __syncthreads();
 #ifdef K_STEP_TRACE
@@ -759,7 +780,7 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
   for (int i = threadIdx.x; i < F * kUStride; i += blockDim.x) {
     double acc = 0.0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) acc += s_U[w * ustride + i];
+    for (int w = 0; w < WARPS; ++w) acc += reinterpret_cast<const double*>(s_warp0 + w * warp_bytes + kOffU)[i];
     if (acc != 0.0) atomicAdd(prm.Xacc + i, acc);
   }
   if (threadIdx.x < kEacc) {
