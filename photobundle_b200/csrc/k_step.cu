@@ -473,12 +473,15 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
     double acc_pt = 0.0;  // lanes 18..23: V entries, 24..26: g_p entries (summed over frames)
     for (int ob = 0; ob < nobs; ob += kObsBatch) {
       const int nb = min(kObsBatch, nobs - ob);
-      // ---- (G1) warp + project: lane i <-> observation ob+i ---------------------------
+      // ---- (G1) warp + project: lanes i, i+8, i+16 <-> observation ob+i (three copies: each forms one
+      // column of the Jacobian in (G2); an FP64 instruction costs the same issue slots for 8 lanes as for 24)
       int g_fast_l = 0;
       double Xc0 = 0.0, Xc1 = 0.0, Xc2 = 1.0;
       const double* pc = s_pose;
-      if (lane < nb) {
-        const int g_f = s_frm_w[ob + lane];
+      const int g_i = lane & 7, g_b = lane >> 3;          // observation within the batch, Jacobian column
+      const bool g_act = g_b < 3 && g_i < nb;
+      if (g_act) {
+        const int g_f = s_frm_w[ob + g_i];
         pc = s_pose + g_f * kPoseConst;
         if (pc[8] == 0.0) {  // ceres::AngleAxisRotatePoint, same operation order (no FMA)
           const double k0 = pc[0], k1 = pc[1], k2 = pc[2], c = pc[6], s = pc[7];
@@ -497,23 +500,25 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
           Xc2 = __dadd_rn(X2, __dsub_rn(__dmul_rn(a0, X1), __dmul_rn(a1, X0)));
         }
         Xc0 = __dadd_rn(Xc0, pc[3]); Xc1 = __dadd_rn(Xc1, pc[4]); Xc2 = __dadd_rn(Xc2, pc[5]);
-        // Calibration::project: u = ((X*fx)/Z) + cx  (IEEE division, T = double path)
-        const double u = __dadd_rn(__ddiv_rn(__dmul_rn(Xc0, prm.fx), Xc2), prm.cx);
-        const double v = __dadd_rn(__ddiv_rn(__dmul_rn(Xc1, prm.fy), Xc2), prm.cy);
-        double* g = s_geo_w + lane * 20;
-        g[0] = u; g[1] = v;
-        // footprint origin and fast-path test (all taps and gradient taps interior)
-        int4 gi = make_int4(g_f, 0, 0, 0);   // {frame, r0, cb (aligned first column), fast}
-        if (fabs(u) < 1.0e8 && fabs(v) < 1.0e8) {
-          const int c0 = (int)floor(u) - R - 1, r0 = (int)floor(v) - R - 1;
-          const int fast = (c0 >= 0 && c0 + FT::ROWS - 1 <= prm.fr.cols - 1 && r0 >= 0 &&
-                            r0 + FT::ROWS - 1 <= prm.fr.rows - 1) ? 1 : 0;
-          gi.y = r0; gi.z = c0 & ~3; gi.w = fast;
+        if (g_b == 0) {
+          // Calibration::project: u = ((X*fx)/Z) + cx  (IEEE division, T = double path)
+          const double u = __dadd_rn(__ddiv_rn(__dmul_rn(Xc0, prm.fx), Xc2), prm.cx);
+          const double v = __dadd_rn(__ddiv_rn(__dmul_rn(Xc1, prm.fy), Xc2), prm.cy);
+          double* g = s_geo_w + g_i * 20;
+          g[0] = u; g[1] = v;
+          // footprint origin and fast-path test (all taps and gradient taps interior)
+          int4 gi = make_int4(g_f, 0, 0, 0);   // {frame, r0, cb (aligned first column), fast}
+          if (fabs(u) < 1.0e8 && fabs(v) < 1.0e8) {
+            const int c0 = (int)floor(u) - R - 1, r0 = (int)floor(v) - R - 1;
+            const int fast = (c0 >= 0 && c0 + FT::ROWS - 1 <= prm.fr.cols - 1 && r0 >= 0 &&
+                              r0 + FT::ROWS - 1 <= prm.fr.rows - 1) ? 1 : 0;
+            gi.y = r0; gi.z = c0 & ~3; gi.w = fast;
+          }
+          s_gi_w[g_i] = gi;
+          g_fast_l = gi.w;
         }
-        s_gi_w[lane] = gi;
-        g_fast_l = gi.w;
       }
-      const unsigned fastmask = __ballot_sync(0xffffffffu, g_fast_l != 0);
+      const unsigned fastmask = __ballot_sync(0xffffffffu, g_fast_l != 0) & 0xffu;
       __syncwarp();
       // ---- (L) 1-channel frames: every footprint of the batch is requested NOW with asynchronous
       // copies (global -> shared, no registers held), so the L2 round trips overlap with (G2) ------
@@ -538,32 +543,29 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
         }
         cp_async_commit();
       }
-      // ---- (G2) the 2x9 matrix A = d(u,v)/d[w t X] of each observation -------------------------
-      if (lane < nb) {
-        double* g = s_geo_w + lane * 20;
+      // ---- (G2) the 2x9 matrix A = d(u,v)/d[w t X] of each observation; lane (i, b) forms column b of the
+      // rotation, translation and point parts --------------------------------------------------------
+      if (g_act) {
+        double* g = s_geo_w + g_i * 20;
+        const int b = g_b;
         const double iz = 1.0 / Xc2;
         const double J00 = prm.fx * iz, J02 = -prm.fx * Xc0 * iz * iz;
         const double J11 = prm.fy * iz, J12 = -prm.fy * Xc1 * iz * iz;
         const double* Rj = pc + 18;
         const double* M = pc + 27;
-        double D[9];   // D = -Rj [X]x M
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-          const double m0 = M[b], m1 = M[3 + b], m2 = M[6 + b];
-          const double t0 = X1 * m2 - X2 * m1, t1 = X2 * m0 - X0 * m2, t2 = X0 * m1 - X1 * m0;
-#pragma unroll
-          for (int a = 0; a < 3; ++a) D[a * 3 + b] = -(Rj[a * 3] * t0 + Rj[a * 3 + 1] * t1 + Rj[a * 3 + 2] * t2);
-        }
+        // column b of D = -Rj [X]x M
+        const double m0 = M[b], m1 = M[3 + b], m2 = M[6 + b];
+        const double t0 = X1 * m2 - X2 * m1, t1 = X2 * m0 - X0 * m2, t2 = X0 * m1 - X1 * m0;
+        const double D0 = -(Rj[0] * t0 + Rj[1] * t1 + Rj[2] * t2);
+        const double D1 = -(Rj[3] * t0 + Rj[4] * t1 + Rj[5] * t2);
+        const double D2 = -(Rj[6] * t0 + Rj[7] * t1 + Rj[8] * t2);
         const double* Rm = pc + 9;
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-          g[2 + b] = J00 * D[b] + J02 * D[6 + b];            // du/dw
-          g[11 + b] = J11 * D[3 + b] + J12 * D[6 + b];       // dv/dw
-          g[8 + b] = J00 * Rm[b] + J02 * Rm[6 + b];          // du/dX
-          g[17 + b] = J11 * Rm[3 + b] + J12 * Rm[6 + b];     // dv/dX
-        }
-        g[5] = J00; g[6] = 0.0; g[7] = J02;                  // du/dt
-        g[14] = 0.0; g[15] = J11; g[16] = J12;               // dv/dt
+        g[2 + b] = J00 * D0 + J02 * D2;                      // du/dw
+        g[11 + b] = J11 * D1 + J12 * D2;                     // dv/dw
+        g[8 + b] = J00 * Rm[b] + J02 * Rm[6 + b];            // du/dX
+        g[17 + b] = J11 * Rm[3 + b] + J12 * Rm[6 + b];       // dv/dX
+        g[5 + b] = b == 0 ? J00 : (b == 1 ? 0.0 : J02);      // du/dt
+        g[14 + b] = b == 0 ? 0.0 : (b == 1 ? J11 : J12);     // dv/dt
       }
       if (kAsyncStage) cp_async_wait_all();
       __syncwarp();
