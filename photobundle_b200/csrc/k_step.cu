@@ -288,6 +288,9 @@ __device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -372,20 +375,44 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
       s_sstep[i] = (st->free_index[i / 6] >= 0) ? st->scale_c[i] * st->step_c[i] : 0.0;
   for (int i = lane; i < F * kUStride; i += 32) s_U_w[i] = 0.0;
   if (lane < kEacc) s_E[warp * kEacc + lane] = 0.0;
-  __syncthreads();
+  // (the CTA barrier that publishes s_pose / s_sstep sits inside the first iteration of the point loop, behind
+  //  the requests for the first point's inputs, so their L2 round trips overlap with the pose constants)
 
   // per-warp scalars {cost, sum g_p^2, max|g_p|, sum|X|^2, s.g, s'Hs, |step|^2, |x+step|^2} accumulate in shared
   // memory (s_E, zeroed before the prologue barrier), not in registers that would stay live across every phase
   double* s_E_w = s_E + warp * kEacc;
-  for (int p = blockIdx.x * WARPS + warp; p < prm.n_points; p += gridDim.x * WARPS) {
-    KTRACE(1);
-    const int o0 = prm.obs_off[p], nobs = prm.obs_off[p + 1] - o0;
-    __syncwarp();
-    if (lane < nobs) s_frm_w[lane] = prm.obs_frame[o0 + lane];
-    double X0 = pts_cur[3 * p], X1 = pts_cur[3 * p + 1], X2 = pts_cur[3 * p + 2];
+  // back-substitution inputs, staged asynchronously: W of the point's observations -> the (idle) reduction
+  // buffer, {V, Vinv, g_p, scale_p} -> the (idle) patch-sum buffer
+  double* s_bsW = s_red_w;       // [nobs][18]
+  double* s_bsR = s_tot_w;       // V[6] | Vinv[6] | g_p[3] | scale_p[3]
+  bool need_barrier = true;
+  for (int p = blockIdx.x * WARPS + warp;; p += gridDim.x * WARPS) {
+    const bool valid = p < prm.n_points;
+    int o0 = 0, nobs = 0, frm_l = 0;
+    double X0 = 0.0, X1 = 0.0, X2 = 0.0;
     double p0c[PR];       // reference descriptor of this point, channel 0 (first use: sampling)
+    if (valid) {
+      o0 = __ldg(prm.obs_off + p); nobs = __ldg(prm.obs_off + p + 1) - o0;
+      __syncwarp();                                        // the previous point is done with the staging buffers
+      if (backsub) {
+        const char* Wc = reinterpret_cast<const char*>(prm.W + ((size_t)cur * prm.nnz + o0) * 18);
+        for (int c = lane; c < nobs * 9; c += 32) cp_async_16(reinterpret_cast<char*>(s_bsW) + 16 * c, Wc + 16 * c);
+        if (lane < 3) cp_async_16(reinterpret_cast<char*>(s_bsR) + 16 * lane, reinterpret_cast<const char*>(prm.V + ((size_t)cur * prm.n_points + p) * 6) + 16 * lane);
+        else if (lane < 6) cp_async_16(reinterpret_cast<char*>(s_bsR + 6) + 16 * (lane - 3), reinterpret_cast<const char*>(prm.Vinv + (size_t)p * 6) + 16 * (lane - 3));
+        else if (lane < 9) cp_async_8(s_bsR + 12 + (lane - 6), prm.gp + ((size_t)cur * prm.n_points + p) * 3 + (lane - 6));
+        else if (lane < 12) cp_async_8(s_bsR + 15 + (lane - 9), prm.scale_p + (size_t)p * 3 + (lane - 9));
+        cp_async_commit();
+      }
+      if (lane < nobs) frm_l = __ldg(prm.obs_frame + o0 + lane);
+      X0 = pts_cur[3 * p]; X1 = pts_cur[3 * p + 1]; X2 = pts_cur[3 * p + 2];
 #pragma unroll
-    for (int r = 0; r < PR; ++r) p0c[r] = (double)__ldg(prm.desc + (size_t)p * CP + min(lane + 32 * r, P - 1));
+      for (int r = 0; r < PR; ++r) p0c[r] = (double)__ldg(prm.desc + (size_t)p * CP + min(lane + 32 * r, P - 1));
+    }
+    if (need_barrier) { __syncthreads(); need_barrier = false; }
+    if (!valid) break;
+    KTRACE(1);
+    if (lane < nobs) s_frm_w[lane] = frm_l;
+    if (backsub) cp_async_wait_all();
     __syncwarp();
 
     // ---- (B) back-substitution (SchurEliminator::BackSubstitute + model cost change) -------
@@ -393,24 +420,14 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
       // lane = b*8 + a accumulates sum_obs W[a][b] * (scale_c*step_c)[f][a]
       const int a = lane & 7, b = lane >> 3;
       const bool act = (a < 6 && b < 3);
-      const double* Wc = prm.W + ((size_t)cur * prm.nnz + o0) * 18;
-      // all of the point's W loads are issued before the first use (one L2 round trip, not nobs)
-      const double* Vc = prm.V + ((size_t)cur * prm.n_points + p) * 6;
-      const double* gc = prm.gp + ((size_t)cur * prm.n_points + p) * 3;
       double sp[3], Vi[6], Vv[6], gcv[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { sp[k] = __ldg(prm.scale_p + (size_t)p * 3 + k); gcv[k] = __ldg(gc + k); }
+      for (int k = 0; k < 3; ++k) { sp[k] = s_bsR[15 + k]; gcv[k] = s_bsR[12 + k]; }
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { Vi[k] = __ldg(prm.Vinv + (size_t)p * 6 + k); Vv[k] = __ldg(Vc + k); }
+      for (int k = 0; k < 6; ++k) { Vi[k] = s_bsR[6 + k]; Vv[k] = s_bsR[k]; }
       double acc = 0.0;
-      for (int i0 = 0; i0 < nobs; i0 += 8) {
-        double wv[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) wv[k] = (act && i0 + k < nobs) ? __ldg(Wc + (i0 + k) * 18 + a * 3 + b) : 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (act && i0 + k < nobs) acc = fma(wv[k], s_sstep[s_frm_w[i0 + k] * 6 + a], acc);
-      }
+      if (act)
+        for (int k = 0; k < nobs; ++k) acc = fma(s_bsW[k * 18 + a * 3 + b], s_sstep[s_frm_w[k] * 6 + a], acc);
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       acc += __shfl_xor_sync(0xffffffffu, acc, 4);
