@@ -951,6 +951,11 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
               (t[16 * i + 5] - t[16 * i + 2]) * 1e-3, (t[16 * i + 6] - t[16 * i + 5]) * 1e-3, (t[16 * i + 7] - t[16 * i + 6]) * 1e-3,
               (t[16 * i + 3] - t[16 * i + 7]) * 1e-3,
               (t[16 * i + 4] - t[16 * i + 3]) * 1e-3, i + 1 < k ? (t[16 * (i + 1)] - t[16 * i + 4]) * 1e-3 : 0.0);
+    for (int i = 1; i < std::min(k, 4); ++i)
+      if (t[16 * i + 12])
+        fprintf(stderr, "[pba timeline] K_B %2d eliminate (last CTA): setup %5.2f us  points %5.2f us  warp merge %5.2f us  atomics+ticket %5.2f us\n", i,
+                (t[16 * i + 12] - t[16 * i + 1]) * 1e-3, (t[16 * i + 13] - t[16 * i + 12]) * 1e-3, (t[16 * i + 14] - t[16 * i + 13]) * 1e-3,
+                (t[16 * i + 2] - t[16 * i + 14]) * 1e-3);
     if (h->use_xchg)
       for (int i = 0; i < std::min(k, 6); ++i)
         fprintf(stderr, "[pba timeline] rank %d K_B %2d S exchange: push %5.2f us  fence+flags %5.2f us  wait %5.2f us  sum %5.2f us\n", h->rank, i,

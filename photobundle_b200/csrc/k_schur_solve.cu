@@ -383,6 +383,7 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
 // the warp's points (108 FMA per 36 shared-memory loads); warps are merged through shared memory
 // and the CTA adds its partial to the global accumulators with one fp64 atomic per entry.
 // sm: per warp Z [D][3] + rh [D] | per CTA S_cta [32*36 + D]
+__shared__ unsigned long long s_tdbg[4];   // PBA_DEBUG_TIMELINE: elimination sub-phases of this CTA
 __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int F = lp.n_frames, D = 6 * F, n = lp.n_points, cur = st.cur, nf = st.n_free;
@@ -440,6 +441,7 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
     }
   };
   const int p_first = blockIdx.x * (kSchurThreads / 32) + warp;
+  if (lp.dbg && tid == 0) s_tdbg[0] = gtime();
   if (p_first < n) load_point(p_first);
   for (int p = p_first; p < n; p += pstride) {
     if (first) {
@@ -504,6 +506,7 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
   // one atomic per entry.  Buffers: warp w writes into slot w of Smerge [warps/2][32*36 + 64].
   double* Smerge = sm;   // the Z / rh staging area is dead now
   __syncthreads();
+  if (lp.dbg && tid == 0) s_tdbg[1] = gtime();
   for (int half = (kSchurThreads / 32) / 2; half >= 1; half >>= 1) {
     if (warp >= half && warp < 2 * half) {
       double* dst = Smerge + (size_t)(warp - half) * (32 * 36 + 64);
@@ -520,6 +523,7 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
     }
     __syncthreads();
   }
+  if (lp.dbg && tid == 0) s_tdbg[2] = gtime();
   if (warp == 0) {
     if (lane < npairs) {
 #pragma unroll
@@ -810,7 +814,10 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
     __threadfence();
   }
   __syncthreads();
-  if (lp.dbg && tid == 0 && s_last) { lp.dbg[0] = t_start; lp.dbg[1] = t_dec; lp.dbg[2] = gtime(); }
+  if (lp.dbg && tid == 0 && s_last) {
+    lp.dbg[0] = t_start; lp.dbg[1] = t_dec; lp.dbg[2] = gtime();
+    if (MODE == 0) { lp.dbg[12] = s_tdbg[0]; lp.dbg[13] = s_tdbg[1]; lp.dbg[14] = s_tdbg[2]; }
+  }
   if (!s_last) return;
   if (lp.split) {
     // multi-GPU: the reduced system is summed across ranks first; k_solve_only finishes the iteration

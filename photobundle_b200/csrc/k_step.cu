@@ -311,6 +311,23 @@ __device__ __forceinline__ void emit_blocks(double dG11, double dG12, double dG2
   }
 }
 
+// The two block entries lane `lane` owns for one observation, straight-line (no divergence, no stores): the
+// caller evaluates a whole batch of observations first - independent chains the scheduler can interleave -
+// and only then touches memory.
+__device__ __forceinline__ void block_entries(const double* __restrict__ t, const double* __restrict__ g, int lane, int e1a,
+                                              int e1b, int e2a, int e2b, double& v1, double& v2) {
+  const double* A = g + 2;
+  const double dG11 = t[1], dG12 = t[2], dG22 = t[3], db1 = t[4], db2 = t[5];
+  const double A0a = A[e1a], A1a = A[9 + e1a], A0b = A[e1b], A1b = A[9 + e1b];
+  const double q1 = A0a * (dG11 * A0b + dG12 * A1b) + A1a * (dG12 * A0b + dG22 * A1b);
+  const double l1 = -(A0a * db1 + A1a * db2);
+  v1 = lane < 21 ? q1 : l1;
+  const double B0a = A[e2a], B1a = A[9 + e2a], B0b = A[e2b], B1b = A[9 + e2b];
+  const double q2 = B0a * (dG11 * B0b + dG12 * B1b) + B1a * (dG12 * B0b + dG22 * B1b);
+  const double l2 = -(B0a * db1 + B1a * db2);
+  v2 = lane < 24 ? q2 : l2;
+}
+
 // NCH: compile-time channel count (1 = Intensity, the north-star descriptor); 0 = runtime count.
 template <int R, bool U8, int NCH>
 __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParams prm) {
@@ -759,14 +776,34 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
           }
         }
         __syncwarp();
-        // ---- (E) block expansion, the batch's observations back to back (independent chains)
+        // ---- (E) block expansion.  Full batch (the common case): the entries of all eight observations are
+        // evaluated first, branch-free, and stored afterwards; otherwise observation by observation.
+        if (nb == kObsBatch && defmask == 0xffu) {
+          constexpr int kE = 4;   // observations evaluated together (8 pushes the kernel over its 72 registers)
+#pragma unroll 1
+          for (int i0 = 0; i0 < kObsBatch; i0 += kE) {
+            double v1[kE], v2[kE];
 #pragma unroll
-        for (int i = 0; i < kObsBatch; ++i) {
-          if (i < nb && ((defmask >> i) & 1u)) {
-            const int f = s_gi_w[i].x;
-            const double* t = s_tot_w + 6 * i;
-            emit_blocks(t[1], t[2], t[3], t[4], t[5], s_geo_w + i * 20, f, f != prm.fixed_frame, lane, e1a, e1b, e2a, e2b,
-                        s_U_w, outW + (size_t)(o0 + ob + i) * 18, acc_pt);
+            for (int i = 0; i < kE; ++i)
+              block_entries(s_tot_w + 6 * (i0 + i), s_geo_w + (i0 + i) * 20, lane, e1a, e1b, e2a, e2b, v1[i], v2[i]);
+#pragma unroll
+            for (int i = 0; i < kE; ++i) {
+              const int f = s_gi_w[i0 + i].x;
+              const bool free_cam = f != prm.fixed_frame;
+              if (lane < 27 && free_cam) s_U_w[f * kUStride + lane] += v1[i];   // warp-private: no atomics
+              if (lane < 18) outW[(size_t)(o0 + ob + i0 + i) * 18 + lane] = free_cam ? v2[i] : 0.0;
+              else if (lane < 27) acc_pt += v2[i];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kObsBatch; ++i) {
+            if (i < nb && ((defmask >> i) & 1u)) {
+              const int f = s_gi_w[i].x;
+              const double* t = s_tot_w + 6 * i;
+              emit_blocks(t[1], t[2], t[3], t[4], t[5], s_geo_w + i * 20, f, f != prm.fixed_frame, lane, e1a, e1b, e2a, e2b,
+                          s_U_w, outW + (size_t)(o0 + ob + i) * 18, acc_pt);
+            }
           }
         }
         __syncwarp();
