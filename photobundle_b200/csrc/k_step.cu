@@ -70,11 +70,6 @@ __device__ long long g_kstep_trace[4096 * 16];
 #define KTRACE(slot) do {} while (0)
 #endif
 
-__constant__ signed char c_pair6[21][2] = {
-    {0, 0}, {0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5},
-    {2, 2}, {2, 3}, {2, 4}, {2, 5}, {3, 3}, {3, 4}, {3, 5}, {4, 4}, {4, 5}, {5, 5}};
-__constant__ signed char c_pair3[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
-
 // ---- per-frame pose constants (computed once per CTA) ---------------------------------
 //  [0..2] unit axis k (or the raw angle-axis when tiny)   [3..5] t   [6] cos  [7] sin
 //  [8] tiny flag   [9..17] R   [18..26] Rj   [27..35] M,  with
@@ -174,7 +169,7 @@ constexpr int kG = K_STEP_GROUP;
 constexpr int kRedStride = 6 * kG + 2;   // doubles per lane row of the reduction transpose (6 sums x group + pad, 16 B aligned)
 
 // ---- shared memory carve-up --------------------------------------------------------------
-// per CTA : pose consts [F][36] f64 | sstep [F][6] f64 (scale_c*step_c) | E [warps][8] f64
+// per CTA : pose consts [F][36] f64 | sstep [F][6] f64 (scale_c*step_c) | E [warps][8] f64 | weights [P] f64
 // per warp: geometry [8][20] f64 | reduction transpose [25][6G+2] f64 | patch sums [8][6] f64 |
 //           pose-block accumulators [F][27] f64 | ints [8] int4 | frames [16] i32 |
 //           footprints [8][ROWS][W] f32
@@ -183,7 +178,7 @@ __host__ __device__ constexpr size_t k_step_smem_bytes(int n_frames) {
   constexpr int WARPS = Geo<U8>::WARPS;
   // footprints: raw uint8 (ROWS x W bytes) on the Intensity path, fp32 otherwise
   constexpr size_t fp_bytes = (size_t)kStageSlots * Foot<R>::FLOATS * (U8 ? 1 : 4);
-  return sizeof(double) * ((size_t)n_frames * (kPoseConst + 6) + WARPS * kEacc) +
+  return sizeof(double) * ((size_t)n_frames * (kPoseConst + 6) + WARPS * kEacc + ((Foot<R>::P + 1) & ~1)) +
          (size_t)WARPS * (sizeof(double) * (kObsBatch * 20 + 25 * kRedStride + 6 * kObsBatch + (size_t)n_frames * kUStride + (n_frames & 1)) +
                           sizeof(int4) * kObsBatch + sizeof(int) * kMaxFrames + ((fp_bytes + 15) / 16) * 16);
 }
@@ -363,6 +358,7 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
   double* s_pose = reinterpret_cast<double*>(smem_raw);                       // [F][36]
   double* s_sstep = s_pose + F * kPoseConst;                                  // [F][6]
   double* s_E = s_sstep + F * 6;                                              // [warps][8] (all offsets even: 16 B alignment)
+  double* s_wts = s_E + WARPS * kEacc;                                        // [P (+1)] patch weights
   // one contiguous block per warp, every region but the last at a compile-time offset of its base: a single
   // live address register instead of one per region (the kernel sits at the 72-register ceiling)
   constexpr int kFpBytes = ((kStageSlots * FT::FLOATS * (int)sizeof(FPT) + 15) / 16) * 16;
@@ -376,7 +372,7 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
   static_assert(kOffGi % 16 == 0 && kOffFp % 16 == 0 && kOffU % 8 == 0, "per-warp shared-memory layout alignment");
   const int ustride = F * kUStride + (F & 1);
   const int warp_bytes = kOffU + 8 * ustride;
-  unsigned char* s_warp0 = reinterpret_cast<unsigned char*>(s_E + WARPS * kEacc);
+  unsigned char* s_warp0 = reinterpret_cast<unsigned char*>(s_wts + ((P + 1) & ~1));
   unsigned char* wbase = s_warp0 + warp * warp_bytes;
   double* s_geo_w = reinterpret_cast<double*>(wbase + kOffGeo);
   double* s_red_w = reinterpret_cast<double*>(wbase + kOffRed);
@@ -392,6 +388,7 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
       s_sstep[i] = (st->free_index[i / 6] >= 0) ? st->scale_c[i] * st->step_c[i] : 0.0;
   for (int i = lane; i < F * kUStride; i += 32) s_U_w[i] = 0.0;
   if (lane < kEacc) s_E[warp * kEacc + lane] = 0.0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) s_wts[i] = __ldg(prm.weights + i);
   // (the CTA barrier that publishes s_pose / s_sstep sits inside the first iteration of the point loop, behind
   //  the requests for the first point's inputs, so their L2 round trips overlap with the pose constants)
 
@@ -476,33 +473,18 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
     double cost_p = 0.0;   // this lane's share of the point's cost
     KTRACE(2);
 
-    // ---- per-lane constants.  Formed HERE, per point, from an opaque copy of the lane id: as loop invariants
-    // they were kept live across the back-substitution, pushed it over the 72-register ceiling and came back
-    // from local memory - which, with the shared-memory carve-out at its maximum, means from L2.
+    // ---- per-lane constants.  Formed per point / per batch from an opaque copy of the lane id: as loop
+    // invariants they were kept live across the back-substitution, pushed it over the 72-register ceiling
+    // and came back from local memory - which, with the shared-memory carve-out at its maximum, means L2.
     int lane_l = lane;
     asm volatile("" : "+r"(lane_l));
-    double pdx[PR], pdy[PR], wj[PR];
-  #pragma unroll
-    for (int r = 0; r < PR; ++r) {
-      const int j = min(lane_l + 32 * r, P - 1);      // lanes beyond the patch re-do pixel P-1 with weight 0
-      const int py = j / FT::SIDE, pxo = j - py * FT::SIDE;
-      pdx[r] = (double)(pxo - R); pdy[r] = (double)(py - R);
-      wj[r] = (lane_l + 32 * r < P) ? __ldg(prm.weights + j) : 0.0;
-    }
     int st_off[FT::ROUNDS];
-  #pragma unroll
+#pragma unroll
     for (int rd = 0; rd < FT::ROUNDS; ++rd) {
       const int wi = lane_l + 32 * rd;
       const int row = wi / FT::NW, wd = wi - row * FT::NW;
       st_off[rd] = (wi < FT::WORDS) ? row * prm.fr.pitch + 4 * wd : -1;
     }
-    int e1a = 0, e1b = 0, e2a = 0, e2b = 0;
-    if (lane_l < 21) { e1a = c_pair6[lane_l][0]; e1b = c_pair6[lane_l][1]; }
-    else if (lane_l < 27) { e1a = lane_l - 21; }
-    if (lane_l < 18) { e2a = lane_l / 3; e2b = 6 + lane_l - 3 * (lane_l / 3); }
-    else if (lane_l < 24) { e2a = 6 + c_pair3[lane_l - 18][0]; e2b = 6 + c_pair3[lane_l - 18][1]; }
-    else if (lane_l < 27) { e2a = 6 + lane_l - 24; }
-
 
     double acc_pt = 0.0;  // lanes 18..23: V entries, 24..26: g_p entries (summed over frames)
     for (int ob = 0; ob < nobs; ob += kObsBatch) {
@@ -601,6 +583,27 @@ __global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParam
         g[5 + b] = b == 0 ? J00 : (b == 1 ? 0.0 : J02);      // du/dt
         g[14 + b] = b == 0 ? 0.0 : (b == 1 ? J11 : J12);     // dv/dt
       }
+      // patch offsets, weights and block-entry indices of this lane: independent integer work placed in the
+      // shadow of the asynchronous footprint copies
+      double pdx[PR], pdy[PR], wj[PR];
+#pragma unroll
+      for (int r = 0; r < PR; ++r) {
+        const int j = min(lane_l + 32 * r, P - 1);      // lanes beyond the patch re-do pixel P-1 with weight 0
+        const int py = j / FT::SIDE, pxo = j - py * FT::SIDE;
+        pdx[r] = (double)(pxo - R); pdy[r] = (double)(py - R);
+        wj[r] = (lane_l + 32 * r < P) ? s_wts[j] : 0.0;
+      }
+      // lane l < 21 <-> upper-triangle entry (a, b) of the 6x6 pose block, rows of length 6, 5, ... 1
+      int e1a = 0, e1b = 0, e2a = 0, e2b = 0;
+      if (lane_l < 21) {
+        e1a = (lane_l >= 6) + (lane_l >= 11) + (lane_l >= 15) + (lane_l >= 18) + (lane_l >= 20);
+        e1b = e1a + lane_l - (e1a * (13 - e1a)) / 2;
+      } else if (lane_l < 27) { e1a = lane_l - 21; }
+      if (lane_l < 18) { e2a = lane_l / 3; e2b = 6 + lane_l - 3 * (lane_l / 3); }
+      else if (lane_l < 24) {          // upper triangle of the 3x3 point block
+        const int i3 = lane_l - 18, a3 = (i3 >= 3) + (i3 >= 5);
+        e2a = 6 + a3; e2b = 6 + a3 + i3 - (a3 * (7 - a3)) / 2;
+      } else if (lane_l < 27) { e2a = 6 + lane_l - 24; }
       if (kAsyncStage) cp_async_wait_all();
       __syncwarp();
       KTRACE(3);

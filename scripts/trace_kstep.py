@@ -10,9 +10,9 @@ s = h.solve()   # the last K_A launches include the back-substitution
 buf = np.zeros(4000 * 16, dtype=np.int64)
 capi.lib().pba_debug_kstep_trace(C.c_void_p(buf.ctypes.data), buf.size)
 t = buf.reshape(4000, 16)
-order = [(1, "after prologue sync"), (8, "obs_off arrived"), (12, "frames/X/desc requested, frames in smem"), (6, "W + point inputs arrived, W.step summed"),
-         (2, "back-substitution done"), (3, "geometry + staging done"), (4, "stage loop entered"), (9, "last group sampled"),
-         (10, "last group reduced"), (11, "last group parked"), (13, "corrector + expansion done (obs loop done)"), (14, "after end sync"), (15, "exit")]
+order = [(1, "after prologue barrier"), (6, "staged inputs arrived"), (2, "back-substitution done"), (3, "geometry + staging done"),
+         (4, "stage loop entered"), (9, "last group sampled"), (10, "last group reduced"), (11, "last group parked"),
+         (13, "corrector + expansion done (obs loop done)"), (14, "after end sync"), (15, "exit")]
 print("phase durations in cycles (median / p90 over 4000 warps):")
 for (a, na), (b, nb) in zip(order, order[1:]):
     d = t[:, b] - t[:, a]
