@@ -418,8 +418,11 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
   const int pstride = gridDim.x * (kSchurThreads / 32);
   double V[6], g0 = 0, g1 = 0, g2 = 0, sp0 = 1, sp1 = 1, sp2 = 1, w[2][3];
   int rf[2], ra[2];
-  auto load_point = [&](int q) {
-    const int o0 = __ldg(lp.obs_off + q), nobs = __ldg(lp.obs_off + q + 1) - o0;
+  // Two-level prefetch: the CSR header of a point is requested one iteration before its data (whose
+  // addresses depend on it), and nothing here CONSUMES a loaded value, so neither call blocks.
+  int hdr_o0 = 0, hdr_n = 0;
+  auto load_header = [&](int q) { hdr_o0 = __ldg(lp.obs_off + q); hdr_n = __ldg(lp.obs_off + q + 1) - hdr_o0; };
+  auto load_point = [&](int q, int o0, int nobs) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) V[k] = __ldg(Vb + (size_t)q * 6 + k);
     g0 = __ldg(gb + (size_t)q * 3); g1 = __ldg(gb + (size_t)q * 3 + 1); g2 = __ldg(gb + (size_t)q * 3 + 2);
@@ -433,8 +436,7 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
       if (row < nobs * 6) {
         const int i = row / 6;
         ra[k] = row - 6 * i;
-        const int f = __ldg(lp.obs_frame + o0 + i);
-        rf[k] = st.free_index[f] >= 0 ? f : -1;
+        rf[k] = __ldg(lp.obs_frame + o0 + i);           // raw frame; free/fixed is resolved at use
         const double* wp = Wb + (size_t)(o0 + i) * 18 + ra[k] * 3;
         w[k][0] = __ldg(wp); w[k][1] = __ldg(wp + 1); w[k][2] = __ldg(wp + 2);
       }
@@ -442,7 +444,11 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
   };
   const int p_first = blockIdx.x * (kSchurThreads / 32) + warp;
   if (lp.dbg && tid == 0) s_tdbg[0] = gtime();
-  if (p_first < n) load_point(p_first);
+  if (p_first < n) {
+    load_header(p_first);
+    load_point(p_first, hdr_o0, hdr_n);
+    if (p_first + pstride < n) load_header(p_first + pstride);
+  }
   for (int p = p_first; p < n; p += pstride) {
     if (first) {
       sp0 = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[0])) : 1.0;
@@ -470,8 +476,8 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
     unsigned mask = 0;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      if (rf[k] >= 0) {
-        const int fi = st.free_index[rf[k]];
+      const int fi = rf[k] >= 0 ? st.free_index[rf[k]] : -1;
+      if (fi >= 0) {
         const double sc = st.scale_c[rf[k] * 6 + ra[k]];
         const double z0 = sc * w[k][0] * sp0 * il00;
         const double z1 = (sc * w[k][1] * sp1 - z0 * l10) * il11;
@@ -484,7 +490,10 @@ __device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
     }
     mask = __reduce_or_sync(0xffffffffu, mask);
     __syncwarp();
-    if (p + pstride < n) load_point(p + pstride);     // prefetch (registers of point p are dead now)
+    if (p + pstride < n) {                            // prefetch (registers of point p are dead now)
+      load_point(p + pstride, hdr_o0, hdr_n);
+      if (p + 2 * pstride < n) load_header(p + 2 * pstride);
+    }
     if (lane < npairs && ((mask >> pa) & 1u) && ((mask >> pb) & 1u)) {
       const double* za = Zw + 18 * pa;
       const double* zb = Zw + 18 * pb;
