@@ -371,9 +371,9 @@ def main():
         "k1": {"us_per_launch_cold_l2": 1e3 * k1_ms, "us_per_launch_warm_l2": 1e3 * k1_ms_warm,
                "observations_per_launch": n_obs_local,
                "residuals_per_sec": 25 * n_obs_local / (k1_ms * 1e-3), "observations_per_sec": n_obs_local / (k1_ms * 1e-3)},
-        "k_b": {"us_per_launch_incl_launch_gaps": (1e3 * dev_s / steps - last["num_evaluations"] * 1e3 * k1_ms_warm) / max(1, last["num_iterations"] - 1),
+        "k_b": {"us_per_launch_incl_launch_gaps": (1e6 * dev_s / steps - last["num_evaluations"] * 1e3 * k1_ms_warm) / max(1, last["num_evaluations"]),
                 "what": "decision + Schur elimination + reduced solve (k_schur_solve); latency-bound single-CTA tail, see DESIGN.md §4; "
-                        "derived as (solve time - K_A launches x warm K_A time) / LM iterations",
+                        "derived as (solve time - K_A launches x warm K_A time) / K_B launches (one decision per evaluation)",
                 "algorithmic_bytes_per_launch": n_obs_local * 112 + (win.n_points // world) * 12},
         "roofline": {"bound": "hbm", "kernel": "k_step<2,u8,1> (K_A)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": k1_traffic_from_profile(),
