@@ -216,6 +216,23 @@ int pba_prepare_frame_u8(pba_handle* h, const uint8_t* image, int32_t descriptor
 int pba_saliency_map(pba_handle* h, float* out /* rows x cols */);
 int pba_extract_descriptors(pba_handle* h, int32_t n, const int32_t* xy /* n x {x, y} */, double* desc /* n x C*P */);
 
+/* ---- addFrame's front end on the device, all on the frame of pba_prepare_frame_u8 ------
+ * Data association (src/photobundle.cc:508-542): for each of n live points uv = normHomog(K (T_c X)); when
+ * the rounded pixel (row, col) lies inside the border band the point is tested: score = ZNCC
+ * (ZnccPatch_<2,float>, :315-361) of its stored mean-free 5x5 patch (ref_patch, ref_norm) against the patch
+ * interpolated at uv (interp2, :262-294).  score = -2: not tested.  T_c: column-major 4x4 world->camera,
+ * K: row-major 3x3.  Results are bit-identical to the host arithmetic of photobundle_b200/host. */
+int pba_associate(pba_handle* h, int32_t n, const double* xyz, const float* ref_patch, const float* ref_norm,
+                  const double* T_c, const double* K, int32_t border, float* score, int32_t* row_col);
+/* New-point candidates (:545-575): pixels inside the border band with min_depth <= depth <= max_depth that
+ * are strict local maxima of the saliency map over (2 nms_radius + 1)^2 (IsLocalMax_, src/imgproc.h:175-212)
+ * and not masked by a (2 mask_radius + 1)^2 block around a re-observed point.  Returned in scan order
+ * (row-major); *n_out may exceed capacity (then only the first `capacity` of an arbitrary order were
+ * stored and the call should be repeated with more room). */
+int pba_select_candidates(pba_handle* h, const float* depth, int32_t n_masked, const int32_t* masked_row_col,
+                          int32_t mask_radius, int32_t nms_radius, int32_t border, double min_depth, double max_depth,
+                          int32_t capacity, int32_t* cand_row_col, float* cand_saliency, int32_t* n_out);
+
 /* Multi-GPU: one process per GPU; points are sharded, frames/poses replicated, one
  * exchange of the pose blocks and of the reduced camera system per LM iteration.  Rank 0 calls
  * pba_comm_unique_id() and distributes the 128 bytes by any means (torch.distributed,

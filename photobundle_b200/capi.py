@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_get_poses", "pba_get_points", "pba_get_iterations",
     "pba_comm_unique_id", "pba_comm_init", "pba_shard_range", "pba_comm_exchange_kind",
     "pba_descriptor_channels", "pba_set_frames_u8_descriptor", "pba_get_channel_plane", "pba_prepare_frame_u8",
-    "pba_saliency_map", "pba_extract_descriptors",
+    "pba_saliency_map", "pba_extract_descriptors", "pba_associate", "pba_select_candidates",
 ]
 
 

@@ -97,6 +97,12 @@ struct pba_handle {
   int new_channels = 0, new_active = 0;   // planes allocated / channels of the prepared frame
   float* d_sal = nullptr;          // saliency map, dense
   int* d_xy = nullptr;  double* d_desc_out = nullptr;  int xy_cap = 0;
+  // addFrame front end (pba_associate / pba_select_candidates)
+  double* d_as_xyz = nullptr;  float *d_as_patch = nullptr, *d_as_norm = nullptr, *d_as_score = nullptr;  int* d_as_rc = nullptr;
+  double* d_as_mats = nullptr;   // T_c (16) | K (9)
+  int as_cap = 0;
+  uint8_t* d_mask = nullptr;  float* d_depth = nullptr;  int *d_cand_rc = nullptr, *d_count = nullptr, *d_masked_rc = nullptr;
+  float* d_cand_sal = nullptr;  int cand_cap = 0, masked_cap = 0;
   float* p_desc = nullptr;         // pinned staging of pba_set_points (descriptors as float, local offsets)
   int32_t* p_off = nullptr;
   bool frames_are_u8 = false;
@@ -150,6 +156,9 @@ static void free_all(pba_handle* h) {
   cudaFree(h->d_u8); cudaFree(h->d_stage_u8); cudaFree(h->d_f32);
   cudaFree(h->d_scr_a); cudaFree(h->d_scr_b); cudaFree(h->d_new_u8); cudaFree(h->d_new_planes); cudaFree(h->d_sal);
   cudaFree(h->d_xy); cudaFree(h->d_desc_out);
+  cudaFree(h->d_as_xyz); cudaFree(h->d_as_patch); cudaFree(h->d_as_norm); cudaFree(h->d_as_score); cudaFree(h->d_as_rc);
+  cudaFree(h->d_as_mats); cudaFree(h->d_mask); cudaFree(h->d_depth); cudaFree(h->d_cand_rc); cudaFree(h->d_count);
+  cudaFree(h->d_masked_rc); cudaFree(h->d_cand_sal);
   if (h->p_desc) cudaFreeHost(h->p_desc);
   if (h->p_off) cudaFreeHost(h->p_off); cudaFree(h->d_cams); cudaFree(h->d_pts); cudaFree(h->d_weights);
   cudaFree(h->d_desc); cudaFree(h->d_obs_off); cudaFree(h->d_obs_frame); cudaFree(h->d_V); cudaFree(h->d_gp);
@@ -575,6 +584,90 @@ int pba_extract_descriptors(pba_handle* h, int32_t n, const int32_t* xy, double*
                                   h->d_xy, h->d_desc_out, h->stream));
   CUDA_TRY(cudaMemcpyAsync(desc, h->d_desc_out, sizeof(double) * (size_t)n * CP, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PBA_OK;
+}
+
+int pba_associate(pba_handle* h, int32_t n, const double* xyz, const float* ref_patch, const float* ref_norm,
+                  const double* T_c, const double* K, int32_t border, float* score, int32_t* row_col) {
+  if (!h || !T_c || !K || (n > 0 && (!xyz || !ref_patch || !ref_norm || !score || !row_col)))
+    return fail(PBA_ERR_ARGUMENT, "pba_associate: null argument");
+  if (h->new_active <= 0) return fail(PBA_ERR_STATE, "pba_associate: call pba_prepare_frame_u8 first");
+  if (n < 0 || border < 2) return fail(PBA_ERR_ARGUMENT, "pba_associate: n < 0 or border < 2 (the 5x5 ZNCC patch)");
+  if (n == 0) return PBA_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->as_cap < n) {
+    cudaFree(h->d_as_xyz); cudaFree(h->d_as_patch); cudaFree(h->d_as_norm); cudaFree(h->d_as_score); cudaFree(h->d_as_rc);
+    h->d_as_xyz = nullptr; h->d_as_patch = h->d_as_norm = h->d_as_score = nullptr; h->d_as_rc = nullptr; h->as_cap = 0;
+    const size_t cap = (size_t)n + n / 2 + 64;
+    CUDA_TRY(cudaMalloc(&h->d_as_xyz, sizeof(double) * 3 * cap));
+    CUDA_TRY(cudaMalloc(&h->d_as_patch, sizeof(float) * 25 * cap));
+    CUDA_TRY(cudaMalloc(&h->d_as_norm, sizeof(float) * cap));
+    CUDA_TRY(cudaMalloc(&h->d_as_score, sizeof(float) * cap));
+    CUDA_TRY(cudaMalloc(&h->d_as_rc, sizeof(int) * 2 * cap));
+    h->as_cap = (int)cap;
+  }
+  if (!h->d_as_mats) CUDA_TRY(cudaMalloc(&h->d_as_mats, sizeof(double) * 25));
+  CUDA_TRY(cudaMemcpyAsync(h->d_as_xyz, xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_as_patch, ref_patch, sizeof(float) * 25 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_as_norm, ref_norm, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_as_mats, T_c, sizeof(double) * 16, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(h->d_as_mats + 16, K, sizeof(double) * 9, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(launch_associate(h->d_new_u8, h->cfg.rows, h->cfg.cols, h->pitch, n, h->d_as_xyz, h->d_as_patch, h->d_as_norm, h->d_as_mats,
+                            h->d_as_mats + 16, border, h->d_as_score, h->d_as_rc, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(score, h->d_as_score, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(row_col, h->d_as_rc, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PBA_OK;
+}
+
+int pba_select_candidates(pba_handle* h, const float* depth, int32_t n_masked, const int32_t* masked_row_col,
+                          int32_t mask_radius, int32_t nms_radius, int32_t border, double min_depth, double max_depth,
+                          int32_t capacity, int32_t* cand_row_col, float* cand_saliency, int32_t* n_out) {
+  if (!h || !depth || !n_out || (n_masked > 0 && !masked_row_col) || (capacity > 0 && (!cand_row_col || !cand_saliency)))
+    return fail(PBA_ERR_ARGUMENT, "pba_select_candidates: null argument");
+  if (h->new_active <= 0) return fail(PBA_ERR_STATE, "pba_select_candidates: call pba_prepare_frame_u8 first");
+  if (n_masked < 0 || capacity < 0 || mask_radius < 0 || nms_radius < 0 || border < nms_radius || border < mask_radius)
+    return fail(PBA_ERR_ARGUMENT, "pba_select_candidates: negative size, or border smaller than a radius");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t dense = (size_t)h->cfg.rows * h->cfg.cols;
+  if (!h->d_mask) {
+    CUDA_TRY(cudaMalloc(&h->d_mask, dense));
+    CUDA_TRY(cudaMalloc(&h->d_depth, sizeof(float) * dense));
+    CUDA_TRY(cudaMalloc(&h->d_count, sizeof(int)));
+  }
+  if (h->cand_cap < capacity) {
+    cudaFree(h->d_cand_rc); cudaFree(h->d_cand_sal); h->d_cand_rc = nullptr; h->d_cand_sal = nullptr; h->cand_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->d_cand_rc, sizeof(int) * 2 * (size_t)capacity));
+    CUDA_TRY(cudaMalloc(&h->d_cand_sal, sizeof(float) * (size_t)capacity));
+    h->cand_cap = capacity;
+  }
+  if (h->masked_cap < n_masked) {
+    cudaFree(h->d_masked_rc); h->d_masked_rc = nullptr; h->masked_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->d_masked_rc, sizeof(int) * 2 * ((size_t)n_masked + n_masked / 2 + 64)));
+    h->masked_cap = n_masked + n_masked / 2 + 64;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_depth, depth, sizeof(float) * dense, cudaMemcpyHostToDevice, h->stream));
+  if (n_masked > 0) CUDA_TRY(cudaMemcpyAsync(h->d_masked_rc, masked_row_col, sizeof(int) * 2 * (size_t)n_masked, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(launch_saliency(h->d_new_planes, h->new_active, h->cfg.rows, h->cfg.cols, h->pitch, h->plane, h->d_sal, h->stream));
+  CUDA_TRY(launch_candidates(h->d_sal, h->d_mask, h->d_depth, h->cfg.rows, h->cfg.cols, border, nms_radius, n_masked, h->d_masked_rc,
+                             mask_radius, min_depth, max_depth, capacity, h->d_count, h->d_cand_rc, h->d_cand_sal, h->stream));
+  int count = 0;
+  CUDA_TRY(cudaMemcpyAsync(&count, h->d_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *n_out = count;
+  const int m = count < capacity ? count : capacity;
+  if (m > 0) {
+    std::vector<int32_t> rc(2 * (size_t)m);
+    std::vector<float> sal(m);
+    CUDA_TRY(cudaMemcpy(rc.data(), h->d_cand_rc, sizeof(int) * 2 * (size_t)m, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(sal.data(), h->d_cand_sal, sizeof(float) * (size_t)m, cudaMemcpyDeviceToHost));
+    // the compaction order is arbitrary: back into scan order (row-major), which is what addFrame produces
+    std::vector<int> idx(m);
+    for (int i = 0; i < m; ++i) idx[i] = i;
+    const int cols = h->cfg.cols;
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return (long long)rc[2 * a] * cols + rc[2 * a + 1] < (long long)rc[2 * b] * cols + rc[2 * b + 1]; });
+    for (int i = 0; i < m; ++i) { cand_row_col[2 * i] = rc[2 * idx[i]]; cand_row_col[2 * i + 1] = rc[2 * idx[i] + 1]; cand_saliency[i] = sal[idx[i]]; }
+  }
   return PBA_OK;
 }
 

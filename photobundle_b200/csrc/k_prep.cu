@@ -170,7 +170,132 @@ __global__ void __launch_bounds__(128) k_extract_patches(const float* __restrict
   }
 }
 
+// ---- addFrame on the device -----------------------------------------------------------
+// interp2 (src/photobundle.cc:262-294) on the uint8 image with the reference's mixed float/double
+// promotions spelled out (the host build uses no FMA contraction either).
+__device__ __forceinline__ float interp2_u8(const uint8_t* __restrict__ I, int rows, int cols, int pitch, float xf, float yf) {
+  const int max_cols = cols - 1, max_rows = rows - 1;
+  const int xi = (int)floorf(xf), yi = (int)floorf(yf);
+  xf = __fsub_rn(xf, (float)xi); yf = __fsub_rn(yf, (float)yi);
+  auto at = [&](int y, int x) -> float { return (float)I[(size_t)y * pitch + x]; };
+  if (xi >= 0 && xi < max_cols && yi >= 0 && yi < max_rows) {
+    const float wx = __double2float_rn(__dsub_rn(1.0, (double)xf));
+    const float t0 = __fadd_rn(__fmul_rn(at(yi, xi), wx), __fmul_rn(at(yi, xi + 1), xf));
+    const float t1 = __fadd_rn(__fmul_rn(at(yi + 1, xi), wx), __fmul_rn(at(yi + 1, xi + 1), xf));
+    return __double2float_rn(__dadd_rn(__dmul_rn(__dsub_rn(1.0, (double)yf), (double)t0), (double)__fmul_rn(yf, t1)));
+  }
+  if (xi == max_cols && yi < max_rows && yi >= 0)
+    return (xf > 0) ? 0.f : __double2float_rn(__dadd_rn(__dmul_rn(__dsub_rn(1.0, (double)yf), (double)at(yi, xi)), (double)__fmul_rn(yf, at(yi + 1, xi))));
+  if (yi == max_rows && xi < max_cols && xi >= 0)
+    return (yf > 0) ? 0.f : __double2float_rn(__dadd_rn(__dmul_rn(__dsub_rn(1.0, (double)xf), (double)at(yi, xi)), (double)__fmul_rn(xf, at(yi, xi + 1))));
+  if (xi == max_cols && yi == max_rows) return (xf > 0 || yf > 0) ? 0.f : at(yi, xi);
+  return 0.f;
+}
+
+// Data association of addFrame (src/photobundle.cc:508-542): one thread per live scene point.
+//   uv = normHomog(K * (T_c * X)); tested iff the rounded pixel lies inside the border band; score =
+//   ZnccPatch_<2,float>::score (:315-361) of the stored (mean-free) patch against the patch interpolated
+//   at uv in the new image.  score = -2 marks "not tested".
+__global__ void __launch_bounds__(128) k_associate(const uint8_t* __restrict__ img, int rows, int cols, int pitch, int n,
+                                                   const double* __restrict__ xyz, const float* __restrict__ ref_patch,
+                                                   const float* __restrict__ ref_norm, const double* __restrict__ Tc /*col-major 4x4*/,
+                                                   const double* __restrict__ K /*row-major 3x3*/, int border,
+                                                   float* __restrict__ score, int* __restrict__ rc) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double x0 = xyz[3 * p], x1 = xyz[3 * p + 1], x2 = xyz[3 * p + 2];
+  double Xc[3], q[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)     // Mat44::transform: ((m0*x0 + m1*x1) + m2*x2) + m3, column-major storage
+    Xc[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(Tc[i], x0), __dmul_rn(Tc[4 + i], x1)), __dmul_rn(Tc[8 + i], x2)), Tc[12 + i]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    q[i] = __dadd_rn(__dadd_rn(__dmul_rn(K[3 * i], Xc[0]), __dmul_rn(K[3 * i + 1], Xc[1])), __dmul_rn(K[3 * i + 2], Xc[2]));
+  const double u = __ddiv_rn(q[0], q[2]), v = __ddiv_rn(q[1], q[2]);
+  const int max_rows = rows - border - 1, max_cols = cols - border - 1;
+  float sc = -2.0f;
+  int r = -1, c = -1;
+  if (isfinite(u) && isfinite(v) && fabs(u) < 1e9 && fabs(v) < 1e9) { r = (int)round(v); c = (int)round(u); }
+  if (r >= border && r < max_rows && c >= border && c <= max_cols) {
+    const float x = (float)u, y = (float)v;
+    float d[25];
+    int i = 0;
+    for (int rr = -2; rr <= 2; ++rr)
+      for (int cc = -2; cc <= 2; ++cc) d[i++] = interp2_u8(img, rows, cols, pitch, __fadd_rn((float)cc, x), __fadd_rn((float)rr, y));
+    float sum = 0.f;
+    for (int k = 0; k < 25; ++k) sum = __fadd_rn(sum, d[k]);
+    const float mean = __fdiv_rn(sum, 25.0f);
+    float ss = 0.f;
+    for (int k = 0; k < 25; ++k) { d[k] = __fsub_rn(d[k], mean); ss = __fadd_rn(ss, __fmul_rn(d[k], d[k])); }
+    const float norm = __fsqrt_rn(ss);
+    const float den = __fmul_rn(ref_norm[p], norm);
+    float dot = 0.f;
+    for (int k = 0; k < 25; ++k) dot = __fadd_rn(dot, __fmul_rn(ref_patch[(size_t)p * 25 + k], d[k]));
+    sc = ((double)den > 1e-6) ? __fdiv_rn(dot, den) : -1.0f;
+  }
+  score[p] = sc;
+  rc[2 * p] = r; rc[2 * p + 1] = c;
+}
+
+// mask blocks around the re-observed points (src/photobundle.cc:533-536); mask: 1 = free
+__global__ void k_mask_blocks(uint8_t* __restrict__ mask, int rows, int cols, int n, const int* __restrict__ rc, int radius) {
+  const int side = 2 * radius + 1, per = side * side;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * per) return;
+  const int p = (int)(t / per), e = (int)(t - (long long)p * per);
+  const int r = rc[2 * p] + e / side - radius, c = rc[2 * p + 1] + e % side - radius;
+  if (r >= 0 && r < rows && c >= 0 && c < cols) mask[(size_t)r * cols + c] = 0;
+}
+
+// new-point candidates (src/photobundle.cc:545-575): valid depth and IsLocalMax_ (src/imgproc.h:175-212) of the
+// saliency map over the (2*nms+1)^2 neighbourhood with `>=`, masked pixels excluded; compacted with an atomic
+// counter (the caller sorts them back into scan order)
+__global__ void __launch_bounds__(256) k_candidates(const float* __restrict__ sal, const uint8_t* __restrict__ mask,
+                                                    const float* __restrict__ depth, int rows, int cols, int border, int nms,
+                                                    double min_depth, double max_depth, int capacity, int* __restrict__ count,
+                                                    int* __restrict__ cand_rc, float* __restrict__ cand_sal) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int max_rows = rows - border - 1, max_cols = cols - border - 1;
+  if (y < border || y >= max_rows || x < border || x >= max_cols) return;
+  const float z = depth[(size_t)y * cols + x];
+  if (!((double)z >= min_depth && (double)z <= max_depth)) return;
+  const float v = sal[(size_t)y * cols + x];
+  if (nms > 0) {
+    if (!mask[(size_t)y * cols + x] || v < 0.0f) return;
+    for (int r = -nms; r <= nms; ++r)
+      for (int c = -nms; c <= nms; ++c)
+        if (!(!r && !c) && sal[(size_t)(y + r) * cols + x + c] >= v) return;
+  }
+  const int slot = atomicAdd(count, 1);
+  if (slot < capacity) { cand_rc[2 * slot] = y; cand_rc[2 * slot + 1] = x; cand_sal[slot] = v; }
+}
+
 static dim3 grid_px(int rows, int cols) { return dim3((cols + 31) / 32, (rows + 7) / 8); }
+
+cudaError_t launch_associate(const uint8_t* img, int rows, int cols, int pitch, int n, const double* xyz, const float* ref_patch,
+                             const float* ref_norm, const double* Tc, const double* K, int border, float* score, int* rc,
+                             cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  k_associate<<<(n + 127) / 128, 128, 0, stream>>>(img, rows, cols, pitch, n, xyz, ref_patch, ref_norm, Tc, K, border, score, rc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_candidates(const float* sal, uint8_t* mask, const float* depth, int rows, int cols, int border, int nms,
+                              int n_masked, const int* masked_rc, int mask_radius, double min_depth, double max_depth, int capacity,
+                              int* count, int* cand_rc, float* cand_sal, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(mask, 1, (size_t)rows * cols, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(count, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  if (n_masked > 0) {
+    const long long tot = (long long)n_masked * (2 * mask_radius + 1) * (2 * mask_radius + 1);
+    k_mask_blocks<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(mask, rows, cols, n_masked, masked_rc, mask_radius);
+  }
+  k_candidates<<<grid_px(rows, cols), 256, 0, stream>>>(sal, mask, depth, rows, cols, border, nms, min_depth, max_depth, capacity, count,
+                                                         cand_rc, cand_sal);
+  return cudaGetLastError();
+}
+
 
 cudaError_t launch_channels(int descriptor_type, const uint8_t* src, int rows, int cols, int spitch, uint8_t* scratch_a,
                             uint8_t* scratch_b, float* dst, int dpitch, size_t dplane, cudaStream_t stream) {

@@ -216,6 +216,13 @@ cudaError_t launch_saliency(const float* planes, int n_channels, int rows, int c
                             cudaStream_t stream);
 cudaError_t launch_extract_patches(const float* planes, int n_channels, int rows, int cols, int pitch, size_t plane, int radius,
                                    int n, const int* xy, double* desc, cudaStream_t stream);
+// addFrame front end (k_prep.cu)
+cudaError_t launch_associate(const uint8_t* img, int rows, int cols, int pitch, int n, const double* xyz, const float* ref_patch,
+                             const float* ref_norm, const double* Tc, const double* K, int border, float* score, int* rc,
+                             cudaStream_t stream);
+cudaError_t launch_candidates(const float* sal, uint8_t* mask, const float* depth, int rows, int cols, int border, int nms,
+                              int n_masked, const int* masked_rc, int mask_radius, double min_depth, double max_depth, int capacity,
+                              int* count, int* cand_rc, float* cand_sal, cudaStream_t stream);
 cudaError_t launch_pyrdown_u8(const uint8_t* src, int srows, int scols, int spitch, uint8_t* dst, int dpitch,
                               cudaStream_t stream);
 

@@ -16,7 +16,7 @@ static thread_local std::string g_herr;
 
 struct pbah_options {
   int32_t maxNumPoints, slidingWindowSize, patchRadius, maskBlockRadius, maxFrameDistance, nonMaxSuppRadius;
-  int32_t doGaussianWeighting, verbose, device, descriptorType /* 0 Intensity, 1 IntensityAndGradient, 2 BitPlanes */;
+  int32_t doGaussianWeighting, verbose, device, descriptorType /* 0 Intensity, 1 IntensityAndGradient, 2 BitPlanes */, gpuFrontEnd;
   double minScore, robustThreshold, minValidDepth, maxValidDepth;
 };
 
@@ -28,7 +28,7 @@ void pbah_default_options(pbah_options* o) {
   PhotometricBundleAdjustment::Options d;
   o->maxNumPoints = d.maxNumPoints; o->slidingWindowSize = d.slidingWindowSize; o->patchRadius = d.patchRadius;
   o->maskBlockRadius = d.maskBlockRadius; o->maxFrameDistance = d.maxFrameDistance; o->nonMaxSuppRadius = d.nonMaxSuppRadius;
-  o->doGaussianWeighting = d.doGaussianWeighting; o->verbose = d.verbose; o->device = d.device; o->descriptorType = (int32_t)d.descriptorType;
+  o->doGaussianWeighting = d.doGaussianWeighting; o->verbose = d.verbose; o->device = d.device; o->descriptorType = (int32_t)d.descriptorType; o->gpuFrontEnd = d.gpuFrontEnd ? 1 : 0;
   o->minScore = d.minScore; o->robustThreshold = d.robustThreshold; o->minValidDepth = d.minValidDepth; o->maxValidDepth = d.maxValidDepth;
 }
 
@@ -43,6 +43,7 @@ int pbah_create(int32_t rows, int32_t cols, double fx, double fy, double cx, dou
     opt.doGaussianWeighting = o->doGaussianWeighting != 0; opt.verbose = o->verbose != 0; opt.device = o->device;
     if (o->descriptorType < 0 || o->descriptorType > 2) throw std::runtime_error("descriptorType outside [0, 2]");
     opt.descriptorType = (PhotometricBundleAdjustment::Options::DescriptorType)o->descriptorType;
+    opt.gpuFrontEnd = o->gpuFrontEnd != 0;
     opt.minScore = o->minScore; opt.robustThreshold = o->robustThreshold; opt.minValidDepth = o->minValidDepth; opt.maxValidDepth = o->maxValidDepth;
     pbah_handle* h = new pbah_handle();
     h->ba = new PhotometricBundleAdjustment(Calibration(K, baseline), ImageSize(rows, cols), opt);

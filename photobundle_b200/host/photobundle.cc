@@ -368,8 +368,41 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
             mask_radius = _options.maskBlockRadius;
 
   // ---- visibility of the existing points in the new frame (src/photobundle.cc:508-542)
+  const bool multi = _desc_type != PBA_DESC_INTENSITY;
+  const bool on_gpu = _options.gpuFrontEnd;     // association + candidate selection on the device
+  auto check = [&](int rc, const char* what) { if (rc != PBA_OK) throw std::runtime_error(std::string(what) + ": " + pba_last_error()); };
+  if (multi || on_gpu) {
+    ensureGpu(0, 0);
+    check(pba_prepare_frame_u8(_gpu, I_ptr, _desc_type), "pba_prepare_frame_u8");
+  }
   std::fill(_mask.begin(), _mask.end(), (uint16_t)1);
   int num_updated = 0, max_num_to_update = 0;
+  std::vector<int32_t> masked_rc;               // re-observed pixels (device path)
+  if (on_gpu) {
+    std::vector<ScenePoint*> live;
+    std::vector<double> xyz;
+    std::vector<float> ref_patch, ref_norm;
+    for (auto& sp : _scene_points)
+      if ((int)_frame_id - (int)sp->lastFrameId() <= _options.maxFrameDistance) {
+        live.push_back(sp.get());
+        for (int k = 0; k < 3; ++k) xyz.push_back(sp->X[k]);
+        ref_patch.insert(ref_patch.end(), sp->patch.data, sp->patch.data + 25);
+        ref_norm.push_back(sp->patch.norm);
+      }
+    max_num_to_update = (int)live.size();
+    std::vector<float> score(live.size());
+    std::vector<int32_t> rc(2 * live.size());
+    double Kr[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Kr[3 * i + j] = _calib.K()(i, j);
+    check(pba_associate(_gpu, (int32_t)live.size(), xyz.data(), ref_patch.data(), ref_norm.data(), T_c.m, Kr, B, score.data(), rc.data()),
+          "pba_associate");
+    for (size_t i = 0; i < live.size(); ++i)
+      if (score[i] > _options.minScore) {        // not-tested points carry -2
+        num_updated++;
+        live[i]->f.push_back(_frame_id);
+        masked_rc.push_back(rc[2 * i]); masked_rc.push_back(rc[2 * i + 1]);
+      }
+  } else
   for (size_t i = 0; i < _scene_points.size(); ++i) {
     ScenePoint& pt = *_scene_points[i];
     const int f_dist = (int)_frame_id - (int)pt.lastFrameId();
@@ -394,11 +427,9 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
   // ---- new points: saliency = sum over channels of |Ix| + |Iy| (imgradient, zero borders), local maxima
   // with valid depth.  Multi-channel descriptors: the new frame's channels, their saliency and (below) the
   // reference descriptors come from the device (pba_prepare_frame_u8 / pba_saliency_map / pba_extract_descriptors).
-  const bool multi = _desc_type != PBA_DESC_INTENSITY;
-  auto check = [&](int rc, const char* what) { if (rc != PBA_OK) throw std::runtime_error(std::string(what) + ": " + pba_last_error()); };
-  if (multi) {
-    ensureGpu(0, 0);
-    check(pba_prepare_frame_u8(_gpu, I_ptr, _desc_type), "pba_prepare_frame_u8");
+  if (on_gpu) {
+    // candidates come back in scan order with their saliency; the map itself stays on the device
+  } else if (multi) {
     check(pba_saliency_map(_gpu, _saliency_map.data()), "pba_saliency_map");
   } else {
   std::fill(_saliency_map.begin(), _saliency_map.end(), 0.0f);
@@ -421,25 +452,43 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
     return true;
   };
   ScenePointPointerList new_scene_points;
+  auto make_point = [&](int y, int x, float z, float saliency) {
+    // X = T_w * (z * K_inv * [x y 1]^T)   (src/photobundle.cc:560)
+    const double zd = z, v[3] = {(double)x, (double)y, 1.0};
+    Vec3 Xc;
+    for (int i = 0; i < 3; ++i)
+      Xc[i] = (zd * _K_inv(i, 0)) * v[0] + (zd * _K_inv(i, 1)) * v[1] + (zd * _K_inv(i, 2)) * v[2];
+    UniquePointer<ScenePoint> p(new ScenePoint(T_w.transform(Xc), _frame_id));
+    p->patch.set(I_ptr, rows, cols, (double)x, (double)y);
+    p->descriptor.resize(descriptor_dim);
+    p->saliency = saliency;
+    p->x = x; p->y = y;
+    new_scene_points.push_back(std::move(p));
+  };
+  if (on_gpu) {
+    int32_t cap = std::max(4096, (rows * cols) / 16), n_cand = 0;
+    std::vector<int32_t> cand_rc;
+    std::vector<float> cand_sal;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      cand_rc.resize(2 * (size_t)cap); cand_sal.resize(cap);
+      check(pba_select_candidates(_gpu, Z_ptr, (int32_t)(masked_rc.size() / 2), masked_rc.data(), mask_radius, nms, B, _options.minValidDepth,
+                                  _options.maxValidDepth, cap, cand_rc.data(), cand_sal.data(), &n_cand), "pba_select_candidates");
+      if (n_cand <= cap) break;
+      cap = n_cand;                              // rare: more candidates than room; once more with enough
+    }
+    for (int i = 0; i < n_cand; ++i) {
+      const int y = cand_rc[2 * i], x = cand_rc[2 * i + 1];
+      make_point(y, x, Z_ptr[(size_t)y * cols + x], cand_sal[i]);
+    }
+  } else {
   for (int y = B; y < max_rows; ++y) {
     for (int x = B; x < max_cols; ++x) {
       const float z = Z_ptr[(size_t)y * cols + x];
       if (z >= _options.minValidDepth && z <= _options.maxValidDepth) {
-        if (is_local_max(y, x)) {
-          // X = T_w * (z * K_inv * [x y 1]^T)   (src/photobundle.cc:560)
-          const double zd = z, v[3] = {(double)x, (double)y, 1.0};
-          Vec3 Xc;
-          for (int i = 0; i < 3; ++i)
-            Xc[i] = (zd * _K_inv(i, 0)) * v[0] + (zd * _K_inv(i, 1)) * v[1] + (zd * _K_inv(i, 2)) * v[2];
-          UniquePointer<ScenePoint> p(new ScenePoint(T_w.transform(Xc), _frame_id));
-          p->patch.set(I_ptr, rows, cols, (double)x, (double)y);
-          p->descriptor.resize(descriptor_dim);
-          p->saliency = _saliency_map[(size_t)y * cols + x];
-          p->x = x; p->y = y;
-          new_scene_points.push_back(std::move(p));
-        }
+        if (is_local_max(y, x)) make_point(y, x, z, _saliency_map[(size_t)y * cols + x]);
       }
     }
+  }
   }
   // ---- keep the best N by saliency (src/photobundle.cc:578-585)
   if (new_scene_points.size() > (size_t)_options.maxNumPoints) {

@@ -38,7 +38,8 @@ class PhotometricBundleAdjustment {
     // The reference leaves this uninitialised in the default ctor (src/photobundle.h:77-79, UB);
     // here it defaults to Intensity, the value its ConfigFile ctor falls back to (:102).
     DescriptorType descriptorType = DescriptorType::Intensity;
-    int device = -1;                // CUDA ordinal (-1: current) — the only added option
+    int device = -1;                // CUDA ordinal (-1: current)
+    bool gpuFrontEnd = false;       // addFrame's data association and new-point selection on the device (added option)
     Options() {}
     Options(const utils::ConfigFile& cf);
   };

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpba_host.so")
 class Options(C.Structure):
     _fields_ = [("maxNumPoints", C.c_int32), ("slidingWindowSize", C.c_int32), ("patchRadius", C.c_int32),
                 ("maskBlockRadius", C.c_int32), ("maxFrameDistance", C.c_int32), ("nonMaxSuppRadius", C.c_int32),
-                ("doGaussianWeighting", C.c_int32), ("verbose", C.c_int32), ("device", C.c_int32), ("descriptorType", C.c_int32),
+                ("doGaussianWeighting", C.c_int32), ("verbose", C.c_int32), ("device", C.c_int32), ("descriptorType", C.c_int32), ("gpuFrontEnd", C.c_int32),
                 ("minScore", C.c_double), ("robustThreshold", C.c_double), ("minValidDepth", C.c_double),
                 ("maxValidDepth", C.c_double)]
 
