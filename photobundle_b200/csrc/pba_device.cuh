@@ -27,7 +27,6 @@ namespace pba {
 
 constexpr int kMaxFrames = 16;
 constexpr int kMaxD = 6 * kMaxFrames;
-constexpr int kWarpsPerCta = 8;       // K_A: one warp per point
 constexpr int kObsBatch = 8;          // observations whose geometry / footprints are staged together
 constexpr int kStageSlots = 8;        // (observation, channel) footprints staged together
 constexpr int kPoseConst = 36;        // doubles per frame, see pose_consts()
