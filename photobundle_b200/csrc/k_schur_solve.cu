@@ -136,7 +136,7 @@ __device__ __forceinline__ double sym3(const double* s, int a, int b) {
 // cameras.  K_B accumulates only the upper block triangle of S (frame pairs g <= f), so the lower
 // triangle the factorisation works on is read transposed.  Threads are a 16x16 grid over the
 // matrix (no integer divisions in the inner loops).
-__device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F) {
+__device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F, const double* xs) {
   const int D = 6 * F, nf = st.n_free, N = 6 * nf;
   const int cur = st.cur, eb = st.eval_buf, tid = threadIdx.x, nthr = blockDim.x;
   const int ty = tid >> 4, tx = tid & 15;
@@ -153,7 +153,13 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
     s_ok = 1;
     for (int f = 0; f < F; ++f) if (st.free_index[f] >= 0) s_fr[st.free_index[f]] = f;
   }
-  for (int i = tid; i < F * kUStride; i += nthr) Us[i] = lp.Ucur[i];
+  // the right-hand side accumulators are requested first (their frame mapping is applied after the barrier);
+  // the accepted point's pose blocks come from the evaluation just adopted when there is one (no round trip
+  // through the copy that was stored to global memory a moment ago)
+  __shared__ double s_rawb[kMaxD];
+  const double rb = tid < D ? __ldcg(lp.S + D * D + tid) : 0.0;
+  for (int i = tid; i < F * kUStride; i += nthr) Us[i] = (xs && st.took_step) ? xs[i] : lp.Ucur[i];
+  if (tid < D) s_rawb[tid] = rb;
   __syncthreads();
   // assemble S + Us + Dc² (lower triangle) and rhs + gs_c; a 3x3 batch of loads is in flight per thread
   for (int r0 = ty; r0 < N; r0 += 48) {
@@ -191,7 +197,7 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
   }
   for (int r = tid; r < N; r += nthr) {
     const int fi = r / 6, a = r - fi * 6, f = s_fr[fi];
-    bb[r] = __ldcg(lp.S + D * D + 6 * f + a) + st.scale_c[6 * f + a] * Us[f * kUStride + 21 + a];
+    bb[r] = s_rawb[6 * f + a] + st.scale_c[6 * f + a] * Us[f * kUStride + 21 + a];
   }
   __syncthreads();
   for (int e = tid; e < D * D + D; e += nthr) lp.S[e] = 0.0;   // accumulators start from zero next time
@@ -563,7 +569,7 @@ __device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, in
   if (st.took_step)
     for (int i = tid; i < F * kUStride; i += blockDim.x) lp.Ucur[i] = xs ? xs[i] : __ldcg(lp.Xacc + i);
   __syncthreads();
-  solve_reduced(lp, st, sm, F);
+  solve_reduced(lp, st, sm, F, xs);
   if (lp.dbg && tid == 0) lp.dbg[3] = gtime();
   for (int i = tid; i < F * kUStride + kEacc + kMaxRanks; i += blockDim.x) lp.Xacc[i] = 0.0;
   if (tid == 0) *lp.ticket = 0u;
@@ -591,8 +597,33 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
   const unsigned long long t_start = lp.dbg ? gtime() : 0ull;
 
   // ---- (D) decision, redundantly per CTA ------------------------------------------------
+  // Everything the decision reads is requested in ONE round of loads: the state, the evaluation's
+  // accumulators (single-GPU / NCCL path) and both buffers of the cameras (which one is the candidate is
+  // only known once the state has arrived) - three dependent L2 round trips otherwise.
+  const int xn = F * kUStride + kEacc + kMaxRanks;
+  const bool xmode = lp.xc.n_ranks > 1;
+  constexpr int kXPre = (kMaxFrames * kUStride + kEacc + kMaxRanks + kSchurThreads - 1) / kSchurThreads;
+  double x_pre[kXPre];
+  if (!xmode) {
+#pragma unroll
+    for (int k = 0; k < kXPre; ++k) x_pre[k] = (tid + k * kSchurThreads < xn) ? __ldcg(lp.Xacc + tid + k * kSchurThreads) : 0.0;
+  }
+  double cam_pre[2][(kMaxD + 31) / 32];
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < (kMaxD + 31) / 32; ++k) {
+      const int i = lane + 32 * k;
+      cam_pre[0][k] = i < F * 6 ? lp.cams[i] : 0.0;
+      cam_pre[1][k] = i < F * 6 ? lp.cams[(size_t)F * 6 + i] : 0.0;
+    }
+  }
   for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
     reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_in)[i];
+  if (!xmode) {
+#pragma unroll
+    for (int k = 0; k < kXPre; ++k)
+      if (tid + k * kSchurThreads < xn) s_xs[tid + k * kSchurThreads] = x_pre[k];
+  }
   __syncthreads();
   if (s_st.done) {
     if (blockIdx.x == 0) {
@@ -604,8 +635,6 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
   }
   // the evaluation's accumulators: local (one GPU / NCCL path: already all-reduced) or the sum of every
   // rank's slot in rank order (peer-memory exchange: wait for the flags first)
-  const int xn = F * kUStride + kEacc + kMaxRanks;
-  const bool xmode = lp.xc.n_ranks > 1;
   if (xmode) {
     if (tid == 0) s_xok = 1;
     __syncthreads();
@@ -630,20 +659,22 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
       }
       return;
     }
-  } else {
-    for (int i = tid; i < xn; i += blockDim.x) s_xs[i] = __ldcg(lp.Xacc + i);
+    __syncthreads();
   }
-  __syncthreads();
   if (warp == 0) {
     const int buf = s_st.eval_buf;
     double gm = 0.0, g2 = 0.0, csq = 0.0;
-    for (int i = lane; i < F * 6; i += 32) {
-      const int f = i / 6, a = i - f * 6;
-      if (s_st.free_index[f] >= 0) {
-        const double g = s_xs[f * kUStride + 21 + a];
-        gm = fmax(gm, fabs(g)); g2 += g * g;
-        const double c = lp.cams[((size_t)buf * F + f) * 6 + a];
-        csq += c * c;
+#pragma unroll
+    for (int k = 0; k < (kMaxD + 31) / 32; ++k) {
+      const int i = lane + 32 * k;
+      if (i < F * 6) {
+        const int f = i / 6, a = i - f * 6;
+        if (s_st.free_index[f] >= 0) {
+          const double g = s_xs[f * kUStride + 21 + a];
+          gm = fmax(gm, fabs(g)); g2 += g * g;
+          const double c = buf ? cam_pre[1][k] : cam_pre[0][k];
+          csq += c * c;
+        }
       }
     }
     double e = lane < kEacc ? s_xs[F * kUStride + lane] : 0.0;
