@@ -390,9 +390,11 @@ def main():
     # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     if world == 1 and rank == 0:
         r = cpu_oracle_run(win, 3, 1)
+        r4 = cpu_oracle_run(win, 2, 1, threads=4)      # the reference caps Ceres at 4 threads (src/photobundle.cc:823-829)
         line["cpu_baseline"] = {
             "value": r["residual_evals"] / r["seconds"], "unit": "residuals/s", "cores": ncores, "kind": "port",
             "lm_iters_per_sec": r["lm_iters"] / r["seconds"],
+            "at_reference_thread_cap": {"cores": 4, "value": r4["residual_evals"] / r4["seconds"], "lm_iters_per_sec": r4["lm_iters"] / r4["seconds"]},
             "sample": f"3 full LM solves of the same window by the CPU oracle (reference's Ceres/autodiff structure), "
                       f"{ncores} OpenMP threads; final cost {r['summary']['final_cost']:.4f}"}
         line["parity"] = {"gpu_final_cost": last["final_cost"], "cpu_final_cost": r["summary"]["final_cost"],
