@@ -173,9 +173,8 @@ constexpr int kRedStride = 6 * kG + 2;   // doubles per lane row of the reductio
 // per warp: geometry [8][20] f64 | reduction transpose [25][6G+2] f64 | patch sums [8][6] f64 |
 //           pose-block accumulators [F][27] f64 | ints [8] int4 | frames [16] i32 |
 //           footprints [8][ROWS][W] f32
-template <int R, bool U8>
+template <int R, bool U8, int WARPS = Geo<U8>::WARPS>
 __host__ __device__ constexpr size_t k_step_smem_bytes(int n_frames) {
-  constexpr int WARPS = Geo<U8>::WARPS;
   // footprints: raw uint8 (ROWS x W bytes) on the Intensity path, fp32 otherwise
   constexpr size_t fp_bytes = (size_t)kStageSlots * Foot<R>::FLOATS * (U8 ? 1 : 4);
   return sizeof(double) * ((size_t)n_frames * (kPoseConst + 6) + WARPS * kEacc + ((Foot<R>::P + 1) & ~1)) +
@@ -324,11 +323,12 @@ __device__ __forceinline__ void block_entries(const double* __restrict__ t, cons
 }
 
 // NCH: compile-time channel count (1 = Intensity, the north-star descriptor); 0 = runtime count.
-template <int R, bool U8, int NCH>
-__global__ void __launch_bounds__(Geo<U8>::WARPS * 32, 2) k_step(const StepParams prm) {
+// WARPS: warps per CTA (two CTAs per SM); the default keeps a 4 000-point window in one wave, wide windows
+// (per-warp pose-block accumulators grow with the frame count) use fewer so that two CTAs still fit.
+template <int R, bool U8, int NCH, int WARPS = Geo<U8>::WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
   using FT = Foot<R>;
   using FPT = typename std::conditional<U8, uint8_t, float>::type;   // footprint element in shared memory
-  constexpr int WARPS = Geo<U8>::WARPS;
   constexpr int P = FT::P;
   constexpr int PR = (P + 31) / 32;             // pixel rounds per lane
   constexpr bool kQuad = (NCH == 1 && PR == 1); // ILP-4 fast path available
@@ -889,19 +889,18 @@ extern "C" void pba_debug_kstep_trace(long long* out, int n) {
 #endif
 
 // ---- host launcher -----------------------------------------------------------------------
-template <int R, bool U8, int NCH>
+template <int R, bool U8, int NCH, int WARPS = Geo<U8>::WARPS>
 static cudaError_t launch_one(const StepParams& prm, cudaStream_t stream) {
-  constexpr int WARPS = Geo<U8>::WARPS;
-  const size_t smem = k_step_smem_bytes<R, U8>(prm.n_frames);
+  const size_t smem = k_step_smem_bytes<R, U8, WARPS>(prm.n_frames);
   static bool configured[64] = {};
   static int sm_count[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k_step<R, U8, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_step<R, U8, NCH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
     // two CTAs per SM need the large shared-memory carve-out
-    cudaFuncSetAttribute(k_step<R, U8, NCH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_step<R, U8, NCH, WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
@@ -909,7 +908,7 @@ static cudaError_t launch_one(const StepParams& prm, cudaStream_t stream) {
   const int want = (prm.n_points + WARPS - 1) / WARPS, cap = 2 * sm_count[dev & 63];
   const int grid = want < cap ? want : cap;
   if (grid == 0) return cudaSuccess;
-  k_step<R, U8, NCH><<<grid, WARPS * 32, smem, stream>>>(prm);
+  k_step<R, U8, NCH, WARPS><<<grid, WARPS * 32, smem, stream>>>(prm);
   return cudaGetLastError();
 }
 
@@ -917,7 +916,13 @@ int k_step_grid(int n_points) { return (n_points + K_STEP_WARPS_U8 - 1) / K_STEP
 
 template <int R>
 static cudaError_t launch_r(const StepParams& prm, cudaStream_t stream) {
-  if (prm.fr.u8) return launch_one<R, true, 1>(prm, stream);      // uint8 planes are always 1-channel Intensity
+  if (prm.fr.u8) {                                                // uint8 planes are always 1-channel Intensity
+    // two CTAs per SM: 228 KB of shared memory, 1 KB reserved per CTA
+    constexpr size_t kPerCta = (233472 - 2 * 1024) / 2;
+    if constexpr (R == 2)
+      if (k_step_smem_bytes<R, true>(prm.n_frames) > kPerCta) return launch_one<R, true, 1, 11>(prm, stream);
+    return launch_one<R, true, 1>(prm, stream);
+  }
   if (prm.fr.n_channels == 1) return launch_one<R, false, 1>(prm, stream);
   return launch_one<R, false, 0>(prm, stream);
 }
