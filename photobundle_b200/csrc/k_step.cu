@@ -912,7 +912,6 @@ static cudaError_t launch_one(const StepParams& prm, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-int k_step_grid(int n_points) { return (n_points + K_STEP_WARPS_U8 - 1) / K_STEP_WARPS_U8; }
 
 template <int R>
 static cudaError_t launch_r(const StepParams& prm, cudaStream_t stream) {

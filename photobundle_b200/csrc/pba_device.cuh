@@ -201,7 +201,6 @@ __device__ __forceinline__ bool xchg_wait(const unsigned long long* flag, unsign
 }
 
 // launchers
-int k_step_grid(int n_points);
 cudaError_t launch_k_step(const StepParams& prm, int radius, cudaStream_t stream);
 int schur_grid(int n_points, int sm_count);
 cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t stream);
