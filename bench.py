@@ -146,7 +146,9 @@ def build_window():
 def cpu_oracle_run(win, steps: int, warmup: int, threads: int = 0):
     """Times oracle_solve (Jet<double,9> autodiff structure) on the host cores."""
     from oracle import binding as ob
-    ow = ob.OracleWindow(win, num_threads=threads)
+    # explicit thread count: torch.distributed.run exports OMP_NUM_THREADS=1, which would otherwise turn the
+    # "all host cores" baseline into a single-threaded one whenever the bench runs under torchrun
+    ow = ob.OracleWindow(win, num_threads=threads or (os.cpu_count() or 1))
     evals, iters, secs = 0, 0, 0.0
     summ = None
     for i in range(warmup + steps):
