@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
     if (lane < nobs) s_frm_w[lane] = frm_l;
     if (backsub) cp_async_wait_all();
     __syncwarp();
+    KTRACE(6);
 
     // ---- (B) back-substitution (SchurEliminator::BackSubstitute + model cost change) -------
     if (backsub) {
@@ -664,7 +665,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
               const double hx = wj[0] * (double)gx, hy = wj[0] * (double)gy;
               v6[i][0] = rr * rr; v6[i][1] = hx * hx; v6[i][2] = hx * hy; v6[i][3] = hy * hy; v6[i][4] = rr * hx; v6[i][5] = rr * hy;
             }
-            KTRACE(5 + (qb ? 4 : 0));
+            KTRACE(9);
             // transpose-reduce the 24 sums of the group through shared memory: lane r <- sum over pixels of value r
             if (lane < P) {
               double2* row = reinterpret_cast<double2*>(s_red_w + lane * kRedStride);
@@ -679,13 +680,13 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
 #pragma unroll
               for (int l = 0; l < P; ++l) tot += s_red_w[l * kRedStride + lane];
             }
-            KTRACE(6 + (qb ? 4 : 0));
+            KTRACE(10);
             // lane 6i+k holds sum k of observation i: park the raw sums; the loss corrector and the block
             // expansion of the whole batch follow the sampling loop (one latency chain per batch, not per group)
             if (lane < 6 * nq) s_tot_w[(sb + qb) * 6 + lane] = tot;
             defmask |= ((1u << nq) - 1u) << (sb + qb);
             __syncwarp();
-            KTRACE(7 + (qb ? 4 : 0));
+            KTRACE(11);
           } else {
             // generic path: any channel count / patch size / border handling, one observation at a time
             for (int i = 0; i < nq; ++i) {
