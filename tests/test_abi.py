@@ -87,3 +87,10 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
                 text = open(os.path.join(dp, f), errors="ignore").read()
                 assert "pba_oracle" not in text and "oracle.binding" not in text and "from oracle" not in text, os.path.join(dp, f)
+
+
+def test_descriptor_channel_counts():
+    """pba_descriptor_channels is host arithmetic (DescriptorFrame::Create's channel counts, src/photobundle.cc:225-245)."""
+    L = capi.lib()
+    assert [L.pba_descriptor_channels(t) for t in (0, 1, 2)] == [1, 3, 8]
+    assert L.pba_descriptor_channels(3) == -1 and L.pba_descriptor_channels(-1) == -1
