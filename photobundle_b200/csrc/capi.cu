@@ -186,7 +186,7 @@ static int setup_xchg(pba_handle* h) {
   const char* mode = getenv("PBA_MGPU_EXCHANGE");
   int want = !(mode && strcmp(mode, "nccl") == 0);
   const size_t F = h->cfg.max_frames, D = 6 * F;
-  const size_t xa_n = F * kUStride + kEacc + kMaxRanks, s_n = D * D + D;
+  const size_t xa_n = F * kUStride + kEacc + kMaxRanks, s_n = reduced_capacity((int)F);
   const size_t n_cells = 2 * n * (xa_n + s_n);   // 16-byte LL cells
   const size_t bytes = sizeof(ulonglong2) * n_cells + sizeof(unsigned long long) * n + 64;
   if (h->d_xchg) { cudaFree(h->d_xchg); h->d_xchg = nullptr; }
@@ -331,7 +331,7 @@ int pba_create(const pba_config* cfg, pba_handle** out) {
   CREATE_TRY(cudaMalloc(&h->d_Ucur, sizeof(double) * F * kUStride));
   CREATE_TRY(cudaMalloc(&h->d_scale_p, sizeof(double) * n * 3));
   CREATE_TRY(cudaMalloc(&h->d_Vinv, sizeof(double) * n * 6));
-  CREATE_TRY(cudaMalloc(&h->d_S, sizeof(double) * (D * D + D)));
+  CREATE_TRY(cudaMalloc(&h->d_S, sizeof(double) * reduced_capacity((int)F)));
   CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
   CREATE_TRY(cudaMalloc(&h->d_state, 2 * sizeof(LmState)));
   CREATE_TRY(cudaMallocHost(&h->h_state, sizeof(LmState)));
@@ -965,7 +965,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   rc = zero_accumulators(h);
   if (rc) return rc;
   const size_t D = 6 * (size_t)F;
-  CUDA_TRY(cudaMemsetAsync(h->d_S, 0, sizeof(double) * (D * D + D), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_S, 0, sizeof(double) * reduced_capacity(h->cfg.max_frames), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
 
   LmParams lp = make_lm_params(h);
@@ -1014,8 +1014,8 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
       CUDA_TRY(launch_schur_solve(lp, sgrid, s->n_free, h->stream));
       launches += 1;
       if (multi) {   // reduced camera system, summed over the point shards, then the (replicated) solve
-        NCCL_TRY(g_nccl.AllReduce(h->d_S, h->d_S, D * D + D, ncclDouble, ncclSum, h->comm, h->stream));
-        CUDA_TRY(launch_solve_only(lp, h->stream));
+        NCCL_TRY(g_nccl.AllReduce(h->d_S, h->d_S, (size_t)(6 * s->n_free) * reduced_ld(6 * s->n_free), ncclDouble, ncclSum, h->comm, h->stream));
+        CUDA_TRY(launch_solve_only(lp, s->n_free, h->stream));
         ++collectives; launches += 1;
       }
       CUDA_TRY(launch_k_step(make_step_params(h, lp.st_out), h->cfg.patch_radius, h->stream));

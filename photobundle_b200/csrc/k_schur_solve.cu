@@ -11,12 +11,19 @@
 //  (D) every CTA redundantly takes the trust-region decision for the candidate K_A has just
 //      evaluated (accept / reject / converged, new radius) from the complete accumulators —
 //      identical inputs, identical arithmetic, so all CTAs agree without a grid barrier;
-//  (E) warp per point: Vs = sp V sp + D_p², its inverse, Ws = sc W sp, Y = Ws Vs^-1 into shared
-//      memory; thread per 3x3 tile of the D x D reduced matrix (accumulators in registers across
-//      all of the CTA's points): S -= Y Wsᵀ; one fp64 atomic per entry per CTA;
-//  (S) the last CTA to finish (ticket) assembles S + Us + D_c², factors it with a blocked (6x6)
-//      Cholesky in fp64 in shared memory, solves, and writes the camera step, the candidate
-//      cameras and the next LmState.  The back-substitution of the points is fused into K_A.
+//  (E) elimination.  One lane per OBSERVATION (8 or 16 lanes per point, 4 or 2 points per warp): the
+//      lanes of a point factor Vs + D_p² = L Lᵀ (3x3) redundantly, each forms its own Z_a = Ws_a L^-T
+//      (6x3) and parks it as rows of a CTA-wide matrix Zt [6 n_free + 1][3 x points] in shared memory
+//      (the last row holds L^-1 gs), so that the whole batch's contribution to the reduced system is
+//      ONE symmetric product  P = Zt Ztᵀ  — which runs on the fp64 TENSOR pipe (mma.sync m8n8k4.f64,
+//      SASS DMMA; the accumulator fragments stay in registers across all of the CTA's points); one
+//      fp64 atomic per entry per CTA adds the upper triangle of P to the global accumulator;
+//  (S) the last CTA to finish (ticket) assembles S = U_s + D_c² - P with the right-hand side as an
+//      extra ROW (so the forward substitution falls out of the factorisation), factors it with a
+//      blocked (6x6) Cholesky in fp64 in shared memory — every panel thread factors the diagonal block
+//      redundantly in registers, two barriers per block step —, back-substitutes on one warp and
+//      writes the camera step, the candidate cameras and the next LmState.  The back-substitution
+//      of the points is fused into K_A.
 //
 // LM state ping-pongs between two LmState structs (st_in is read-only during the kernel).
 
@@ -28,9 +35,17 @@
 namespace pba {
 
 __device__ __forceinline__ unsigned long long gtime() {
+#ifdef PBA_SOLVE_UBENCH
+  return (unsigned long long)clock64();   // scripts/ubench/solve_bench.cu: cycles instead of nanoseconds
+#define UB_STAMP(slot) do { if (lp.dbg && jb == 1 && tid == 0) lp.dbg[slot] = (unsigned long long)clock64(); } while (0)
+#define UB_ARRIVE(k) do { if (lp.dbg && jb == 1 && (tid & 31) == 0) lp.dbg[32 + 8 * (k) + (tid >> 5)] = (unsigned long long)clock64(); } while (0)
+#else
+#define UB_STAMP(slot) do {} while (0)
+#define UB_ARRIVE(k) do {} while (0)
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+#endif
 }
 __device__ __forceinline__ int utri6(int a, int b) { return a * (13 - a) / 2 + (b - a); }  // a <= b
 __device__ __forceinline__ double usym6(const double* u21, int a, int b) { return u21[a <= b ? utri6(a, b) : utri6(b, a)]; }
@@ -115,244 +130,285 @@ __device__ bool decide(LmState& st, const double* E, double gm, double g2, doubl
   return true;
 }
 
-__device__ __forceinline__ void inv_sym3(const double* a /*00 01 02 11 12 22*/, double* inv) {
-  const double c00 = a[3] * a[5] - a[4] * a[4];
-  const double c01 = a[2] * a[4] - a[1] * a[5];
-  const double c02 = a[1] * a[4] - a[2] * a[3];
-  const double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
-  const double id = 1.0 / det;
-  inv[0] = c00 * id; inv[1] = c01 * id; inv[2] = c02 * id;
-  inv[3] = (a[0] * a[5] - a[2] * a[2]) * id;
-  inv[4] = (a[1] * a[2] - a[0] * a[4]) * id;
-  inv[5] = (a[0] * a[3] - a[1] * a[1]) * id;
-}
-__device__ __forceinline__ double sym3(const double* s, int a, int b) {
-  const int lo = a < b ? a : b, hi = a < b ? b : a;
-  return s[lo * (5 - lo) / 2 + hi];  // 00 01 02 11 12 22
+
+// fp64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds A[l/4][l%4], B[l%4][l/4] and
+// C[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// ---- reduced camera system: blocked (6x6) Cholesky + solve, whole CTA -----------------------
-// sm: A [N][N+1] | Li [nf][36] | bb [N] | Us [F][27].  Writes the step into st and the candidate
-// cameras.  K_B accumulates only the upper block triangle of S (frame pairs g <= f), so the lower
-// triangle the factorisation works on is read transposed.  Threads are a 16x16 grid over the
-// matrix (no integer divisions in the inner loops).
-__device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F, const double* xs) {
-  const int D = 6 * F, nf = st.n_free, N = 6 * nf;
-  const int cur = st.cur, eb = st.eval_buf, tid = threadIdx.x, nthr = blockDim.x;
-  const int ty = tid >> 4, tx = tid & 15;
+// 1/sqrt(d) for a positive, normal d without the library routine's slow-path branch (which splits the basic block
+// and keeps the scheduler from overlapping the refinement with independent work): hardware approximation
+// (MUFU.RSQ64H, ~2^-22) + one cubic-convergence correction  y0 (1 + e/2 + 3e²/8),  e = 1 - d y0²  (error term
+// 5e³/16 < 2^-66).  Zero / negative / non-finite pivots give a non-finite or garbage result; the caller checks d.
+__device__ __forceinline__ double rsqrt_pos(double d) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+  const double e = fma(-(d * y0), y0, 1.0);
+  return fma(y0, e * fma(0.375, e, 0.5), y0);
+}
+
+constexpr int kSchurWarps = kSchurThreads / 32;
+constexpr int kMBase = 224;   // thread kMBase keeps the factored diagonal block for the back-substitution
+
+// Reduced system in global memory: S [N][ld] in FREE-camera index space (N = 6 n_free, ld = reduced_ld(N)),
+// upper triangle r <= c only; column N is the right-hand-side part.  It accumulates P = sum_p Zt_p Zt_pᵀ
+// (K_B's atomics); the solver forms U_s + D_c² - P in a shared-memory copy of the same shape.
+
+// ---- (S) reduced camera system: blocked (6x6) Cholesky of the bordered matrix + solve, whole CTA ------
+// Works on Ut = the UPPER triangle (row k holds column k of the Cholesky factor, i.e. Ut = Lᵀ when done)
+// with the right-hand side as column N, so the forward substitution falls out of the factorisation.
+// Per block step: every thread that owns a column of the panel factors the 6x6 diagonal block redundantly
+// in registers and solves its own column (no factor -> barrier -> panel sequence); the trailing update
+// Ut22 -= PᵀP (P = the 6 x m panel) runs on the fp64 tensor pipe, one 8x8 tile per DMMA pair.
+// The code is deliberately compact: these phases execute once per launch, from a cold instruction cache.
+// sm: Ut [N+8][ld] | Ldd [nf][36] (factored diagonal blocks, transposed) | idv [N] (reciprocal pivots) | xb [N] |
+//     yv [N] | Us [F][27].
+// Writes the step into st and the candidate cameras.  s_cams: both camera buffers [2][kMaxD] (or null).
+template <int TPW>
+__device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams) {
+  const int nf = st.n_free, N = 6 * nf, ld = reduced_ld(N);
+  const int cur = st.cur, eb = st.eval_buf, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const double radius = st.radius;
-  const int ld = N + 1;
-  double* A = sm;
-  double* Li = A + N * ld;
-  double* bb = Li + nf * 36;
-  double* Us = bb + N;            // [F][27] pose blocks of the accepted point
+  const int Npad = (N + 1) & ~1;
+  double* Ut = sm;
+  double* Ldd = Ut + (N + 8) * ld;
+  double* idv = Ldd + nf * 36;
+  double* xb = idv + Npad;
+  double* yv = xb + Npad;
+  double* Us = yv + Npad;                      // [F][27] pose blocks of the accepted point
+  // this warp's 8x8 tiles (tr <= tc) of the ABSOLUTE tile grid over Ut — the same assignment in every block step,
+  // so every address below is formed once: C fragment, and the panel-row-relative A / B fragment offsets
+  const int Tabs = (N + 8) >> 3, n_tiles = Tabs * (Tabs + 1) / 2;
+  const int fr = lane & 3, fc = lane >> 2;
+  int offc[TPW], offa[TPW], offb[TPW];
+  unsigned tile_rc[TPW];
+#pragma unroll
+  for (int k = 0; k < TPW; ++k) {
+    const int t = warp + kSchurWarps * k;
+    int tr = 0, rem = t < n_tiles ? t : 0;
+    while (rem >= Tabs - tr) { rem -= Tabs - tr; ++tr; }
+    const int tc = tr + rem;
+    offc[k] = (8 * tr + fc) * ld + 8 * tc + 2 * fr;
+    offa[k] = fr * ld + 8 * tr + fc;
+    offb[k] = fr * ld + 8 * tc + fc;
+    tile_rc[k] = t < n_tiles ? (unsigned)(tr | (tc << 8)) : 0xffffu;
+  }
   __shared__ int s_fr[kMaxFrames];
   __shared__ int s_ok;
-  __shared__ double s_v6[6];
   if (tid == 0) {
     s_ok = 1;
     for (int f = 0; f < F; ++f) if (st.free_index[f] >= 0) s_fr[st.free_index[f]] = f;
   }
-  // the right-hand side accumulators are requested first (their frame mapping is applied after the barrier);
-  // the accepted point's pose blocks come from the evaluation just adopted when there is one (no round trip
-  // through the copy that was stored to global memory a moment ago)
-  __shared__ double s_rawb[kMaxD];
-  const double rb = tid < D ? __ldcg(lp.S + D * D + tid) : 0.0;
-  for (int i = tid; i < F * kUStride; i += nthr) Us[i] = (xs && st.took_step) ? xs[i] : lp.Ucur[i];
-  if (tid < D) s_rawb[tid] = rb;
-  __syncthreads();
-  // assemble S + Us + Dc² (lower triangle) and rhs + gs_c; a 3x3 batch of loads is in flight per thread
-  for (int r0 = ty; r0 < N; r0 += 48) {
-    for (int c0 = tx; c0 < N && c0 <= r0 + 32; c0 += 48) {
-      double v[3][3];
+  // -P: a linear copy of the accumulator (all loads of a thread in flight at once); the accumulator is
+  // re-zeroed on the way, so that the next elimination starts from zero
+  {
+    constexpr int kCopyB = 10;
+    const int tot = N * ld;
+    for (int e0 = tid; e0 < tot; e0 += kCopyB * nthr) {
+      double v[kCopyB];
 #pragma unroll
-      for (int u = 0; u < 3; ++u)
+      for (int u = 0; u < kCopyB; ++u) v[u] = (e0 + u * nthr < tot) ? __ldcg(lp.S + e0 + u * nthr) : 0.0;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const int r = r0 + 16 * u, c = c0 + 16 * q;
-          v[u][q] = 0.0;
-          if (r < N && c <= r) {
-            const int f = s_fr[r / 6], a = r % 6, g = s_fr[c / 6], b = c % 6;
-            v[u][q] = __ldcg(lp.S + (6 * g + b) * D + 6 * f + a);    // upper block (g <= f), transposed
-          }
-        }
-#pragma unroll
-      for (int u = 0; u < 3; ++u)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const int r = r0 + 16 * u, c = c0 + 16 * q;
-          if (r < N && c <= r) {
-            double val = v[u][q];
-            const int fi = r / 6, a = r - fi * 6, fj = c / 6, b = c - fj * 6;
-            if (fi == fj) {
-              const int f = s_fr[fi];
-              const double uu = st.scale_c[6 * f + a] * usym6(Us + f * kUStride, a, b) * st.scale_c[6 * f + b];
-              val += uu;
-              if (a == b) val += fmin(fmax(uu, st.min_diag), st.max_diag) / radius;
-            }
-            A[r * ld + c] = val;
-          }
-        }
+      for (int u = 0; u < kCopyB; ++u)
+        if (e0 + u * nthr < tot) { Ut[e0 + u * nthr] = -v[u]; lp.S[e0 + u * nthr] = 0.0; }
     }
   }
-  for (int r = tid; r < N; r += nthr) {
-    const int fi = r / 6, a = r - fi * 6, f = s_fr[fi];
-    bb[r] = s_rawb[6 * f + a] + st.scale_c[6 * f + a] * Us[f * kUStride + 21 + a];
+  // the accepted point's pose blocks come from the evaluation just adopted when there is one (no round trip
+  // through the copy that was stored to global memory a moment ago)
+  for (int i = tid; i < F * kUStride; i += nthr) Us[i] = (xs && st.took_step) ? xs[i] : lp.Ucur[i];
+  __syncthreads();
+  // + U_s + D_c² on the diagonal blocks, + gs_c on the right-hand-side column: one entry per thread
+  for (int t = tid; t < nf * kUStride; t += nthr) {
+    const int fi = t / kUStride, k = t - fi * kUStride, f = s_fr[fi];
+    if (k < 21) {
+      const int a = (k >= 6) + (k >= 11) + (k >= 15) + (k >= 18) + (k >= 20), b = a + k - (a * (13 - a)) / 2;
+      const double uu = st.scale_c[6 * f + a] * Us[f * kUStride + k] * st.scale_c[6 * f + b];
+      double val = Ut[(6 * fi + a) * ld + 6 * fi + b] + uu;
+      if (a == b) val += fmin(fmax(uu, st.min_diag), st.max_diag) / radius;
+      Ut[(6 * fi + a) * ld + 6 * fi + b] = val;
+    } else {
+      const int a = k - 21;
+      Ut[(6 * fi + a) * ld + N] += st.scale_c[6 * f + a] * Us[f * kUStride + 21 + a];
+    }
   }
   __syncthreads();
-  for (int e = tid; e < D * D + D; e += nthr) lp.S[e] = 0.0;   // accumulators start from zero next time
   if (lp.dbg && tid == 0) lp.dbg[5] = gtime();
 
   for (int jb = 0; jb < nf; ++jb) {
-    const int j0 = 6 * jb, m = N - j0 - 6;
-    if (tid == 0) {
-      // 6x6 Cholesky of the diagonal block, right-looking in registers (short dependency chain);
-      // the reciprocal diagonal goes to Li[.][j][j]
-      double L[6][6];
+    const int j0 = 6 * jb, m = N - j0 - 6;     // panel columns i = j0 + 6 + t, t = 0..m (t == m: the rhs column N)
+    const bool col_thr = tid <= m, inv_thr = tid == kMBase;
+    UB_STAMP(16);
+#if defined(UB_TRAIL) && UB_TRAIL == 3   // ubench: no diagonal / panel work (is the trailing phase slow on its own?)
+    if (false) {
+#else
+    if (col_thr || inv_thr) {
+#endif
+      // 6x6 Cholesky of the diagonal block, right-looking in registers, REDUNDANTLY in every thread that
+      // needs it (broadcast shared-memory reads instead of a factor -> barrier -> panel sequence).  The
+      // positivity check stays off the dependency chain: a bad pivot poisons the step, which is then rejected.
+      double L[6][6], id[6], r[6];
       bool ok = true;
 #pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int k = 0; k <= i; ++k) L[i][k] = A[(j0 + i) * ld + j0 + k];
+        for (int k = 0; k <= i; ++k) L[i][k] = Ut[(j0 + k) * ld + j0 + i];
+      if (col_thr) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) r[k] = Ut[(j0 + k) * ld + j0 + 6 + tid];
+      }
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
-        double d = L[j][j];
-        if (!(d > 0.0) || !isfinite(d)) { ok = false; d = 1.0; }
-        const double id = rsqrt(d);
-        L[j][j] = d * id;
-        Li[jb * 36 + j * 7] = id;
+        const double d = L[j][j];
+        ok = ok && (d > 0.0) && (d < DBL_MAX);
+        id[j] = rsqrt_pos(d);
 #pragma unroll
-        for (int i = j + 1; i < 6; ++i) L[i][j] *= id;
+        for (int i = j + 1; i < 6; ++i) L[i][j] *= id[j];
 #pragma unroll
         for (int i = j + 1; i < 6; ++i)
 #pragma unroll
           for (int k = j + 1; k <= i; ++k) L[i][k] -= L[i][j] * L[k][j];
       }
+      UB_STAMP(17);
+      if (col_thr) {
+        // panel: this column of L_dd^-1 A_12 (forward substitution)
 #pragma unroll
-      for (int i = 0; i < 6; ++i)
+        for (int c = 0; c < 6; ++c) {
+          r[c] *= id[c];
 #pragma unroll
-        for (int k = 0; k <= i; ++k) A[(j0 + i) * ld + j0 + k] = L[i][k];
-      if (!ok) s_ok = 0;
-    }
-    __syncthreads();
-    if (tid < m) {
-      // panel: solve L_p L_dd^T = A_p row by row (right-looking forward substitution)
-      const int i = j0 + 6 + tid;
-      double r[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) r[k] = A[i * ld + j0 + k];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        r[c] *= Li[jb * 36 + c * 7];
-#pragma unroll
-        for (int k = c + 1; k < 6; ++k) r[k] -= r[c] * A[(j0 + k) * ld + j0 + c];
-      }
-#pragma unroll
-      for (int c = 0; c < 6; ++c) A[i * ld + j0 + c] = r[c];
-    } else if (tid >= 224 && tid < 230) {
-      // meanwhile: column c of M = L_dd^-1 (used by the triangular solves), off the critical path
-      const int c = tid - 224;
-      double M[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        if (i < c) { M[i] = 0.0; continue; }
-        double sacc = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-          if (k >= c && k < i) sacc -= A[(j0 + i) * ld + j0 + k] * M[k];
-        M[i] = sacc * Li[jb * 36 + i * 7];
-      }
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-        if (i != c) Li[jb * 36 + i * 6 + c] = M[i];
-    }
-    __syncthreads();
-    // trailing update (lower triangle), 16x16 thread grid; all loads of a 3x3 batch of entries are
-    // issued before any store (the panel columns read and the trailing columns written never alias)
-    for (int i0 = ty; i0 < m; i0 += 48) {
-      for (int k0 = tx; k0 <= i0 + 32 && k0 < m; k0 += 48) {
-        double rkv[3][6], res[3][3];
-#pragma unroll
-        for (int v = 0; v < 3; ++v) {
-          const int kk = k0 + 16 * v;
-          const double* rk = A + (j0 + 6 + (kk < m ? kk : 0)) * ld + j0;
-#pragma unroll
-          for (int c = 0; c < 6; ++c) rkv[v][c] = rk[c];
+          for (int k = c + 1; k < 6; ++k) r[k] -= r[c] * L[k][c];
         }
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          const int ii = i0 + 16 * u;
-          const bool rok = ii < m;
-          const double* ri = A + (j0 + 6 + (rok ? ii : 0)) * ld + j0;
-          const double r0 = ri[0], r1 = ri[1], r2 = ri[2], r3 = ri[3], r4 = ri[4], r5 = ri[5];
+        for (int c = 0; c < 6; ++c) Ut[(j0 + c) * ld + j0 + 6 + tid] = r[c];
+        if (tid == 0 && !ok) s_ok = 0;
+      } else {
+        // the factored diagonal block and its reciprocal pivots (for the back-substitution)
 #pragma unroll
-          for (int v = 0; v < 3; ++v) {
-            const int kk = k0 + 16 * v;
-            const bool ok = rok && kk <= ii;
-            const double sa = r0 * rkv[v][0] + r2 * rkv[v][2] + r4 * rkv[v][4];
-            const double sb = r1 * rkv[v][1] + r3 * rkv[v][3] + r5 * rkv[v][5];
-            res[u][v] = ok ? A[(j0 + 6 + ii) * ld + j0 + 6 + kk] - (sa + sb) : 0.0;
+        for (int cc = 0; cc < 6; ++cc) {
+#pragma unroll
+          for (int i = cc + 1; i < 6; ++i) Ldd[jb * 36 + cc * 6 + i] = L[i][cc];   // not in place: the panel threads may still be reading the block
+          idv[j0 + cc] = id[cc];
+        }
+      }
+    }
+    UB_STAMP(18);
+    UB_ARRIVE(0);
+    __syncthreads();
+    UB_STAMP(19);
+    // trailing update Ut22 -= PᵀP on the tensor pipe (P = the 6 x m panel, rows j0..j0+5): per 8x8 tile two
+    // DMMAs (k = 6, the second half-empty).  Tiles straddling the factored part get zeros for rows / columns
+    // < j0 + 6, so whole tiles are stored without predicates; padding rows / columns absorb the overhang.
+    {
+      const int base = j0 + 6, tb = base >> 3;
+      const double* pr = Ut + j0 * ld;
+      constexpr int CH = TPW < 3 ? TPW : 3;               // tiles whose operands are in flight together
+#pragma unroll
+      for (int k0 = 0; k0 < TPW; k0 += CH) {
+        double a0[CH], a1[CH], b0[CH], b1[CH];
+        double2 c[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          const int k = k0 + u;
+          if (tile_rc[k] != 0xffffu && (int)(tile_rc[k] & 0xffu) >= tb) {
+            a0[u] = pr[offa[k]]; b0[u] = pr[offb[k]];
+            a1[u] = fr < 2 ? pr[4 * ld + offa[k]] : 0.0; b1[u] = fr < 2 ? pr[4 * ld + offb[k]] : 0.0;
+            c[u] = *reinterpret_cast<const double2*>(Ut + offc[k]);
           }
         }
 #pragma unroll
-        for (int u = 0; u < 3; ++u)
-#pragma unroll
-          for (int v = 0; v < 3; ++v) {
-            const int ii = i0 + 16 * u, kk = k0 + 16 * v;
-            if (ii < m && kk <= ii) A[(j0 + 6 + ii) * ld + j0 + 6 + kk] = res[u][v];
+        for (int u = 0; u < CH; ++u) {
+          const int k = k0 + u;
+          if (tile_rc[k] != 0xffffu && (int)(tile_rc[k] & 0xffu) >= tb) {
+            const bool ra = 8 * (int)(tile_rc[k] & 0xffu) + fc >= base, cb = 8 * (int)(tile_rc[k] >> 8) + fc >= base;
+            const double x0 = ra ? -a0[u] : 0.0, x1 = ra ? -a1[u] : 0.0, y0 = cb ? b0[u] : 0.0, y1 = cb ? b1[u] : 0.0;
+            dmma884(c[u].x, c[u].y, x0, y0);
+            dmma884(c[u].x, c[u].y, x1, y1);
+            *reinterpret_cast<double2*>(Ut + offc[k]) = c[u];
           }
+        }
       }
     }
+    UB_STAMP(20);
+    UB_ARRIVE(1);
     __syncthreads();
+    UB_STAMP(21);
   }
   if (lp.dbg && tid == 0) lp.dbg[6] = gtime();
-  // forward substitution L y = b (block-wise with the inverted diagonal blocks)
-  for (int jb = 0; jb < nf; ++jb) {
-    const int j0 = 6 * jb;
-    if (tid < 6) {
-      double sacc = 0.0;
+  // column N now holds y = L^-1 rhs; backward substitution Lᵀ x = y on one warp: lane 0 solves the 6x6
+  // triangle of a block (the chain runs through one multiply-add + one multiply per unknown; everything it reads
+  // that does not depend on the unknowns is loaded first), every lane then removes the block's unknowns from
+  // the rows above (two rows per lane in flight)
+  if (warp == 0) {
+    for (int i = lane; i < N; i += 32) yv[i] = Ut[i * ld + N];
+    __syncwarp();
+    for (int jb = nf - 1; jb >= 0; --jb) {
+      const int j0 = 6 * jb;
+      // rows this lane updates afterwards: request them before the triangular solve
+      double rw[2][6], yo[2];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) sacc += Li[jb * 36 + tid * 6 + k] * bb[j0 + k];
-      s_v6[tid] = sacc;
-    }
-    __syncthreads();
-    if (tid < 6) bb[j0 + tid] = s_v6[tid];
-    const int i = j0 + 6 + tid;
-    if (i < N) {
-      double sacc = 0.0;
+      for (int u = 0; u < 2; ++u) {
+        const int i = lane + 32 * u;
+        const double* row = Ut + (i < j0 ? i : 0) * ld + j0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) sacc += A[i * ld + j0 + k] * s_v6[k];
-      bb[i] -= sacc;
+        for (int k = 0; k < 6; ++k) rw[u][k] = row[k];
+        yo[u] = yv[i < j0 ? i : 0];
+      }
+      if (lane == 0) {
+        double x[6], Lt[15], yy[6], idd[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { yy[c] = yv[j0 + c]; idd[c] = idv[j0 + c]; }
+        {
+          int e = 0;
+#pragma unroll
+          for (int c = 0; c < 5; ++c)
+#pragma unroll
+            for (int k = c + 1; k < 6; ++k) Lt[e++] = Ldd[jb * 36 + c * 6 + k];
+        }
+#pragma unroll
+        for (int c = 5; c >= 0; --c) {
+          double acc = yy[c];
+          const int e0 = c * 5 - (c * (c - 1)) / 2 - (c + 1);   // index of (c, k) in Lt is e0 + k
+#pragma unroll
+          for (int k = 5; k > c; --k) acc -= Lt[e0 + k] * x[k];   // newest unknown last: short chain
+          x[c] = acc * idd[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) xb[j0 + c] = x[c];
+      }
+      __syncwarp();
+      double xv[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) xv[k] = xb[j0 + k];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = lane + 32 * u;
+        if (i < j0) {
+          const double sa = rw[u][0] * xv[0] + rw[u][2] * xv[2] + rw[u][4] * xv[4];
+          const double sb = rw[u][1] * xv[1] + rw[u][3] * xv[3] + rw[u][5] * xv[5];
+          yv[i] = yo[u] - (sa + sb);
+        }
+      }
+      for (int i = lane + 64; i < j0; i += 32) {   // wide systems (more than 11 cameras)
+        const double* row = Ut + i * ld + j0;
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k += 2) { sa += row[k] * xv[k]; sb += row[k + 1] * xv[k + 1]; }
+        yv[i] -= sa + sb;
+      }
+      __syncwarp();
     }
-    __syncthreads();
   }
-  // backward substitution L^T x = y
-  for (int jb = nf - 1; jb >= 0; --jb) {
-    const int j0 = 6 * jb;
-    if (tid < 6) {
-      double sacc = 0.0;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) sacc += Li[jb * 36 + k * 6 + tid] * bb[j0 + k];   // (L_dd^-T)[tid][k]
-      s_v6[tid] = sacc;
-    }
-    __syncthreads();
-    if (tid < 6) bb[j0 + tid] = s_v6[tid];
-    if (tid < j0) {
-      double sacc = 0.0;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) sacc += A[(j0 + k) * ld + tid] * s_v6[k];
-      bb[tid] -= sacc;
-    }
-    __syncthreads();
-  }
+  __syncthreads();
   if (lp.dbg && tid == 0) lp.dbg[7] = gtime();
-  // step (scaled space) = -y ; candidate cameras ; camera part of the model cost change
+  // step (scaled space) = -x ; candidate cameras ; camera part of the model cost change
+  const double* bb = xb;
+  const int D = 6 * F;
   if (tid < 32) {
     double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
     bool bad = false;
     for (int i = tid; i < D; i += 32) {
       const int f = i / 6, a = i - f * 6, fi = st.free_index[f];
-      const double x = lp.cams[((size_t)cur * F + f) * 6 + a];
+      const double x = s_cams ? s_cams[cur * kMaxD + i] : lp.cams[((size_t)cur * F + f) * 6 + a];
       double step = 0.0, cand = x;
       if (fi >= 0) {
         step = -bb[6 * fi + a];
@@ -382,194 +438,155 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
   __syncthreads();
 }
 
-// ---- Schur elimination, fast path: <= 32 pairs of optimised frames (<= 7 free cameras) --------
-// Warp per point.  Vs + D_p² = L Lᵀ (3x3 Cholesky); Z_a = Ws_a L^-T (6x3) for each observing free
-// frame, so the point's contribution is the symmetric rank-3 update  S_ab -= Z_a Z_bᵀ  and
-// rhs_a -= Z_a (L^-1 gs).  Lane l owns the 6x6 block of frame pair l in REGISTERS across all of
-// the warp's points (108 FMA per 36 shared-memory loads); warps are merged through shared memory
-// and the CTA adds its partial to the global accumulators with one fp64 atomic per entry.
-// sm: per warp Z [D][3] + rh [D] | per CTA S_cta [32*36 + D]
+// ---- (E) Schur elimination of this CTA's points --------------------------------------------------------
+// LPP lanes per point (one per observation slot; 8 for windows of <= 8 frames, else 16), TPW 8x8 output
+// tiles per warp.  sm: Zt [Dp][LD], Dp = roundup(N + 1, 8) rows (6 fi + a; row N = L^-1 gs), LD = 3 * points
+// per batch + 4 (rows 32 bytes apart modulo 128: the DMMA fragment loads are bank-conflict free).
 __shared__ unsigned long long s_tdbg[4];   // PBA_DEBUG_TIMELINE: elimination sub-phases of this CTA
-__device__ void schur_pairs(const LmParams& lp, const LmState& st, double* sm) {
+template <int LPP, int TPW>
+__device__ void eliminate(const LmParams& lp, const LmState& st, double* Zt) {
+  constexpr int PPW = 32 / LPP, PPB = kSchurWarps * PPW, K = 3 * PPB, LD = K + 4;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int F = lp.n_frames, D = 6 * F, n = lp.n_points, cur = st.cur, nf = st.n_free;
-  const int npairs = nf * (nf + 1) / 2;
+  const int n = lp.n_points, cur = st.cur, N = 6 * st.n_free, NS = reduced_ld(N);
+  const int Dp = (N + 8) & ~7, T = Dp >> 3, n_tiles = T * (T + 1) / 2;
   const double radius = st.radius, dmin = st.min_diag, dmax = st.max_diag;
   const bool first = (st.iteration == 1);
-  double* Zw = sm + warp * (D * 4);                 // [D][3] + rh [D]
-  double* rhw = Zw + D * 3;
-  double* Scta = sm + 4 * (32 * 36 + 64);          // after the merge buffers (which alias Z/rh)
-  __shared__ int s_fr2[kMaxFrames];
-  if (tid == 0)
-    for (int f = 0; f < F; ++f) if (st.free_index[f] >= 0) s_fr2[st.free_index[f]] = f;
-  for (int i = tid; i < 32 * 36 + D; i += blockDim.x) Scta[i] = 0.0;
-  // lane's pair (pa <= pb) in free-frame indices
-  int pa = 0, pb = 0;
-  if (lane < npairs) {
-    int rem = lane;
-    while (rem >= nf - pa) { rem -= nf - pa; ++pa; }
-    pb = pa + rem;
+  // this CTA's contiguous block of points
+  const int per_cta = (n + gridDim.x - 1) / gridDim.x;
+  const int p_begin = blockIdx.x * per_cta, p_end = min(n, p_begin + per_cta);
+  // this warp's output tiles (tr <= tc): shared-memory row offsets of the A and B fragments
+  int offa[TPW], offb[TPW];
+  unsigned tile_rc[TPW];
+#pragma unroll
+  for (int k = 0; k < TPW; ++k) {
+    const int t = warp + kSchurWarps * k;
+    int tr = 0, rem = t < n_tiles ? t : 0;
+    while (rem >= T - tr) { rem -= T - tr; ++tr; }
+    const int tc = tr + rem;
+    offa[k] = (8 * tr + (lane >> 2)) * LD + (lane & 3);
+    offb[k] = (8 * tc + (lane >> 2)) * LD + (lane & 3);
+    tile_rc[k] = t < n_tiles ? (unsigned)(tr | (tc << 8)) : 0xffffu;
   }
-  __syncthreads();
+  double acc[TPW][2];
+#pragma unroll
+  for (int k = 0; k < TPW; ++k) acc[k][0] = acc[k][1] = 0.0;
+
   const double* Vb = lp.V + (size_t)cur * n * 6;
   const double* gb = lp.gp + (size_t)cur * n * 3;
   const double* Wb = lp.W + (size_t)cur * lp.nnz * 18;
-  double acc[36];
-#pragma unroll
-  for (int e = 0; e < 36; ++e) acc[e] = 0.0;
-  double racc0 = 0.0, racc1 = 0.0;
-
-  // Per-point inputs are loaded one point ahead: the loads of point p+stride are issued right
-  // after point p's phase A has consumed its registers, so their latency hides behind phase B.
-  const int pstride = gridDim.x * (kSchurThreads / 32);
-  double V[6], g0 = 0, g1 = 0, g2 = 0, sp0 = 1, sp1 = 1, sp2 = 1, w[2][3];
-  int rf[2], ra[2];
-  // Two-level prefetch: the CSR header of a point is requested one iteration before its data (whose
-  // addresses depend on it), and nothing here CONSUMES a loaded value, so neither call blocks.
-  int hdr_o0 = 0, hdr_n = 0;
-  auto load_header = [&](int q) { hdr_o0 = __ldg(lp.obs_off + q); hdr_n = __ldg(lp.obs_off + q + 1) - hdr_o0; };
-  auto load_point = [&](int q, int o0, int nobs) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) V[k] = __ldg(Vb + (size_t)q * 6 + k);
-    g0 = __ldg(gb + (size_t)q * 3); g1 = __ldg(gb + (size_t)q * 3 + 1); g2 = __ldg(gb + (size_t)q * 3 + 2);
-    if (!first) { sp0 = lp.scale_p[(size_t)q * 3]; sp1 = lp.scale_p[(size_t)q * 3 + 1]; sp2 = lp.scale_p[(size_t)q * 3 + 2]; }
-    // rows (observation i, pose parameter a): lane + 32k  (nobs <= 8 on this path -> 2 rounds)
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int row = lane + 32 * k;
-      rf[k] = -1; ra[k] = 0;
-      w[k][0] = w[k][1] = w[k][2] = 0.0;
-      if (row < nobs * 6) {
-        const int i = row / 6;
-        ra[k] = row - 6 * i;
-        rf[k] = __ldg(lp.obs_frame + o0 + i);           // raw frame; free/fixed is resolved at use
-        const double* wp = Wb + (size_t)(o0 + i) * 18 + ra[k] * 3;
-        w[k][0] = __ldg(wp); w[k][1] = __ldg(wp + 1); w[k][2] = __ldg(wp + 2);
-      }
-    }
-  };
-  const int p_first = blockIdx.x * (kSchurThreads / 32) + warp;
+  const int q = warp * PPW + lane / LPP, g = lane % LPP;   // point within the batch, observation slot
   if (lp.dbg && tid == 0) s_tdbg[0] = gtime();
-  if (p_first < n) {
-    load_header(p_first);
-    load_point(p_first, hdr_o0, hdr_n);
-    if (p_first + pstride < n) load_header(p_first + pstride);
-  }
-  for (int p = p_first; p < n; p += pstride) {
-    if (first) {
-      sp0 = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[0])) : 1.0;
-      sp1 = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[3])) : 1.0;
-      sp2 = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[5])) : 1.0;
-      if (lane == 0) { lp.scale_p[(size_t)p * 3] = sp0; lp.scale_p[(size_t)p * 3 + 1] = sp1; lp.scale_p[(size_t)p * 3 + 2] = sp2; }
+  for (int b0 = p_begin; b0 < p_end; b0 += PPB) {
+    const int npb = min(PPB, p_end - b0), p = b0 + q;
+    const bool valid = q < npb;
+    // first round of loads: CSR header and the point's own blocks
+    int o0 = 0, nobs = 0;
+    double V[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0}, g0 = 0.0, g1 = 0.0, g2 = 0.0, sp0 = 1.0, sp1 = 1.0, sp2 = 1.0;
+    if (valid) {
+      o0 = __ldg(lp.obs_off + p); nobs = __ldg(lp.obs_off + p + 1) - o0;
+      const double2* v2 = reinterpret_cast<const double2*>(Vb + (size_t)p * 6);
+      const double2 va = __ldg(v2), vb = __ldg(v2 + 1), vc = __ldg(v2 + 2);
+      V[0] = va.x; V[1] = va.y; V[2] = vb.x; V[3] = vb.y; V[4] = vc.x; V[5] = vc.y;
+      g0 = __ldg(gb + (size_t)p * 3); g1 = __ldg(gb + (size_t)p * 3 + 1); g2 = __ldg(gb + (size_t)p * 3 + 2);
+      if (!first) { sp0 = lp.scale_p[(size_t)p * 3]; sp1 = lp.scale_p[(size_t)p * 3 + 1]; sp2 = lp.scale_p[(size_t)p * 3 + 2]; }
     }
-    double a00 = sp0 * V[0] * sp0, a01 = sp0 * V[1] * sp1, a02 = sp0 * V[2] * sp2;
-    double a11 = sp1 * V[3] * sp1, a12 = sp1 * V[4] * sp2, a22 = sp2 * V[5] * sp2;
-    a00 += fmin(fmax(a00, dmin), dmax) / radius;
-    a11 += fmin(fmax(a11, dmin), dmax) / radius;
-    a22 += fmin(fmax(a22, dmin), dmax) / radius;
-    // 3x3 Cholesky and its inverse
-    const double il00 = rsqrt(a00), l10 = a01 * il00, l20 = a02 * il00;
-    const double il11 = rsqrt(a11 - l10 * l10), l21 = (a12 - l20 * l10) * il11;
-    const double il22 = rsqrt(a22 - l20 * l20 - l21 * l21);
-    const double m10 = -l10 * il00 * il11, m20 = -(l20 * il00 + l21 * m10) * il22, m21 = -l21 * il11 * il22;
-    if (lane == 0) {
-      double* vi = lp.Vinv + (size_t)p * 6;   // (Vs + D²)^-1 = M^T M, used by K_A's back-substitution
-      vi[0] = il00 * il00 + m10 * m10 + m20 * m20; vi[1] = m10 * il11 + m20 * m21; vi[2] = m20 * il22;
-      vi[3] = il11 * il11 + m21 * m21; vi[4] = m21 * il22; vi[5] = il22 * il22;
-    }
-    const double gs0 = sp0 * g0, gs1 = sp1 * g1, gs2 = sp2 * g2;
-    const double zg0 = gs0 * il00, zg1 = (gs1 - l10 * zg0) * il11, zg2 = (gs2 - l20 * zg0 - l21 * zg1) * il22;
-    unsigned mask = 0;
+    // zero the staging matrix (rows of frames that do not observe a point must read as zero)
+    if (b0 != p_begin) __syncthreads();                       // the previous batch's product is done with it
+    for (int i = tid; i < Dp * (LD / 2); i += kSchurThreads) reinterpret_cast<double2*>(Zt)[i] = make_double2(0.0, 0.0);
+    // second round: this lane's observation
+    int f = -1;
+    double2 w2[9];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int fi = rf[k] >= 0 ? st.free_index[rf[k]] : -1;
+    for (int k = 0; k < 9; ++k) w2[k] = make_double2(0.0, 0.0);
+    if (valid && g < nobs) {
+      f = __ldg(lp.obs_frame + o0 + g);
+      const double2* wp = reinterpret_cast<const double2*>(Wb + (size_t)(o0 + g) * 18);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w2[k] = __ldg(wp + k);
+    }
+    __syncthreads();
+    if (valid) {
+      if (first) {
+        sp0 = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[0])) : 1.0;
+        sp1 = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[3])) : 1.0;
+        sp2 = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[5])) : 1.0;
+        if (g == 0) { lp.scale_p[(size_t)p * 3] = sp0; lp.scale_p[(size_t)p * 3 + 1] = sp1; lp.scale_p[(size_t)p * 3 + 2] = sp2; }
+      }
+      double a00 = sp0 * V[0] * sp0, a01 = sp0 * V[1] * sp1, a02 = sp0 * V[2] * sp2;
+      double a11 = sp1 * V[3] * sp1, a12 = sp1 * V[4] * sp2, a22 = sp2 * V[5] * sp2;
+      a00 += fmin(fmax(a00, dmin), dmax) / radius;
+      a11 += fmin(fmax(a11, dmin), dmax) / radius;
+      a22 += fmin(fmax(a22, dmin), dmax) / radius;
+      // 3x3 Cholesky and its inverse
+      const double il00 = rsqrt(a00), l10 = a01 * il00, l20 = a02 * il00;
+      const double il11 = rsqrt(a11 - l10 * l10), l21 = (a12 - l20 * l10) * il11;
+      const double il22 = rsqrt(a22 - l20 * l20 - l21 * l21);
+      const double gs0 = sp0 * g0, gs1 = sp1 * g1, gs2 = sp2 * g2;
+      const double zg0 = gs0 * il00, zg1 = (gs1 - l10 * zg0) * il11, zg2 = (gs2 - l20 * zg0 - l21 * zg1) * il22;
+      if (g == 0) {
+        const double m10 = -l10 * il00 * il11, m20 = -(l20 * il00 + l21 * m10) * il22, m21 = -l21 * il11 * il22;
+        double* vi = lp.Vinv + (size_t)p * 6;   // (Vs + D²)^-1 = M^T M, used by K_A's back-substitution
+        vi[0] = il00 * il00 + m10 * m10 + m20 * m20; vi[1] = m10 * il11 + m20 * m21; vi[2] = m20 * il22;
+        vi[3] = il11 * il11 + m21 * m21; vi[4] = m21 * il22; vi[5] = il22 * il22;
+        double* zr = Zt + N * LD + 3 * q;
+        zr[0] = zg0; zr[1] = zg1; zr[2] = zg2;
+      }
+      const int fi = f >= 0 ? st.free_index[f] : -1;
       if (fi >= 0) {
-        const double sc = st.scale_c[rf[k] * 6 + ra[k]];
-        const double z0 = sc * w[k][0] * sp0 * il00;
-        const double z1 = (sc * w[k][1] * sp1 - z0 * l10) * il11;
-        const double z2 = (sc * w[k][2] * sp2 - z0 * l20 - z1 * l21) * il22;
-        double* zr = Zw + (6 * fi + ra[k]) * 3;
-        zr[0] = z0; zr[1] = z1; zr[2] = z2;
-        rhw[6 * fi + ra[k]] = -(z0 * zg0 + z1 * zg1 + z2 * zg2);
-        mask |= 1u << fi;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          const double sc = st.scale_c[f * 6 + a];
+          // W row a = elements 3a .. 3a+2 of the 18-double block (compile-time selects after unrolling)
+          const double wa0 = ((3 * a) & 1) ? w2[(3 * a) >> 1].y : w2[(3 * a) >> 1].x;
+          const double wa1 = ((3 * a + 1) & 1) ? w2[(3 * a + 1) >> 1].y : w2[(3 * a + 1) >> 1].x;
+          const double wa2 = ((3 * a + 2) & 1) ? w2[(3 * a + 2) >> 1].y : w2[(3 * a + 2) >> 1].x;
+          const double z0 = sc * wa0 * sp0 * il00;
+          const double z1 = (sc * wa1 * sp1 - z0 * l10) * il11;
+          const double z2 = (sc * wa2 * sp2 - z0 * l20 - z1 * l21) * il22;
+          double* zr = Zt + (6 * fi + a) * LD + 3 * q;
+          zr[0] = z0; zr[1] = z1; zr[2] = z2;
+        }
       }
     }
-    mask = __reduce_or_sync(0xffffffffu, mask);
-    __syncwarp();
-    if (p + pstride < n) {                            // prefetch (registers of point p are dead now)
-      load_point(p + pstride, hdr_o0, hdr_n);
-      if (p + 2 * pstride < n) load_header(p + 2 * pstride);
-    }
-    if (lane < npairs && ((mask >> pa) & 1u) && ((mask >> pb) & 1u)) {
-      const double* za = Zw + 18 * pa;
-      const double* zb = Zw + 18 * pb;
-      double zbv[18];
+    __syncthreads();
+    // P += Zt Ztᵀ on the fp64 tensor pipe: 4 columns (k) per DMMA, independent accumulator chains per tile
+    const int ksteps = (3 * npb + 3) >> 2;
+    for (int ks = 0; ks < ksteps; ++ks) {
 #pragma unroll
-      for (int e = 0; e < 18; ++e) zbv[e] = zb[e];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const double x0 = za[3 * i], x1 = za[3 * i + 1], x2 = za[3 * i + 2];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) acc[i * 6 + j] -= x0 * zbv[3 * j] + x1 * zbv[3 * j + 1] + x2 * zbv[3 * j + 2];
+      for (int k = 0; k < TPW; ++k) {
+        if (tile_rc[k] != 0xffffu) {
+          const double a = Zt[offa[k] + 4 * ks];
+          const double b = Zt[offb[k] + 4 * ks];
+          dmma884(acc[k][0], acc[k][1], a, b);
+        }
       }
     }
-    if (lane < 6 * nf && ((mask >> (lane / 6)) & 1u)) racc0 += rhw[lane];
-    if (lane + 32 < 6 * nf && ((mask >> ((lane + 32) / 6)) & 1u)) racc1 += rhw[lane + 32];
-    __syncwarp();
   }
-  // merge the warps pairwise through shared memory (fixed tree: deterministic inside the CTA), then
-  // one atomic per entry.  Buffers: warp w writes into slot w of Smerge [warps/2][32*36 + 64].
-  double* Smerge = sm;   // the Z / rh staging area is dead now
-  __syncthreads();
   if (lp.dbg && tid == 0) s_tdbg[1] = gtime();
-  for (int half = (kSchurThreads / 32) / 2; half >= 1; half >>= 1) {
-    if (warp >= half && warp < 2 * half) {
-      double* dst = Smerge + (size_t)(warp - half) * (32 * 36 + 64);
+  // one fp64 atomic per entry of the upper triangle per CTA
 #pragma unroll
-      for (int e = 0; e < 36; ++e) dst[e * 32 + lane] = acc[e];
-      dst[32 * 36 + lane] = racc0; dst[32 * 36 + 32 + lane] = racc1;
+  for (int k = 0; k < TPW; ++k) {
+    if (tile_rc[k] != 0xffffu) {
+      const int r = 8 * (int)(tile_rc[k] & 0xffu) + (lane >> 2);
+      const int c = 8 * (int)(tile_rc[k] >> 8) + 2 * (lane & 3);
+      if (r < N) {
+        if (r <= c && c <= N && acc[k][0] != 0.0) atomicAdd(lp.S + r * NS + c, acc[k][0]);
+        if (r <= c + 1 && c + 1 <= N && acc[k][1] != 0.0) atomicAdd(lp.S + r * NS + c + 1, acc[k][1]);
+      }
     }
-    __syncthreads();
-    if (warp < half) {
-      const double* src = Smerge + (size_t)warp * (32 * 36 + 64);
-#pragma unroll
-      for (int e = 0; e < 36; ++e) acc[e] += src[e * 32 + lane];
-      racc0 += src[32 * 36 + lane]; racc1 += src[32 * 36 + 32 + lane];
-    }
-    __syncthreads();
   }
   if (lp.dbg && tid == 0) s_tdbg[2] = gtime();
-  if (warp == 0) {
-    if (lane < npairs) {
-#pragma unroll
-      for (int e = 0; e < 36; ++e) Scta[lane * 36 + e] = acc[e];
-    }
-    if (lane < 6 * nf) Scta[32 * 36 + lane] = racc0;
-    if (lane + 32 < 6 * nf) Scta[32 * 36 + lane + 32] = racc1;
-  }
-  __syncthreads();
-  for (int t = tid; t < npairs * 36; t += blockDim.x) {
-    const int pr = t / 36, e = t - pr * 36, i = e / 6, j = e - i * 6;
-    int qa = 0, rem = pr;
-    while (rem >= nf - qa) { rem -= nf - qa; ++qa; }
-    const int fa = s_fr2[qa], fb = s_fr2[qa + rem];
-    const double v = Scta[t];
-    if (v != 0.0) atomicAdd(lp.S + (6 * fa + i) * D + 6 * fb + j, v);
-  }
-  if (tid < 6 * nf) {
-    const double v = Scta[32 * 36 + tid];
-    if (v != 0.0) atomicAdd(lp.S + D * D + 6 * s_fr2[tid / 6] + tid % 6, v);
-  }
 }
 
 // Tail of an LM iteration (one CTA): adopt the candidate's pose blocks if the step was taken, solve
 // the reduced camera system, re-zero the accumulators K_A fills next, publish the new state.
-__device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, int F, const double* xs) {
+template <int TPW>
+__device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams) {
   const int tid = threadIdx.x;
   if (st.took_step)
     for (int i = tid; i < F * kUStride; i += blockDim.x) lp.Ucur[i] = xs ? xs[i] : __ldcg(lp.Xacc + i);
   __syncthreads();
-  solve_reduced(lp, st, sm, F, xs);
+  solve_reduced<TPW>(lp, st, sm, F, xs, s_cams);
   if (lp.dbg && tid == 0) lp.dbg[3] = gtime();
   for (int i = tid; i < F * kUStride + kEacc + kMaxRanks; i += blockDim.x) lp.Xacc[i] = 0.0;
   if (tid == 0) *lp.ticket = 0u;
@@ -579,21 +596,20 @@ __device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, in
   if (lp.dbg && tid == 0) lp.dbg[4] = gtime();
 }
 
-// MODE 0: pairs fast path (<= 7 optimised cameras, <= 8 frames); MODE k>0: generic 3x3-tile path, k tiles/thread
-template <int MODE>
-__global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp) {
-  constexpr int TPT = MODE > 0 ? MODE : 1;
+// LPP: lanes per point in the elimination (8: windows of <= 8 frames; 16 otherwise); TPW: 8x8 tiles of the
+// reduced system per warp (3: <= 24 tiles, i.e. <= 7 optimised cameras; 12: up to 16 cameras)
+template <int LPP, int TPW>
+__global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams lp) {
   __shared__ LmState s_st;
   __shared__ IterSummary s_it;
   __shared__ int s_push, s_last;
-  __shared__ unsigned s_mask[kSchurChunk];
-  __shared__ unsigned char s_pair[kMaxFrames * (kMaxFrames + 1) / 2][2];   // upper block pairs (g <= f)
   __shared__ double s_xs[kMaxFrames * kUStride + kEacc + kMaxRanks];        // the evaluation's pose blocks + scalars (summed over ranks)
   __shared__ int s_xok;
-  extern __shared__ double sm[];
+  __shared__ double s_cams[2 * kMaxD];                                       // both camera buffers (decision, candidate)
+  extern __shared__ __align__(16) double sm[];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int F = lp.n_frames, D = 6 * F, n = lp.n_points;
+  const int F = lp.n_frames;
   const unsigned long long t_start = lp.dbg ? gtime() : 0ull;
 
   // ---- (D) decision, redundantly per CTA ------------------------------------------------
@@ -619,6 +635,13 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
   }
   for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
     reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_in)[i];
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < (kMaxD + 31) / 32; ++k) {
+      const int i = lane + 32 * k;
+      if (i < F * 6) { s_cams[i] = cam_pre[0][k]; s_cams[kMaxD + i] = cam_pre[1][k]; }
+    }
+  }
   if (!xmode) {
 #pragma unroll
     for (int k = 0; k < kXPre; ++k)
@@ -705,145 +728,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
 
   const unsigned long long t_dec = lp.dbg ? gtime() : 0ull;
   // ---- (E) eliminate the point blocks -----------------------------------------------------
-  if (MODE == 0) {
-    schur_pairs(lp, s_st, sm);
-  } else {
-  const int cur = s_st.cur;
-  const double radius = s_st.radius, dmin = s_st.min_diag, dmax = s_st.max_diag;
-  const bool first = (s_st.iteration == 1);
-  double* Yf = sm;                                  // [chunk][D*3]
-  double* Wf = Yf + kSchurChunk * D * 3;            // [chunk][D*3]
-  double* rh = Wf + kSchurChunk * D * 3;            // [chunk][D]
-  const double* Vb = lp.V + (size_t)cur * n * 6;
-  const double* gb = lp.gp + (size_t)cur * n * 3;
-  const double* Wb = lp.W + (size_t)cur * lp.nnz * 18;
-
-  // each thread owns up to TPT 3x3 tiles of the UPPER block triangle of S: tile = pair*4 + (sr,sc)
-  const int npairs = F * (F + 1) / 2, ntiles = npairs * 4;
-  if (tid < npairs) {
-    int g = 0, rem = tid;
-    while (rem >= F - g) { rem -= F - g; ++g; }
-    s_pair[tid][0] = (unsigned char)g; s_pair[tid][1] = (unsigned char)(g + rem);
-  }
-  __syncthreads();
-  double acc[TPT][9];
-#pragma unroll
-  for (int k = 0; k < TPT; ++k)
-#pragma unroll
-    for (int e = 0; e < 9; ++e) acc[k][e] = 0.0;
-  double racc = 0.0;
-
-  const int n_chunks = (n + kSchurChunk - 1) / kSchurChunk;
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int p = chunk * kSchurChunk + warp;
-    unsigned mask = 0;
-    if (p < n) {
-      const int o0 = lp.obs_off[p], nobs = lp.obs_off[p + 1] - o0;
-      const int my_f = lane < nobs ? lp.obs_frame[o0 + lane] : 0;
-      // prefetch the point's W blocks (18 lanes x up to 16 observations in flight)
-      double wreg[kMaxFrames];
-#pragma unroll
-      for (int i = 0; i < kMaxFrames; ++i) wreg[i] = (i < nobs && lane < 18) ? __ldg(Wb + (size_t)(o0 + i) * 18 + lane) : 0.0;
-      double sp[3], Vs[6], Vi[6], gs[3];
-      double V[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) V[k] = __ldg(Vb + (size_t)p * 6 + k);
-      const double gp0 = __ldg(gb + (size_t)p * 3), gp1 = __ldg(gb + (size_t)p * 3 + 1), gp2 = __ldg(gb + (size_t)p * 3 + 2);
-      if (first) {
-        sp[0] = s_st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[0])) : 1.0;
-        sp[1] = s_st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[3])) : 1.0;
-        sp[2] = s_st.jacobi_scaling ? 1.0 / (1.0 + sqrt(V[5])) : 1.0;
-        if (lane < 3) lp.scale_p[(size_t)p * 3 + lane] = sp[lane];
-      } else {
-        sp[0] = lp.scale_p[(size_t)p * 3]; sp[1] = lp.scale_p[(size_t)p * 3 + 1]; sp[2] = lp.scale_p[(size_t)p * 3 + 2];
-      }
-      Vs[0] = sp[0] * V[0] * sp[0]; Vs[1] = sp[0] * V[1] * sp[1]; Vs[2] = sp[0] * V[2] * sp[2];
-      Vs[3] = sp[1] * V[3] * sp[1]; Vs[4] = sp[1] * V[4] * sp[2]; Vs[5] = sp[2] * V[5] * sp[2];
-      Vs[0] += fmin(fmax(Vs[0], dmin), dmax) / radius;
-      Vs[3] += fmin(fmax(Vs[3], dmin), dmax) / radius;
-      Vs[5] += fmin(fmax(Vs[5], dmin), dmax) / radius;
-      inv_sym3(Vs, Vi);
-      if (lane < 6) lp.Vinv[(size_t)p * 6 + lane] = Vi[lane];
-      gs[0] = sp[0] * gp0; gs[1] = sp[1] * gp1; gs[2] = sp[2] * gp2;
-      const int a = lane / 3, b = lane - a * 3;
-      const double spb = b == 0 ? sp[0] : (b == 1 ? sp[1] : sp[2]);
-      const double vi0 = sym3(Vi, 0, b), vi1 = sym3(Vi, 1, b), vi2 = sym3(Vi, 2, b);
-      const double gsb = b == 0 ? gs[0] : (b == 1 ? gs[1] : gs[2]);
-#pragma unroll
-      for (int i = 0; i < kMaxFrames; ++i) {
-        if (i < nobs) {
-          const int f = __shfl_sync(0xffffffffu, my_f, i);
-          if (s_st.free_index[f] >= 0) {
-            mask |= 1u << f;
-            double ws = 0.0;
-            if (lane < 18) {
-              ws = s_st.scale_c[f * 6 + a] * wreg[i] * spb;
-              Wf[(warp * D + 6 * f) * 3 + lane] = ws;
-            }
-            // Y[a][b] = sum_q Ws[a][q] Vi[q][b]: gather the row's three entries with shuffles
-            const int base = lane < 18 ? a * 3 : 0;
-            const double w0 = __shfl_sync(0xffffffffu, ws, base);
-            const double w1 = __shfl_sync(0xffffffffu, ws, base + 1);
-            const double w2 = __shfl_sync(0xffffffffu, ws, base + 2);
-            const double y = w0 * vi0 + w1 * vi1 + w2 * vi2;
-            // rhs[a] -= sum_b Y[a][b] gs[b]: combine the three lanes of a row
-            const double t = y * gsb;
-            const double t1 = __shfl_down_sync(0xffffffffu, t, 1);
-            const double t2 = __shfl_down_sync(0xffffffffu, t, 2);
-            if (lane < 18) {
-              Yf[(warp * D + 6 * f) * 3 + lane] = y;
-              if (b == 0) rh[warp * D + 6 * f + a] = -(t + t1 + t2);
-            }
-          }
-        }
-      }
-    }
-    if (lane == 0) s_mask[warp] = mask;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < TPT; ++k) {
-      const int t = tid + k * kSchurThreads;
-      if (t < ntiles) {
-        const int fr = s_pair[t >> 2][0], fc = s_pair[t >> 2][1];
-        const int tr = 2 * fr + ((t >> 1) & 1), tc = 2 * fc + (t & 1);
-#pragma unroll
-        for (int w = 0; w < kSchurChunk; ++w) {
-          const unsigned m = s_mask[w];
-          if (((m >> fr) & 1u) && ((m >> fc) & 1u)) {
-            const double* y = Yf + (w * D + 3 * tr) * 3;
-            const double* ww = Wf + (w * D + 3 * tc) * 3;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-              for (int j = 0; j < 3; ++j)
-                acc[k][i * 3 + j] -= y[i * 3] * ww[j * 3] + y[i * 3 + 1] * ww[j * 3 + 1] + y[i * 3 + 2] * ww[j * 3 + 2];
-          }
-        }
-      }
-    }
-    if (tid < D) {
-      const int f = tid / 6;
-#pragma unroll
-      for (int w = 0; w < kSchurChunk; ++w)
-        if ((s_mask[w] >> f) & 1u) racc += rh[w * D + tid];
-    }
-    __syncthreads();
-  }
-  // one fp64 atomic per non-zero entry per CTA
-#pragma unroll
-  for (int k = 0; k < TPT; ++k) {
-    const int t = tid + k * kSchurThreads;
-    if (t < ntiles) {
-      const int tr = 2 * s_pair[t >> 2][0] + ((t >> 1) & 1), tc = 2 * s_pair[t >> 2][1] + (t & 1);
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          if (acc[k][i * 3 + j] != 0.0) atomicAdd(lp.S + (3 * tr + i) * D + 3 * tc + j, acc[k][i * 3 + j]);
-    }
-  }
-  if (tid < D && racc != 0.0) atomicAdd(lp.S + D * D + tid, racc);
-  }  // MODE != 0
+  eliminate<LPP, TPW>(lp, s_st, sm);
 
   // ---- (S) the last CTA solves the reduced camera system -------------------------------------
   // bar.sync orders the CTA's atomics before thread 0's cumulative gpu-scope fence + ticket
@@ -856,7 +741,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
   __syncthreads();
   if (lp.dbg && tid == 0 && s_last) {
     lp.dbg[0] = t_start; lp.dbg[1] = t_dec; lp.dbg[2] = gtime();
-    if (MODE == 0) { lp.dbg[12] = s_tdbg[0]; lp.dbg[13] = s_tdbg[1]; lp.dbg[14] = s_tdbg[2]; }
+    lp.dbg[12] = s_tdbg[0]; lp.dbg[13] = s_tdbg[1]; lp.dbg[14] = s_tdbg[2];
   }
   if (!s_last) return;
   if (lp.split) {
@@ -867,10 +752,10 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
     return;
   }
   if (xmode) {
-    // publish this rank's reduced-system contribution (upper block triangle + rhs) to every rank as LL
+    // publish this rank's reduced-system contribution (upper triangle + rhs column) to every rank as LL
     // cells, then sum everybody's in rank order straight out of the cells (polling replaces flag + fence)
     const unsigned long long e = s_st.xepoch;
-    const int sn = D * D + D;
+    const int N = 6 * s_st.n_free, NS = reduced_ld(N), sn = N * NS;
     const size_t off = ((size_t)(e & 1ull) * lp.xc.n_ranks + lp.xc.rank) * lp.xc.s_n;
     constexpr int kB = 4;                    // elements per thread in flight
     for (int i0 = tid; i0 < sn; i0 += kB * blockDim.x) {
@@ -883,7 +768,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
 #pragma unroll
       for (int u = 0; u < kB; ++u) {
         const int i = i0 + u * blockDim.x;
-        const bool need = i < sn && (i >= D * D || (i / D) / 6 <= (i % D) / 6);
+        const bool need = i < sn && (i / NS) <= (i % NS) && (i % NS) <= N;
         if (need)
           for (int q = 0; q < lp.xc.n_ranks; ++q) ll_store(lp.xc.s[q] + off + i, v[u], e);
       }
@@ -896,7 +781,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
 #pragma unroll
       for (int u = 0; u < kB; ++u) {
         const int i = i0 + u * blockDim.x;
-        need[u] = i < sn && (i >= D * D || (i / D) / 6 <= (i % D) / 6);
+        need[u] = i < sn && (i / NS) <= (i % NS) && (i % NS) <= N;
         acc[u] = 0.0;
       }
       for (int q = 0; q < lp.xc.n_ranks; ++q) {
@@ -936,19 +821,20 @@ __global__ void __launch_bounds__(kSchurThreads) k_schur_solve(const LmParams lp
     __syncthreads();
     if (lp.dbg && tid == 0) lp.dbg[11] = gtime();
   }
-  finish_iteration(lp, s_st, sm, F, s_xs);
+  finish_iteration<TPW>(lp, s_st, sm, F, s_xs, s_cams);
 }
 
 // split mode: one CTA, after the all-reduce of S
+template <int TPW>
 __global__ void __launch_bounds__(kSchurThreads) k_solve_only(const LmParams lp) {
   __shared__ LmState s_st;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x;
   for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
     reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_out)[i];
   __syncthreads();
   if (s_st.done) return;
-  finish_iteration(lp, s_st, sm, lp.n_frames, nullptr);
+  finish_iteration<TPW>(lp, s_st, sm, lp.n_frames, nullptr, nullptr);
 }
 
 // Device-side barrier across the ranks of a window (start of a solve): raise my flag in every rank's
@@ -968,55 +854,61 @@ cudaError_t launch_rendezvous(const Xchg& xc, unsigned long long epoch, cudaStre
 }
 
 // ---- launchers ----------------------------------------------------------------------------
+// One contiguous block of points per CTA (at least 8, so that tiny windows do not pay one round of
+// atomics per point), at most one CTA per SM.
 int schur_grid(int n_points, int sm_count) {
-  const int chunks = (n_points + kSchurChunk - 1) / kSchurChunk;
-  const int cap = sm_count;
-  return chunks < cap ? (chunks > 0 ? chunks : 1) : cap;
+  int per_cta = (n_points + sm_count - 1) / sm_count;
+  if (per_cta < 8) per_cta = 8;
+  const int g = (n_points + per_cta - 1) / per_cta;
+  return g > 0 ? g : 1;
 }
 
-template <int MODE>
-static cudaError_t launch_mode(const LmParams& lp, int grid, size_t smem, cudaStream_t s) {
+static size_t solve_smem_doubles(int n_free, int F) {
+  const size_t N = 6 * (size_t)n_free, ld = reduced_ld((int)N), npad = (N + 1) & ~(size_t)1;
+  return (N + 8) * ld + (size_t)n_free * 36 + 3 * npad + (size_t)F * kUStride + 2;
+}
+
+template <int LPP, int TPW>
+static cudaError_t launch_mode(const LmParams& lp, int grid, int n_free, cudaStream_t s) {
   static bool cfg[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!cfg[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k_schur_solve<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_schur_solve<LPP, TPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
     if (e != cudaSuccess) return e;
     cfg[dev & 63] = true;
   }
-  k_schur_solve<MODE><<<grid, kSchurThreads, smem, s>>>(lp);
+  constexpr int PPB = kSchurWarps * (32 / LPP), LD = 3 * PPB + 4;
+  const int N = 6 * n_free, Dp = (N + 8) & ~7;
+  const size_t elim_d = (size_t)Dp * LD, solve_d = solve_smem_doubles(n_free, lp.n_frames);
+  const size_t smem = sizeof(double) * (elim_d > solve_d ? elim_d : solve_d);
+  k_schur_solve<LPP, TPW><<<grid, kSchurThreads, smem, s>>>(lp);
   return cudaGetLastError();
 }
 
 cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t s) {
-  const int F = lp.n_frames, D = 6 * F, N = D;
-  const size_t solve_b = sizeof(double) * ((size_t)N * (N + 1) + (size_t)F * 36 + N + (size_t)F * kUStride);
-  if (F <= 8 && n_free <= 7) {
-    const size_t stage = (size_t)(kSchurThreads / 32) * D * 4, merge = 4 * (32 * 36 + 64);
-    const size_t pairs_b = sizeof(double) * ((stage > merge ? stage : merge) + 32 * 36 + D);
-    return launch_mode<0>(lp, grid, pairs_b > solve_b ? pairs_b : solve_b, s);
-  }
-  const size_t schur_b = sizeof(double) * (size_t)kSchurChunk * (D * 3 * 2 + D);
-  const size_t smem = schur_b > solve_b ? schur_b : solve_b;
-  const int need = (2 * F * (F + 1) + kSchurThreads - 1) / kSchurThreads;   // tiles of the upper block triangle
-  if (need <= 1) return launch_mode<1>(lp, grid, smem, s);
-  if (need <= 2) return launch_mode<2>(lp, grid, smem, s);
-  return launch_mode<3>(lp, grid, smem, s);
+  const int T = (6 * n_free + 8) >> 3, tiles = T * (T + 1) / 2;
+  if (lp.n_frames <= 8) return tiles <= 3 * kSchurWarps ? launch_mode<8, 3>(lp, grid, n_free, s) : launch_mode<8, 12>(lp, grid, n_free, s);
+  return tiles <= 3 * kSchurWarps ? launch_mode<16, 3>(lp, grid, n_free, s) : launch_mode<16, 12>(lp, grid, n_free, s);
 }
 
-cudaError_t launch_solve_only(const LmParams& lp, cudaStream_t s) {
-  const int F = lp.n_frames, N = 6 * F;
-  const size_t solve_b = sizeof(double) * ((size_t)N * (N + 1) + (size_t)F * 36 + N + (size_t)F * kUStride);
+template <int TPW>
+static cudaError_t launch_solve_only_t(const LmParams& lp, int n_free, cudaStream_t s) {
   static bool cfg[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!cfg[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k_solve_only, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_solve_only<TPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
     if (e != cudaSuccess) return e;
     cfg[dev & 63] = true;
   }
-  k_solve_only<<<1, kSchurThreads, solve_b, s>>>(lp);
+  k_solve_only<TPW><<<1, kSchurThreads, sizeof(double) * solve_smem_doubles(n_free, lp.n_frames), s>>>(lp);
   return cudaGetLastError();
+}
+
+cudaError_t launch_solve_only(const LmParams& lp, int n_free, cudaStream_t s) {
+  const int T = (6 * n_free + 8) >> 3, tiles = T * (T + 1) / 2;
+  return tiles <= 3 * kSchurWarps ? launch_solve_only_t<3>(lp, n_free, s) : launch_solve_only_t<12>(lp, n_free, s);
 }
 
 }  // namespace pba

@@ -17,7 +17,8 @@
 //                                            fp64 atomics (one per CTA per entry); this is the buffer
 //                                            that is all-reduced when a window spans several GPUs
 //   Ucur     f64 [F][27]                     pose blocks of the accepted point
-//   S        f64 [D*D + D]                   Schur complement + rhs accumulators, D = 6F
+//   S        f64 [N][ld]                     reduced-system accumulator P = sum Zt Ztᵀ in free-camera index space
+//                                            (N = 6 n_free, ld = reduced_ld(N), upper triangle, column N = rhs part)
 //   state    LmState x2                      ping-pong: K_B reads one, writes the other
 #pragma once
 #include <cstdint>
@@ -32,7 +33,6 @@ constexpr int kStageSlots = 8;        // (observation, channel) footprints stage
 constexpr int kPoseConst = 36;        // doubles per frame, see pose_consts()
 constexpr int kUStride = 27;          // 21 upper-tri U + 6 g_c
 constexpr int kSchurThreads = 256;
-constexpr int kSchurChunk = 8;        // points per chunk (one per warp)
 constexpr int kEacc = 8;
 constexpr int kMaxRanks = 8;         // max|g_p| slots in Xacc (one per rank)
 
@@ -148,7 +148,7 @@ struct LmParams {
   int split;                 // 1: multi-GPU — the reduced system is all-reduced before a separate solve kernel
   double* scale_p;           // [n][3]
   double* Vinv;              // [n][6]
-  double* S;                 // [D*D + D]
+  double* S;                 // [N][reduced_ld(N)], see k_schur_solve.cu
   unsigned long long* dbg;   // optional: globaltimer stamps of the last CTA {start, decided, schur done, solved, end}
   unsigned long long cond;   // non-zero: cudaGraphConditionalHandle of the device-side LM loop, cleared when done
   Xchg xc;                   // multi-GPU exchange over peer memory (xc.n_ranks > 1), else split/NCCL or single GPU
@@ -200,11 +200,17 @@ __device__ __forceinline__ bool xchg_wait(const unsigned long long* flag, unsign
   return true;
 }
 
+// Row stride of the reduced system S [N][ld] (global accumulator and the solver's shared-memory copy): the
+// smallest ld = 4 (mod 16) with ld >= N + 8 — rows 32 bytes apart modulo 128 make the DMMA fragment loads of
+// the trailing update bank-conflict free, and 8x8 tiles may overhang the last column.
+__host__ __device__ constexpr int reduced_ld(int N) { return ((N + 19) >> 4) * 16 + 4; }
+__host__ __device__ constexpr size_t reduced_capacity(int max_frames) { return (size_t)(6 * max_frames) * reduced_ld(6 * max_frames); }
+
 // launchers
 cudaError_t launch_k_step(const StepParams& prm, int radius, cudaStream_t stream);
 int schur_grid(int n_points, int sm_count);
 cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t stream);
-cudaError_t launch_solve_only(const LmParams& lp, cudaStream_t stream);   // split mode, after the all-reduce of S
+cudaError_t launch_solve_only(const LmParams& lp, int n_free, cudaStream_t stream);   // split mode, after the all-reduce of S
 cudaError_t launch_rendezvous(const Xchg& xc, unsigned long long epoch, cudaStream_t stream);   // device-side barrier across the ranks
 
 // descriptor channels (k_prep.cu): type 1 = IntensityAndGradient (3 planes), 2 = BitPlanes (8 planes)
