@@ -68,9 +68,7 @@ __device__ bool decide(LmState& st, const double* E, double gm, double g2, doubl
     // IterationZero
     st.x_cost = cost_e; st.initial_cost = cost_e;
     st.x_norm = sqrt(csq + E[3]);
-    for (int f = 0; f < F; ++f)
-      for (int a = 0; a < 6; ++a)
-        st.scale_c[f * 6 + a] = st.jacobi_scaling ? 1.0 / (1.0 + sqrt(Ubuf[f * kUStride + utri6(a, a)])) : 1.0;
+    // (the Jacobi scaling of the pose columns, 1 / (1 + sqrt(diag U)), is formed by the caller on parallel lanes)
     st.gmax = gmax_e; st.gnorm = gnorm_e;
     st.radius = st.initial_radius; st.decrease_factor = 2.0;
     st.cur = buf; st.eval_buf = 1 - buf; st.took_step = 1;
@@ -177,6 +175,17 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
   double* xb = idv + Npad;
   double* yv = xb + Npad;
   double* Us = yv + Npad;                      // [F][27] pose blocks of the accepted point
+  // Everything this phase reads from global memory is requested FIRST, in one round: the accumulator (-P: a
+  // linear copy, all loads of a thread in flight at once) and, after a rejected step, the accepted point's pose
+  // blocks; the index arithmetic below runs in the shadow of that round trip.
+  constexpr int kCopyB = 10;
+  const int tot = N * ld;
+  const bool us_from_xs = xs && st.took_step;
+  double v[kCopyB], uc[2];
+#pragma unroll
+  for (int u = 0; u < kCopyB; ++u) v[u] = (tid + u * nthr < tot) ? __ldcg(lp.S + tid + u * nthr) : 0.0;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) uc[u] = (!us_from_xs && tid + u * nthr < F * kUStride) ? __ldcg(lp.Ucur + tid + u * nthr) : 0.0;
   // this warp's 8x8 tiles (tr <= tc) of the ABSOLUTE tile grid over Ut — the same assignment in every block step,
   // so every address below is formed once: C fragment, and the panel-row-relative A / B fragment offsets
   const int Tabs = (N + 8) >> 3, n_tiles = Tabs * (Tabs + 1) / 2;
@@ -198,25 +207,25 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
   __shared__ int s_ok;
   if (tid == 0) {
     s_ok = 1;
+#pragma unroll 1
     for (int f = 0; f < F; ++f) if (st.free_index[f] >= 0) s_fr[st.free_index[f]] = f;
-  }
-  // -P: a linear copy of the accumulator (all loads of a thread in flight at once); the accumulator is
-  // re-zeroed on the way, so that the next elimination starts from zero
-  {
-    constexpr int kCopyB = 10;
-    const int tot = N * ld;
-    for (int e0 = tid; e0 < tot; e0 += kCopyB * nthr) {
-      double v[kCopyB];
-#pragma unroll
-      for (int u = 0; u < kCopyB; ++u) v[u] = (e0 + u * nthr < tot) ? __ldcg(lp.S + e0 + u * nthr) : 0.0;
-#pragma unroll
-      for (int u = 0; u < kCopyB; ++u)
-        if (e0 + u * nthr < tot) { Ut[e0 + u * nthr] = -v[u]; lp.S[e0 + u * nthr] = 0.0; }
-    }
   }
   // the accepted point's pose blocks come from the evaluation just adopted when there is one (no round trip
   // through the copy that was stored to global memory a moment ago)
-  for (int i = tid; i < F * kUStride; i += nthr) Us[i] = (xs && st.took_step) ? xs[i] : lp.Ucur[i];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+    if (tid + u * nthr < F * kUStride) Us[tid + u * nthr] = us_from_xs ? xs[tid + u * nthr] : uc[u];
+  // the accumulator is re-zeroed on the way, so that the next elimination starts from zero
+#pragma unroll
+  for (int u = 0; u < kCopyB; ++u)
+    if (tid + u * nthr < tot) { Ut[tid + u * nthr] = -v[u]; lp.S[tid + u * nthr] = 0.0; }
+  for (int e0 = tid + kCopyB * nthr; e0 < tot; e0 += kCopyB * nthr) {   // wide systems: further rounds
+#pragma unroll
+    for (int u = 0; u < kCopyB; ++u) v[u] = (e0 + u * nthr < tot) ? __ldcg(lp.S + e0 + u * nthr) : 0.0;
+#pragma unroll
+    for (int u = 0; u < kCopyB; ++u)
+      if (e0 + u * nthr < tot) { Ut[e0 + u * nthr] = -v[u]; lp.S[e0 + u * nthr] = 0.0; }
+  }
   __syncthreads();
   // + U_s + D_c² on the diagonal blocks, + gs_c on the right-hand-side column: one entry per thread
   for (int t = tid; t < nf * kUStride; t += nthr) {
@@ -443,8 +452,10 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
 // tiles per warp.  sm: Zt [Dp][LD], Dp = roundup(N + 1, 8) rows (6 fi + a; row N = L^-1 gs), LD = 3 * points
 // per batch + 4 (rows 32 bytes apart modulo 128: the DMMA fragment loads are bank-conflict free).
 __shared__ unsigned long long s_tdbg[4];   // PBA_DEBUG_TIMELINE: elimination sub-phases of this CTA
+// (pre_o0, pre_o1): the CSR header of this lane's point in the CTA's first batch, requested by the caller before
+// the decision phase so that its round trip is off the critical path.
 template <int LPP, int TPW>
-__device__ void eliminate(const LmParams& lp, const LmState& st, double* Zt) {
+__device__ void eliminate(const LmParams& lp, const LmState& st, double* Zt, int pre_o0, int pre_o1) {
   constexpr int PPW = 32 / LPP, PPB = kSchurWarps * PPW, K = 3 * PPB, LD = K + 4;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = lp.n_points, cur = st.cur, N = 6 * st.n_free, NS = reduced_ld(N);
@@ -483,7 +494,8 @@ __device__ void eliminate(const LmParams& lp, const LmState& st, double* Zt) {
     int o0 = 0, nobs = 0;
     double V[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0}, g0 = 0.0, g1 = 0.0, g2 = 0.0, sp0 = 1.0, sp1 = 1.0, sp2 = 1.0;
     if (valid) {
-      o0 = __ldg(lp.obs_off + p); nobs = __ldg(lp.obs_off + p + 1) - o0;
+      if (b0 == p_begin) { o0 = pre_o0; nobs = pre_o1 - pre_o0; }
+      else { o0 = __ldg(lp.obs_off + p); nobs = __ldg(lp.obs_off + p + 1) - o0; }
       const double2* v2 = reinterpret_cast<const double2*>(Vb + (size_t)p * 6);
       const double2 va = __ldg(v2), vb = __ldg(v2 + 1), vc = __ldg(v2 + 2);
       V[0] = va.x; V[1] = va.y; V[2] = vb.x; V[3] = vb.y; V[4] = vc.x; V[5] = vc.y;
@@ -602,7 +614,7 @@ template <int LPP, int TPW>
 __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams lp) {
   __shared__ LmState s_st;
   __shared__ IterSummary s_it;
-  __shared__ int s_push, s_last;
+  __shared__ int s_push, s_last, s_it0;
   __shared__ double s_xs[kMaxFrames * kUStride + kEacc + kMaxRanks];        // the evaluation's pose blocks + scalars (summed over ranks)
   __shared__ int s_xok;
   __shared__ double s_cams[2 * kMaxD];                                       // both camera buffers (decision, candidate)
@@ -611,6 +623,13 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int F = lp.n_frames;
   const unsigned long long t_start = lp.dbg ? gtime() : 0ull;
+  // CSR header of this lane's point in the CTA's first elimination batch (does not depend on the LM state)
+  int pre_o0 = 0, pre_o1 = 0;
+  {
+    const int per_cta = (lp.n_points + gridDim.x - 1) / gridDim.x;
+    const int p = blockIdx.x * per_cta + warp * (32 / LPP) + lane / LPP;
+    if (p < lp.n_points && p < (blockIdx.x + 1) * per_cta) { pre_o0 = __ldg(lp.obs_off + p); pre_o1 = __ldg(lp.obs_off + p + 1); }
+  }
 
   // ---- (D) decision, redundantly per CTA ------------------------------------------------
   // Everything the decision reads is requested in ONE round of loads: the state, the evaluation's
@@ -713,9 +732,19 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
 #pragma unroll
     for (int k = 0; k < kEacc; ++k) E[k] = __shfl_sync(0xffffffffu, e, k);
     E[2] = gpm;
-    if (lane == 0) s_push = decide(s_st, E, gm, g2, csq, s_xs, F, s_it) ? 1 : 0;
+    if (lane == 0) {
+      s_it0 = s_st.iteration == 0;
+      s_push = decide(s_st, E, gm, g2, csq, s_xs, F, s_it) ? 1 : 0;
+    }
   }
   __syncthreads();
+  if (s_it0) {   // IterationZero: Jacobi column scaling of the pose columns from the initial evaluation
+    for (int i = tid; i < 6 * F; i += blockDim.x) {
+      const int f = i / 6, a = i - 6 * f;
+      s_st.scale_c[i] = s_st.jacobi_scaling ? 1.0 / (1.0 + sqrt(s_xs[f * kUStride + utri6(a, a)])) : 1.0;
+    }
+    __syncthreads();
+  }
   if (blockIdx.x == 0 && tid == 0 && s_push) lp.trace[s_st.n_trace - 1] = s_it;
   if (s_st.done) {
     if (blockIdx.x == 0) {
@@ -728,7 +757,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
 
   const unsigned long long t_dec = lp.dbg ? gtime() : 0ull;
   // ---- (E) eliminate the point blocks -----------------------------------------------------
-  eliminate<LPP, TPW>(lp, s_st, sm);
+  eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1);
 
   // ---- (S) the last CTA solves the reduced camera system -------------------------------------
   // bar.sync orders the CTA's atomics before thread 0's cumulative gpu-scope fence + ticket
