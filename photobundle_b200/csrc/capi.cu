@@ -886,7 +886,7 @@ static int ensure_lm_graph(pba_handle* h, const LmParams& lp0, int sgrid, int n_
   {
     LmParams k = lp0;
     k.cond = 0; k.st_in = nullptr; k.st_out = nullptr; k.dbg = nullptr;
-    const int extra[3] = {sgrid, n_free, h->cfg.patch_radius};
+    const int extra[3] = {sgrid, n_free, h->cfg.patch_radius + 16 * (getenv("PBA_NO_PDL") == nullptr ? 1 : 0)};
     memcpy(key.data(), sp, sizeof(sp));
     memcpy(key.data() + sizeof(sp), &k, sizeof(k));
     memcpy(key.data() + sizeof(sp) + sizeof(k), extra, sizeof(extra));
@@ -906,11 +906,16 @@ static int ensure_lm_graph(pba_handle* h, const LmParams& lp0, int sgrid, int n_
   cudaGraph_t body = np.conditional.phGraph_out[0];
   CUDA_TRY(cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
   cudaError_t e = cudaSuccess;
+  // kernel-to-kernel edges inside the body are programmatic (PDL): the dependent kernel's launch and the part of
+  // its prologue that does not read its predecessor's output overlap with the predecessor's tail (PBA_NO_PDL=1: off)
+  const int pdl = getenv("PBA_NO_PDL") == nullptr ? 1 : 0;
   for (int half = 0; half < 2 && e == cudaSuccess; ++half) {
     LmParams lp = lp0;
     lp.st_in = h->d_state + half; lp.st_out = h->d_state + (1 - half);
     lp.dbg = nullptr; lp.cond = (unsigned long long)cond;
+    lp.pdl = half > 0 ? pdl : 0;          // the first kernel of the body follows the loop condition, not a kernel
     e = launch_schur_solve(lp, sgrid, n_free, h->stream);
+    sp[half].pdl = pdl;
     if (e == cudaSuccess) e = launch_k_step(sp[half], h->cfg.patch_radius, h->stream);
   }
   cudaGraph_t captured = nullptr;

@@ -635,6 +635,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
   // Everything the decision reads is requested in ONE round of loads: the state, the evaluation's
   // accumulators (single-GPU / NCCL path) and both buffers of the cameras (which one is the candidate is
   // only known once the state has arrived) - three dependent L2 round trips otherwise.
+  if (lp.pdl) pdl_wait();   // K_A has finished (everything above is independent of it)
   const int xn = F * kUStride + kEacc + kMaxRanks;
   const bool xmode = lp.xc.n_ranks > 1;
   constexpr int kXPre = (kMaxFrames * kUStride + kEacc + kMaxRanks + kSchurThreads - 1) / kSchurThreads;
@@ -773,6 +774,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
     lp.dbg[12] = s_tdbg[0]; lp.dbg[13] = s_tdbg[1]; lp.dbg[14] = s_tdbg[2];
   }
   if (!s_last) return;
+  if (lp.pdl) pdl_launch_dependents();   // every other CTA has exited: the next K_A may start its prologue during the solve
   if (lp.split) {
     // multi-GPU: the reduced system is summed across ranks first; k_solve_only finishes the iteration
     if (tid == 0) *lp.ticket = 0u;
@@ -911,6 +913,15 @@ static cudaError_t launch_mode(const LmParams& lp, int grid, int n_free, cudaStr
   const int N = 6 * n_free, Dp = (N + 8) & ~7;
   const size_t elim_d = (size_t)Dp * LD, solve_d = solve_smem_doubles(n_free, lp.n_frames);
   const size_t smem = sizeof(double) * (elim_d > solve_d ? elim_d : solve_d);
+  if (lp.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kSchurThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_schur_solve<LPP, TPW>, lp);
+  }
   k_schur_solve<LPP, TPW><<<grid, kSchurThreads, smem, s>>>(lp);
   return cudaGetLastError();
 }

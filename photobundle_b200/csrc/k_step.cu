@@ -341,9 +341,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
 
   const LmState* st = prm.st;
 #ifdef K_STEP_TRACE
-  { const int p = blockIdx.x * WARPS + warp; KTRACE(0); }
+  const long long t_entry = clock64();
 #endif
+  if (prm.pdl) { pdl_wait(); pdl_launch_dependents(); }   // K_B's tail has finished; the next K_B may queue behind us
   if (st && st->done) return;
+#ifdef K_STEP_TRACE
+  const int p_tr = blockIdx.x * WARPS + warp;
+  { const int p = p_tr; if (lane == 0 && p < 4096) { g_kstep_trace[p * 16 + 0] = t_entry; g_kstep_trace[p * 16 + 7] = clock64(); } }
+#endif
   const int buf = st ? st->eval_buf : 0;
   const int cur = st ? st->cur : 0;
   const bool backsub = st && st->iteration > 0;
@@ -383,12 +388,18 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
   double* s_U_w = reinterpret_cast<double*>(wbase + kOffU);
 
   if (threadIdx.x < 9 * F) pose_consts(cams + 6 * (threadIdx.x / 9), s_pose + (threadIdx.x / 9) * kPoseConst, threadIdx.x % 9);
+#ifdef K_STEP_TRACE
+  { const int p = p_tr; KTRACE(5); }
+#endif
   if (backsub)
     for (int i = threadIdx.x; i < F * 6; i += blockDim.x)
       s_sstep[i] = (st->free_index[i / 6] >= 0) ? st->scale_c[i] * st->step_c[i] : 0.0;
   for (int i = lane; i < F * kUStride; i += 32) s_U_w[i] = 0.0;
   if (lane < kEacc) s_E[warp * kEacc + lane] = 0.0;
   for (int i = threadIdx.x; i < P; i += blockDim.x) s_wts[i] = __ldg(prm.weights + i);
+#ifdef K_STEP_TRACE
+  { const int p = p_tr; KTRACE(8); }
+#endif
   // (the CTA barrier that publishes s_pose / s_sstep sits inside the first iteration of the point loop, behind
   //  the requests for the first point's inputs, so their L2 round trips overlap with the pose constants)
 
@@ -422,7 +433,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
 #pragma unroll
       for (int r = 0; r < PR; ++r) p0c[r] = (double)__ldg(prm.desc + (size_t)p * CP + min(lane + 32 * r, P - 1));
     }
-    if (need_barrier) { __syncthreads(); need_barrier = false; }
+    if (need_barrier) { KTRACE(12); __syncthreads(); need_barrier = false; }
     if (!valid) break;
     KTRACE(1);
     if (lane < nobs) s_frm_w[lane] = frm_l;
@@ -909,6 +920,15 @@ static cudaError_t launch_one(const StepParams& prm, cudaStream_t stream) {
   const int want = (prm.n_points + WARPS - 1) / WARPS, cap = 2 * sm_count[dev & 63];
   const int grid = want < cap ? want : cap;
   if (grid == 0) return cudaSuccess;
+  if (prm.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_step<R, U8, NCH, WARPS>, prm);
+  }
   k_step<R, U8, NCH, WARPS><<<grid, WARPS * 32, smem, stream>>>(prm);
   return cudaGetLastError();
 }

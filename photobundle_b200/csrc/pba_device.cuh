@@ -128,6 +128,7 @@ struct StepParams {
   double* obs_sqnorm;        // optional [nnz]
   double* residuals;         // optional [nnz][C*P]
   Xchg xc;                   // multi-GPU exchange (n_ranks > 1 and st != null: the last CTA publishes Xacc)
+  int pdl;                   // launched with programmatic stream serialization: wait for the previous kernel before reading its output
 };
 
 // K_B parameters (k_schur_solve.cu)
@@ -152,7 +153,15 @@ struct LmParams {
   unsigned long long* dbg;   // optional: globaltimer stamps of the last CTA {start, decided, schur done, solved, end}
   unsigned long long cond;   // non-zero: cudaGraphConditionalHandle of the device-side LM loop, cleared when done
   Xchg xc;                   // multi-GPU exchange over peer memory (xc.n_ranks > 1), else split/NCCL or single GPU
+  int pdl;                   // launched with programmatic stream serialization (see pdl_wait)
 };
+
+// ---- programmatic dependent launch (PDL): the LM loop is a chain K_B -> K_A -> K_B ... of dependent kernels; a
+// kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (launch latency, CTA
+// scheduling, everything that does not read its predecessor's output) while the predecessor's tail still runs,
+// and blocks in pdl_wait() until the predecessor has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- system-scope flag helpers for the peer-memory exchange ---------------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
