@@ -112,7 +112,8 @@ typedef struct {
   int32_t termination_type;        /* 0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE             */
   int32_t num_evaluations;         /* residual+Jacobian passes over all observations (K1)    */
   int32_t kernel_launches;         /* CUDA kernels launched by this solve                    */
-  int32_t num_collectives;         /* all-reduces issued (0 on one GPU)                      */
+  int32_t num_collectives;         /* exchanges between the GPUs of a window: NCCL all-reduces, or in-kernel
+                                      peer-memory exchanges (0 on one GPU)                  */
   double total_time_in_seconds;    /* host wall time of the call                             */
   double device_time_in_seconds;   /* CUDA-event time on the handle's stream                 */
   char message[256];

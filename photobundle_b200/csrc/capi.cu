@@ -112,6 +112,7 @@ struct pba_handle {
   double *d_V = nullptr, *d_gp = nullptr, *d_W = nullptr;
   double *d_Xacc = nullptr, *d_Ucur = nullptr;
   double *d_scale_p = nullptr, *d_Vinv = nullptr, *d_S = nullptr;
+  double* d_Vinv2 = nullptr;       // multi-GPU: (Vs + D²)^-1 under the two hypotheses of the pending decision, [2][n][6]
   unsigned int* d_ticket = nullptr;
   unsigned long long* d_dbg = nullptr;   // PBA_DEBUG_TIMELINE=1: per-iteration K_B timeline
   double *d_obs_sqnorm = nullptr, *d_residuals = nullptr;
@@ -167,7 +168,7 @@ static void free_all(pba_handle* h) {
     if (h->peer_xchg[q] && h->peer_xchg[q] != h->d_xchg) cudaIpcCloseMemHandle(h->peer_xchg[q]);
   cudaFree(h->d_xchg);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  cudaFree(h->d_scale_p); cudaFree(h->d_Vinv); cudaFree(h->d_S); cudaFree(h->d_ticket); cudaFree(h->d_dbg);
+  cudaFree(h->d_scale_p); cudaFree(h->d_Vinv); cudaFree(h->d_S); cudaFree(h->d_Vinv2); cudaFree(h->d_ticket); cudaFree(h->d_dbg);
   cudaFree(h->d_save_cams); cudaFree(h->d_save_pts);
   cudaFree(h->d_obs_sqnorm); cudaFree(h->d_residuals); cudaFree(h->d_state); cudaFree(h->d_trace);
   if (h->h_state) cudaFreeHost(h->h_state);
@@ -186,9 +187,10 @@ static int setup_xchg(pba_handle* h) {
   const char* mode = getenv("PBA_MGPU_EXCHANGE");
   int want = !(mode && strcmp(mode, "nccl") == 0);
   const size_t F = h->cfg.max_frames, D = 6 * F;
-  const size_t xa_n = F * kUStride + kEacc + kMaxRanks, s_n = reduced_capacity((int)F);
-  const size_t n_cells = 2 * n * (xa_n + s_n);   // 16-byte LL cells
-  const size_t bytes = sizeof(ulonglong2) * n_cells + sizeof(unsigned long long) * n + 64;
+  const size_t xa_n = F * kUStride + kEacc + kMaxRanks, nn = D * (D + 1);
+  const size_t x1_n = xa_n + 2 * nn, x2_n = nn;   // exchange 1: evaluation + P under both hypotheses; exchange 2: P
+  const size_t n_cells = 2 * n * (x1_n + x2_n);   // 16-byte LL cells
+  const size_t bytes = sizeof(ulonglong2) * n_cells + sizeof(unsigned long long) * (n + 2) + 64;
   if (h->d_xchg) { cudaFree(h->d_xchg); h->d_xchg = nullptr; }
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
@@ -234,16 +236,17 @@ static int setup_xchg(pba_handle* h) {
   }
   Xchg& x = h->xc;
   memset(&x, 0, sizeof(x));
-  x.n_ranks = n; x.rank = h->rank; x.xa_n = (int)xa_n; x.s_n = (int)s_n;
+  x.n_ranks = n; x.rank = h->rank; x.x1_n = (int)x1_n; x.x2_n = (int)x2_n;
   for (int q = 0; q < n; ++q) {
     ulonglong2* base = static_cast<ulonglong2*>(h->peer_xchg[q]);
-    x.xa[q] = base;
-    x.s[q] = base + 2 * n * xa_n;
+    x.x1[q] = base;
+    x.x2[q] = base + 2 * n * x1_n;
     x.fr[q] = reinterpret_cast<unsigned long long*>(base + n_cells);
   }
   unsigned long long* fl_own = reinterpret_cast<unsigned long long*>(static_cast<ulonglong2*>(h->d_xchg) + n_cells);
-  x.ticket_a = reinterpret_cast<unsigned int*>(fl_own + n);
-  x.error = reinterpret_cast<int*>(fl_own + n) + 2;
+  x.verdict = fl_own + n;
+  x.error = reinterpret_cast<int*>(fl_own + n + 1);
+  if (!h->d_Vinv2) CUDA_TRY(cudaMalloc(&h->d_Vinv2, sizeof(double) * 2 * (size_t)h->cfg.max_points * 6));
   h->use_xchg = true;
   h->epoch_next = 1;
   return PBA_OK;
@@ -331,7 +334,7 @@ int pba_create(const pba_config* cfg, pba_handle** out) {
   CREATE_TRY(cudaMalloc(&h->d_Ucur, sizeof(double) * F * kUStride));
   CREATE_TRY(cudaMalloc(&h->d_scale_p, sizeof(double) * n * 3));
   CREATE_TRY(cudaMalloc(&h->d_Vinv, sizeof(double) * n * 6));
-  CREATE_TRY(cudaMalloc(&h->d_S, sizeof(double) * reduced_capacity((int)F)));
+  CREATE_TRY(cudaMalloc(&h->d_S, sizeof(double) * 3 * reduced_capacity((int)F)));   // x3: the multi-GPU path eliminates under two hypotheses + once more
   CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
   CREATE_TRY(cudaMalloc(&h->d_state, 2 * sizeof(LmState)));
   CREATE_TRY(cudaMallocHost(&h->h_state, sizeof(LmState)));
@@ -773,7 +776,6 @@ static StepParams make_step_params(pba_handle* h, const LmState* st) {
   p.obs_frame = h->d_obs_frame; p.weights = h->d_weights;
   p.V = h->d_V; p.gp = h->d_gp; p.W = h->d_W; p.Xacc = h->d_Xacc; p.rank = h->rank;
   p.scale_p = h->d_scale_p; p.Vinv = h->d_Vinv;
-  if (h->use_xchg) p.xc = h->xc;
   return p;
 }
 
@@ -787,6 +789,7 @@ static LmParams make_lm_params(pba_handle* h) {
   lp.Xacc = h->d_Xacc; lp.Ucur = h->d_Ucur; lp.split = (h->n_ranks > 1 && !h->use_xchg) ? 1 : 0;
   if (h->use_xchg) lp.xc = h->xc;
   lp.scale_p = h->d_scale_p; lp.Vinv = h->d_Vinv; lp.S = h->d_S;
+  lp.s_cap = reduced_capacity(h->cfg.max_frames); lp.Vinv2 = h->d_Vinv2;
   return lp;
 }
 
@@ -970,7 +973,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   rc = zero_accumulators(h);
   if (rc) return rc;
   const size_t D = 6 * (size_t)F;
-  CUDA_TRY(cudaMemsetAsync(h->d_S, 0, sizeof(double) * reduced_capacity(h->cfg.max_frames), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_S, 0, sizeof(double) * 3 * reduced_capacity(h->cfg.max_frames), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
 
   LmParams lp = make_lm_params(h);
@@ -1055,10 +1058,10 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
                 (t[16 * i + 12] - t[16 * i + 1]) * 1e-3, (t[16 * i + 13] - t[16 * i + 12]) * 1e-3, (t[16 * i + 14] - t[16 * i + 13]) * 1e-3,
                 (t[16 * i + 2] - t[16 * i + 14]) * 1e-3);
     if (h->use_xchg)
-      for (int i = 0; i < std::min(k, 6); ++i)
-        fprintf(stderr, "[pba timeline] rank %d K_B %2d S exchange: push %5.2f us  fence+flags %5.2f us  wait %5.2f us  sum %5.2f us\n", h->rank, i,
-                (t[16 * i + 8] - t[16 * i + 2]) * 1e-3, (t[16 * i + 9] - t[16 * i + 8]) * 1e-3, (t[16 * i + 10] - t[16 * i + 9]) * 1e-3,
-                (t[16 * i + 11] - t[16 * i + 10]) * 1e-3);
+      for (int i = 0; i < std::min(k, 14); ++i)
+        fprintf(stderr, "[pba timeline] rank %d K_B %2d exchange: eliminate (both hypotheses) %5.2f us  push %5.2f us  sum+decide %5.2f us  sum P %5.2f us  -> %s\n", h->rank, i,
+                (t[16 * i + 1] - t[16 * i]) * 1e-3, (t[16 * i + 8] - t[16 * i + 1]) * 1e-3, (t[16 * i + 9] - t[16 * i + 8]) * 1e-3,
+                (t[16 * i + 2] - t[16 * i + 9]) * 1e-3, t[16 * i + 10] == 1 ? "accepted, radius tripled" : t[16 * i + 10] == 2 ? "rejected" : "second elimination + exchange");
   }
   h->trace.resize(s->n_trace);
   if (s->n_trace > 0)
@@ -1073,7 +1076,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   summary->num_residual_blocks = h->nnz_total; summary->num_residuals = h->nnz_total * h->CP;
   summary->num_iterations = s->n_trace; summary->termination_type = s->termination_type;
   summary->num_evaluations = s->num_evals;
-  summary->kernel_launches = launches; summary->num_collectives = collectives;
+  summary->kernel_launches = launches; summary->num_collectives = h->use_xchg ? s->n_xchg : collectives;
   summary->device_time_in_seconds = ms * 1e-3;
   if (h->use_xchg) {
     int xerr = 0;

@@ -163,8 +163,9 @@ constexpr int kMBase = 224;   // thread kMBase keeps the factored diagonal block
 // sm: Ut [N+8][ld] | Ldd [nf][36] (factored diagonal blocks, transposed) | idv [N] (reciprocal pivots) | xb [N] |
 //     yv [N] | Us [F][27].
 // Writes the step into st and the candidate cameras.  s_cams: both camera buffers [2][kMaxD] (or null).
+// ut_filled: Ut already holds -P (multi-GPU: the rank-ordered sum of every rank's contribution was written there).
 template <int TPW>
-__device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams) {
+__device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams, bool ut_filled) {
   const int nf = st.n_free, N = 6 * nf, ld = reduced_ld(N);
   const int cur = st.cur, eb = st.eval_buf, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const double radius = st.radius;
@@ -183,7 +184,7 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
   const bool us_from_xs = xs && st.took_step;
   double v[kCopyB], uc[2];
 #pragma unroll
-  for (int u = 0; u < kCopyB; ++u) v[u] = (tid + u * nthr < tot) ? __ldcg(lp.S + tid + u * nthr) : 0.0;
+  for (int u = 0; u < kCopyB; ++u) v[u] = (!ut_filled && tid + u * nthr < tot) ? __ldcg(lp.S + tid + u * nthr) : 0.0;
 #pragma unroll
   for (int u = 0; u < 2; ++u) uc[u] = (!us_from_xs && tid + u * nthr < F * kUStride) ? __ldcg(lp.Ucur + tid + u * nthr) : 0.0;
   // this warp's 8x8 tiles (tr <= tc) of the ABSOLUTE tile grid over Ut — the same assignment in every block step,
@@ -218,8 +219,8 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
   // the accumulator is re-zeroed on the way, so that the next elimination starts from zero
 #pragma unroll
   for (int u = 0; u < kCopyB; ++u)
-    if (tid + u * nthr < tot) { Ut[tid + u * nthr] = -v[u]; lp.S[tid + u * nthr] = 0.0; }
-  for (int e0 = tid + kCopyB * nthr; e0 < tot; e0 += kCopyB * nthr) {   // wide systems: further rounds
+    if (!ut_filled && tid + u * nthr < tot) { Ut[tid + u * nthr] = -v[u]; lp.S[tid + u * nthr] = 0.0; }
+  for (int e0 = tid + kCopyB * nthr; !ut_filled && e0 < tot; e0 += kCopyB * nthr) {   // wide systems: further rounds
 #pragma unroll
     for (int u = 0; u < kCopyB; ++u) v[u] = (e0 + u * nthr < tot) ? __ldcg(lp.S + e0 + u * nthr) : 0.0;
 #pragma unroll
@@ -454,14 +455,17 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
 __shared__ unsigned long long s_tdbg[4];   // PBA_DEBUG_TIMELINE: elimination sub-phases of this CTA
 // (pre_o0, pre_o1): the CSR header of this lane's point in the CTA's first batch, requested by the caller before
 // the decision phase so that its round trip is off the critical path.
+// cur / radius: the buffer holding the blocks to eliminate and the trust-region radius to damp them with (the
+// accepted point after a decision — or a HYPOTHESIS about the decision, multi-GPU path); first: this is the first
+// elimination of the solve (forms the Jacobi scaling of the points); S_dst / Vinv_dst: where P and (Vs + D²)^-1 go.
 template <int LPP, int TPW>
-__device__ void eliminate(const LmParams& lp, const LmState& st, double* Zt, int pre_o0, int pre_o1) {
+__device__ void eliminate(const LmParams& lp, const LmState& st, double* Zt, int pre_o0, int pre_o1, int cur, double radius,
+                          bool first, double* S_dst, double* Vinv_dst) {
   constexpr int PPW = 32 / LPP, PPB = kSchurWarps * PPW, K = 3 * PPB, LD = K + 4;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = lp.n_points, cur = st.cur, N = 6 * st.n_free, NS = reduced_ld(N);
+  const int n = lp.n_points, N = 6 * st.n_free, NS = reduced_ld(N);
   const int Dp = (N + 8) & ~7, T = Dp >> 3, n_tiles = T * (T + 1) / 2;
-  const double radius = st.radius, dmin = st.min_diag, dmax = st.max_diag;
-  const bool first = (st.iteration == 1);
+  const double dmin = st.min_diag, dmax = st.max_diag;
   // this CTA's contiguous block of points
   const int per_cta = (n + gridDim.x - 1) / gridDim.x;
   const int p_begin = blockIdx.x * per_cta, p_end = min(n, p_begin + per_cta);
@@ -537,7 +541,7 @@ __device__ void eliminate(const LmParams& lp, const LmState& st, double* Zt, int
       const double zg0 = gs0 * il00, zg1 = (gs1 - l10 * zg0) * il11, zg2 = (gs2 - l20 * zg0 - l21 * zg1) * il22;
       if (g == 0) {
         const double m10 = -l10 * il00 * il11, m20 = -(l20 * il00 + l21 * m10) * il22, m21 = -l21 * il11 * il22;
-        double* vi = lp.Vinv + (size_t)p * 6;   // (Vs + D²)^-1 = M^T M, used by K_A's back-substitution
+        double* vi = Vinv_dst + (size_t)p * 6;   // (Vs + D²)^-1 = M^T M, used by K_A's back-substitution
         vi[0] = il00 * il00 + m10 * m10 + m20 * m20; vi[1] = m10 * il11 + m20 * m21; vi[2] = m20 * il22;
         vi[3] = il11 * il11 + m21 * m21; vi[4] = m21 * il22; vi[5] = il22 * il22;
         double* zr = Zt + N * LD + 3 * q;
@@ -582,128 +586,20 @@ __device__ void eliminate(const LmParams& lp, const LmState& st, double* Zt, int
       const int r = 8 * (int)(tile_rc[k] & 0xffu) + (lane >> 2);
       const int c = 8 * (int)(tile_rc[k] >> 8) + 2 * (lane & 3);
       if (r < N) {
-        if (r <= c && c <= N && acc[k][0] != 0.0) atomicAdd(lp.S + r * NS + c, acc[k][0]);
-        if (r <= c + 1 && c + 1 <= N && acc[k][1] != 0.0) atomicAdd(lp.S + r * NS + c + 1, acc[k][1]);
+        if (r <= c && c <= N && acc[k][0] != 0.0) atomicAdd(S_dst + r * NS + c, acc[k][0]);
+        if (r <= c + 1 && c + 1 <= N && acc[k][1] != 0.0) atomicAdd(S_dst + r * NS + c + 1, acc[k][1]);
       }
     }
   }
   if (lp.dbg && tid == 0) s_tdbg[2] = gtime();
 }
 
-// Tail of an LM iteration (one CTA): adopt the candidate's pose blocks if the step was taken, solve
-// the reduced camera system, re-zero the accumulators K_A fills next, publish the new state.
-template <int TPW>
-__device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams) {
-  const int tid = threadIdx.x;
-  if (st.took_step)
-    for (int i = tid; i < F * kUStride; i += blockDim.x) lp.Ucur[i] = xs ? xs[i] : __ldcg(lp.Xacc + i);
-  __syncthreads();
-  solve_reduced<TPW>(lp, st, sm, F, xs, s_cams);
-  if (lp.dbg && tid == 0) lp.dbg[3] = gtime();
-  for (int i = tid; i < F * kUStride + kEacc + kMaxRanks; i += blockDim.x) lp.Xacc[i] = 0.0;
-  if (tid == 0) *lp.ticket = 0u;
-  __syncthreads();
-  for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
-    reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&st)[i];
-  if (lp.dbg && tid == 0) lp.dbg[4] = gtime();
-}
-
-// LPP: lanes per point in the elimination (8: windows of <= 8 frames; 16 otherwise); TPW: 8x8 tiles of the
-// reduced system per warp (3: <= 24 tiles, i.e. <= 7 optimised cameras; 12: up to 16 cameras)
-template <int LPP, int TPW>
-__global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams lp) {
-  __shared__ LmState s_st;
-  __shared__ IterSummary s_it;
-  __shared__ int s_push, s_last, s_it0;
-  __shared__ double s_xs[kMaxFrames * kUStride + kEacc + kMaxRanks];        // the evaluation's pose blocks + scalars (summed over ranks)
-  __shared__ int s_xok;
-  __shared__ double s_cams[2 * kMaxD];                                       // both camera buffers (decision, candidate)
-  extern __shared__ __align__(16) double sm[];
-
+// The trust-region decision for the candidate just evaluated, from the complete accumulators xs (pose blocks +
+// scalars); warp 0 reduces, lane 0 decides, and at iteration 0 all threads form the Jacobi scaling of the pose
+// columns.  Called by every thread of the CTA; ends with the CTA synchronised.
+__device__ __forceinline__ void take_decision(LmState& s_st, const double* s_xs, const double* s_cams, int F, IterSummary& s_it,
+                                              int& s_push, int& s_it0) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int F = lp.n_frames;
-  const unsigned long long t_start = lp.dbg ? gtime() : 0ull;
-  // CSR header of this lane's point in the CTA's first elimination batch (does not depend on the LM state)
-  int pre_o0 = 0, pre_o1 = 0;
-  {
-    const int per_cta = (lp.n_points + gridDim.x - 1) / gridDim.x;
-    const int p = blockIdx.x * per_cta + warp * (32 / LPP) + lane / LPP;
-    if (p < lp.n_points && p < (blockIdx.x + 1) * per_cta) { pre_o0 = __ldg(lp.obs_off + p); pre_o1 = __ldg(lp.obs_off + p + 1); }
-  }
-
-  // ---- (D) decision, redundantly per CTA ------------------------------------------------
-  // Everything the decision reads is requested in ONE round of loads: the state, the evaluation's
-  // accumulators (single-GPU / NCCL path) and both buffers of the cameras (which one is the candidate is
-  // only known once the state has arrived) - three dependent L2 round trips otherwise.
-  if (lp.pdl) pdl_wait();   // K_A has finished (everything above is independent of it)
-  const int xn = F * kUStride + kEacc + kMaxRanks;
-  const bool xmode = lp.xc.n_ranks > 1;
-  constexpr int kXPre = (kMaxFrames * kUStride + kEacc + kMaxRanks + kSchurThreads - 1) / kSchurThreads;
-  double x_pre[kXPre];
-  if (!xmode) {
-#pragma unroll
-    for (int k = 0; k < kXPre; ++k) x_pre[k] = (tid + k * kSchurThreads < xn) ? __ldcg(lp.Xacc + tid + k * kSchurThreads) : 0.0;
-  }
-  double cam_pre[2][(kMaxD + 31) / 32];
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < (kMaxD + 31) / 32; ++k) {
-      const int i = lane + 32 * k;
-      cam_pre[0][k] = i < F * 6 ? lp.cams[i] : 0.0;
-      cam_pre[1][k] = i < F * 6 ? lp.cams[(size_t)F * 6 + i] : 0.0;
-    }
-  }
-  for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
-    reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_in)[i];
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < (kMaxD + 31) / 32; ++k) {
-      const int i = lane + 32 * k;
-      if (i < F * 6) { s_cams[i] = cam_pre[0][k]; s_cams[kMaxD + i] = cam_pre[1][k]; }
-    }
-  }
-  if (!xmode) {
-#pragma unroll
-    for (int k = 0; k < kXPre; ++k)
-      if (tid + k * kSchurThreads < xn) s_xs[tid + k * kSchurThreads] = x_pre[k];
-  }
-  __syncthreads();
-  if (s_st.done) {
-    if (blockIdx.x == 0) {
-      for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
-        reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
-      if (lp.cond && tid == 0) cudaGraphSetConditional(lp.cond, 0u);   // leave the while node of the solve graph
-    }
-    return;
-  }
-  // the evaluation's accumulators: local (one GPU / NCCL path: already all-reduced) or the sum of every
-  // rank's slot in rank order (peer-memory exchange: wait for the flags first)
-  if (xmode) {
-    if (tid == 0) s_xok = 1;
-    __syncthreads();
-    const ulonglong2* xb = lp.xc.xa[lp.xc.rank] + (size_t)(s_st.xepoch & 1ull) * lp.xc.n_ranks * lp.xc.xa_n;
-    for (int i = tid; i < xn; i += blockDim.x) {
-      double acc = 0.0;
-      for (int q = 0; q < lp.xc.n_ranks; ++q) {
-        double v;
-        if (!ll_load(xb + (size_t)q * lp.xc.xa_n + i, s_st.xepoch, v)) s_xok = 0;
-        acc += v;
-      }
-      s_xs[i] = acc;
-    }
-    __syncthreads();
-    if (!s_xok) {   // a peer never arrived: fail the solve instead of hanging the GPU
-      if (blockIdx.x == 0) {
-        if (tid == 0) { finish(s_st, 2, kMsgXchgTimeout, (double)s_st.xepoch, 0.0); *lp.xc.error = 1; }
-        __syncthreads();
-        for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
-          reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
-        if (lp.cond && tid == 0) cudaGraphSetConditional(lp.cond, 0u);
-      }
-      return;
-    }
-    __syncthreads();
-  }
   if (warp == 0) {
     const int buf = s_st.eval_buf;
     double gm = 0.0, g2 = 0.0, csq = 0.0;
@@ -715,7 +611,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
         if (s_st.free_index[f] >= 0) {
           const double g = s_xs[f * kUStride + 21 + a];
           gm = fmax(gm, fabs(g)); g2 += g * g;
-          const double c = buf ? cam_pre[1][k] : cam_pre[0][k];
+          const double c = buf ? s_cams[kMaxD + i] : s_cams[i];
           csq += c * c;
         }
       }
@@ -746,6 +642,89 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
     }
     __syncthreads();
   }
+}
+
+// Tail of an LM iteration (one CTA): adopt the candidate's pose blocks if the step was taken, solve
+// the reduced camera system, re-zero the accumulators K_A fills next, publish the new state.
+template <int TPW>
+__device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams, bool ut_filled) {
+  const int tid = threadIdx.x;
+  if (st.took_step)
+    for (int i = tid; i < F * kUStride; i += blockDim.x) lp.Ucur[i] = xs ? xs[i] : __ldcg(lp.Xacc + i);
+  __syncthreads();
+  solve_reduced<TPW>(lp, st, sm, F, xs, s_cams, ut_filled);
+  if (lp.dbg && tid == 0) lp.dbg[3] = gtime();
+  for (int i = tid; i < F * kUStride + kEacc + kMaxRanks; i += blockDim.x) lp.Xacc[i] = 0.0;
+  if (tid == 0) *lp.ticket = 0u;
+  __syncthreads();
+  for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+    reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&st)[i];
+  if (lp.dbg && tid == 0) lp.dbg[4] = gtime();
+}
+
+// LPP: lanes per point in the elimination (8: windows of <= 8 frames; 16 otherwise); TPW: 8x8 tiles of the
+// reduced system per warp (3: <= 24 tiles, i.e. <= 7 optimised cameras; 12: up to 16 cameras)
+template <int LPP, int TPW>
+__global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams lp) {
+  __shared__ LmState s_st;
+  __shared__ IterSummary s_it;
+  __shared__ int s_push, s_last, s_it0;
+  __shared__ double s_xs[kMaxFrames * kUStride + kEacc + kMaxRanks];        // the evaluation's pose blocks + scalars (summed over ranks)
+  __shared__ double s_cams[2 * kMaxD];                                       // both camera buffers (decision, candidate)
+  extern __shared__ __align__(16) double sm[];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int F = lp.n_frames;
+  const unsigned long long t_start = lp.dbg ? gtime() : 0ull;
+  // CSR header of this lane's point in the CTA's first elimination batch (does not depend on the LM state)
+  int pre_o0 = 0, pre_o1 = 0;
+  {
+    const int per_cta = (lp.n_points + gridDim.x - 1) / gridDim.x;
+    const int p = blockIdx.x * per_cta + warp * (32 / LPP) + lane / LPP;
+    if (p < lp.n_points && p < (blockIdx.x + 1) * per_cta) { pre_o0 = __ldg(lp.obs_off + p); pre_o1 = __ldg(lp.obs_off + p + 1); }
+  }
+
+  // ---- (D) decision, redundantly per CTA ------------------------------------------------
+  // Everything the decision reads is requested in ONE round of loads: the state, the evaluation's
+  // accumulators (single-GPU / NCCL path) and both buffers of the cameras (which one is the candidate is
+  // only known once the state has arrived) - three dependent L2 round trips otherwise.
+  if (lp.pdl) pdl_wait();   // K_A has finished (everything above is independent of it)
+  const int xn = F * kUStride + kEacc + kMaxRanks;
+  constexpr int kXPre = (kMaxFrames * kUStride + kEacc + kMaxRanks + kSchurThreads - 1) / kSchurThreads;
+  double x_pre[kXPre];
+#pragma unroll
+  for (int k = 0; k < kXPre; ++k) x_pre[k] = (tid + k * kSchurThreads < xn) ? __ldcg(lp.Xacc + tid + k * kSchurThreads) : 0.0;
+  double cam_pre[2][(kMaxD + 31) / 32];
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < (kMaxD + 31) / 32; ++k) {
+      const int i = lane + 32 * k;
+      cam_pre[0][k] = i < F * 6 ? lp.cams[i] : 0.0;
+      cam_pre[1][k] = i < F * 6 ? lp.cams[(size_t)F * 6 + i] : 0.0;
+    }
+  }
+  for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+    reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_in)[i];
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < (kMaxD + 31) / 32; ++k) {
+      const int i = lane + 32 * k;
+      if (i < F * 6) { s_cams[i] = cam_pre[0][k]; s_cams[kMaxD + i] = cam_pre[1][k]; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kXPre; ++k)
+    if (tid + k * kSchurThreads < xn) s_xs[tid + k * kSchurThreads] = x_pre[k];
+  __syncthreads();
+  if (s_st.done) {
+    if (blockIdx.x == 0) {
+      for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+        reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
+      if (lp.cond && tid == 0) cudaGraphSetConditional(lp.cond, 0u);   // leave the while node of the solve graph
+    }
+    return;
+  }
+  take_decision(s_st, s_xs, s_cams, F, s_it, s_push, s_it0);
   if (blockIdx.x == 0 && tid == 0 && s_push) lp.trace[s_st.n_trace - 1] = s_it;
   if (s_st.done) {
     if (blockIdx.x == 0) {
@@ -758,7 +737,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
 
   const unsigned long long t_dec = lp.dbg ? gtime() : 0ull;
   // ---- (E) eliminate the point blocks -----------------------------------------------------
-  eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1);
+  eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, s_st.cur, s_st.radius, s_st.iteration == 1, lp.S, lp.Vinv);
 
   // ---- (S) the last CTA solves the reduced camera system -------------------------------------
   // bar.sync orders the CTA's atomics before thread 0's cumulative gpu-scope fence + ticket
@@ -782,77 +761,238 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
       reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
     return;
   }
-  if (xmode) {
-    // publish this rank's reduced-system contribution (upper triangle + rhs column) to every rank as LL
-    // cells, then sum everybody's in rank order straight out of the cells (polling replaces flag + fence)
-    const unsigned long long e = s_st.xepoch;
-    const int N = 6 * s_st.n_free, NS = reduced_ld(N), sn = N * NS;
-    const size_t off = ((size_t)(e & 1ull) * lp.xc.n_ranks + lp.xc.rank) * lp.xc.s_n;
-    constexpr int kB = 4;                    // elements per thread in flight
-    for (int i0 = tid; i0 < sn; i0 += kB * blockDim.x) {
-      double v[kB];
+  finish_iteration<TPW>(lp, s_st, sm, F, s_xs, s_cams, false);
+}
+
+// ---- multi-GPU kernel: speculative elimination, one exchange per LM iteration (pba_device.cuh `Xchg`) -----------
+// sum over the ranks, in rank order, of cell i of every rank's slot; all first attempts are in flight together
+__device__ __forceinline__ bool ll_sum(const ulonglong2* base, size_t slot_stride, int n_ranks, size_t i, unsigned long long e, double& out) {
+  double v[kMaxRanks];
+  bool got[kMaxRanks];
 #pragma unroll
-      for (int u = 0; u < kB; ++u) {
-        const int i = i0 + u * blockDim.x;
-        v[u] = (i < sn) ? __ldcg(lp.S + i) : 0.0;
-      }
+  for (int q = 0; q < kMaxRanks; ++q) { v[q] = 0.0; got[q] = q >= n_ranks || ll_try_load(base + q * slot_stride + i, e, v[q]); }
+  bool ok = true;
+  double acc = 0.0;
 #pragma unroll
-      for (int u = 0; u < kB; ++u) {
-        const int i = i0 + u * blockDim.x;
-        const bool need = i < sn && (i / NS) <= (i % NS) && (i % NS) <= N;
-        if (need)
-          for (int q = 0; q < lp.xc.n_ranks; ++q) ll_store(lp.xc.s[q] + off + i, v[u], e);
-      }
-    }
-    if (lp.dbg && tid == 0) lp.dbg[8] = gtime();
-    const ulonglong2* sb = lp.xc.s[lp.xc.rank] + (size_t)(e & 1ull) * lp.xc.n_ranks * lp.xc.s_n;
-    for (int i0 = tid; i0 < sn; i0 += kB * blockDim.x) {
-      double acc[kB];
-      bool need[kB];
-#pragma unroll
-      for (int u = 0; u < kB; ++u) {
-        const int i = i0 + u * blockDim.x;
-        need[u] = i < sn && (i / NS) <= (i % NS) && (i % NS) <= N;
-        acc[u] = 0.0;
-      }
-      for (int q = 0; q < lp.xc.n_ranks; ++q) {
-        double v[kB];
-        bool got[kB];
-#pragma unroll
-        for (int u = 0; u < kB; ++u) {     // first try: all loads in flight
-          const int i = i0 + u * blockDim.x;
-          v[u] = 0.0;
-          got[u] = !need[u] || ll_try_load(sb + (size_t)q * lp.xc.s_n + i, e, v[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < kB; ++u) {
-          const int i = i0 + u * blockDim.x;
-          if (!got[u] && !ll_load(sb + (size_t)q * lp.xc.s_n + i, e, v[u])) s_xok = 0;
-          acc[u] += v[u];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kB; ++u) {
-        const int i = i0 + u * blockDim.x;
-        if (need[u]) lp.S[i] = acc[u];
-      }
-    }
-    __threadfence();
-    __syncthreads();
-    if (lp.dbg && tid == 0) { lp.dbg[9] = lp.dbg[8]; lp.dbg[10] = lp.dbg[8]; }
-    if (!s_xok) {
-      if (tid == 0) { finish(s_st, 2, kMsgXchgTimeout, (double)e, 1.0); *lp.xc.error = 1; *lp.ticket = 0u; }
-      __syncthreads();
+  for (int q = 0; q < kMaxRanks; ++q) {
+    if (!got[q] && !ll_load(base + q * slot_stride + i, e, v[q])) ok = false;
+    if (q < n_ranks) acc += v[q];
+  }
+  out = acc;
+  return ok;
+}
+
+template <int LPP, int TPW>
+__global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmParams lp) {
+  __shared__ LmState s_st;
+  __shared__ IterSummary s_it;
+  __shared__ int s_push, s_last, s_it0, s_xok, s_code;
+  __shared__ double s_xs[kMaxFrames * kUStride + kEacc + kMaxRanks];        // the evaluation's pose blocks + scalars: local, then summed over ranks
+  __shared__ double s_cams[2 * kMaxD];
+  extern __shared__ __align__(16) double sm[];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int F = lp.n_frames, nr = lp.xc.n_ranks;
+  const unsigned long long t_start = lp.dbg ? gtime() : 0ull;
+  int pre_o0 = 0, pre_o1 = 0;
+  const int per_cta = (lp.n_points + gridDim.x - 1) / gridDim.x;
+  {
+    const int p = blockIdx.x * per_cta + warp * (32 / LPP) + lane / LPP;
+    if (p < lp.n_points && p < (blockIdx.x + 1) * per_cta) { pre_o0 = __ldg(lp.obs_off + p); pre_o1 = __ldg(lp.obs_off + p + 1); }
+  }
+  if (lp.pdl) pdl_wait();
+  const int xn = F * kUStride + kEacc + kMaxRanks;
+  for (int i = tid; i < xn; i += blockDim.x) s_xs[i] = __ldcg(lp.Xacc + i);
+  for (int i = tid; i < F * 6; i += blockDim.x) { s_cams[i] = lp.cams[i]; s_cams[kMaxD + i] = lp.cams[(size_t)F * 6 + i]; }
+  for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+    reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_in)[i];
+  if (tid == 0) s_xok = 1;
+  __syncthreads();
+  if (s_st.done) {   // the state is replicated: every rank leaves here together
+    if (blockIdx.x == 0) {
       for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
         reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
       if (lp.cond && tid == 0) cudaGraphSetConditional(lp.cond, 0u);
+    }
+    return;
+  }
+  const unsigned long long e = s_st.xepoch;
+  const bool it0 = s_st.iteration == 0;
+  const int N = 6 * s_st.n_free, NS = reduced_ld(N), NC = N + 1, NN = N * NC;
+  double* S_A = lp.S;
+  double* S_R = lp.S + lp.s_cap;
+  double* S_M = lp.S + 2 * lp.s_cap;
+  double* Vinv_A = lp.Vinv2;
+  double* Vinv_R = lp.Vinv2 + (size_t)lp.n_points * 6;
+  // the two outcomes of the pending decision whose radius is known in advance (same expressions as decide())
+  const double rad_A = fmin(s_st.max_radius, s_st.radius / fmax(1.0 / 3.0, 1.0 / 3.0));
+  const double rad_R = s_st.radius / s_st.decrease_factor;
+  const int buf_A = s_st.eval_buf, buf_R = s_st.cur;
+  if (!it0) {
+    eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, buf_A, rad_A, false, S_A, Vinv_A);
+    __syncthreads();
+    eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, buf_R, rad_R, false, S_R, Vinv_R);
+  }
+  // ---- ticket 1: the last CTA exchanges, decides; the others wait for its verdict ------------------------
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(lp.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __threadfence();
+  }
+  __syncthreads();
+  const int p_begin = blockIdx.x * per_cta, p_end = min(lp.n_points, p_begin + per_cta);
+  bool redo = false;
+  if (!s_last) {
+    if (tid == 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned long long v;
+      while (((v = ld_acquire_sys(lp.xc.verdict)) >> 3) != e) {
+        if (globaltimer_ns() - t0 > kXchgTimeoutNs) { v = (e << 3) | kXFail; break; }
+        __nanosleep(200);
+      }
+      s_code = (int)(v & 7ull);
+    }
+    __syncthreads();
+    const int code = s_code;
+    if (code == kXHitA || code == kXHitR) {   // adopt (Vs + D²)^-1 of the outcome that came true for this CTA's points
+      const double* src = (code == kXHitA ? Vinv_A : Vinv_R);
+      for (int i = p_begin * 6 + tid; i < p_end * 6; i += blockDim.x) lp.Vinv[i] = __ldcg(src + i);
       return;
     }
-    if (tid == 0) s_st.xepoch = e + 1;
+    if (code != kXRedo) return;
+    for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+      reinterpret_cast<int*>(&s_st)[i] = __ldcg(reinterpret_cast<const int*>(lp.st_out) + i);
     __syncthreads();
-    if (lp.dbg && tid == 0) lp.dbg[11] = gtime();
+    redo = true;
+  } else {
+    if (lp.dbg && tid == 0) { lp.dbg[0] = t_start; lp.dbg[1] = gtime(); }
+    // push: evaluation part, then both hypotheses (local accumulators are re-zeroed on the way)
+    const size_t slot1 = ((size_t)(e & 1ull) * nr + lp.xc.rank) * lp.xc.x1_n;
+    for (int i = tid; i < xn; i += blockDim.x)
+      for (int q = 0; q < nr; ++q) ll_store(lp.xc.x1[q] + slot1 + i, s_xs[i], e);
+    if (!it0) {
+      for (int r = tid >> 4; r < N; r += 16)
+        for (int c = r + (tid & 15); c <= N; c += 16) {
+          const double a = __ldcg(S_A + r * NS + c), b = __ldcg(S_R + r * NS + c);
+          S_A[r * NS + c] = 0.0; S_R[r * NS + c] = 0.0;
+          for (int q = 0; q < nr; ++q) {
+            ll_store(lp.xc.x1[q] + slot1 + xn + r * NC + c, a, e);
+            ll_store(lp.xc.x1[q] + slot1 + xn + NN + r * NC + c, b, e);
+          }
+        }
+    }
+    if (lp.dbg && tid == 0) lp.dbg[8] = gtime();
+    // sum everybody's evaluation part in rank order, decide
+    const ulonglong2* in1 = lp.xc.x1[lp.xc.rank] + (size_t)(e & 1ull) * nr * lp.xc.x1_n;
+    __syncthreads();
+    for (int i = tid; i < xn; i += blockDim.x) {
+      double v;
+      if (!ll_sum(in1, lp.xc.x1_n, nr, i, e, v)) s_xok = 0;
+      s_xs[i] = v;
+    }
+    __syncthreads();
+    if (!s_xok) {   // a peer never arrived: fail the solve instead of hanging the GPU
+      if (tid == 0) { finish(s_st, 2, kMsgXchgTimeout, (double)e, 0.0); *lp.xc.error = 1; *lp.ticket = 0u; }
+      __syncthreads();
+      for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+        reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
+      if (tid == 0) {
+        __threadfence();
+        st_release_sys(lp.xc.verdict, (e << 3) | kXFail);
+        if (lp.cond) cudaGraphSetConditional(lp.cond, 0u);
+      }
+      return;
+    }
+    take_decision(s_st, s_xs, s_cams, F, s_it, s_push, s_it0);
+    if (tid == 0 && s_push) lp.trace[s_st.n_trace - 1] = s_it;
+    if (lp.dbg && tid == 0) lp.dbg[9] = gtime();
+    if (s_st.done) {
+      if (tid == 0) s_st.n_xchg += 1;
+      __syncthreads();
+      for (int i = tid; i < xn; i += blockDim.x) lp.Xacc[i] = 0.0;
+      for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+        reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
+      __syncthreads();
+      if (tid == 0) {
+        *lp.ticket = 0u;
+        __threadfence();
+        st_release_sys(lp.xc.verdict, (e << 3) | kXDone);
+        if (lp.cond) cudaGraphSetConditional(lp.cond, 0u);
+      }
+      return;
+    }
+    const bool hitA = !it0 && s_st.took_step && s_st.radius == rad_A;
+    const bool hitR = !it0 && !s_st.took_step && s_st.radius == rad_R;
+    if (hitA || hitR) {
+      if (tid == 0) st_release_sys(lp.xc.verdict, (e << 3) | (hitA ? kXHitA : kXHitR));
+      // -P of the outcome that came true: the rank-ordered sum goes straight into the solver's matrix
+      double* Ut = sm;
+      for (int i = tid; i < (N + 8) * NS; i += blockDim.x) Ut[i] = 0.0;
+      __syncthreads();
+      const size_t hoff = xn + (hitA ? 0 : NN);
+      for (int r = tid >> 4; r < N; r += 16)
+        for (int c = r + (tid & 15); c <= N; c += 16) {
+          double v;
+          if (!ll_sum(in1, lp.xc.x1_n, nr, hoff + r * NC + c, e, v)) s_xok = 0;
+          Ut[r * NS + c] = -v;
+        }
+      {
+        const double* src = hitA ? Vinv_A : Vinv_R;
+        for (int i = p_begin * 6 + tid; i < p_end * 6; i += blockDim.x) lp.Vinv[i] = __ldcg(src + i);
+      }
+      if (tid == 0) { s_st.xepoch = e + 1; s_st.n_xchg += 1; if (lp.dbg) { lp.dbg[2] = gtime(); lp.dbg[10] = hitA ? 1 : 2; } }
+      __syncthreads();
+      if (!s_xok && tid == 0) *lp.xc.error = 1;
+      if (lp.pdl) pdl_launch_dependents();
+      finish_iteration<TPW>(lp, s_st, sm, F, s_xs, s_cams, true);
+      return;
+    }
+    // neither outcome holds (iteration 0: the Jacobi scaling needs the global pose blocks first; or an accepted
+    // step whose radius did not triple): publish the decided state and the summed evaluation, everybody eliminates again
+    for (int i = tid; i < xn; i += blockDim.x) lp.Xacc[i] = s_xs[i];
+    for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
+      reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
+    __syncthreads();
+    if (tid == 0) { __threadfence(); st_release_sys(lp.xc.verdict, (e << 3) | kXRedo); }
+    redo = true;
   }
-  finish_iteration<TPW>(lp, s_st, sm, F, s_xs, s_cams);
+  if (!redo) return;
+  // ---- second elimination with the decided radius, second exchange ---------------------------------------
+  eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, s_st.cur, s_st.radius, s_st.iteration == 1, S_M, lp.Vinv);
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(lp.ticket, 1u) == 2 * gridDim.x - 1) ? 1 : 0;
+    __threadfence();
+  }
+  __syncthreads();
+  if (!s_last) return;
+  {
+    const size_t slot2 = ((size_t)(e & 1ull) * nr + lp.xc.rank) * lp.xc.x2_n;
+    for (int r = tid >> 4; r < N; r += 16)
+      for (int c = r + (tid & 15); c <= N; c += 16) {
+        const double a = __ldcg(S_M + r * NS + c);
+        S_M[r * NS + c] = 0.0;
+        for (int q = 0; q < nr; ++q) ll_store(lp.xc.x2[q] + slot2 + r * NC + c, a, e);
+      }
+    const ulonglong2* in2 = lp.xc.x2[lp.xc.rank] + (size_t)(e & 1ull) * nr * lp.xc.x2_n;
+    double* Ut = sm;
+    __syncthreads();
+    for (int i = tid; i < (N + 8) * NS; i += blockDim.x) Ut[i] = 0.0;
+    __syncthreads();
+    for (int r = tid >> 4; r < N; r += 16)
+      for (int c = r + (tid & 15); c <= N; c += 16) {
+        double v;
+        if (!ll_sum(in2, lp.xc.x2_n, nr, (size_t)r * NC + c, e, v)) s_xok = 0;
+        Ut[r * NS + c] = -v;
+      }
+    if (tid == 0) { s_st.xepoch = e + 1; s_st.n_xchg += 2; s_st.n_respec += 1; if (lp.dbg) { lp.dbg[2] = gtime(); lp.dbg[10] = 0; } }
+    __syncthreads();
+    if (!s_xok && tid == 0) *lp.xc.error = 1;
+    if (lp.pdl) pdl_launch_dependents();
+    finish_iteration<TPW>(lp, s_st, sm, F, nullptr, s_cams, true);
+  }
 }
 
 // split mode: one CTA, after the all-reduce of S
@@ -865,7 +1005,7 @@ __global__ void __launch_bounds__(kSchurThreads) k_solve_only(const LmParams lp)
     reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_out)[i];
   __syncthreads();
   if (s_st.done) return;
-  finish_iteration<TPW>(lp, s_st, sm, lp.n_frames, nullptr, nullptr);
+  finish_iteration<TPW>(lp, s_st, sm, lp.n_frames, nullptr, nullptr, false);
 }
 
 // Device-side barrier across the ranks of a window (start of a solve): raise my flag in every rank's
@@ -926,8 +1066,40 @@ static cudaError_t launch_mode(const LmParams& lp, int grid, int n_free, cudaStr
   return cudaGetLastError();
 }
 
+template <int LPP, int TPW>
+static cudaError_t launch_mode_x(const LmParams& lp, int grid, int n_free, cudaStream_t s) {
+  static bool cfg[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!cfg[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k_schur_solve_x<LPP, TPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    if (e != cudaSuccess) return e;
+    cfg[dev & 63] = true;
+  }
+  constexpr int PPB = kSchurWarps * (32 / LPP), LD = 3 * PPB + 4;
+  const int N = 6 * n_free, Dp = (N + 8) & ~7;
+  const size_t elim_d = (size_t)Dp * LD, solve_d = solve_smem_doubles(n_free, lp.n_frames);
+  const size_t smem = sizeof(double) * (elim_d > solve_d ? elim_d : solve_d);
+  // every CTA must be resident at once (the CTAs wait for the deciding CTA's verdict): one CTA per SM, grid <= SMs
+  if (lp.pdl) {
+    cudaLaunchConfig_t cfg2 = {};
+    cfg2.gridDim = dim3(grid); cfg2.blockDim = dim3(kSchurThreads); cfg2.dynamicSmemBytes = smem; cfg2.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg2.attrs = at; cfg2.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg2, k_schur_solve_x<LPP, TPW>, lp);
+  }
+  k_schur_solve_x<LPP, TPW><<<grid, kSchurThreads, smem, s>>>(lp);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t s) {
   const int T = (6 * n_free + 8) >> 3, tiles = T * (T + 1) / 2;
+  if (lp.xc.n_ranks > 1) {
+    if (lp.n_frames <= 8) return tiles <= 3 * kSchurWarps ? launch_mode_x<8, 3>(lp, grid, n_free, s) : launch_mode_x<8, 12>(lp, grid, n_free, s);
+    return tiles <= 3 * kSchurWarps ? launch_mode_x<16, 3>(lp, grid, n_free, s) : launch_mode_x<16, 12>(lp, grid, n_free, s);
+  }
   if (lp.n_frames <= 8) return tiles <= 3 * kSchurWarps ? launch_mode<8, 3>(lp, grid, n_free, s) : launch_mode<8, 12>(lp, grid, n_free, s);
   return tiles <= 3 * kSchurWarps ? launch_mode<16, 3>(lp, grid, n_free, s) : launch_mode<16, 12>(lp, grid, n_free, s);
 }

@@ -866,31 +866,6 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
       if (acc != 0.0) atomicAdd(prm.Xacc + F * kUStride + threadIdx.x, acc);
     }
   }
-  // ---- multi-GPU: the last CTA publishes this rank's pose blocks + scalars into every rank's exchange
-  // buffer as self-validating LL cells (plain stores over NVLink peer mappings: no fence, no flag); the
-  // consumer (K_B on every rank) polls the cells and sums the slots in rank order.  No collective call,
-  // no extra launch.
-  if (prm.xc.n_ranks > 1 && st) {
-    __shared__ int s_last_a;
-    __syncthreads();                         // this CTA's atomics are issued
-    if (threadIdx.x == 0) {
-      __threadfence();
-      s_last_a = (atomicAdd(prm.xc.ticket_a, 1u) == gridDim.x - 1) ? 1 : 0;
-      __threadfence();
-    }
-    __syncthreads();
-    if (s_last_a) {
-      const unsigned long long e = st->xepoch;
-      const int n_act = F * kUStride + kEacc + kMaxRanks;
-      const size_t off = ((size_t)(e & 1ull) * prm.xc.n_ranks + prm.xc.rank) * prm.xc.xa_n;
-      for (int i = threadIdx.x; i < n_act; i += blockDim.x) {
-        const double v = __ldcg(prm.Xacc + i);
-        for (int q = 0; q < prm.xc.n_ranks; ++q) ll_store(prm.xc.xa[q] + off + i, v, e);
-        prm.Xacc[i] = 0.0;                   // the accumulators start from zero at the next launch
-      }
-      if (threadIdx.x == 0) *prm.xc.ticket_a = 0u;
-    }
-  }
   KTRACE(15);
 }
 

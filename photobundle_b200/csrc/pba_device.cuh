@@ -83,28 +83,35 @@ struct LmState {
   double scale_c[kMaxD];          // Jacobi column scaling of the pose columns (iteration 0)
   double step_c[kMaxD];           // trust-region step of the pose columns, scaled space
   unsigned long long xepoch;      // multi-GPU: epoch of the exchange this state waits for / publishes (monotone across solves)
+  int n_xchg, n_respec;           // multi-GPU: exchanges so far, and how many LM iterations needed the second one (mis-speculation)
 };
 
-// Multi-GPU exchange over NVLink peer memory.  Every rank owns one exchange buffer
-// (cudaMalloc + CUDA IPC) that all peers map:
-//   xa  [2 parity][n_ranks][xa_n] cells   rank q's pose blocks + cost scalars of the evaluation (K_A pushes)
-//   s   [2 parity][n_ranks][s_n]  cells   rank q's reduced-system contribution               (K_B pushes)
-// A cell is 16 bytes = two self-validating 8-byte packets {32 data bits, 32-bit epoch tag} (the "LL"
-// idea: an aligned 8-byte store is single-copy atomic, so a packet whose tag matches carries valid data
-// and neither a fence nor a separate flag round trip is needed).  A rank writes its vector into slot
-// [own rank] of EVERY rank's buffer with plain peer stores; consumers poll the cells and sum the slots in
-// rank order, so every rank obtains bit-identical sums (identical LM decisions) without any collective
-// call.  Slots alternate by epoch parity; the tag tells a fresh cell from the one written two epochs ago.
+// Multi-GPU exchange over NVLink peer memory.  Points are sharded over the ranks; per LM iteration
+// ONE exchange carries everything the replicated reduced solve needs.  K_B eliminates its shard under the two
+// outcomes of the pending decision that are known in advance — (A) the candidate is accepted and the radius triples,
+// (R) it is rejected and the radius shrinks by the current decrease factor — and the last CTA pushes
+//   x1 slot = [pose blocks + cost scalars of the evaluation | P under A | P under R]
+// into slot [own rank] of EVERY rank's buffer, sums everybody's evaluation part in rank order (bit-identical on all
+// ranks), takes the decision, and then sums only the chosen hypothesis.  When neither hypothesis holds (iteration 0,
+// or an accepted step with another radius) all CTAs — which have been waiting for the verdict — eliminate again
+// with the true radius and a second exchange (x2 slot = [P]) follows.
+// Every rank owns one exchange buffer (cudaMalloc + CUDA IPC) that all peers map:
+//   x1  [2 parity][n_ranks][x1_n] cells,  x2  [2 parity][n_ranks][x2_n] cells
+// A cell is 16 bytes = two self-validating 8-byte packets {32 data bits, 32-bit epoch tag} (the "LL" idea: an
+// aligned 8-byte store is single-copy atomic, so a packet whose tag matches carries valid data and neither a fence
+// nor a separate flag round trip is needed).  Slots alternate by epoch parity; the tag tells a fresh cell from the
+// one written two epochs ago.
 //   fr  u64 [n_ranks]                     rendezvous flags (start of a solve)
 struct Xchg {
   int n_ranks, rank;              // n_ranks <= 1: single GPU, everything below unused
-  int xa_n, s_n;                  // doubles per slot
-  ulonglong2* xa[kMaxRanks];      // rank q's xa region (peer mapping; [rank] = local)
-  ulonglong2* s[kMaxRanks];
+  int x1_n, x2_n;                 // cells per slot
+  ulonglong2* x1[kMaxRanks];      // rank q's x1 region (peer mapping; [rank] = local)
+  ulonglong2* x2[kMaxRanks];
   unsigned long long* fr[kMaxRanks];   // rendezvous flags (start of a solve)
-  unsigned int* ticket_a;         // K_A last-CTA detection (local)
+  unsigned long long* verdict;    // local: (epoch << 3) | code, from the deciding CTA to the waiting CTAs of the same kernel
   int* error;                     // local: set when a wait timed out
 };
+enum XVerdict { kXHitA = 1, kXHitR = 2, kXDone = 3, kXRedo = 4, kXFail = 5 };
 
 // K_A parameters (k_step.cu)
 struct StepParams {
@@ -127,7 +134,6 @@ struct StepParams {
   const double* Vinv;        // [n][6]
   double* obs_sqnorm;        // optional [nnz]
   double* residuals;         // optional [nnz][C*P]
-  Xchg xc;                   // multi-GPU exchange (n_ranks > 1 and st != null: the last CTA publishes Xacc)
   int pdl;                   // launched with programmatic stream serialization: wait for the previous kernel before reading its output
 };
 
@@ -149,7 +155,9 @@ struct LmParams {
   int split;                 // 1: multi-GPU — the reduced system is all-reduced before a separate solve kernel
   double* scale_p;           // [n][3]
   double* Vinv;              // [n][6]
-  double* S;                 // [N][reduced_ld(N)], see k_schur_solve.cu
+  double* S;                 // [N][reduced_ld(N)], see k_schur_solve.cu; multi-GPU: three of them (hypotheses A, R, re-elimination), s_cap apart
+  size_t s_cap;
+  double* Vinv2;             // multi-GPU: [2][n][6], (Vs + D²)^-1 under hypothesis A / R
   unsigned long long* dbg;   // optional: globaltimer stamps of the last CTA {start, decided, schur done, solved, end}
   unsigned long long cond;   // non-zero: cudaGraphConditionalHandle of the device-side LM loop, cleared when done
   Xchg xc;                   // multi-GPU exchange over peer memory (xc.n_ranks > 1), else split/NCCL or single GPU
@@ -218,7 +226,7 @@ __host__ __device__ constexpr size_t reduced_capacity(int max_frames) { return (
 // launchers
 cudaError_t launch_k_step(const StepParams& prm, int radius, cudaStream_t stream);
 int schur_grid(int n_points, int sm_count);
-cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t stream);
+cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t stream);   // lp.xc.n_ranks > 1: the multi-GPU kernel
 cudaError_t launch_solve_only(const LmParams& lp, int n_free, cudaStream_t stream);   // split mode, after the all-reduce of S
 cudaError_t launch_rendezvous(const Xchg& xc, unsigned long long epoch, cudaStream_t stream);   // device-side barrier across the ranks
 

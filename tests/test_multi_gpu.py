@@ -95,7 +95,9 @@ def test_two_gpus_equal_one_gpu():
             assert two["exchange"] == "nccl" and two["collectives"] > 0
         else:
             assert two["exchange"] in ("peer-memory", "nccl")   # nccl only where peer mappings are unavailable
-            assert (two["collectives"] == 0) == (two["exchange"] == "peer-memory")
+            if two["exchange"] == "peer-memory":
+                # one in-kernel exchange per LM decision, a second one only when the speculated outcome missed
+                assert two["iters"] <= two["collectives"] <= 2 * two["iters"] + 1
         assert two["ranks_agree"]
         assert two["accepts"] == one["accepts"]
         assert abs(two["final_cost"] - one["final_cost"]) <= 1e-9 * one["final_cost"]
