@@ -3,24 +3,28 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Workload (BASELINE.json configs[1]/[2]): synthetic 8-frame x 4 000-point x
-5x5-patch window at KITTI size (32 000 observations, 800 000 residuals).  One *step* = one
-full Levenberg-Marquardt solve of the window from its initial poses/points through the
-C ABI (pba_solve): K1 residual+Jacobian passes + Schur + reduced solve per iteration.
+Headline workload (BASELINE.json configs[1]/[2]): synthetic 8-frame x 4 000-point x
+5x5-patch window at KITTI size (32 000 observations, 800 000 residuals).  One *step* = one full
+Levenberg-Marquardt solve of the window from its initial poses/points through the C ABI (pba_solve):
+per LM iteration K_A (back-substitution + residual/Jacobian/blocks) and K_B (decision + Schur
+elimination + reduced camera solve).
 
-    value      point-residual evaluations / second = numResiduals x K1 passes / device time,
-               inputs resident in HBM (pba_restore_state between steps), device time from the
-               CUDA events the library records on its own stream around the solve
-    e2e        same metric through the same C ABI with HOST buffers: per step the frames,
-               poses, points, descriptors are copied host->device from pinned memory, the
-               window is solved, poses+points are read back; host wall clock
-    roofline   K1 (the dominant kernel): algorithmic bytes 656 B/observation x
-               32 000 / the live CUDA-event launch duration; peak = MEASURED_PEAKS.json hbm_gbs
-    cpu_baseline  the CPU oracle restating the reference's Ceres/autodiff path (Ceres itself is
-               not installable here), all host cores, one bounded sample of the same window
+    value      point-residual evaluations / second = numResiduals x K_A passes / device time, inputs
+               resident in HBM (pba_restore_state between steps), device time from the CUDA events the
+               library records on its own stream around the solve
+    e2e        same metric through the same C ABI with HOST buffers: per step the frames, poses, points,
+               descriptors are copied host->device from pinned memory, the window is solved, poses +
+               points are read back; host wall clock
+    roofline   the time-dominant kernel against the measured HBM peak (MEASURED_PEAKS.json), with the
+               other kernel's and the whole solve's fractions beside it; algorithmic bytes per SURVEY §8d:
+               K_A 656 B/observation, K_B 112 B/observation + 12 B/point
+    cfg4       second workload (BASELINE.json configs[3]): 16 frames x 16 000 points x 3 pyramid levels,
+               reported at every N; with N > 1 the points of the window are sharded over the GPUs
+    cpu_baseline  the CPU oracle restating the reference's Ceres/autodiff path (Ceres itself is not
+               installable here), all host cores, a bounded sample of the same window
 
-`--impl reference` times that CPU path as the step itself (rank 0 only).
-N > 1: one process per GPU (torchrun); see DESIGN.md §multi-GPU for what is sharded.
+`--impl reference` times that CPU path as the step itself (rank 0 only), same --steps / --warmup.
+N > 1: one process per GPU (torchrun); see DESIGN.md §7 for what is sharded and exchanged.
 """
 from __future__ import annotations
 
@@ -36,9 +40,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALGO_BYTES_PER_OBS_K1 = 656          # 544 B read + 112 B written per observation
-ALGO_BYTES_PER_OBS_LM_ITER = 916     # one Jacobian pass + one cost pass (reference structure)
+ALGO_BYTES_PER_OBS_KA = 656          # 544 B read + 112 B written per observation
+ALGO_BYTES_PER_OBS_KB = 112          # the Schur/solve pass re-reads the 112 B/observation ...
+ALGO_BYTES_PER_POINT_KB = 12         # ... and writes 12 B/point
 HBM_FALLBACK_GBS = 6650.0            # /opt/skills/guides/B200_PROFILING.md fallback
+
+WORKLOAD = "8-frame x 4000-point x 5x5-patch synthetic window at KITTI size, full LM solve (BASELINE configs[2])"
+
+
+def workload_config(n_obs: int, n_res: int) -> dict:
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "n_observations": n_obs, "n_residuals": n_res,
+            "cache_hygiene": "GPU arm: L2 flushed (256 MiB write) between timed steps, outside the timed intervals"}
 
 
 def measured_peak():
@@ -51,9 +64,9 @@ def measured_peak():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def k1_traffic_from_profile():
-    """dram__bytes_read+write per K1 launch from the committed ncu capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "k1_ncu_summary.json")
+def static_traffic(name: str):
+    """dram__bytes_read+write per launch from the committed ncu --set full capture of this round (profiles/)."""
+    p = os.path.join(ROOT, "profiles", name)
     if os.path.exists(p):
         try:
             return float(json.load(open(p))["dram_bytes_per_launch"])
@@ -126,7 +139,7 @@ class ClockSampler(threading.Thread):
 
 def build_window():
     import numpy as np
-    from photobundle_b200 import synthetic
+    from workloads import synthetic
     cache = os.path.join("/tmp", "pba_cfg3_images_v1.npy")
     images = None
     if os.path.exists(cache):
@@ -141,6 +154,33 @@ def build_window():
         except Exception:
             pass
     return win
+
+
+def build_cfg4_levels(levels: int = 3):
+    """BASELINE configs[3]: 16 frames x 16 000 points, `levels` pyramid levels (level l = frames reduced l times with
+    the cv::pyrDown rule, intrinsics halved, descriptors re-extracted; workloads/synthetic.py).  Cached in /tmp."""
+    import pickle
+    from workloads import synthetic
+    cache = os.path.join("/tmp", f"pba_cfg4_levels{levels}_v1.pkl")
+    if os.path.exists(cache):
+        try:
+            return pickle.load(open(cache, "rb"))
+        except Exception:
+            pass
+    import numpy as np
+    win = synthetic.make_window(n_frames=16, grid=(100, 160))
+    px, ref = synthetic.reference_pixels(win)
+    imgs = [win.images]
+    for _ in range(levels - 1):
+        imgs.append(np.stack([synthetic.pyr_down_u8(i) for i in imgs[-1]]))
+    wins = [synthetic.pyramid_level(win, lv, imgs[lv], px, ref) for lv in range(levels)]
+    try:
+        tmp = cache + f".{os.getpid()}"
+        pickle.dump(wins, open(tmp, "wb"))
+        os.replace(tmp, cache)
+    except Exception:
+        pass
+    return wins
 
 
 def cpu_oracle_run(win, steps: int, warmup: int, threads: int = 0):
@@ -162,12 +202,27 @@ def cpu_oracle_run(win, steps: int, warmup: int, threads: int = 0):
     return {"residual_evals": evals * win.n_residuals, "lm_iters": iters, "seconds": secs, "summary": summ}
 
 
+def make_handle(capi, win, local_rank, rank, world, comm_id, levels_down=0, images0=None):
+    h = capi.Handle(win.rows, win.cols, win.fx, win.fy, win.cx, win.cy, radius=win.radius, huber=win.huber,
+                    max_frames=win.n_frames, max_points=win.n_points, max_observations=win.n_obs, device=local_rank)
+    if world > 1:
+        h.comm_init(comm_id, rank, world)
+    if levels_down:
+        h.set_frames_u8_pyr(images0, levels_down)      # level-0 frames in, reduced on the device
+    else:
+        h.set_frames_u8(win.images)
+    h.set_poses(win.cams_init, win.fixed_frame)
+    h.set_points(win.points_init, win.desc, win.obs_offsets, win.obs_frame, win.weights)
+    return h
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the second workload (developer runs)")
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(0, args.warmup)
 
@@ -181,20 +236,19 @@ def main():
         if rank != 0:
             return 0
         win = build_window()
-        k = min(steps, 5)  # bounded: each step is one full CPU solve (~0.2-1 s)
-        r = cpu_oracle_run(win, k, min(warmup, 1))
+        r = cpu_oracle_run(win, steps, warmup)     # one step = one full CPU solve of the same window (~50 ms on 16 cores)
         val = r["residual_evals"] / r["seconds"]
         line = {
             "impl": "reference", "metric": "point_residual_evaluations_per_sec", "value": val, "unit": "residuals/s",
-            "n_gpus": args.gpus, "steps": k, "warmup": min(warmup, 1), "ms_per_step": 1e3 * r["seconds"] / k,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (fp32 sampler)",
             "data": "synthetic", "lm_iters_per_sec": r["lm_iters"] / r["seconds"],
-            "config": {"workload": "8-frame x 4000-point x 5x5 window, full LM solve (BASELINE configs[2])",
-                       "what": "CPU oracle restating the reference's Ceres/autodiff path (Ceres 1.x, Eigen, Boost, OpenCV "
-                               "are not installable in this image, so the reference binary cannot run)",
-                       "n_observations": win.n_obs, "n_residuals": win.n_residuals},
+            "config": workload_config(win.n_obs, win.n_residuals),
+            "what": "CPU oracle restating the reference's Ceres/autodiff path (Ceres 1.x, Eigen, Boost, OpenCV are not "
+                    "installable in this image, so the reference binary cannot run); one step = one full LM solve",
             "cpu_baseline": {"value": val, "unit": "residuals/s", "cores": ncores, "kind": "port",
-                             "sample": f"{k} full LM solves of the bench window, OpenMP over {ncores} host threads"},
+                             "sample": f"{steps} full LM solves of the bench window, OpenMP over {ncores} host threads; "
+                                       f"final cost {r['summary']['final_cost']:.4f}"},
             "e2e": {"value": val, "unit": "residuals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -216,20 +270,16 @@ def main():
     ge.build()
     from photobundle_b200 import capi
 
-    win = build_window()
-    if world > 1:
-        # one window sharded by point block over the ranks (frames/poses replicated); the exchange per LM
-        # iteration is the all-reduce of the pose blocks + cost and of the reduced camera system
+    def comm_id():
+        if world == 1:
+            return None
         ids = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
-        h = capi.Handle(win.rows, win.cols, win.fx, win.fy, win.cx, win.cy, radius=win.radius, huber=win.huber,
-                        max_frames=win.n_frames, max_points=win.n_points, max_observations=win.n_obs, device=local_rank)
-        h.comm_init(ids[0], rank, world)
-        h.set_frames_u8(win.images)
-        h.set_poses(win.cams_init, win.fixed_frame)
-        h.set_points(win.points_init, win.desc, win.obs_offsets, win.obs_frame, win.weights)
-    else:
-        h = capi.Handle.for_window(win, device=local_rank)
+        return ids[0]
+
+    win = build_window()
+    # N > 1: one window sharded by point block over the ranks (frames/poses replicated)
+    h = make_handle(capi, win, local_rank, rank, world, comm_id())
     h.save_state()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -245,12 +295,13 @@ def main():
         torch.cuda.synchronize()
         return h.solve()
 
-    for _ in range(max(3, warmup)):
+    nwarm = max(3, warmup)
+    for _ in range(nwarm):
         one_step()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    dev_s, evals, iters, launches = 0.0, 0, 0, 0
+    dev_s, evals, iters, launches, xchg, decisions, kb_s, kb_n = 0.0, 0, 0, 0, 0, 0, 0.0, 0
     last = None
     for _ in range(steps):
         s = one_step()
@@ -258,21 +309,25 @@ def main():
         evals += s["num_evaluations"]
         iters += s["num_iterations"] - 1
         launches += s["kernel_launches"]
+        xchg += s["num_collectives"]
+        decisions += s["num_evaluations"]
+        kb_s += s["kb_device_time_in_seconds"]
+        kb_n += s["num_evaluations"] - 1      # the last K_B only takes the terminating decision
         last = s
     barrier()
 
-    # K1 alone (config 2): average launch duration, CUDA events on the library's stream
+    # K_A alone (config 2): average launch duration, CUDA events on the library's stream
     h.restore_state()
-    k1_iters = 200
+    ka_iters = 200
     h.eval_timed(20)
-    k1_ms_cold = []
+    ka_ms_cold = []
     for _ in range(10):           # cold-L2 launches: flush, then time ONE launch
         flush.fill_(2)
         torch.cuda.synchronize()
-        k1_ms_cold.append(h.eval_timed(1))
-    k1_ms_warm = h.eval_timed(k1_iters) / k1_iters
-    launches += 20 + 10 + k1_iters
-    k1_ms = statistics.median(k1_ms_cold)
+        ka_ms_cold.append(h.eval_timed(1))
+    ka_ms_warm = h.eval_timed(ka_iters) / ka_iters
+    launches += 20 + 10 + ka_iters
+    ka_ms = statistics.median(ka_ms_cold)
 
     # batched windows (auxiliary): B independent windows solved concurrently, one handle + stream + host
     # thread each — a single 8x4k window is latency-bound and leaves most of the GPU idle
@@ -337,6 +392,57 @@ def main():
     barrier()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
+    n_obs_local = h.n_obs_local if world > 1 else win.n_obs
+    n_pts_local = win.n_points // world
+    exchange_kind = h.exchange_kind()
+    h.close()
+
+    # ---- second workload: BASELINE configs[3], 16 frames x 16 000 points x 3 levels, coarse to fine ----------
+    cfg4 = None
+    if not args.no_cfg4:
+        wins = build_cfg4_levels(3)
+        hl = [make_handle(capi, wins[lv], local_rank, rank, world, comm_id(), levels_down=lv, images0=wins[0].images)
+              for lv in range(3)]
+        hl[2].save_state()
+        c4_steps = max(2, min(steps, 5))
+        def cfg4_step():
+            hl[2].restore_state()
+            flush.fill_(3)
+            torch.cuda.synchronize()
+            out = []
+            for lv in (2, 1, 0):
+                if lv < 2:
+                    hl[lv].copy_state_from(hl[lv + 1])    # device-to-device hand-over, coarse -> fine
+                out.append(hl[lv].solve())
+            return out
+        for _ in range(2):
+            cfg4_step()
+        barrier()
+        c4_dev, c4_evals, c4_iters, c4_fine, c4_last = 0.0, 0, 0, 0.0, None
+        for _ in range(c4_steps):
+            out = cfg4_step()
+            c4_dev += sum(s["device_time_in_seconds"] for s in out)
+            c4_fine += out[-1]["device_time_in_seconds"]
+            c4_evals += sum(s["num_evaluations"] for s in out)
+            c4_iters += sum(s["num_iterations"] - 1 for s in out)
+            launches += sum(s["kernel_launches"] for s in out)
+            c4_last = out
+        barrier()
+        if dist is not None:
+            t = torch.tensor([c4_dev, c4_fine], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            c4_dev, c4_fine = float(t[0]), float(t[1])
+        cfg4 = {"workload": "16-frame x 16000-point x 5x5-patch window, 3-level pyramid coarse to fine (BASELINE configs[3]); "
+                            "levels handed over on the device (pba_copy_state)",
+                "n_observations_per_level": wins[0].n_obs, "n_residuals_per_level": wins[0].n_residuals,
+                "ms_per_solve_all_levels": 1e3 * c4_dev / c4_steps, "ms_per_solve_finest_level": 1e3 * c4_fine / c4_steps,
+                "residuals_per_sec": c4_evals * wins[0].n_residuals / c4_dev, "lm_iters_per_sec": c4_iters / c4_dev,
+                "lm_iterations_per_level": [s["num_iterations"] - 1 for s in c4_last],
+                "final_cost_per_level": [s["final_cost"] for s in c4_last], "steps": c4_steps,
+                "exchanges_per_solve_all_levels": sum(s["num_collectives"] for s in c4_last),
+                "timing": "sum of the three levels' CUDA-event intervals, max over ranks"}
+        for hx in hl:
+            hx.close()
 
     # max over ranks (device-timed)
     if dist is not None:
@@ -348,39 +454,61 @@ def main():
         launches = float(c[0])   # evals / iters are global already: one window, sharded
 
     peak, peak_src = measured_peak()
-    n_obs_local = h.n_obs_local if world > 1 else win.n_obs
-    achieved = n_obs_local * ALGO_BYTES_PER_OBS_K1 / (k1_ms * 1e-3) / 1e9
+    n_ka, n_kb = last["num_evaluations"], last["num_evaluations"] - 1   # per solve; the last K_B only takes the terminating decision
+    ka_bytes = n_obs_local * ALGO_BYTES_PER_OBS_KA
+    kb_bytes = n_obs_local * ALGO_BYTES_PER_OBS_KB + n_pts_local * ALGO_BYTES_PER_POINT_KB
+    solve_us = 1e6 * dev_s / steps
+    kb_us = 1e6 * kb_s / max(1, kb_n)                      # the kernel's own start/end stamps (globaltimer), averaged
+    ka_loop_us = (solve_us - n_kb * kb_us) / max(1, n_ka)  # in-loop K_A (with back-substitution) + the two launch gaps of an iteration
+    ka_frac = ka_bytes / (ka_ms * 1e-3) / 1e9 / peak
+    kb_frac = kb_bytes / (kb_us * 1e-6) / 1e9 / peak
+    whole_frac = (n_ka * ka_bytes + n_kb * kb_bytes) / (solve_us * 1e-6) / 1e9 / peak
+    ka_dominant = n_ka * ka_loop_us >= n_kb * kb_us
     value = evals * win.n_residuals / dev_s
     line = {
         "metric": "point_residual_evaluations_per_sec", "value": value, "unit": "residuals/s",
-        "n_gpus": world, "steps": steps, "warmup": max(3, warmup), "ms_per_step": 1e3 * dev_s / steps,
+        "n_gpus": world, "steps": steps, "warmup": nwarm, "ms_per_step": 1e3 * dev_s / steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64 (fp32 sampler)", "data": "synthetic",
         "lm_iters_per_sec": iters / dev_s,
-        "config": {
-            "workload": "8-frame x 4000-point x 5x5 window, full LM solve incl. Schur + reduced-pose solve "
-                        "(BASELINE configs[2]; K1-only numbers of configs[1] under `k1`)",
-            "n_observations": win.n_obs, "n_residuals": win.n_residuals,
-            "lm_iterations_per_solve": last["num_iterations"] - 1, "k1_passes_per_solve": last["num_evaluations"],
+        "config": workload_config(win.n_obs, win.n_residuals),
+        "run": {
+            "lm_iterations_per_solve": last["num_iterations"] - 1, "ka_passes_per_solve": last["num_evaluations"],
             "final_cost": last["final_cost"], "initial_cost": last["initial_cost"], "termination": last["message"],
             "timing": "sum of per-step CUDA-event intervals recorded by the library on its own stream; "
                       "L2 flushed (256 MiB write) between steps outside the intervals",
             "parallelism": "1 window on 1 GPU" if world == 1 else
                            f"1 window, points sharded over {world} GPUs (frames/poses replicated); per LM iteration the pose "
-                           f"blocks+cost and the reduced camera system are exchanged by {h.exchange_kind()} "
-                           f"({last['num_collectives']} NCCL collectives/solve)",
+                           f"blocks + cost and the reduced camera system travel in ONE in-kernel exchange ({exchange_kind}); a second "
+                           f"one only when neither speculated outcome of the decision held",
+            "exchanges_per_solve": xchg / steps if world > 1 else 0,
+            "mis_speculation_rate": (xchg - decisions) / max(1, decisions) if (world > 1 and exchange_kind == "peer-memory") else None,
         },
-        "k1": {"us_per_launch_cold_l2": 1e3 * k1_ms, "us_per_launch_warm_l2": 1e3 * k1_ms_warm,
-               "observations_per_launch": n_obs_local,
-               "residuals_per_sec": 25 * n_obs_local / (k1_ms * 1e-3), "observations_per_sec": n_obs_local / (k1_ms * 1e-3)},
-        "k_b": {"us_per_launch_incl_launch_gaps": (1e6 * dev_s / steps - last["num_evaluations"] * 1e3 * k1_ms_warm) / max(1, last["num_evaluations"]),
-                "what": "decision + Schur elimination + reduced solve (k_schur_solve); latency-bound single-CTA tail, see DESIGN.md §4; "
-                        "derived as (solve time - K_A launches x warm K_A time) / K_B launches (one decision per evaluation)",
-                "algorithmic_bytes_per_launch": n_obs_local * 112 + (win.n_points // world) * 12},
-        "roofline": {"bound": "hbm", "kernel": "k_step<2,u8,1> (K_A)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": k1_traffic_from_profile(),
-                     "algorithmic_bytes_per_launch": n_obs_local * ALGO_BYTES_PER_OBS_K1, "peak_source": peak_src,
-                     "note": "duration = median of 10 single launches after an L2 flush, CUDA events on the launching stream"},
+        "k_a": {"us_per_launch_cold_l2": 1e3 * ka_ms, "us_per_launch_warm_l2": 1e3 * ka_ms_warm,
+                "observations_per_launch": n_obs_local,
+                "residuals_per_sec": 25 * n_obs_local / (ka_ms * 1e-3), "observations_per_sec": n_obs_local / (ka_ms * 1e-3),
+                "what": "evaluation-only launch of k_step (BASELINE configs[1]); in the LM loop the same kernel also back-substitutes"},
+        "k_b": {"us_per_launch": kb_us,
+                "what": "decision + Schur elimination (DMMA) + reduced camera solve (k_schur_solve): the kernel's own start/end "
+                        "stamps (globaltimer), averaged over the LM iterations of the timed solves",
+                "algorithmic_bytes_per_launch": kb_bytes},
+        "k_a_in_loop": {"us_per_iteration_incl_launch_gaps": ka_loop_us,
+                        "what": "(solve time - K_B time) / K_A launches: the in-loop K_A (with back-substitution) plus the two "
+                                "kernel-to-kernel gaps of an LM iteration"},
+        "roofline": {"bound": "hbm",
+                     "kernel": "k_step<2,u8,1> (K_A)" if ka_dominant else "k_schur_solve (K_B)",
+                     "achieved": (ka_frac if ka_dominant else kb_frac) * peak, "peak": peak, "unit": "GB/s",
+                     "frac": ka_frac if ka_dominant else kb_frac,
+                     "traffic": static_traffic("k_a_ncu_summary.json" if ka_dominant else "k_b_ncu_summary.json"),
+                     "traffic_source": "static: dram__bytes_read+write per launch of this kernel from this round's ncu --set full "
+                                       "capture (profiles/k_a_ncu_summary.json, k_b_ncu_summary.json); not re-measured in this run",
+                     "algorithmic_bytes_per_launch": ka_bytes if ka_dominant else kb_bytes, "peak_source": peak_src,
+                     "k_a": {"frac": ka_frac, "share_of_solve_incl_launch_gaps": n_ka * ka_loop_us / solve_us, "traffic": static_traffic("k_a_ncu_summary.json")},
+                     "k_b": {"frac": kb_frac, "share_of_solve": n_kb * kb_us / solve_us, "traffic": static_traffic("k_b_ncu_summary.json")},
+                     "whole_solve": {"frac": whole_frac, "algorithmic_bytes": n_ka * ka_bytes + n_kb * kb_bytes},
+                     "tensor_pipe": "fp64 DMMA (mma.sync.m8n8k4.f64) carries the Schur products Zt Zt^T and the trailing updates of the "
+                                    "reduced factorisation inside K_B; utilisation in profiles/ (ncu sm__pipe_tensor_subpipe_dmma_cycles_active)",
+                     "note": "K_A duration = median of 10 single launches after an L2 flush, CUDA events on the launching stream"},
         "e2e": {"value": e2e_evals * win.n_residuals / e2e_s, "unit": "residuals/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / steps, "lm_iters_per_sec": e2e_iters / e2e_s},
         "gpu_launches": int(launches),
@@ -388,6 +516,8 @@ def main():
     }
     if batched is not None:
         line["batched"] = batched
+    if cfg4 is not None:
+        line["cfg4"] = cfg4
 
     # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     if world == 1 and rank == 0:
@@ -400,10 +530,10 @@ def main():
             "sample": f"3 full LM solves of the same window by the CPU oracle (reference's Ceres/autodiff structure), "
                       f"{ncores} OpenMP threads; final cost {r['summary']['final_cost']:.4f}"}
         line["parity"] = {"gpu_final_cost": last["final_cost"], "cpu_final_cost": r["summary"]["final_cost"],
-                          "rel_cost_diff": abs(last["final_cost"] - r["summary"]["final_cost"]) / r["summary"]["final_cost"]}
+                          "rel_cost_diff": abs(last["final_cost"] - r["summary"]["final_cost"]) / r["summary"]["final_cost"],
+                          "note": "oracle = restated reference path; Ceres semantics themselves are unpinned (DESIGN.md §2)"}
     if rank == 0:
         print(json.dumps(line))
-    h.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -116,6 +116,8 @@ typedef struct {
                                       peer-memory exchanges (0 on one GPU)                  */
   double total_time_in_seconds;    /* host wall time of the call                             */
   double device_time_in_seconds;   /* CUDA-event time on the handle's stream                 */
+  double kb_device_time_in_seconds;/* of which inside K_B (decision + Schur + reduced solve): sum over the LM
+                                      iterations of the kernel's own start/end stamps (globaltimer)   */
   char message[256];
 } pba_summary;
 
@@ -190,6 +192,12 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt, pba_summary* summary
  * (bench.py's HBM-resident `value` leg; also what a pyramid level-to-level hand-over uses). */
 int pba_save_state(pba_handle* h);
 int pba_restore_state(pba_handle* h);
+
+/* Device-to-device hand-over of the current poses and points from one handle to another with the same frame and
+ * point counts (and the same sharding): the coarse-to-fine step of a pyramid (what the reference intends at
+ * src/photobundle_pyramid.cc:61-65, T_init of the finer level = the coarser level's result) without a host round
+ * trip.  Ordered on dst's stream. */
+int pba_copy_state(pba_handle* dst, pba_handle* src);
 
 int pba_get_poses(pba_handle* h, double* cam6);
 int pba_get_points(pba_handle* h, double* xyz);

@@ -21,7 +21,7 @@ PBA_UNIQUE_ID_BYTES = 128
 EXPORTED_SYMBOLS = [
     "pba_last_error", "pba_version", "pba_default_solver_options", "pba_create", "pba_destroy",
     "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_frames_u8_pyr", "pba_pyrdown_u8", "pba_set_poses", "pba_set_points",
-    "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_get_poses", "pba_get_points", "pba_get_iterations",
+    "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_copy_state", "pba_get_poses", "pba_get_points", "pba_get_iterations",
     "pba_comm_unique_id", "pba_comm_init", "pba_shard_range", "pba_comm_exchange_kind",
     "pba_descriptor_channels", "pba_set_frames_u8_descriptor", "pba_get_channel_plane", "pba_prepare_frame_u8",
     "pba_saliency_map", "pba_extract_descriptors", "pba_associate", "pba_select_candidates",
@@ -72,7 +72,7 @@ class Summary(C.Structure):
         ("num_residuals", C.c_int32), ("num_residual_blocks", C.c_int32), ("num_iterations", C.c_int32),
         ("termination_type", C.c_int32), ("num_evaluations", C.c_int32), ("kernel_launches", C.c_int32),
         ("num_collectives", C.c_int32), ("total_time_in_seconds", C.c_double),
-        ("device_time_in_seconds", C.c_double), ("message", C.c_char * 256),
+        ("device_time_in_seconds", C.c_double), ("kb_device_time_in_seconds", C.c_double), ("message", C.c_char * 256),
     ]
 
 
@@ -270,6 +270,10 @@ class Handle:
 
     def restore_state(self):
         _check(lib().pba_restore_state(self._h), "pba_restore_state")
+
+    def copy_state_from(self, src: "Handle"):
+        """Poses and points of `src` (same window at another pyramid level) become this handle's, on the device."""
+        _check(lib().pba_copy_state(self._h, src._h), "pba_copy_state")
 
     def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
         """One process per GPU: join the window's communicator (before set_points)."""

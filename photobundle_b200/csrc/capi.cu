@@ -115,8 +115,11 @@ struct pba_handle {
   double* d_Vinv2 = nullptr;       // multi-GPU: (Vs + D²)^-1 under the two hypotheses of the pending decision, [2][n][6]
   unsigned int* d_ticket = nullptr;
   unsigned long long* d_dbg = nullptr;   // PBA_DEBUG_TIMELINE=1: per-iteration K_B timeline
+  unsigned long long* d_stamps = nullptr;   // [trace_cap][2] start/end of every K_B launch (pba_summary.kb_device_time_in_seconds)
   double *d_obs_sqnorm = nullptr, *d_residuals = nullptr;
   double *d_save_cams = nullptr, *d_save_pts = nullptr;
+  uint8_t* d_pyr_scratch = nullptr;  size_t pyr_scratch_bytes = 0;   // pba_set_frames_u8_pyr ping-pong planes
+  double* d_pts_full = nullptr;      // multi-GPU: all shards gathered (pba_get_points)
   bool have_saved = false;
   LmState* d_state = nullptr;
   IterSummary* d_trace = nullptr;
@@ -126,6 +129,7 @@ struct pba_handle {
   int n_frames = 0, fixed_frame = -1, n_points = 0, nnz = 0;
   bool have_frames = false, have_poses = false, have_points = false;
   std::vector<int> frame_used;
+  int max_obs_frame = -1;          // largest frame index any observation refers to (re-checked against n_frames before a launch)
   std::vector<IterSummary> trace;
   // multi-GPU: points sharded by contiguous block, frames/poses replicated
   int rank = 0, n_ranks = 1;
@@ -168,8 +172,8 @@ static void free_all(pba_handle* h) {
     if (h->peer_xchg[q] && h->peer_xchg[q] != h->d_xchg) cudaIpcCloseMemHandle(h->peer_xchg[q]);
   cudaFree(h->d_xchg);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  cudaFree(h->d_scale_p); cudaFree(h->d_Vinv); cudaFree(h->d_S); cudaFree(h->d_Vinv2); cudaFree(h->d_ticket); cudaFree(h->d_dbg);
-  cudaFree(h->d_save_cams); cudaFree(h->d_save_pts);
+  cudaFree(h->d_scale_p); cudaFree(h->d_Vinv); cudaFree(h->d_S); cudaFree(h->d_Vinv2); cudaFree(h->d_ticket); cudaFree(h->d_dbg); cudaFree(h->d_stamps);
+  cudaFree(h->d_save_cams); cudaFree(h->d_save_pts); cudaFree(h->d_pyr_scratch); cudaFree(h->d_pts_full);
   cudaFree(h->d_obs_sqnorm); cudaFree(h->d_residuals); cudaFree(h->d_state); cudaFree(h->d_trace);
   if (h->h_state) cudaFreeHost(h->h_state);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -374,7 +378,7 @@ int pba_set_frames_u8(pba_handle* h, int32_t n_frames, const uint8_t* const* ima
   if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(PBA_ERR_CAPACITY, "pba_set_frames_u8: %d frames, capacity %d", n_frames, h->cfg.max_frames);
   CUDA_TRY(cudaSetDevice(h->device));
   if (!h->d_u8) {
-    CUDA_TRY(cudaMalloc(&h->d_u8, (size_t)h->cfg.max_frames * h->plane));
+    CUDA_TRY(cudaMalloc(&h->d_u8, (size_t)h->cfg.max_frames * h->plane + 64));
     CUDA_TRY(cudaMemsetAsync(h->d_u8, 0, (size_t)h->cfg.max_frames * h->plane, h->stream));
   }
   for (int f = 0; f < n_frames; ++f) {
@@ -400,15 +404,19 @@ int pba_set_frames_u8_pyr(pba_handle* h, int32_t n_frames, const uint8_t* const*
                 levels_down, r, c, h->cfg.rows, h->cfg.cols);
   CUDA_TRY(cudaSetDevice(h->device));
   if (!h->d_u8) {
-    CUDA_TRY(cudaMalloc(&h->d_u8, (size_t)h->cfg.max_frames * h->plane));
+    CUDA_TRY(cudaMalloc(&h->d_u8, (size_t)h->cfg.max_frames * h->plane + 64));
     CUDA_TRY(cudaMemsetAsync(h->d_u8, 0, (size_t)h->cfg.max_frames * h->plane, h->stream));
   }
   // two ping-pong scratch planes at level-0 size
   const int p0 = (src_cols + 15) / 16 * 16;
-  uint8_t* scratch = nullptr;
-  CUDA_TRY(cudaMalloc(&scratch, 2 * (size_t)src_rows * p0));
+  if (h->pyr_scratch_bytes < 2 * (size_t)src_rows * p0) {
+    cudaFree(h->d_pyr_scratch); h->d_pyr_scratch = nullptr; h->pyr_scratch_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->d_pyr_scratch, 2 * (size_t)src_rows * p0));
+    h->pyr_scratch_bytes = 2 * (size_t)src_rows * p0;
+  }
+  uint8_t* scratch = h->d_pyr_scratch;
   for (int f = 0; f < n_frames; ++f) {
-    if (!images[f]) { cudaFree(scratch); return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8_pyr: images[%d] is null", f); }
+    if (!images[f]) return fail(PBA_ERR_ARGUMENT, "pba_set_frames_u8_pyr: images[%d] is null", f);
     uint8_t* a = scratch;
     uint8_t* b = scratch + (size_t)src_rows * p0;
     CUDA_TRY(cudaMemcpyAsync(a, images[f], (size_t)src_rows * src_cols, cudaMemcpyHostToDevice, h->stream));   // dense: pitch = cols
@@ -424,7 +432,6 @@ int pba_set_frames_u8_pyr(pba_handle* h, int32_t n_frames, const uint8_t* const*
     }
   }
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  cudaFree(scratch);
   h->frames_are_u8 = true; h->have_frames = true; h->n_frames = n_frames;
   return PBA_OK;
 }
@@ -462,7 +469,7 @@ int pba_set_frames_f32(pba_handle* h, int32_t n_frames, const float* const* plan
   CUDA_TRY(cudaSetDevice(h->device));
   const int C = h->cfg.n_channels;
   if (!h->d_f32) {
-    CUDA_TRY(cudaMalloc(&h->d_f32, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane));
+    CUDA_TRY(cudaMalloc(&h->d_f32, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane + 64));
     CUDA_TRY(cudaMemsetAsync(h->d_f32, 0, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane, h->stream));
   }
   for (int i = 0; i < n_frames * C; ++i) {
@@ -497,11 +504,11 @@ int pba_set_frames_u8_descriptor(pba_handle* h, int32_t n_frames, const uint8_t*
   if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(PBA_ERR_CAPACITY, "pba_set_frames_u8_descriptor: %d frames, capacity %d", n_frames, h->cfg.max_frames);
   CUDA_TRY(cudaSetDevice(h->device));
   if (!h->d_u8) {
-    CUDA_TRY(cudaMalloc(&h->d_u8, (size_t)h->cfg.max_frames * h->plane));
+    CUDA_TRY(cudaMalloc(&h->d_u8, (size_t)h->cfg.max_frames * h->plane + 64));
     CUDA_TRY(cudaMemsetAsync(h->d_u8, 0, (size_t)h->cfg.max_frames * h->plane, h->stream));
   }
   if (!h->d_f32) {
-    CUDA_TRY(cudaMalloc(&h->d_f32, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane));
+    CUDA_TRY(cudaMalloc(&h->d_f32, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane + 64));
     CUDA_TRY(cudaMemsetAsync(h->d_f32, 0, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane, h->stream));
   }
   int rc = ensure_descriptor_scratch(h);
@@ -720,11 +727,20 @@ int pba_set_points(pba_handle* h, int32_t n_points, const double* xyz, const dou
   if (nnz < 0 || nnz > h->cfg.max_observations) return fail(PBA_ERR_CAPACITY, "pba_set_points: %d observations, capacity %d", nnz, h->cfg.max_observations);
   const int F = h->have_poses || h->have_frames ? h->n_frames : h->cfg.max_frames;
   h->frame_used.assign(h->cfg.max_frames, 0);
+  h->max_obs_frame = -1;
   for (int p = 0; p < n_points; ++p) {
     if (obs_offsets[p + 1] < obs_offsets[p]) return fail(PBA_ERR_ARGUMENT, "pba_set_points: obs_offsets not monotone at %d", p);
+    // one residual block per (point, frame): at most one observation per frame (the kernels hold a point's
+    // observations in per-frame slots)
+    if (obs_offsets[p + 1] - obs_offsets[p] > F)
+      return fail(PBA_ERR_ARGUMENT, "pba_set_points: point %d has %d observations in a window of %d frames", p, obs_offsets[p + 1] - obs_offsets[p], F);
+    unsigned seen = 0;
     for (int o = obs_offsets[p]; o < obs_offsets[p + 1]; ++o) {
       if (obs_frame[o] < 0 || obs_frame[o] >= F) return fail(PBA_ERR_ARGUMENT, "pba_set_points: obs_frame[%d]=%d outside [0,%d)", o, obs_frame[o], F);
+      if (seen & (1u << obs_frame[o])) return fail(PBA_ERR_ARGUMENT, "pba_set_points: point %d observes frame %d more than once", p, obs_frame[o]);
+      seen |= 1u << obs_frame[o];
       h->frame_used[obs_frame[o]] = 1;
+      if (obs_frame[o] > h->max_obs_frame) h->max_obs_frame = obs_frame[o];
     }
   }
   CUDA_TRY(cudaSetDevice(h->device));
@@ -759,6 +775,8 @@ static int check_ready(pba_handle* h, const char* who) {
   if (!h->have_frames) return fail(PBA_ERR_STATE, "%s: frames not set", who);
   if (!h->have_poses) return fail(PBA_ERR_STATE, "%s: poses not set", who);
   if (!h->have_points) return fail(PBA_ERR_STATE, "%s: points not set", who);
+  if (h->max_obs_frame >= h->n_frames)
+    return fail(PBA_ERR_STATE, "%s: an observation refers to frame %d but the window has %d frames (points were set for a wider window)", who, h->max_obs_frame, h->n_frames);
   return PBA_OK;
 }
 
@@ -782,7 +800,7 @@ static StepParams make_step_params(pba_handle* h, const LmState* st) {
 static LmParams make_lm_params(pba_handle* h) {
   LmParams lp;
   memset(&lp, 0, sizeof(lp));
-  lp.trace = h->d_trace; lp.ticket = h->d_ticket;
+  lp.trace = h->d_trace; lp.ticket = h->d_ticket; lp.stamps = h->d_stamps;
   lp.n_frames = h->n_frames; lp.n_points = h->n_points; lp.nnz = h->nnz;
   lp.obs_off = h->d_obs_off; lp.obs_frame = h->d_obs_frame;
   lp.cams = h->d_cams; lp.V = h->d_V; lp.gp = h->d_gp; lp.W = h->d_W;
@@ -947,7 +965,11 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
     h->d_trace = nullptr;
     h->trace_cap = opt.max_num_iterations + 2;
     CUDA_TRY(cudaMalloc(&h->d_trace, sizeof(IterSummary) * h->trace_cap));
+    cudaFree(h->d_stamps);
+    h->d_stamps = nullptr;
+    CUDA_TRY(cudaMalloc(&h->d_stamps, sizeof(unsigned long long) * 2 * (h->trace_cap + 2)));
   }
+  CUDA_TRY(cudaMemsetAsync(h->d_stamps, 0, sizeof(unsigned long long) * 2 * (h->trace_cap + 2), h->stream));
   LmState* s = h->h_state;
   memset(s, 0, sizeof(*s));
   s->max_num_iterations = opt.max_num_iterations; s->max_invalid = opt.max_num_consecutive_invalid_steps;
@@ -1078,6 +1100,14 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   summary->num_evaluations = s->num_evals;
   summary->kernel_launches = launches; summary->num_collectives = h->use_xchg ? s->n_xchg : collectives;
   summary->device_time_in_seconds = ms * 1e-3;
+  {
+    std::vector<unsigned long long> st2(2 * (size_t)(s->num_evals + 1));
+    CUDA_TRY(cudaMemcpy(st2.data(), h->d_stamps, sizeof(unsigned long long) * st2.size(), cudaMemcpyDeviceToHost));
+    double kb = 0.0;
+    for (int i = 0; i < s->num_evals; ++i)
+      if (st2[2 * i] && st2[2 * i + 1] > st2[2 * i]) kb += (double)(st2[2 * i + 1] - st2[2 * i]) * 1e-9;
+    summary->kb_device_time_in_seconds = kb;
+  }
   if (h->use_xchg) {
     int xerr = 0;
     CUDA_TRY(cudaMemcpy(&xerr, h->xc.error, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1117,6 +1147,28 @@ int pba_restore_state(pba_handle* h) {
   return PBA_OK;
 }
 
+int pba_copy_state(pba_handle* dst, pba_handle* src) {
+  if (!dst || !src) return fail(PBA_ERR_ARGUMENT, "pba_copy_state: null handle");
+  if (!src->have_poses || !src->have_points || !dst->have_poses || !dst->have_points)
+    return fail(PBA_ERR_STATE, "pba_copy_state: both handles need poses and points (the copy replaces their values, not their layout)");
+  if (src->n_frames != dst->n_frames || src->n_points != dst->n_points || src->n_points_total != dst->n_points_total)
+    return fail(PBA_ERR_ARGUMENT, "pba_copy_state: %d frames / %d points into %d frames / %d points", src->n_frames, src->n_points, dst->n_frames, dst->n_points);
+  CUDA_TRY(cudaSetDevice(src->device));
+  CUDA_TRY(cudaStreamSynchronize(src->stream));    // the source solve has finished (pba_solve returns synchronised; cheap)
+  CUDA_TRY(cudaSetDevice(dst->device));
+  const size_t cb = sizeof(double) * (size_t)src->n_frames * 6, pb = sizeof(double) * (size_t)src->n_points * 3;
+  if (src->device == dst->device) {
+    CUDA_TRY(cudaMemcpyAsync(dst->d_cams, src->d_cams, cb, cudaMemcpyDeviceToDevice, dst->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst->d_pts, src->d_pts, pb, cudaMemcpyDeviceToDevice, dst->stream));
+  } else {
+    CUDA_TRY(cudaMemcpyPeerAsync(dst->d_cams, dst->device, src->d_cams, src->device, cb, dst->stream));
+    CUDA_TRY(cudaMemcpyPeerAsync(dst->d_pts, dst->device, src->d_pts, src->device, pb, dst->stream));
+  }
+  // buffer 1 of the points mirrors buffer 0 until the first accepted step (as after pba_set_points)
+  CUDA_TRY(cudaMemcpyAsync(dst->d_pts + (size_t)dst->n_points * 3, dst->d_pts, pb, cudaMemcpyDeviceToDevice, dst->stream));
+  return PBA_OK;   // ordered on dst's stream: the next pba_solve(dst) sees it
+}
+
 int pba_get_poses(pba_handle* h, double* cam6) {
   if (!h || !cam6) return fail(PBA_ERR_ARGUMENT, "pba_get_poses: null argument");
   if (!h->have_poses) return fail(PBA_ERR_STATE, "pba_get_poses: poses not set");
@@ -1134,8 +1186,8 @@ int pba_get_points(pba_handle* h, double* xyz) {
     return PBA_OK;
   }
   // gather the shards: every rank broadcasts its block into a full-size device array
-  double* full = nullptr;
-  CUDA_TRY(cudaMalloc(&full, sizeof(double) * (size_t)std::max(1, h->n_points_total) * 3));
+  if (!h->d_pts_full) CUDA_TRY(cudaMalloc(&h->d_pts_full, sizeof(double) * (size_t)h->cfg.max_points * 3));
+  double* full = h->d_pts_full;
   CUDA_TRY(cudaMemcpyAsync(full + (size_t)h->shard_begin[h->rank] * 3, h->d_pts, sizeof(double) * (size_t)h->n_points * 3,
                            cudaMemcpyDeviceToDevice, h->stream));
   NCCL_TRY(g_nccl.GroupStart());
@@ -1146,7 +1198,6 @@ int pba_get_points(pba_handle* h, double* xyz) {
   NCCL_TRY(g_nccl.GroupEnd());
   CUDA_TRY(cudaMemcpyAsync(xyz, full, sizeof(double) * (size_t)h->n_points_total * 3, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  cudaFree(full);
   return PBA_OK;
 }
 

@@ -660,6 +660,7 @@ __device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, in
   for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
     reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&st)[i];
   if (lp.dbg && tid == 0) lp.dbg[4] = gtime();
+  if (lp.stamps && tid == 0) lp.stamps[2 * (st.num_evals - 1) + 1] = globaltimer_ns();
 }
 
 // LPP: lanes per point in the elimination (8: windows of <= 8 frames; 16 otherwise); TPW: 8x8 tiles of the
@@ -689,6 +690,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
   // accumulators (single-GPU / NCCL path) and both buffers of the cameras (which one is the candidate is
   // only known once the state has arrived) - three dependent L2 round trips otherwise.
   if (lp.pdl) pdl_wait();   // K_A has finished (everything above is independent of it)
+  const unsigned long long t_entry = globaltimer_ns();
   const int xn = F * kUStride + kEacc + kMaxRanks;
   constexpr int kXPre = (kMaxFrames * kUStride + kEacc + kMaxRanks + kSchurThreads - 1) / kSchurThreads;
   double x_pre[kXPre];
@@ -724,6 +726,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
     }
     return;
   }
+  if (lp.stamps && blockIdx.x == 0 && tid == 0) lp.stamps[2 * s_st.num_evals] = t_entry;
   take_decision(s_st, s_xs, s_cams, F, s_it, s_push, s_it0);
   if (blockIdx.x == 0 && tid == 0 && s_push) lp.trace[s_st.n_trace - 1] = s_it;
   if (s_st.done) {
@@ -801,6 +804,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
     if (p < lp.n_points && p < (blockIdx.x + 1) * per_cta) { pre_o0 = __ldg(lp.obs_off + p); pre_o1 = __ldg(lp.obs_off + p + 1); }
   }
   if (lp.pdl) pdl_wait();
+  const unsigned long long t_entry = globaltimer_ns();
   const int xn = F * kUStride + kEacc + kMaxRanks;
   for (int i = tid; i < xn; i += blockDim.x) s_xs[i] = __ldcg(lp.Xacc + i);
   for (int i = tid; i < F * 6; i += blockDim.x) { s_cams[i] = lp.cams[i]; s_cams[kMaxD + i] = lp.cams[(size_t)F * 6 + i]; }
@@ -808,6 +812,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
     reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_in)[i];
   if (tid == 0) s_xok = 1;
   __syncthreads();
+  if (lp.stamps && !s_st.done && blockIdx.x == 0 && tid == 0) lp.stamps[2 * s_st.num_evals] = t_entry;
   if (s_st.done) {   // the state is replicated: every rank leaves here together
     if (blockIdx.x == 0) {
       for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)

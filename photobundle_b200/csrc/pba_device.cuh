@@ -159,6 +159,7 @@ struct LmParams {
   size_t s_cap;
   double* Vinv2;             // multi-GPU: [2][n][6], (Vs + D²)^-1 under hypothesis A / R
   unsigned long long* dbg;   // optional: globaltimer stamps of the last CTA {start, decided, schur done, solved, end}
+  unsigned long long* stamps;// [capacity][2]: globaltimer at the start / end of the K_B launch that takes decision number num_evals
   unsigned long long cond;   // non-zero: cudaGraphConditionalHandle of the device-side LM loop, cleared when done
   Xchg xc;                   // multi-GPU exchange over peer memory (xc.n_ranks > 1), else split/NCCL or single GPU
   int pdl;                   // launched with programmatic stream serialization (see pdl_wait)

@@ -3,7 +3,8 @@ import sys, time
 import numpy as np
 import torch
 sys.path.insert(0, ".")
-from photobundle_b200 import capi, synthetic
+from photobundle_b200 import capi
+from workloads import synthetic
 w = synthetic.make_window()
 h = capi.Handle.for_window(w)
 pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()

@@ -1,7 +1,8 @@
 import sys
 import numpy as np
 sys.path.insert(0, ".")
-from photobundle_b200 import host_capi, synthetic
+from photobundle_b200 import host_capi
+from workloads import synthetic
 seq = synthetic.make_sequence(n_frames=10)
 rows, cols = seq.images.shape[1:]
 n = seq.images.shape[0]

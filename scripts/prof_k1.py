@@ -2,7 +2,8 @@
 import sys
 import numpy as np
 sys.path.insert(0, ".")
-from photobundle_b200 import capi, synthetic
+from photobundle_b200 import capi
+from workloads import synthetic
 import os
 img = "/tmp/cfg3_images.npy"
 w = synthetic.make_window(images=np.load(img) if os.path.exists(img) else None)

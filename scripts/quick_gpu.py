@@ -3,8 +3,8 @@ import sys, time
 import numpy as np
 sys.path.insert(0, ".")
 from oracle import binding as ob
-from photobundle_b200 import capi, synthetic
-
+from photobundle_b200 import capi
+from workloads import synthetic
 w = synthetic.make_window()
 ow = ob.OracleWindow(w)
 h = capi.Handle.for_window(w)

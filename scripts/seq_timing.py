@@ -2,7 +2,8 @@
 import sys, time
 import numpy as np
 sys.path.insert(0, ".")
-from photobundle_b200 import host_capi, synthetic
+from photobundle_b200 import host_capi
+from workloads import synthetic
 seq = synthetic.make_sequence(n_frames=12, rows=376, cols=1241, intrinsics=(718.856, 718.856, 607.1928, 185.2157))
 rows, cols = seq.images.shape[1:]
 for gpu in (0, 1):

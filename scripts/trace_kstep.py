@@ -2,7 +2,8 @@
 import ctypes as C, sys
 import numpy as np
 sys.path.insert(0, ".")
-from photobundle_b200 import capi, synthetic
+from photobundle_b200 import capi
+from workloads import synthetic
 w = synthetic.make_window()
 h = capi.Handle.for_window(w)
 for _ in range(3): h.eval(want_residuals=False)

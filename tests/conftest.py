@@ -16,18 +16,18 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def small_win():
-    from photobundle_b200 import synthetic
+    from workloads import synthetic
     return synthetic.small_window()
 
 
 @pytest.fixture(scope="session")
 def small_ragged_win():
-    from photobundle_b200 import synthetic
+    from workloads import synthetic
     return synthetic.small_window(seed=11, ragged=True, n_frames=8, grid=(10, 14))
 
 
 @pytest.fixture(scope="session")
 def cfg3_win():
     """BASELINE cfg2/3: 8 frames x 4000 points x 5x5 at KITTI size (~2.5 s to render)."""
-    from photobundle_b200 import synthetic
+    from workloads import synthetic
     return synthetic.make_window()

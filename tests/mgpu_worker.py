@@ -10,7 +10,8 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from photobundle_b200 import capi, synthetic  # noqa: E402
+from photobundle_b200 import capi  # noqa: E402
+from workloads import synthetic  # noqa: E402
 
 
 def main():

@@ -13,9 +13,8 @@ import pytest
 
 from conftest import GOLDEN
 from oracle import binding as ob
-from photobundle_b200 import capi, synthetic
-
-
+from photobundle_b200 import capi
+from workloads import synthetic
 def _golden():
     return np.load(os.path.join(GOLDEN, "bitplanes_ref.npz"))
 

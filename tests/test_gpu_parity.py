@@ -12,8 +12,8 @@ import numpy as np
 import pytest
 
 from oracle import binding as ob
-from photobundle_b200 import capi, synthetic
-
+from photobundle_b200 import capi
+from workloads import synthetic
 pytestmark = pytest.mark.gpu
 
 

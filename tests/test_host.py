@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from conftest import ROOT
-from photobundle_b200 import host_capi, synthetic
+from photobundle_b200 import host_capi
+from workloads import synthetic
 from ref_addframe import RefFrontEnd
 
 

@@ -12,9 +12,8 @@ import numpy as np
 import pytest
 
 from conftest import ROOT
-from photobundle_b200 import capi, synthetic
-
-
+from photobundle_b200 import capi
+from workloads import synthetic
 def test_shard_range_partitions_and_balances(small_ragged_win):
     off = small_ragged_win.obs_offsets
     n = off.shape[0] - 1

@@ -15,9 +15,7 @@ import pytest
 
 from conftest import GOLDEN
 from oracle import binding
-from photobundle_b200 import synthetic
-
-
+from workloads import synthetic
 def _sample(I, gx, gy, y, x):
     out = np.zeros(3, dtype=np.float32)
     rows, cols = I.shape

@@ -1,12 +1,12 @@
 """Pyramid support (BASELINE config 4): the pyrDown rule and coarse-to-fine solves.
 The reference's own pyramid class is unfinished and unused; the level
-semantics are the builder's (photobundle_b200/synthetic.py), the image reduction is cv::pyrDown."""
+semantics are the builder's (workloads/synthetic.py), the image reduction is cv::pyrDown."""
 import numpy as np
 import pytest
 
-from photobundle_b200 import capi, synthetic
+from photobundle_b200 import capi
 
-
+from workloads import synthetic
 def test_pyrdown_restatement_matches_opencv():
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(4)
