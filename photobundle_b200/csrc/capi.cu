@@ -1001,7 +1001,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   LmParams lp = make_lm_params(h);
   const bool timeline = getenv("PBA_DEBUG_TIMELINE") != nullptr;
   if (timeline && !h->d_dbg) CUDA_TRY(cudaMalloc(&h->d_dbg, sizeof(unsigned long long) * 16 * 1024));
-  const int sgrid = schur_grid(h->n_points, h->sm_count);
+  const int sgrid = h->use_xchg ? schur_grid_x(h->n_points, h->sm_count) : schur_grid(h->n_points, h->sm_count);
   int launches = 0;
   if (h->use_xchg) {   // align the ranks before the clock starts (device-side barrier over peer memory)
     CUDA_TRY(launch_rendezvous(h->xc, s->xepoch, h->stream));

@@ -458,17 +458,18 @@ __shared__ unsigned long long s_tdbg[4];   // PBA_DEBUG_TIMELINE: elimination su
 // cur / radius: the buffer holding the blocks to eliminate and the trust-region radius to damp them with (the
 // accepted point after a decision — or a HYPOTHESIS about the decision, multi-GPU path); first: this is the first
 // elimination of the solve (forms the Jacobi scaling of the points); S_dst / Vinv_dst: where P and (Vs + D²)^-1 go.
+// bidx / nblk: this CTA's index among the nblk CTAs that share the elimination (the multi-GPU kernel runs two groups).
 template <int LPP, int TPW>
 __device__ void eliminate(const LmParams& lp, const LmState& st, double* Zt, int pre_o0, int pre_o1, int cur, double radius,
-                          bool first, double* S_dst, double* Vinv_dst) {
+                          bool first, double* S_dst, double* Vinv_dst, int bidx, int nblk) {
   constexpr int PPW = 32 / LPP, PPB = kSchurWarps * PPW, K = 3 * PPB, LD = K + 4;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = lp.n_points, N = 6 * st.n_free, NS = reduced_ld(N);
   const int Dp = (N + 8) & ~7, T = Dp >> 3, n_tiles = T * (T + 1) / 2;
   const double dmin = st.min_diag, dmax = st.max_diag;
   // this CTA's contiguous block of points
-  const int per_cta = (n + gridDim.x - 1) / gridDim.x;
-  const int p_begin = blockIdx.x * per_cta, p_end = min(n, p_begin + per_cta);
+  const int per_cta = (n + nblk - 1) / nblk;
+  const int p_begin = bidx * per_cta, p_end = min(n, p_begin + per_cta);
   // this warp's output tiles (tr <= tc): shared-memory row offsets of the A and B fragments
   int offa[TPW], offb[TPW];
   unsigned tile_rc[TPW];
@@ -740,7 +741,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
 
   const unsigned long long t_dec = lp.dbg ? gtime() : 0ull;
   // ---- (E) eliminate the point blocks -----------------------------------------------------
-  eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, s_st.cur, s_st.radius, s_st.iteration == 1, lp.S, lp.Vinv);
+  eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, s_st.cur, s_st.radius, s_st.iteration == 1, lp.S, lp.Vinv, blockIdx.x, gridDim.x);
 
   // ---- (S) the last CTA solves the reduced camera system -------------------------------------
   // bar.sync orders the CTA's atomics before thread 0's cumulative gpu-scope fence + ticket
@@ -797,11 +798,14 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int F = lp.n_frames, nr = lp.xc.n_ranks;
   const unsigned long long t_start = lp.dbg ? gtime() : 0ull;
+  // two groups of G = gridDim.x / 2 CTAs: group 0 eliminates under hypothesis A, group 1 under hypothesis R, each
+  // over the same blocks of points
+  const int G = gridDim.x >> 1, hyp = blockIdx.x >= G ? 1 : 0, bidx = blockIdx.x - hyp * G;
   int pre_o0 = 0, pre_o1 = 0;
-  const int per_cta = (lp.n_points + gridDim.x - 1) / gridDim.x;
+  const int per_cta = (lp.n_points + G - 1) / G;
   {
-    const int p = blockIdx.x * per_cta + warp * (32 / LPP) + lane / LPP;
-    if (p < lp.n_points && p < (blockIdx.x + 1) * per_cta) { pre_o0 = __ldg(lp.obs_off + p); pre_o1 = __ldg(lp.obs_off + p + 1); }
+    const int p = bidx * per_cta + warp * (32 / LPP) + lane / LPP;
+    if (p < lp.n_points && p < (bidx + 1) * per_cta) { pre_o0 = __ldg(lp.obs_off + p); pre_o1 = __ldg(lp.obs_off + p + 1); }
   }
   if (lp.pdl) pdl_wait();
   const unsigned long long t_entry = globaltimer_ns();
@@ -824,6 +828,16 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
   const unsigned long long e = s_st.xepoch;
   const bool it0 = s_st.iteration == 0;
   const int N = 6 * s_st.n_free, NS = reduced_ld(N), NC = N + 1, NN = N * NC;
+  // the entries of the reduced system that travel: r <= c <= N (upper triangle + rhs column), as a flat list so
+  // that the push / sum loops keep several independent loads in flight per thread
+  constexpr int kXB = 4;
+  __shared__ unsigned short s_ent[kMaxD * (kMaxD + 3) / 2];
+  const int n_ent = N * (N + 3) / 2;
+  for (int r = tid; r < N; r += blockDim.x) {
+    int k = r * NC - r * (r - 1) / 2;          // entries of the rows above: sum_{i<r} (N + 1 - i)
+    for (int c = r; c <= N; ++c) s_ent[k++] = (unsigned short)((r << 8) | c);
+  }
+  __syncthreads();
   double* S_A = lp.S;
   double* S_R = lp.S + lp.s_cap;
   double* S_M = lp.S + 2 * lp.s_cap;
@@ -834,9 +848,8 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
   const double rad_R = s_st.radius / s_st.decrease_factor;
   const int buf_A = s_st.eval_buf, buf_R = s_st.cur;
   if (!it0) {
-    eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, buf_A, rad_A, false, S_A, Vinv_A);
-    __syncthreads();
-    eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, buf_R, rad_R, false, S_R, Vinv_R);
+    if (hyp == 0) eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, buf_A, rad_A, false, S_A, Vinv_A, bidx, G);
+    else eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, buf_R, rad_R, false, S_R, Vinv_R, bidx, G);
   }
   // ---- ticket 1: the last CTA exchanges, decides; the others wait for its verdict ------------------------
   __syncthreads();
@@ -846,7 +859,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
     __threadfence();
   }
   __syncthreads();
-  const int p_begin = blockIdx.x * per_cta, p_end = min(lp.n_points, p_begin + per_cta);
+  const int p_begin = bidx * per_cta, p_end = min(lp.n_points, p_begin + per_cta);
   bool redo = false;
   if (!s_last) {
     if (tid == 0) {
@@ -860,32 +873,48 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
     }
     __syncthreads();
     const int code = s_code;
-    if (code == kXHitA || code == kXHitR) {   // adopt (Vs + D²)^-1 of the outcome that came true for this CTA's points
-      const double* src = (code == kXHitA ? Vinv_A : Vinv_R);
-      for (int i = p_begin * 6 + tid; i < p_end * 6; i += blockDim.x) lp.Vinv[i] = __ldcg(src + i);
+    if (code == kXHitA || code == kXHitR) {   // adopt (Vs + D²)^-1 of the outcome that came true (the group that formed it)
+      if ((code == kXHitA) == (hyp == 0)) {
+        const double* src = (code == kXHitA ? Vinv_A : Vinv_R);
+        for (int i = p_begin * 6 + tid; i < p_end * 6; i += blockDim.x) lp.Vinv[i] = __ldcg(src + i);
+      }
       return;
     }
-    if (code != kXRedo) return;
+    if (code != kXRedo || hyp != 0) return;   // the second elimination is group 0's
     for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
       reinterpret_cast<int*>(&s_st)[i] = __ldcg(reinterpret_cast<const int*>(lp.st_out) + i);
     __syncthreads();
     redo = true;
   } else {
     if (lp.dbg && tid == 0) { lp.dbg[0] = t_start; lp.dbg[1] = gtime(); }
-    // push: evaluation part, then both hypotheses (local accumulators are re-zeroed on the way)
+    // push: evaluation part, then both hypotheses (local accumulators are re-zeroed on the way); kXB entries per
+    // thread in flight
     const size_t slot1 = ((size_t)(e & 1ull) * nr + lp.xc.rank) * lp.xc.x1_n;
     for (int i = tid; i < xn; i += blockDim.x)
       for (int q = 0; q < nr; ++q) ll_store(lp.xc.x1[q] + slot1 + i, s_xs[i], e);
     if (!it0) {
-      for (int r = tid >> 4; r < N; r += 16)
-        for (int c = r + (tid & 15); c <= N; c += 16) {
-          const double a = __ldcg(S_A + r * NS + c), b = __ldcg(S_R + r * NS + c);
-          S_A[r * NS + c] = 0.0; S_R[r * NS + c] = 0.0;
-          for (int q = 0; q < nr; ++q) {
-            ll_store(lp.xc.x1[q] + slot1 + xn + r * NC + c, a, e);
-            ll_store(lp.xc.x1[q] + slot1 + xn + NN + r * NC + c, b, e);
+      for (int k0 = tid; k0 < n_ent; k0 += kXB * blockDim.x) {
+        double a[kXB], b[kXB];
+        int rc[kXB];
+#pragma unroll
+        for (int u = 0; u < kXB; ++u) {
+          const int k = k0 + u * blockDim.x;
+          rc[u] = k < n_ent ? s_ent[k] : -1;
+          a[u] = rc[u] >= 0 ? __ldcg(S_A + (rc[u] >> 8) * NS + (rc[u] & 255)) : 0.0;
+          b[u] = rc[u] >= 0 ? __ldcg(S_R + (rc[u] >> 8) * NS + (rc[u] & 255)) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kXB; ++u) {
+          if (rc[u] >= 0) {
+            const int r = rc[u] >> 8, c = rc[u] & 255;
+            S_A[r * NS + c] = 0.0; S_R[r * NS + c] = 0.0;
+            for (int q = 0; q < nr; ++q) {
+              ll_store(lp.xc.x1[q] + slot1 + xn + r * NC + c, a[u], e);
+              ll_store(lp.xc.x1[q] + slot1 + xn + NN + r * NC + c, b[u], e);
+            }
           }
         }
+      }
     }
     if (lp.dbg && tid == 0) lp.dbg[8] = gtime();
     // sum everybody's evaluation part in rank order, decide
@@ -931,26 +960,29 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
     const bool hitR = !it0 && !s_st.took_step && s_st.radius == rad_R;
     if (hitA || hitR) {
       if (tid == 0) st_release_sys(lp.xc.verdict, (e << 3) | (hitA ? kXHitA : kXHitR));
-      // -P of the outcome that came true: the rank-ordered sum goes straight into the solver's matrix
+      // -P of the outcome that came true: the rank-ordered sum goes straight into the solver's matrix (entries
+      // outside the upper triangle keep whatever the staging left there: they never reach a valid entry)
       double* Ut = sm;
-      for (int i = tid; i < (N + 8) * NS; i += blockDim.x) Ut[i] = 0.0;
-      __syncthreads();
       const size_t hoff = xn + (hitA ? 0 : NN);
-      for (int r = tid >> 4; r < N; r += 16)
-        for (int c = r + (tid & 15); c <= N; c += 16) {
-          double v;
-          if (!ll_sum(in1, lp.xc.x1_n, nr, hoff + r * NC + c, e, v)) s_xok = 0;
-          Ut[r * NS + c] = -v;
-        }
-      {
-        const double* src = hitA ? Vinv_A : Vinv_R;
-        for (int i = p_begin * 6 + tid; i < p_end * 6; i += blockDim.x) lp.Vinv[i] = __ldcg(src + i);
+      for (int k0 = tid; k0 < n_ent; k0 += 2 * blockDim.x) {      // two entries (2 x n_ranks loads) in flight per thread
+        const int k1 = k0 + blockDim.x;
+        const int rc0 = s_ent[k0], rc1 = k1 < n_ent ? s_ent[k1] : rc0;
+        double v0, v1;
+        const bool ok0 = ll_sum(in1, lp.xc.x1_n, nr, hoff + (rc0 >> 8) * NC + (rc0 & 255), e, v0);
+        const bool ok1 = ll_sum(in1, lp.xc.x1_n, nr, hoff + (rc1 >> 8) * NC + (rc1 & 255), e, v1);
+        if (!ok0 || !ok1) s_xok = 0;
+        Ut[(rc0 >> 8) * NS + (rc0 & 255)] = -v0;
+        if (k1 < n_ent) Ut[(rc1 >> 8) * NS + (rc1 & 255)] = -v1;
       }
       if (tid == 0) { s_st.xepoch = e + 1; s_st.n_xchg += 1; if (lp.dbg) { lp.dbg[2] = gtime(); lp.dbg[10] = hitA ? 1 : 2; } }
       __syncthreads();
       if (!s_xok && tid == 0) *lp.xc.error = 1;
       if (lp.pdl) pdl_launch_dependents();
       finish_iteration<TPW>(lp, s_st, sm, F, s_xs, s_cams, true);
+      if (hitA == (hyp == 0)) {   // this CTA's own share of (Vs + D²)^-1, off the critical path
+        const double* src = hitA ? Vinv_A : Vinv_R;
+        for (int i = p_begin * 6 + tid; i < p_end * 6; i += blockDim.x) lp.Vinv[i] = __ldcg(src + i);
+      }
       return;
     }
     // neither outcome holds (iteration 0: the Jacobi scaling needs the global pose blocks first; or an accepted
@@ -960,38 +992,53 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
       reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
     __syncthreads();
     if (tid == 0) { __threadfence(); st_release_sys(lp.xc.verdict, (e << 3) | kXRedo); }
-    redo = true;
+    redo = hyp == 0;   // the deciding CTA takes part in the second elimination only if it belongs to group 0
+    if (!redo) return;
   }
   if (!redo) return;
   // ---- second elimination with the decided radius, second exchange ---------------------------------------
-  eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, s_st.cur, s_st.radius, s_st.iteration == 1, S_M, lp.Vinv);
+  eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, s_st.cur, s_st.radius, s_st.iteration == 1, S_M, lp.Vinv, bidx, G);
   __syncthreads();
   if (tid == 0) {
     __threadfence();
-    s_last = (atomicAdd(lp.ticket, 1u) == 2 * gridDim.x - 1) ? 1 : 0;
+    s_last = (atomicAdd(lp.ticket, 1u) == gridDim.x + G - 1) ? 1 : 0;   // ticket 1 counted every CTA, ticket 2 counts group 0
     __threadfence();
   }
   __syncthreads();
   if (!s_last) return;
   {
     const size_t slot2 = ((size_t)(e & 1ull) * nr + lp.xc.rank) * lp.xc.x2_n;
-    for (int r = tid >> 4; r < N; r += 16)
-      for (int c = r + (tid & 15); c <= N; c += 16) {
-        const double a = __ldcg(S_M + r * NS + c);
-        S_M[r * NS + c] = 0.0;
-        for (int q = 0; q < nr; ++q) ll_store(lp.xc.x2[q] + slot2 + r * NC + c, a, e);
+    for (int k0 = tid; k0 < n_ent; k0 += kXB * blockDim.x) {
+      double a[kXB];
+      int rc[kXB];
+#pragma unroll
+      for (int u = 0; u < kXB; ++u) {
+        const int k = k0 + u * blockDim.x;
+        rc[u] = k < n_ent ? s_ent[k] : -1;
+        a[u] = rc[u] >= 0 ? __ldcg(S_M + (rc[u] >> 8) * NS + (rc[u] & 255)) : 0.0;
       }
+#pragma unroll
+      for (int u = 0; u < kXB; ++u) {
+        if (rc[u] >= 0) {
+          const int r = rc[u] >> 8, c = rc[u] & 255;
+          S_M[r * NS + c] = 0.0;
+          for (int q = 0; q < nr; ++q) ll_store(lp.xc.x2[q] + slot2 + r * NC + c, a[u], e);
+        }
+      }
+    }
     const ulonglong2* in2 = lp.xc.x2[lp.xc.rank] + (size_t)(e & 1ull) * nr * lp.xc.x2_n;
     double* Ut = sm;
     __syncthreads();
-    for (int i = tid; i < (N + 8) * NS; i += blockDim.x) Ut[i] = 0.0;
-    __syncthreads();
-    for (int r = tid >> 4; r < N; r += 16)
-      for (int c = r + (tid & 15); c <= N; c += 16) {
-        double v;
-        if (!ll_sum(in2, lp.xc.x2_n, nr, (size_t)r * NC + c, e, v)) s_xok = 0;
-        Ut[r * NS + c] = -v;
-      }
+    for (int k0 = tid; k0 < n_ent; k0 += 2 * blockDim.x) {
+      const int k1 = k0 + blockDim.x;
+      const int rc0 = s_ent[k0], rc1 = k1 < n_ent ? s_ent[k1] : rc0;
+      double v0, v1;
+      const bool ok0 = ll_sum(in2, lp.xc.x2_n, nr, (size_t)(rc0 >> 8) * NC + (rc0 & 255), e, v0);
+      const bool ok1 = ll_sum(in2, lp.xc.x2_n, nr, (size_t)(rc1 >> 8) * NC + (rc1 & 255), e, v1);
+      if (!ok0 || !ok1) s_xok = 0;
+      Ut[(rc0 >> 8) * NS + (rc0 & 255)] = -v0;
+      if (k1 < n_ent) Ut[(rc1 >> 8) * NS + (rc1 & 255)] = -v1;
+    }
     if (tid == 0) { s_st.xepoch = e + 1; s_st.n_xchg += 2; s_st.n_respec += 1; if (lp.dbg) { lp.dbg[2] = gtime(); lp.dbg[10] = 0; } }
     __syncthreads();
     if (!s_xok && tid == 0) *lp.xc.error = 1;
@@ -1030,14 +1077,16 @@ cudaError_t launch_rendezvous(const Xchg& xc, unsigned long long epoch, cudaStre
 }
 
 // ---- launchers ----------------------------------------------------------------------------
-// One contiguous block of points per CTA (at least 8, so that tiny windows do not pay one round of
-// atomics per point), at most one CTA per SM.
+// One contiguous block of points per CTA (at least 32 = a full elimination batch for windows of <= 8 frames, so that
+// small windows do not pay one round of atomics per handful of points), at most one CTA per SM.
 int schur_grid(int n_points, int sm_count) {
   int per_cta = (n_points + sm_count - 1) / sm_count;
-  if (per_cta < 8) per_cta = 8;
+  if (per_cta < 32) per_cta = 32;   // a full batch of the elimination: fewer CTAs, fewer rounds of atomics
   const int g = (n_points + per_cta - 1) / per_cta;
   return g > 0 ? g : 1;
 }
+
+int schur_grid_x(int n_points, int sm_count) { return 2 * schur_grid(n_points, sm_count / 2); }
 
 static size_t solve_smem_doubles(int n_free, int F) {
   const size_t N = 6 * (size_t)n_free, ld = reduced_ld((int)N), npad = (N + 1) & ~(size_t)1;
@@ -1085,7 +1134,8 @@ static cudaError_t launch_mode_x(const LmParams& lp, int grid, int n_free, cudaS
   const int N = 6 * n_free, Dp = (N + 8) & ~7;
   const size_t elim_d = (size_t)Dp * LD, solve_d = solve_smem_doubles(n_free, lp.n_frames);
   const size_t smem = sizeof(double) * (elim_d > solve_d ? elim_d : solve_d);
-  // every CTA must be resident at once (the CTAs wait for the deciding CTA's verdict): one CTA per SM, grid <= SMs
+  // every CTA must be resident at once (the CTAs wait for the deciding CTA's verdict): one CTA per SM, grid <= SMs;
+  // `grid` = 2 G, two groups of G CTAs (schur_grid_x)
   if (lp.pdl) {
     cudaLaunchConfig_t cfg2 = {};
     cfg2.gridDim = dim3(grid); cfg2.blockDim = dim3(kSchurThreads); cfg2.dynamicSmemBytes = smem; cfg2.stream = s;

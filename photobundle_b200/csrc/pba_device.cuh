@@ -227,6 +227,7 @@ __host__ __device__ constexpr size_t reduced_capacity(int max_frames) { return (
 // launchers
 cudaError_t launch_k_step(const StepParams& prm, int radius, cudaStream_t stream);
 int schur_grid(int n_points, int sm_count);
+int schur_grid_x(int n_points, int sm_count);   // multi-GPU kernel: two groups of CTAs (one per hypothesis), all resident at once
 cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t stream);   // lp.xc.n_ranks > 1: the multi-GPU kernel
 cudaError_t launch_solve_only(const LmParams& lp, int n_free, cudaStream_t stream);   // split mode, after the all-reduce of S
 cudaError_t launch_rendezvous(const Xchg& xc, unsigned long long epoch, cudaStream_t stream);   // device-side barrier across the ranks
