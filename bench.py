@@ -369,12 +369,12 @@ def main():
     d2h = cams0.nbytes + pts0.nbytes
 
     def e2e_step():
+        h.begin_batch()           # uploads are enqueued; the (pinned) host buffers stay alive until solve() returns
         h.set_frames_u8(images)
         h.set_poses(cams0, win.fixed_frame)
         h.set_points(pts0, desc, obs_off, obs_frame, weights)
         s = h.solve()
-        h.get_poses()
-        h.get_points()
+        h.get_results()           # poses + points, one synchronisation
         return s
 
     for _ in range(2):

@@ -199,6 +199,19 @@ int pba_restore_state(pba_handle* h);
  * trip.  Ordered on dst's stream. */
 int pba_copy_state(pba_handle* dst, pba_handle* src);
 
+/* Uploads without a host round trip per call.  Between pba_begin_batch() and the next pba_solve() (or pba_end_batch())
+ * the pba_set_* calls only ENQUEUE their host->device copies; the caller keeps every buffer it passed alive and
+ * unchanged until that pba_solve() / pba_end_batch() returns (at most one pba_set_points per batch).  A sliding window
+ * changes one frame per solve: pba_set_frame_u8_ex() replaces the frame in `slot` of a window set earlier - the level-0
+ * uint8 image is reduced `levels_down` times on the device (cv::pyrDown rule) and / or expanded into the channels of
+ * `descriptor_type`.  pba_get_results() reads poses and points back with one synchronisation.
+ * (what the reference does per frame: DescriptorFrame::Create + ring buffer push, src/photobundle.cc:495, :608) */
+int pba_begin_batch(pba_handle* h);
+int pba_end_batch(pba_handle* h);
+int pba_set_frame_u8_ex(pba_handle* h, int32_t slot, const uint8_t* image, int32_t src_rows, int32_t src_cols, int32_t levels_down,
+                        int32_t descriptor_type);
+int pba_get_results(pba_handle* h, double* cam6, double* xyz);
+
 int pba_get_poses(pba_handle* h, double* cam6);
 int pba_get_points(pba_handle* h, double* xyz);
 int pba_get_iterations(pba_handle* h, pba_iteration_summary* out, int32_t capacity, int32_t* n);

@@ -21,7 +21,7 @@ PBA_UNIQUE_ID_BYTES = 128
 EXPORTED_SYMBOLS = [
     "pba_last_error", "pba_version", "pba_default_solver_options", "pba_create", "pba_destroy",
     "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_frames_u8_pyr", "pba_pyrdown_u8", "pba_set_poses", "pba_set_points",
-    "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_copy_state", "pba_get_poses", "pba_get_points", "pba_get_iterations",
+    "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_copy_state", "pba_begin_batch", "pba_end_batch", "pba_set_frame_u8_ex", "pba_get_results", "pba_get_poses", "pba_get_points", "pba_get_iterations",
     "pba_comm_unique_id", "pba_comm_init", "pba_shard_range", "pba_comm_exchange_kind",
     "pba_descriptor_channels", "pba_set_frames_u8_descriptor", "pba_get_channel_plane", "pba_prepare_frame_u8",
     "pba_saliency_map", "pba_extract_descriptors", "pba_associate", "pba_select_candidates",
@@ -160,6 +160,7 @@ class Handle:
         images = np.ascontiguousarray(images, dtype=np.uint8)
         F = images.shape[0]
         arr = (C.c_void_p * F)(*[images[f].ctypes.data for f in range(F)])
+        getattr(self, "_batch_keepalive", []).append(images)    # batch mode: the copy is still in flight when we return
         _check(lib().pba_set_frames_u8(self._h, F, arr), "pba_set_frames_u8")
         self.n_frames = F
 
@@ -214,8 +215,34 @@ class Handle:
         _check(lib().pba_extract_descriptors(self._h, xy.shape[0], _ptr(xy), _ptr(out)), "pba_extract_descriptors")
         return out
 
+    def associate(self, xyz, ref_patch, ref_norm, T_c, K, border: int):
+        """addFrame's data association on the frame of prepare_frame_u8: (score [n], row_col [n, 2]); score -2 = not tested."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        n = xyz.shape[0]
+        ref_patch = np.ascontiguousarray(ref_patch, dtype=np.float32).reshape(n, 25)
+        ref_norm = np.ascontiguousarray(ref_norm, dtype=np.float32).reshape(n)
+        Tc = np.ascontiguousarray(np.asarray(T_c, dtype=np.float64).T)   # column-major 4x4
+        Kr = np.ascontiguousarray(K, dtype=np.float64)                   # row-major 3x3
+        score, rc = np.zeros(n, dtype=np.float32), np.zeros((n, 2), dtype=np.int32)
+        _check(lib().pba_associate(self._h, n, _ptr(xyz), _ptr(ref_patch), _ptr(ref_norm), _ptr(Tc), _ptr(Kr), int(border),
+                                   _ptr(score), _ptr(rc)), "pba_associate")
+        return score, rc
+
+    def select_candidates(self, depth, masked_rc, mask_radius: int, nms_radius: int, border: int, min_depth: float, max_depth: float,
+                          capacity: int = 1 << 20):
+        """New-point candidates of addFrame on the frame of prepare_frame_u8: (row_col [m, 2] in scan order, saliency [m])."""
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        masked = np.ascontiguousarray(masked_rc, dtype=np.int32).reshape(-1, 2)
+        rc, sal, n_out = np.zeros((capacity, 2), dtype=np.int32), np.zeros(capacity, dtype=np.float32), C.c_int32()
+        _check(lib().pba_select_candidates(self._h, _ptr(depth), masked.shape[0], _ptr(masked), int(mask_radius), int(nms_radius), int(border),
+                                           C.c_double(min_depth), C.c_double(max_depth), capacity, _ptr(rc), _ptr(sal), C.byref(n_out)),
+               "pba_select_candidates")
+        assert n_out.value <= capacity
+        return rc[:n_out.value], sal[:n_out.value]
+
     def set_poses(self, cams: np.ndarray, fixed_frame: int = 0):
         cams = np.ascontiguousarray(cams, dtype=np.float64)
+        getattr(self, "_batch_keepalive", []).append(cams)
         _check(lib().pba_set_poses(self._h, cams.shape[0], _ptr(cams), int(fixed_frame)), "pba_set_poses")
         self.n_frames = cams.shape[0]
 
@@ -227,6 +254,7 @@ class Handle:
         weights = np.ascontiguousarray(weights, dtype=np.float64)
         n = xyz.shape[0]
         assert desc.shape == (n, self.CP) and obs_offsets.shape == (n + 1,) and weights.shape == (self.P,)
+        getattr(self, "_batch_keepalive", []).extend([xyz, desc, obs_offsets, obs_frame, weights])
         _check(lib().pba_set_points(self._h, n, _ptr(xyz), _ptr(desc), _ptr(obs_offsets), _ptr(obs_frame),
                                     _ptr(weights)), "pba_set_points")
         self.n_points = n
@@ -270,6 +298,26 @@ class Handle:
 
     def restore_state(self):
         _check(lib().pba_restore_state(self._h), "pba_restore_state")
+
+    def begin_batch(self):
+        """Uploads until the next solve() only enqueue their copies (the arrays passed must stay alive until then)."""
+        _check(lib().pba_begin_batch(self._h), "pba_begin_batch")
+        self._batch_keepalive = []
+
+    def end_batch(self):
+        _check(lib().pba_end_batch(self._h), "pba_end_batch")
+        self._batch_keepalive = []
+
+    def set_frame_u8_ex(self, slot: int, image: np.ndarray, levels_down: int = 0, descriptor_type: int = 0):
+        img = np.ascontiguousarray(image, dtype=np.uint8)
+        getattr(self, "_batch_keepalive", []).append(img)
+        _check(lib().pba_set_frame_u8_ex(self._h, int(slot), _ptr(img), img.shape[0], img.shape[1], int(levels_down), int(descriptor_type)),
+               "pba_set_frame_u8_ex")
+
+    def get_results(self):
+        cams, pts = np.zeros((self.n_frames, 6)), np.zeros((self.n_points, 3))
+        _check(lib().pba_get_results(self._h, _ptr(cams), _ptr(pts)), "pba_get_results")
+        return cams, pts
 
     def copy_state_from(self, src: "Handle"):
         """Poses and points of `src` (same window at another pyramid level) become this handle's, on the device."""

@@ -121,6 +121,7 @@ struct pba_handle {
   uint8_t* d_pyr_scratch = nullptr;  size_t pyr_scratch_bytes = 0;   // pba_set_frames_u8_pyr ping-pong planes
   double* d_pts_full = nullptr;      // multi-GPU: all shards gathered (pba_get_points)
   bool have_saved = false;
+  bool defer_sync = false;         // between pba_begin_batch and the next pba_solve / pba_end_batch: uploads do not block
   LmState* d_state = nullptr;
   IterSummary* d_trace = nullptr;
   int trace_cap = 0;
@@ -256,6 +257,13 @@ static int setup_xchg(pba_handle* h) {
   return PBA_OK;
 }
 
+// End of an upload call: block until the borrowed host buffers have been consumed - unless the caller has opened a
+// batch (pba_begin_batch) and keeps the buffers alive until pba_solve / pba_end_batch returns.
+static int upload_done(pba_handle* h) {
+  if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PBA_OK;
+}
+
 extern "C" {
 
 const char* pba_last_error(void) { return g_err; }
@@ -386,7 +394,7 @@ int pba_set_frames_u8(pba_handle* h, int32_t n_frames, const uint8_t* const* ima
     int rc = upload_plane_u8(h, f, images[f]);
     if (rc) return rc;
   }
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  { int rc_ = upload_done(h); if (rc_) return rc_; }
   h->frames_are_u8 = true; h->have_frames = true; h->n_frames = n_frames;
   return PBA_OK;
 }
@@ -431,7 +439,7 @@ int pba_set_frames_u8_pyr(pba_handle* h, int32_t n_frames, const uint8_t* const*
       if (!last) { /* a now holds the reduced image */ }
     }
   }
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  { int rc_ = upload_done(h); if (rc_) return rc_; }
   h->frames_are_u8 = true; h->have_frames = true; h->n_frames = n_frames;
   return PBA_OK;
 }
@@ -459,7 +467,7 @@ int pba_set_frame_u8(pba_handle* h, int32_t slot, const uint8_t* image) {
   CUDA_TRY(cudaSetDevice(h->device));
   int rc = upload_plane_u8(h, slot, image);
   if (rc) return rc;
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  { int rc_ = upload_done(h); if (rc_) return rc_; }
   return PBA_OK;
 }
 
@@ -520,7 +528,7 @@ int pba_set_frames_u8_descriptor(pba_handle* h, int32_t n_frames, const uint8_t*
     CUDA_TRY(launch_channels(type, h->d_u8 + (size_t)f * h->plane, h->cfg.rows, h->cfg.cols, h->pitch, h->d_scr_a, h->d_scr_b,
                              h->d_f32 + (size_t)f * C * h->plane, h->pitch, h->plane, h->stream));
   }
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  { int rc_ = upload_done(h); if (rc_) return rc_; }
   h->frames_are_u8 = false; h->have_frames = true; h->n_frames = n_frames;
   return PBA_OK;
 }
@@ -691,7 +699,7 @@ int pba_set_poses(pba_handle* h, int32_t n_frames, const double* cam6, int32_t f
   const size_t stride = (size_t)n_frames * 6;
   CUDA_TRY(cudaMemcpyAsync(h->d_cams, cam6, sizeof(double) * stride, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->d_cams + stride, cam6, sizeof(double) * stride, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  { int rc_ = upload_done(h); if (rc_) return rc_; }
   h->n_frames = n_frames; h->fixed_frame = fixed_frame; h->have_poses = true;
   return PBA_OK;
 }
@@ -765,7 +773,7 @@ int pba_set_points(pba_handle* h, int32_t n_points, const double* xyz, const dou
   CUDA_TRY(cudaMemcpyAsync(h->d_obs_off, off_loc, sizeof(int) * (n_loc + 1), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->d_obs_frame, obs_frame + o_base, sizeof(int) * nnz_loc, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaMemcpyAsync(h->d_weights, weights, sizeof(double) * h->P, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  { int rc_ = upload_done(h); if (rc_) return rc_; }
   h->n_points = n_loc; h->nnz = nnz_loc; h->n_points_total = n_points; h->nnz_total = nnz; h->have_points = true;
   return PBA_OK;
 }
@@ -1117,6 +1125,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
     }
   }
   if (!s->done) { s->msg_code = kMsgMaxIter; s->msg_a = opt.max_num_iterations; summary->termination_type = 1; }
+  h->defer_sync = false;   // every upload enqueued before this solve has been consumed
   format_message(*s, summary->message, sizeof(summary->message));
   summary->total_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
   return PBA_OK;
@@ -1167,6 +1176,79 @@ int pba_copy_state(pba_handle* dst, pba_handle* src) {
   // buffer 1 of the points mirrors buffer 0 until the first accepted step (as after pba_set_points)
   CUDA_TRY(cudaMemcpyAsync(dst->d_pts + (size_t)dst->n_points * 3, dst->d_pts, pb, cudaMemcpyDeviceToDevice, dst->stream));
   return PBA_OK;   // ordered on dst's stream: the next pba_solve(dst) sees it
+}
+
+int pba_begin_batch(pba_handle* h) {
+  if (!h) return fail(PBA_ERR_ARGUMENT, "pba_begin_batch: null handle");
+  h->defer_sync = true;
+  return PBA_OK;
+}
+
+int pba_end_batch(pba_handle* h) {
+  if (!h) return fail(PBA_ERR_ARGUMENT, "pba_end_batch: null handle");
+  h->defer_sync = false;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PBA_OK;
+}
+
+int pba_set_frame_u8_ex(pba_handle* h, int32_t slot, const uint8_t* image, int32_t src_rows, int32_t src_cols, int32_t levels_down,
+                        int32_t descriptor_type) {
+  if (!h || !image) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8_ex: null argument");
+  if (!h->have_frames) return fail(PBA_ERR_STATE, "pba_set_frame_u8_ex: replaces one frame of a window that has been set (pba_set_frames_* first)");
+  if (slot < 0 || slot >= h->n_frames) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8_ex: slot %d of %d frames", slot, h->n_frames);
+  const int C = pba_descriptor_channels(descriptor_type);
+  if (C < 0 || C != h->cfg.n_channels) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8_ex: descriptor type %d does not match the handle's %d channels", descriptor_type, h->cfg.n_channels);
+  if (levels_down < 0 || (levels_down > 0 && C != 1)) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8_ex: pyramid levels are built for the Intensity descriptor only");
+  int r = src_rows, cc = src_cols;
+  for (int l = 0; l < levels_down; ++l) { r = (r + 1) / 2; cc = (cc + 1) / 2; }
+  if (r != h->cfg.rows || cc != h->cfg.cols)
+    return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8_ex: %dx%d reduced %d times is %dx%d, handle is %dx%d", src_rows, src_cols, levels_down, r, cc, h->cfg.rows, h->cfg.cols);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (levels_down == 0) {
+    int rc = upload_plane_u8(h, slot, image);
+    if (rc) return rc;
+    if (C > 1) {
+      rc = ensure_descriptor_scratch(h);
+      if (rc) return rc;
+      CUDA_TRY(launch_channels(descriptor_type, h->d_u8 + (size_t)slot * h->plane, h->cfg.rows, h->cfg.cols, h->pitch, h->d_scr_a, h->d_scr_b,
+                               h->d_f32 + (size_t)slot * C * h->plane, h->pitch, h->plane, h->stream));
+    }
+  } else {
+    const int p0 = (src_cols + 15) / 16 * 16;
+    if (h->pyr_scratch_bytes < 2 * (size_t)src_rows * p0) {
+      cudaFree(h->d_pyr_scratch); h->d_pyr_scratch = nullptr; h->pyr_scratch_bytes = 0;
+      CUDA_TRY(cudaMalloc(&h->d_pyr_scratch, 2 * (size_t)src_rows * p0));
+      h->pyr_scratch_bytes = 2 * (size_t)src_rows * p0;
+    }
+    uint8_t* a = h->d_pyr_scratch;
+    uint8_t* b = h->d_pyr_scratch + (size_t)src_rows * p0;
+    CUDA_TRY(cudaMemcpyAsync(a, image, (size_t)src_rows * src_cols, cudaMemcpyHostToDevice, h->stream));
+    int rr = src_rows, wc = src_cols, pa = src_cols;
+    for (int l = 0; l < levels_down; ++l) {
+      const bool last = (l == levels_down - 1);
+      uint8_t* dst = last ? h->d_u8 + (size_t)slot * h->plane : b;
+      const int pd = last ? h->pitch : p0;
+      CUDA_TRY(launch_pyrdown_u8(a, rr, wc, pa, dst, pd, h->stream));
+      rr = (rr + 1) / 2; wc = (wc + 1) / 2; pa = pd;
+      std::swap(a, b);
+    }
+  }
+  return upload_done(h);
+}
+
+int pba_get_results(pba_handle* h, double* cam6, double* xyz) {
+  if (!h || !cam6 || !xyz) return fail(PBA_ERR_ARGUMENT, "pba_get_results: null argument");
+  if (!h->have_poses || !h->have_points) return fail(PBA_ERR_STATE, "pba_get_results: poses/points not set");
+  if (h->n_ranks > 1) {   // sharded points: gather (pba_get_points), poses are replicated
+    int rc = pba_get_poses(h, cam6);
+    return rc ? rc : pba_get_points(h, xyz);
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(cam6, h->d_cams, sizeof(double) * (size_t)h->n_frames * 6, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(xyz, h->d_pts, sizeof(double) * (size_t)h->n_points * 3, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PBA_OK;
 }
 
 int pba_get_poses(pba_handle* h, double* cam6) {

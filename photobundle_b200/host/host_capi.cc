@@ -18,6 +18,7 @@ struct pbah_options {
   int32_t maxNumPoints, slidingWindowSize, patchRadius, maskBlockRadius, maxFrameDistance, nonMaxSuppRadius;
   int32_t doGaussianWeighting, verbose, device, descriptorType /* 0 Intensity, 1 IntensityAndGradient, 2 BitPlanes */, gpuFrontEnd;
   double minScore, robustThreshold, minValidDepth, maxValidDepth;
+  int32_t numPyramidLevels, reserved;
 };
 
 extern "C" {
@@ -30,6 +31,7 @@ void pbah_default_options(pbah_options* o) {
   o->maskBlockRadius = d.maskBlockRadius; o->maxFrameDistance = d.maxFrameDistance; o->nonMaxSuppRadius = d.nonMaxSuppRadius;
   o->doGaussianWeighting = d.doGaussianWeighting; o->verbose = d.verbose; o->device = d.device; o->descriptorType = (int32_t)d.descriptorType; o->gpuFrontEnd = d.gpuFrontEnd ? 1 : 0;
   o->minScore = d.minScore; o->robustThreshold = d.robustThreshold; o->minValidDepth = d.minValidDepth; o->maxValidDepth = d.maxValidDepth;
+  o->numPyramidLevels = d.numPyramidLevels; o->reserved = 0;
 }
 
 int pbah_create(int32_t rows, int32_t cols, double fx, double fy, double cx, double cy, double baseline,
@@ -45,6 +47,7 @@ int pbah_create(int32_t rows, int32_t cols, double fx, double fy, double cx, dou
     opt.descriptorType = (PhotometricBundleAdjustment::Options::DescriptorType)o->descriptorType;
     opt.gpuFrontEnd = o->gpuFrontEnd != 0;
     opt.minScore = o->minScore; opt.robustThreshold = o->robustThreshold; opt.minValidDepth = o->minValidDepth; opt.maxValidDepth = o->maxValidDepth;
+    opt.numPyramidLevels = o->numPyramidLevels > 0 ? o->numPyramidLevels : 1;
     pbah_handle* h = new pbah_handle();
     h->ba = new PhotometricBundleAdjustment(Calibration(K, baseline), ImageSize(rows, cols), opt);
     *out = h;
@@ -103,6 +106,10 @@ int32_t pbah_scene_point(pbah_handle* h, int32_t i, double* X3, int32_t* xy2, ui
   for (int k = 0; k < (int)v.visibility->size() && k < vis_cap; ++k) vis[k] = (*v.visibility)[k];
   for (int k = 0; k < (int)v.descriptor->size() && k < desc_cap; ++k) desc[k] = (*v.descriptor)[k];
   return (int32_t)v.visibility->size();
+}
+
+void pbah_disparity_to_depth(const float* disparity, int32_t rows, int32_t cols, float Bf, float* depth) {
+  disparityToDepth(disparity, ImageSize(rows, cols), Bf, depth);
 }
 
 int pbah_write_poses_kitti(pbah_handle* h, const char* filename) {

@@ -1,7 +1,8 @@
-// photobundle.cc — host side of the drop-in: the reference's addFrame() bookkeeping
-// (src/photobundle.cc:482-615) restated without Eigen/Boost, and optimize()
-// (src/photobundle.cc:764-876) re-implemented as "pack the window, call the B200 kernels through
-// the C ABI, write the poses/points back, evict, fill Result".
+// photobundle.cc — host side of the drop-in.  addFrame() keeps the reference's observable behaviour
+// (src/photobundle.cc:482-615: which points are re-observed, which pixels become new points, their descriptors)
+// with its own structure; optimize() (src/photobundle.cc:764-876) packs the window, keeps the frames of the ring
+// buffer resident on the device (one upload per new frame), runs the pyramid levels coarse to fine through the C
+// ABI (include/pba_b200.h) with the level hand-over on the device, writes poses/points back, evicts, fills Result.
 
 #include "photobundle.h"
 
@@ -17,6 +18,7 @@
 
 #include "../../include/pba_b200.h"
 #include "config.h"
+#include "photobundle_pyramid.h"
 #include "pose_utils.h"
 
 // ---------------------------------------------------------------------------- compat math
@@ -75,73 +77,82 @@ Mat44 Mat44::rigidInverse() const {
 }
 
 // ---------------------------------------------------------------------------- Trajectory
+// World poses keyed by frame id.  push_back() chains a frame-to-frame estimate: T_w,i = T_w,i-1 * T_i^-1
+// (behaviour of src/trajectory.cc:7-16); lookups by id throw when the id is unknown (:18-39).
 int Trajectory::find(const Id_t id) const {
-  for (size_t i = 0; i < _data.size(); ++i) if (_data[i].id == id) return (int)i;
+  // ids arrive in increasing order: the newest are the ones asked for, search from the back
+  for (size_t k = _data.size(); k-- > 0;)
+    if (_data[k].id == id) return (int)k;
   return -1;
 }
 void Trajectory::push_back(const Mat44& pose, const Id_t id) {
   if (find(id) >= 0) throw std::runtime_error("duplicate id in trajectory\n");
-  const Mat44 T_inv = pose.inverse();
-  if (!_data.empty()) _data.push_back({back() * T_inv, id});
-  else _data.push_back({T_inv, id});
+  PoseWithId e;
+  e.id = id;
+  e.pose = _data.empty() ? pose.inverse() : back() * pose.inverse();
+  _data.push_back(e);
 }
 const Mat44& Trajectory::atId(const Id_t id) const {
-  const int i = find(id);
-  if (i < 0) throw std::runtime_error("could not find pose with id");
-  return _data[i].pose;
+  const int k = find(id);
+  if (k < 0) throw std::runtime_error("could not find pose with id");
+  return _data[(size_t)k].pose;
 }
-Mat44& Trajectory::atId(const Id_t id) {
-  const int i = find(id);
-  if (i < 0) throw std::runtime_error("could not find pose with id");
-  return _data[i].pose;
-}
+Mat44& Trajectory::atId(const Id_t id) { return const_cast<Mat44&>(static_cast<const Trajectory*>(this)->atId(id)); }
 EigenAlignedContainer_<Mat44> Trajectory::poses() const {
-  EigenAlignedContainer_<Mat44> ret(_data.size());
-  for (size_t i = 0; i < ret.size(); ++i) ret[i] = _data[i].pose;
-  return ret;
+  EigenAlignedContainer_<Mat44> out;
+  out.reserve(_data.size());
+  for (const PoseWithId& e : _data) out.push_back(e.pose);
+  return out;
 }
 EigenAlignedContainer_<Vec3> Trajectory::cameraPositions() const {
-  EigenAlignedContainer_<Vec3> ret(_data.size());
-  for (size_t i = 0; i < ret.size(); ++i) ret[i] = Vec3(_data[i].pose(0, 3), _data[i].pose(1, 3), _data[i].pose(2, 3));
-  return ret;
+  EigenAlignedContainer_<Vec3> out;
+  out.reserve(_data.size());
+  for (const PoseWithId& e : _data) out.emplace_back(e.pose(0, 3), e.pose(1, 3), e.pose(2, 3));
+  return out;
 }
 
-// ---------------------------------------------------------------------------- pose utils
-PoseList loadPosesKittiFormat(std::string fn) {
-  std::ifstream ifs(fn);
-  if (!ifs.is_open()) throw std::runtime_error("failed to open pose file");
-  PoseList ret;
-  std::string line;
-  while (std::getline(ifs, line)) {
-    if (line.empty()) continue;
-    std::stringstream ss(line);
-    double vals[12];
-    for (int i = 0; i < 12; ++i) ss >> vals[i];
+// ---------------------------------------------------------------------------- pose text I/O
+// KITTI odometry format: one pose per line, the 12 entries of the top 3x4 of the 4x4 matrix, row by row
+// (what src/pose_utils.cc:9-59 reads and writes; the writer's layout — every number followed by one blank — is kept
+// so that files compare byte for byte with the reference's output).
+PoseList loadPosesKittiFormat(std::string filename) {
+  std::ifstream in(filename);
+  if (!in.is_open()) throw std::runtime_error("failed to open pose file");
+  PoseList poses;
+  for (std::string line; std::getline(in, line);) {
+    if (line.find_first_not_of(" \t\r") == std::string::npos) continue;
+    std::istringstream fields(line);
     Mat44 T = Mat44::Identity();
-    for (int i = 0, c = 0; i < 3; ++i) for (int j = 0; j < 4; ++j) T(i, j) = vals[c++];
-    ret.push_back(T);
+    for (int k = 0; k < 12; ++k) fields >> T(k / 4, k % 4);
+    poses.push_back(T);
   }
-  return ret;
+  return poses;
 }
-bool writePosesKittiFormat(std::string fn, const PoseList& T) {
-  std::ofstream ofs(fn);
-  if (!ofs.is_open()) return false;
-  for (size_t i = 0; i < T.size(); ++i) {
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) ofs << (T[i](r, c)) << " ";
-    ofs << "\n";
+bool writePosesKittiFormat(std::string filename, const PoseList& poses) {
+  std::ofstream out(filename);
+  if (!out.is_open()) return false;
+  for (const Mat44& T : poses) {
+    for (int k = 0; k < 12; ++k) out << T(k / 4, k % 4) << " ";
+    out << "\n";
   }
   return true;
 }
-PoseList convertPoseToLocal(const PoseList& T_w) {
-  if (T_w.empty()) throw std::runtime_error("no poses");
-  PoseList T_i(T_w.size());
-  T_i[0] = T_w[0].rigidInverse();
-  for (size_t i = 1; i < T_w.size(); ++i) T_i[i] = T_w[i].rigidInverse() * T_w[i - 1];
-  return T_i;
+// world poses -> frame-to-frame poses, the inverse of Trajectory::push_back's chaining (src/pose_utils.cc:62-74)
+PoseList convertPoseToLocal(const PoseList& world) {
+  if (world.empty()) throw std::runtime_error("no poses");
+  PoseList local;
+  local.reserve(world.size());
+  for (size_t k = 0; k < world.size(); ++k)
+    local.push_back(k == 0 ? world[0].rigidInverse() : world[k].rigidInverse() * world[k - 1]);
+  return local;
 }
+// depth = (baseline * focal) / disparity where the disparity is usable (> 0.01), the invalid mark -0.1 elsewhere
+// (src/imgproc.cc:280-322; the reference's vector body uses the ~12-bit _mm_rcp_ps, here the reciprocal is exact)
 void disparityToDepth(const float* dmap, const ImageSize& sz, float Bf, float* zmap) {
-  const int N = sz.numel();
-  for (int i = 0; i < N; ++i) zmap[i] = dmap[i] > 0.01f ? Bf * (1.0f / dmap[i]) : -0.10f;
+  for (int k = 0, n = sz.numel(); k < n; ++k) {
+    const float d = dmap[k];
+    zmap[k] = d > 0.01f ? Bf * (1.0f / d) : -0.10f;
+  }
 }
 
 // ---------------------------------------------------------------------------- pose <-> params
@@ -194,74 +205,119 @@ static Mat44 ParamsToPose(const double* p) {
   return T;
 }
 
-// src/photobundle.cc:617-644
+// Weights of the patch pixels (behaviour of src/photobundle.cc:617-644): uniform, or an isotropic unit-variance
+// Gaussian normalised to sum 1, row-major over the (2r+1)^2 patch.
 static std::vector<double> MakePatchWeights(int radius, bool do_gaussian) {
-  const int n = (2 * radius + 1) * (2 * radius + 1);
-  if (!do_gaussian) return std::vector<double>(n, 1.0);
-  std::vector<double> ret(n);
-  double sum = 0.0;
-  for (int r = -radius, i = 0; r <= radius; ++r) {
-    const double d_r = (r * r) / 1.0;
-    for (int c = -radius; c <= radius; ++c, ++i) {
-      const double d_c = (c * c) / 1.0;
-      const double w = 1.0 * std::exp(-0.5 * (d_r + d_c));
-      ret[i] = w; sum += w;
-    }
+  const int side = 2 * radius + 1;
+  std::vector<double> w((size_t)side * side, 1.0);
+  if (!do_gaussian) return w;
+  double total = 0.0;
+  for (int k = 0; k < side * side; ++k) {
+    const int dy = k / side - radius, dx = k % side - radius;
+    w[(size_t)k] = 1.0 * std::exp(-0.5 * ((dy * dy) / 1.0 + (dx * dx) / 1.0));
+    total += w[(size_t)k];
   }
-  for (int i = 0; i < n; ++i) ret[i] /= sum;
-  return ret;
+  for (double& v : w) v /= total;
+  return w;
 }
 
-// ---------------------------------------------------------------------------- ZNCC patch
-// interp2 (src/photobundle.cc:262-294) with T = float on a uint8 image, same mixed precision.
+// ---------------------------------------------------------------------------- image helpers
+// Bilinear look-up in a uint8 image at (xf, yf) with the reference's border policy and mixed float/double arithmetic
+// (src/photobundle.cc:262-294 with T = float): inside -> 4 taps; exactly on the last column / row -> the 1-D
+// interpolation along the border; anywhere else -> fillval.  The device front end (pba_associate) reproduces this
+// bit for bit, so the expressions keep their promotions.
 static inline float interp2_u8(const uint8_t* I, int rows, int cols, float xf, float yf, float fillval = 0.0f) {
-  const int max_cols = cols - 1, max_rows = rows - 1;
-  int xi = (int)std::floor(xf), yi = (int)std::floor(yf);
+  const int last_col = cols - 1, last_row = rows - 1;
+  const int xi = (int)std::floor(xf), yi = (int)std::floor(yf);
   xf -= xi; yf -= yi;
-  auto at = [&](int y, int x) -> int { return I[(size_t)y * cols + x]; };
-  if (xi >= 0 && xi < max_cols && yi >= 0 && yi < max_rows) {
+  const uint8_t* p = I + (size_t)yi * cols + xi;
+  const bool x_in = xi >= 0 && xi < last_col, y_in = yi >= 0 && yi < last_row;
+  if (x_in && y_in) {
     const float wx = 1.0 - xf;
-    return (1.0 - yf) * (at(yi, xi) * wx + at(yi, xi + 1) * xf) + yf * (at(yi + 1, xi) * wx + at(yi + 1, xi + 1) * xf);
-  } else {
-    if (xi == max_cols && yi < max_rows && yi >= 0) return (xf > 0) ? fillval : (float)((1.0 - yf) * at(yi, xi) + yf * at(yi + 1, xi));
-    else if (yi == max_rows && xi < max_cols && xi >= 0) return (yf > 0) ? fillval : (float)((1.0 - xf) * at(yi, xi) + xf * at(yi, xi + 1));
-    else if (xi == max_cols && yi == max_rows) return (xf > 0 || yf > 0) ? fillval : (float)at(yi, xi);
-    else return fillval;
+    return (1.0 - yf) * ((int)p[0] * wx + (int)p[1] * xf) + yf * ((int)p[cols] * wx + (int)p[cols + 1] * xf);
   }
+  if (xi == last_col && y_in) return (xf > 0) ? fillval : (float)((1.0 - yf) * (int)p[0] + yf * (int)p[cols]);
+  if (yi == last_row && x_in) return (yf > 0) ? fillval : (float)((1.0 - xf) * (int)p[0] + xf * (int)p[1]);
+  if (xi == last_col && yi == last_row) return (xf > 0 || yf > 0) ? fillval : (float)(int)p[0];
+  return fillval;
 }
 
-// ZnccPatch_<2, float> (src/photobundle.cc:315-361)
+// Mean-free 5x5 patch and its norm for the zero-normalised cross correlation of the data association
+// (ZnccPatch_<2, float>, src/photobundle.cc:315-361).
 struct ZnccPatch {
-  float data[25];
+  static constexpr int kSide = 5, kLen = kSide * kSide;
+  float data[kLen];
   float norm = 0.f;
   void set(const uint8_t* I, int rows, int cols, double px, double py) {
     const float x = (float)px, y = (float)py;
-    int i = 0;
-    for (int r = -2; r <= 2; ++r)
-      for (int c = -2; c <= 2; ++c) data[i++] = interp2_u8(I, rows, cols, c + x, r + y);
+    for (int k = 0; k < kLen; ++k) data[k] = interp2_u8(I, rows, cols, (k % kSide - 2) + x, (k / kSide - 2) + y);
     float sum = 0.f;
-    for (int k = 0; k < 25; ++k) sum += data[k];
-    const float mean = sum / 25.0f;
+    for (float v : data) sum += v;
+    const float mean = sum / (float)kLen;
     float ss = 0.f;
-    for (int k = 0; k < 25; ++k) { data[k] -= mean; ss += data[k] * data[k]; }
+    for (float& v : data) { v -= mean; ss += v * v; }
     norm = std::sqrt(ss);
   }
   float score(const ZnccPatch& o) const {
     const float d = norm * o.norm;
     float dot = 0.f;
-    for (int k = 0; k < 25; ++k) dot += data[k] * o.data[k];
+    for (int k = 0; k < kLen; ++k) dot += data[k] * o.data[k];
     return d > 1e-6 ? dot / d : -1.0f;
   }
 };
+
+// cv::pyrDown for CV_8U on the host (the device has its own, k_pyrdown_u8): separable [1 4 6 4 1] with
+// BORDER_REFLECT_101, result (sum + 128) >> 8.  Only used to read the reference descriptors of new points at
+// the coarser pyramid levels.
+static int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+  return i;
+}
+static std::vector<uint8_t> PyrDownU8(const std::vector<uint8_t>& src, int rows, int cols) {
+  const int drows = (rows + 1) / 2, dcols = (cols + 1) / 2;
+  static const int w[5] = {1, 4, 6, 4, 1};
+  std::vector<int> h((size_t)rows * dcols);
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < dcols; ++x) {
+      int s = 0;
+      for (int k = 0; k < 5; ++k) s += w[k] * src[(size_t)y * cols + reflect101(2 * x + k - 2, cols)];
+      h[(size_t)y * dcols + x] = s;
+    }
+  std::vector<uint8_t> dst((size_t)drows * dcols);
+  for (int y = 0; y < drows; ++y)
+    for (int x = 0; x < dcols; ++x) {
+      int s = 0;
+      for (int k = 0; k < 5; ++k) s += w[k] * h[(size_t)reflect101(2 * y + k - 2, rows) * dcols + x];
+      dst[(size_t)y * dcols + x] = (uint8_t)((s + 128) >> 8);
+    }
+  return dst;
+}
+// Reference descriptor of a point at a coarser level: the bilinear patch of the reduced reference frame at the
+// point's level-0 pixel divided by 2^level (workloads/synthetic.py `pyramid_level` — the level semantics are ours,
+// SURVEY App. C #12); channel values are floats widened to double like every descriptor.
+static void BilinearPatch(double* dst, const std::vector<uint8_t>& img, int rows, int cols, double x, double y, int radius) {
+  int k = 0;
+  for (int dy = -radius; dy <= radius; ++dy)
+    for (int dx = -radius; dx <= radius; ++dx, ++k) {
+      const double xx = std::min(std::max(x + dx, 0.0), cols - 1.0), yy = std::min(std::max(y + dy, 0.0), rows - 1.0);
+      const int x0 = std::min((int)xx, cols - 2), y0 = std::min((int)yy, rows - 2);
+      const double ax = xx - x0, ay = yy - y0;
+      const double v = (1 - ay) * ((1 - ax) * img[(size_t)y0 * cols + x0] + ax * img[(size_t)y0 * cols + x0 + 1]) +
+                       ay * ((1 - ax) * img[(size_t)(y0 + 1) * cols + x0] + ax * img[(size_t)(y0 + 1) * cols + x0 + 1]);
+      dst[k] = (double)(float)v;
+    }
+}
 
 struct PhotometricBundleAdjustment::ScenePoint {
   Vec3 X, X_original;
   std::vector<uint32_t> f;      // visibility list, first = reference frame
   ZnccPatch patch;
-  std::vector<double> descriptor;
+  std::vector<double> descriptor;                 // finest level
+  std::vector<std::vector<double>> coarse_desc;   // levels 1 .. numPyramidLevels-1
   double saliency = 0.0;
   bool was_refined = false;
-  int x = 0, y = 0;             // first projection
+  int x = 0, y = 0;             // pixel in the reference frame
   ScenePoint(const Vec3& X_, uint32_t f_id) : X(X_), X_original(X_) { f.reserve(8); f.push_back(f_id); }
   uint32_t refFrameId() const { return f.front(); }
   uint32_t lastFrameId() const { return f.back(); }
@@ -285,7 +341,7 @@ static PhotometricBundleAdjustment::Options::DescriptorType DescriptorTypeFromSt
   return DT::Intensity;
 }
 
-PhotometricBundleAdjustment::Options::Options(const utils::ConfigFile& cf)   // src/photobundle.cc:88-103
+PhotometricBundleAdjustment::Options::Options(const utils::ConfigFile& cf)   // keys and defaults of src/photobundle.cc:88-103
     : maxNumPoints(cf.get<int>("maxNumPoints", 4096)),
       slidingWindowSize(cf.get<int>("slidingWindowSize", 5)),
       patchRadius(cf.get<int>("patchRadius", 2)),
@@ -299,7 +355,8 @@ PhotometricBundleAdjustment::Options::Options(const utils::ConfigFile& cf)   // 
       minValidDepth(cf.get<double>("minValidDepth", 0.01)),
       maxValidDepth(cf.get<double>("maxValidDepth", 1000.0)),
       nonMaxSuppRadius(cf.get<int>("nonMaxSuppRadius", 1)),
-      descriptorType(DescriptorTypeFromString(cf.get<std::string>("descriptorType", "Intensity"))) {}
+      descriptorType(DescriptorTypeFromString(cf.get<std::string>("descriptorType", "Intensity"))),
+      numPyramidLevels(cf.get<int>("numPyramidLevels", 1)) {}
 
 // ---------------------------------------------------------------------------- ctor / dtor
 PhotometricBundleAdjustment::PhotometricBundleAdjustment(const Calibration& calib, const ImageSize& image_size,
@@ -312,210 +369,225 @@ PhotometricBundleAdjustment::PhotometricBundleAdjustment(const Calibration& cali
              : _options.descriptorType == Options::DescriptorType::IntensityAndGradient ? PBA_DESC_INTENSITY_AND_GRADIENT
                                                                                          : PBA_DESC_BITPLANES;
   _n_channels = pba_descriptor_channels(_desc_type);
+  if (_options.numPyramidLevels < 1 || _options.numPyramidLevels > 6) throw std::runtime_error("numPyramidLevels outside [1, 6]");
+  if (_options.numPyramidLevels > 1 && _desc_type != PBA_DESC_INTENSITY)
+    throw std::runtime_error("pyramid levels are defined for the Intensity descriptor");
   _mask.resize((size_t)_image_size.rows * _image_size.cols);
   _saliency_map.resize((size_t)_image_size.rows * _image_size.cols);
   _K_inv = calib.K().inverse();
+  // the levels: image size by (n + 1) / 2 (src/types.h:70-73), intrinsics by Calibration::pyrDown (src/calibration.h:72-78)
+  _dev.resize((size_t)_options.numPyramidLevels);
+  Calibration c = calib;
+  ImageSize s = image_size;
+  for (int l = 0; l < _options.numPyramidLevels; ++l) {
+    _dev[(size_t)l].calib = c; _dev[(size_t)l].size = s; _dev[(size_t)l].levels_down = l;
+    _dev[(size_t)l].resident.assign((size_t)_options.slidingWindowSize, -1);
+    c = c.pyrDown(); s = s.pyrDown();
+  }
 }
 
 PhotometricBundleAdjustment::~PhotometricBundleAdjustment() {
-  if (_gpu) pba_destroy(_gpu);
+  for (DeviceLevel& d : _dev)
+    if (d.h) pba_destroy(d.h);
 }
 
-void PhotometricBundleAdjustment::ensureGpu(int n_points, int n_obs) {
-  if (_gpu && n_points <= _gpu_max_points && n_obs <= _gpu_max_obs) return;
-  if (_gpu) { pba_destroy(_gpu); _gpu = nullptr; }
+static void check_pba(int rc, const char* what) {
+  if (rc != PBA_OK) throw std::runtime_error(std::string(what) + ": " + pba_last_error());
+}
+
+// The device handle of a level, with room for n_points / n_obs (recreated with more room when a window outgrows it).
+pba_handle* PhotometricBundleAdjustment::deviceLevel(int level, int n_points, int n_obs) {
+  DeviceLevel& d = _dev[(size_t)level];
+  if (d.h && n_points <= d.cap_points && n_obs <= d.cap_obs) return d.h;
+  if (d.h) { pba_destroy(d.h); d.h = nullptr; }
   pba_config cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.rows = _image_size.rows; cfg.cols = _image_size.cols; cfg.n_channels = _n_channels;
+  cfg.rows = d.size.rows; cfg.cols = d.size.cols; cfg.n_channels = _n_channels;
   cfg.patch_radius = _options.patchRadius; cfg.max_frames = _options.slidingWindowSize;
-  _gpu_max_points = std::max(n_points, _options.maxNumPoints * _options.slidingWindowSize);
-  _gpu_max_obs = std::max(n_obs, _gpu_max_points * std::min(_options.slidingWindowSize, 4));
-  cfg.max_points = _gpu_max_points; cfg.max_observations = _gpu_max_obs;
+  d.cap_points = std::max(n_points, _options.maxNumPoints * _options.slidingWindowSize);
+  d.cap_obs = std::max(n_obs, d.cap_points * std::min(_options.slidingWindowSize, 4));
+  cfg.max_points = d.cap_points; cfg.max_observations = d.cap_obs;
   cfg.device = _options.device;
-  cfg.fx = _calib.fx(); cfg.fy = _calib.fy(); cfg.cx = _calib.cx(); cfg.cy = _calib.cy();
+  cfg.fx = d.calib.fx(); cfg.fy = d.calib.fy(); cfg.cx = d.calib.cx(); cfg.cy = d.calib.cy();
   cfg.huber = _options.robustThreshold;
-  if (pba_create(&cfg, &_gpu) != PBA_OK) throw std::runtime_error(std::string("pba_create: ") + pba_last_error());
+  check_pba(pba_create(&cfg, &d.h), "pba_create");
+  std::fill(d.resident.begin(), d.resident.end(), (long long)-1);
+  return d.h;
 }
 
 // ---------------------------------------------------------------------------- addFrame
-static inline int PatchSizeFromRadius(int r) { return (2 * r + 1) * (2 * r + 1); }
-
-// ExtractPatch, src/photobundle.cc:466-479 (channel = uint8 image cast to float)
+// Integer-pixel patch of the reference frame, clamped so that the whole patch stays inside the image
+// (ExtractPatch, src/photobundle.cc:466-479; the channel is the uint8 image cast to float, widened to double).
 static void ExtractPatch(double* dst, const uint8_t* I, int rows, int cols, int ux, int uy, int radius) {
-  const int max_cols = cols - radius - 1, max_rows = rows - radius - 1;
-  for (int r = -radius, i = 0; r <= radius; ++r) {
-    const int r_i = std::max(radius, std::min(uy + r, max_rows));
-    for (int c = -radius; c <= radius; ++c, ++i) {
-      const int c_i = std::max(radius, std::min(ux + c, max_cols));
-      dst[i] = static_cast<double>(static_cast<float>(I[(size_t)r_i * cols + c_i]));
-    }
+  const int side = 2 * radius + 1;
+  for (int k = 0; k < side * side; ++k) {
+    const int yy = std::max(radius, std::min(uy + k / side - radius, rows - radius - 1));
+    const int xx = std::max(radius, std::min(ux + k % side - radius, cols - radius - 1));
+    dst[k] = static_cast<double>(static_cast<float>(I[(size_t)yy * cols + xx]));
   }
 }
 
 void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_ptr, const Mat44& T, Result* result) {
   _trajectory.push_back(T, (int)_frame_id);
-  const Mat44 T_w = _trajectory.back();
-  const Mat44 T_c = T_w.rigidInverse();
+  const Mat44 T_w = _trajectory.back(), T_c = T_w.rigidInverse();
   const int rows = _image_size.rows, cols = _image_size.cols;
+  const int radius = _options.patchRadius, descriptor_dim = (2 * radius + 1) * (2 * radius + 1) * _n_channels;
+  // border band in which points may live (src/photobundle.cc:498-503): the wider of the mask block, the ZNCC patch
+  // and the descriptor patch
+  const int border = std::max(_options.maskBlockRadius, std::max(2, radius));
+  const int row_end = rows - border - 1, col_end = cols - border - 1, mask_radius = _options.maskBlockRadius;
+  const bool multi = _desc_type != PBA_DESC_INTENSITY, on_gpu = _options.gpuFrontEnd;
 
   Frame frame;
   frame.id = _frame_id;
   frame.image.assign(I_ptr, I_ptr + (size_t)rows * cols);
+  if (multi || on_gpu) check_pba(pba_prepare_frame_u8(deviceLevel(0, 0, 0), I_ptr, _desc_type), "pba_prepare_frame_u8");
+  pba_handle* const gpu0 = _dev[0].h;
 
-  const int B = std::max(_options.maskBlockRadius, std::max(2, _options.patchRadius));
-  const int max_rows = rows - B - 1, max_cols = cols - B - 1, radius = _options.patchRadius,
-            patch_length = PatchSizeFromRadius(radius), descriptor_dim = patch_length * _n_channels,
-            mask_radius = _options.maskBlockRadius;
-
-  // ---- visibility of the existing points in the new frame (src/photobundle.cc:508-542)
-  const bool multi = _desc_type != PBA_DESC_INTENSITY;
-  const bool on_gpu = _options.gpuFrontEnd;     // association + candidate selection on the device
-  auto check = [&](int rc, const char* what) { if (rc != PBA_OK) throw std::runtime_error(std::string(what) + ": " + pba_last_error()); };
-  if (multi || on_gpu) {
-    ensureGpu(0, 0);
-    check(pba_prepare_frame_u8(_gpu, I_ptr, _desc_type), "pba_prepare_frame_u8");
-  }
+  // ---- (1) which live points are seen again in this frame (src/photobundle.cc:508-542): project with the INITIAL
+  // pose, compare the stored 5x5 patch with the one around the projection (ZNCC), block the neighbourhood of a hit
   std::fill(_mask.begin(), _mask.end(), (uint16_t)1);
-  int num_updated = 0, max_num_to_update = 0;
-  std::vector<int32_t> masked_rc;               // re-observed pixels (device path)
+  int n_reobserved = 0, n_tested = 0;
+  std::vector<int32_t> hit_rc;                  // (row, col) of the hits, for the device-side mask
+  auto is_live = [&](const ScenePoint& p) { return (int)_frame_id - (int)p.lastFrameId() <= _options.maxFrameDistance; };
   if (on_gpu) {
     std::vector<ScenePoint*> live;
     std::vector<double> xyz;
-    std::vector<float> ref_patch, ref_norm;
-    for (auto& sp : _scene_points)
-      if ((int)_frame_id - (int)sp->lastFrameId() <= _options.maxFrameDistance) {
-        live.push_back(sp.get());
-        for (int k = 0; k < 3; ++k) xyz.push_back(sp->X[k]);
-        ref_patch.insert(ref_patch.end(), sp->patch.data, sp->patch.data + 25);
-        ref_norm.push_back(sp->patch.norm);
-      }
-    max_num_to_update = (int)live.size();
+    std::vector<float> patches, norms;
+    for (auto& sp : _scene_points) {
+      if (!is_live(*sp)) continue;
+      live.push_back(sp.get());
+      xyz.insert(xyz.end(), sp->X.data(), sp->X.data() + 3);
+      patches.insert(patches.end(), sp->patch.data, sp->patch.data + ZnccPatch::kLen);
+      norms.push_back(sp->patch.norm);
+    }
+    n_tested = (int)live.size();
     std::vector<float> score(live.size());
     std::vector<int32_t> rc(2 * live.size());
-    double Kr[9];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Kr[3 * i + j] = _calib.K()(i, j);
-    check(pba_associate(_gpu, (int32_t)live.size(), xyz.data(), ref_patch.data(), ref_norm.data(), T_c.m, Kr, B, score.data(), rc.data()),
-          "pba_associate");
-    for (size_t i = 0; i < live.size(); ++i)
-      if (score[i] > _options.minScore) {        // not-tested points carry -2
-        num_updated++;
-        live[i]->f.push_back(_frame_id);
-        masked_rc.push_back(rc[2 * i]); masked_rc.push_back(rc[2 * i + 1]);
-      }
-  } else
-  for (size_t i = 0; i < _scene_points.size(); ++i) {
-    ScenePoint& pt = *_scene_points[i];
-    const int f_dist = (int)_frame_id - (int)pt.lastFrameId();
-    if (f_dist <= _options.maxFrameDistance) {
+    double K_rowmajor[9];
+    for (int k = 0; k < 9; ++k) K_rowmajor[k] = _calib.K()(k / 3, k % 3);
+    check_pba(pba_associate(gpu0, (int32_t)live.size(), xyz.data(), patches.data(), norms.data(), T_c.m, K_rowmajor, border, score.data(), rc.data()),
+              "pba_associate");
+    for (size_t k = 0; k < live.size(); ++k) {
+      if (!(score[k] > _options.minScore)) continue;   // points outside the band carry -2
+      ++n_reobserved;
+      live[k]->f.push_back(_frame_id);
+      hit_rc.push_back(rc[2 * k]); hit_rc.push_back(rc[2 * k + 1]);
+    }
+  } else {
+    for (auto& sp : _scene_points) {
+      ScenePoint& pt = *sp;
+      if (!is_live(pt)) continue;
+      ++n_tested;
       const Vec2 uv = _calib.project(T_c.transform(pt.X));
-      ++max_num_to_update;
       const int r = (int)std::round(uv[1]), c = (int)std::round(uv[0]);
-      if (r >= B && r < max_rows && c >= B && c <= max_cols) {
-        ZnccPatch other;
-        other.set(I_ptr, rows, cols, uv[0], uv[1]);
-        const float score = pt.patch.score(other);
-        if (score > _options.minScore) {
-          num_updated++;
-          pt.f.push_back(_frame_id);
-          for (int r_i = -mask_radius; r_i <= mask_radius; ++r_i)
-            for (int c_i = -mask_radius; c_i <= mask_radius; ++c_i) _mask[(size_t)(r + r_i) * cols + c + c_i] = 0;
-        }
-      }
+      if (!(r >= border && r < row_end && c >= border && c <= col_end)) continue;   // (the reference's band is closed on the right)
+      ZnccPatch seen;
+      seen.set(I_ptr, rows, cols, uv[0], uv[1]);
+      if (!(pt.patch.score(seen) > _options.minScore)) continue;
+      ++n_reobserved;
+      pt.f.push_back(_frame_id);
+      for (int dr = -mask_radius; dr <= mask_radius; ++dr)
+        for (int dc = -mask_radius; dc <= mask_radius; ++dc) _mask[(size_t)(r + dr) * cols + c + dc] = 0;
     }
   }
 
-  // ---- new points: saliency = sum over channels of |Ix| + |Iy| (imgradient, zero borders), local maxima
-  // with valid depth.  Multi-channel descriptors: the new frame's channels, their saliency and (below) the
-  // reference descriptors come from the device (pba_prepare_frame_u8 / pba_saliency_map / pba_extract_descriptors).
-  if (on_gpu) {
-    // candidates come back in scan order with their saliency; the map itself stays on the device
-  } else if (multi) {
-    check(pba_saliency_map(_gpu, _saliency_map.data()), "pba_saliency_map");
-  } else {
-  std::fill(_saliency_map.begin(), _saliency_map.end(), 0.0f);
-  for (int y = 1; y < rows - 1; ++y)
-    for (int x = 1; x < cols - 1; ++x) {
-      const float ix = 0.5f * ((float)I_ptr[(size_t)y * cols + x + 1] - (float)I_ptr[(size_t)y * cols + x - 1]);
-      const float iy = 0.5f * ((float)I_ptr[(size_t)(y + 1) * cols + x] - (float)I_ptr[(size_t)(y - 1) * cols + x]);
-      _saliency_map[(size_t)y * cols + x] = std::fabs(ix) + std::fabs(iy);
-    }
-  }
-  const int nms = _options.nonMaxSuppRadius;
-  auto is_local_max = [&](int row, int col) -> bool {   // IsLocalMax_, src/imgproc.h:175-212
-    if (nms > 0) {
-      const float v = _saliency_map[(size_t)row * cols + col];
-      if (!_mask[(size_t)row * cols + col] || v < 0.0f) return false;
-      for (int r = -nms; r <= nms; ++r)
-        for (int c = -nms; c <= nms; ++c)
-          if (!(!r && !c) && _saliency_map[(size_t)(r + row) * cols + c + col] >= v) return false;
-    }
-    return true;
-  };
-  ScenePointPointerList new_scene_points;
-  auto make_point = [&](int y, int x, float z, float saliency) {
-    // X = T_w * (z * K_inv * [x y 1]^T)   (src/photobundle.cc:560)
-    const double zd = z, v[3] = {(double)x, (double)y, 1.0};
+  // ---- (2) new points (src/photobundle.cc:545-575): unmasked strict local maxima of the saliency map (sum over the
+  // channels of |Ix| + |Iy|, central differences, zero on the image border) that carry a valid depth
+  ScenePointPointerList fresh;
+  auto lift = [&](int y, int x, float z, float saliency) {
+    // X = T_w * (z * K^-1 * [x y 1]^T), the products in the reference's order (src/photobundle.cc:560)
+    const double zd = z, pix[3] = {(double)x, (double)y, 1.0};
     Vec3 Xc;
-    for (int i = 0; i < 3; ++i)
-      Xc[i] = (zd * _K_inv(i, 0)) * v[0] + (zd * _K_inv(i, 1)) * v[1] + (zd * _K_inv(i, 2)) * v[2];
+    for (int i = 0; i < 3; ++i) Xc[i] = (zd * _K_inv(i, 0)) * pix[0] + (zd * _K_inv(i, 1)) * pix[1] + (zd * _K_inv(i, 2)) * pix[2];
     UniquePointer<ScenePoint> p(new ScenePoint(T_w.transform(Xc), _frame_id));
     p->patch.set(I_ptr, rows, cols, (double)x, (double)y);
-    p->descriptor.resize(descriptor_dim);
+    p->descriptor.resize((size_t)descriptor_dim);
     p->saliency = saliency;
     p->x = x; p->y = y;
-    new_scene_points.push_back(std::move(p));
+    fresh.push_back(std::move(p));
   };
   if (on_gpu) {
-    int32_t cap = std::max(4096, (rows * cols) / 16), n_cand = 0;
+    // saliency, mask, non-maximum suppression and the depth test run on the device; candidates come back in scan order
+    int32_t room = std::max(4096, (rows * cols) / 16), n_cand = 0;
     std::vector<int32_t> cand_rc;
     std::vector<float> cand_sal;
     for (int attempt = 0; attempt < 2; ++attempt) {
-      cand_rc.resize(2 * (size_t)cap); cand_sal.resize(cap);
-      check(pba_select_candidates(_gpu, Z_ptr, (int32_t)(masked_rc.size() / 2), masked_rc.data(), mask_radius, nms, B, _options.minValidDepth,
-                                  _options.maxValidDepth, cap, cand_rc.data(), cand_sal.data(), &n_cand), "pba_select_candidates");
-      if (n_cand <= cap) break;
-      cap = n_cand;                              // rare: more candidates than room; once more with enough
+      cand_rc.resize(2 * (size_t)room); cand_sal.resize((size_t)room);
+      check_pba(pba_select_candidates(gpu0, Z_ptr, (int32_t)(hit_rc.size() / 2), hit_rc.data(), mask_radius, _options.nonMaxSuppRadius, border,
+                                      _options.minValidDepth, _options.maxValidDepth, room, cand_rc.data(), cand_sal.data(), &n_cand),
+                "pba_select_candidates");
+      if (n_cand <= room) break;
+      room = n_cand;                             // rare: more candidates than room; once more with enough
     }
-    for (int i = 0; i < n_cand; ++i) {
-      const int y = cand_rc[2 * i], x = cand_rc[2 * i + 1];
-      make_point(y, x, Z_ptr[(size_t)y * cols + x], cand_sal[i]);
-    }
+    for (int k = 0; k < n_cand; ++k) lift(cand_rc[2 * k], cand_rc[2 * k + 1], Z_ptr[(size_t)cand_rc[2 * k] * cols + cand_rc[2 * k + 1]], cand_sal[k]);
   } else {
-  for (int y = B; y < max_rows; ++y) {
-    for (int x = B; x < max_cols; ++x) {
-      const float z = Z_ptr[(size_t)y * cols + x];
-      if (z >= _options.minValidDepth && z <= _options.maxValidDepth) {
-        if (is_local_max(y, x)) make_point(y, x, z, _saliency_map[(size_t)y * cols + x]);
+    if (multi) {
+      check_pba(pba_saliency_map(gpu0, _saliency_map.data()), "pba_saliency_map");
+    } else {
+      std::fill(_saliency_map.begin(), _saliency_map.end(), 0.0f);
+      for (int y = 1; y < rows - 1; ++y) {
+        const uint8_t* up = I_ptr + (size_t)(y - 1) * cols, *mid = up + cols, *down = mid + cols;
+        for (int x = 1; x < cols - 1; ++x)
+          _saliency_map[(size_t)y * cols + x] = std::fabs(0.5f * ((float)mid[x + 1] - (float)mid[x - 1])) + std::fabs(0.5f * ((float)down[x] - (float)up[x]));
+      }
+    }
+    const int nms = _options.nonMaxSuppRadius;
+    auto beats_neighbours = [&](int row, int col) -> bool {   // IsLocalMax_ (src/imgproc.h:175-212): ties lose
+      if (nms <= 0) return true;
+      const float v = _saliency_map[(size_t)row * cols + col];
+      if (!_mask[(size_t)row * cols + col] || v < 0.0f) return false;
+      for (int dr = -nms; dr <= nms; ++dr)
+        for (int dc = -nms; dc <= nms; ++dc)
+          if ((dr || dc) && _saliency_map[(size_t)(row + dr) * cols + col + dc] >= v) return false;
+      return true;
+    };
+    for (int y = border; y < row_end; ++y)
+      for (int x = border; x < col_end; ++x) {
+        const float z = Z_ptr[(size_t)y * cols + x];
+        if (z >= _options.minValidDepth && z <= _options.maxValidDepth && beats_neighbours(y, x)) lift(y, x, z, _saliency_map[(size_t)y * cols + x]);
+      }
+  }
+  // ---- (3) keep the maxNumPoints most salient (src/photobundle.cc:578-585; std::nth_element, so which of several
+  // equally salient points survives is the standard library's choice, as in the reference)
+  if (fresh.size() > (size_t)_options.maxNumPoints) {
+    auto cut = fresh.begin() + _options.maxNumPoints;
+    std::nth_element(fresh.begin(), cut, fresh.end(),
+                     [](const UniquePointer<ScenePoint>& a, const UniquePointer<ScenePoint>& b) { return a->saliency > b->saliency; });
+    fresh.erase(cut, fresh.end());
+  }
+  if (_options.verbose)
+    printf("updated %d [%0.2f%%] max %d new %d\n", n_reobserved, 100.0 * n_reobserved / _scene_points.size(), n_tested, (int)fresh.size());
+  // ---- (4) reference descriptors of the new points (src/photobundle.cc:597-606), every pyramid level
+  if (multi) {
+    const int n_new = (int)fresh.size();
+    std::vector<int32_t> xy((size_t)2 * n_new);
+    for (int k = 0; k < n_new; ++k) { xy[2 * k] = fresh[(size_t)k]->x; xy[2 * k + 1] = fresh[(size_t)k]->y; }
+    std::vector<double> dsc((size_t)n_new * descriptor_dim);
+    check_pba(pba_extract_descriptors(gpu0, n_new, xy.data(), dsc.data()), "pba_extract_descriptors");
+    for (int k = 0; k < n_new; ++k)
+      std::copy(dsc.begin() + (size_t)k * descriptor_dim, dsc.begin() + (size_t)(k + 1) * descriptor_dim, fresh[(size_t)k]->descriptor.begin());
+  } else {
+    for (auto& p : fresh) ExtractPatch(p->descriptor.data(), I_ptr, rows, cols, p->x, p->y, radius);
+  }
+  if (_options.numPyramidLevels > 1) {
+    std::vector<uint8_t> img = frame.image;
+    int lr = rows, lc = cols;
+    for (int l = 1; l < _options.numPyramidLevels; ++l) {
+      img = PyrDownU8(img, lr, lc);
+      lr = (lr + 1) / 2; lc = (lc + 1) / 2;
+      const double s = (double)(1 << l);
+      for (auto& p : fresh) {
+        if (p->coarse_desc.empty()) p->coarse_desc.resize((size_t)_options.numPyramidLevels - 1);
+        p->coarse_desc[(size_t)l - 1].resize((size_t)descriptor_dim);
+        BilinearPatch(p->coarse_desc[(size_t)l - 1].data(), img, lr, lc, p->x / s, p->y / s, radius);
       }
     }
   }
-  }
-  // ---- keep the best N by saliency (src/photobundle.cc:578-585)
-  if (new_scene_points.size() > (size_t)_options.maxNumPoints) {
-    auto nth = new_scene_points.begin() + _options.maxNumPoints;
-    std::nth_element(new_scene_points.begin(), nth, new_scene_points.end(),
-                     [&](const UniquePointer<ScenePoint>& a, const UniquePointer<ScenePoint>& b) { return a->saliency > b->saliency; });
-    new_scene_points.erase(nth, new_scene_points.end());
-  }
-  if (_options.verbose)
-    printf("updated %d [%0.2f%%] max %d new %d\n", num_updated, 100.0 * num_updated / _scene_points.size(),
-           max_num_to_update, (int)new_scene_points.size());
-  if (multi) {
-    // ExtractPatch of every channel (src/photobundle.cc:466-479, :601-606) on the device
-    const int n_new = (int)new_scene_points.size();
-    std::vector<int32_t> xy((size_t)2 * n_new);
-    for (int i = 0; i < n_new; ++i) { xy[2 * i] = new_scene_points[i]->x; xy[2 * i + 1] = new_scene_points[i]->y; }
-    std::vector<double> dsc((size_t)n_new * descriptor_dim);
-    check(pba_extract_descriptors(_gpu, n_new, xy.data(), dsc.data()), "pba_extract_descriptors");
-    for (int i = 0; i < n_new; ++i)
-      std::copy(dsc.begin() + (size_t)i * descriptor_dim, dsc.begin() + (size_t)(i + 1) * descriptor_dim, new_scene_points[i]->descriptor.begin());
-  } else {
-    for (auto& p : new_scene_points) ExtractPatch(p->descriptor.data(), I_ptr, rows, cols, p->x, p->y, radius);
-  }
-  _scene_points.reserve(_scene_points.size() + new_scene_points.size());
-  std::move(new_scene_points.begin(), new_scene_points.end(), std::back_inserter(_scene_points));
+  _scene_points.reserve(_scene_points.size() + fresh.size());
+  for (auto& p : fresh) _scene_points.push_back(std::move(p));
 
-  // boost::circular_buffer(slidingWindowSize)::push_back
+  // ring buffer of slidingWindowSize frames (boost::circular_buffer in the reference, :608); a full window is solved
   if ((int)_frame_buffer.size() == _options.slidingWindowSize) _frame_buffer.pop_front();
   _frame_buffer.push_back(std::move(frame));
   if ((int)_frame_buffer.size() == _options.slidingWindowSize) optimize(result);
@@ -523,109 +595,153 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
 }
 
 // ---------------------------------------------------------------------------- optimize
+// Frames live in device slots id % slidingWindowSize: a new frame replaces the one that left the window, everything
+// else stays resident (the reference's ring buffer, on the device).  The window-local frame index of the C ABI is
+// that slot.
+void PhotometricBundleAdjustment::uploadWindowFrames(int level, pba_handle* h) {
+  DeviceLevel& d = _dev[(size_t)level];
+  const int W = _options.slidingWindowSize, rows = _image_size.rows, cols = _image_size.cols;
+  bool any_resident = false;
+  for (long long id : d.resident) any_resident = any_resident || id >= 0;
+  if (!any_resident) {   // first solve on this handle: the whole window, in slot order
+    std::vector<const uint8_t*> imgs((size_t)W, nullptr);
+    for (const Frame& f : _frame_buffer) imgs[(size_t)(f.id % (uint32_t)W)] = f.image.data();
+    if (level == 0) check_pba(pba_set_frames_u8_descriptor(h, W, imgs.data(), _desc_type), "pba_set_frames_u8_descriptor");
+    else check_pba(pba_set_frames_u8_pyr(h, W, imgs.data(), rows, cols, d.levels_down), "pba_set_frames_u8_pyr");
+    for (const Frame& f : _frame_buffer) d.resident[(size_t)(f.id % (uint32_t)W)] = f.id;
+    return;
+  }
+  for (const Frame& f : _frame_buffer) {
+    const size_t slot = (size_t)(f.id % (uint32_t)W);
+    if (d.resident[slot] == (long long)f.id) continue;
+    check_pba(pba_set_frame_u8_ex(h, (int32_t)slot, f.image.data(), rows, cols, d.levels_down, _desc_type), "pba_set_frame_u8_ex");
+    d.resident[slot] = f.id;
+  }
+}
+
+struct PhotometricBundleAdjustment::SolveOutcome {
+  pba_summary summary;
+  std::vector<pba_iteration_summary> iters;
+};
+
 void PhotometricBundleAdjustment::optimize(Result* result) {
   const auto t0 = std::chrono::steady_clock::now();
-  const uint32_t frame_id_start = _frame_buffer.front().id, frame_id_end = _frame_buffer.back().id;
-  const int F = (int)(frame_id_end - frame_id_start + 1);
+  const uint32_t first_id = _frame_buffer.front().id, last_id = _frame_buffer.back().id;
+  const int W = _options.slidingWindowSize, L = _options.numPyramidLevels;
   const std::vector<double> patch_weights = MakePatchWeights(_options.patchRadius, _options.doGaussianWeighting);
-  const int P = (int)patch_weights.size();
+  auto slot_of = [&](uint32_t id) { return (int)(id % (uint32_t)W); };
 
-  // camera parameters of the window: inverse world pose as [angle-axis, t] (src/photobundle.cc:774-778)
-  std::vector<double> cams((size_t)F * 6);
-  for (uint32_t id = frame_id_start; id <= frame_id_end; ++id)
-    PoseToParams(_trajectory.atId((int)id).rigidInverse(), &cams[(size_t)(id - frame_id_start) * 6]);
+  // camera parameters: the INVERSE world pose of every window frame as [angle-axis, t] (src/photobundle.cc:774-778)
+  std::vector<double> cams((size_t)W * 6, 0.0);
+  for (uint32_t id = first_id; id <= last_id; ++id) PoseToParams(_trajectory.atId((int)id).rigidInverse(), &cams[(size_t)slot_of(id) * 6]);
 
-  // residual blocks (src/photobundle.cc:786-806)
-  std::vector<ScenePoint*> selected;
-  std::vector<double> xyz, desc;
+  // residual blocks (src/photobundle.cc:786-806): points seen in >= 3 frames whose reference frame is inside the
+  // window, one block per frame of the visibility list that lies in the window (the reference frame included)
+  std::vector<ScenePoint*> chosen;
+  std::vector<double> xyz;
+  std::vector<std::vector<double>> desc((size_t)L);
   std::vector<int32_t> obs_off(1, 0), obs_frame;
-  for (auto& pt : _scene_points) {
-    if (pt->numFrames() >= 3 && pt->refFrameId() >= frame_id_start) {
-      int n = 0;
-      for (uint32_t id : pt->f)
-        if (id >= frame_id_start && id <= frame_id_end) { obs_frame.push_back((int32_t)(id - frame_id_start)); ++n; }
-      if (n > 0) pt->was_refined = true;
-      selected.push_back(pt.get());
-      for (int k = 0; k < 3; ++k) xyz.push_back(pt->X[k]);
-      desc.insert(desc.end(), pt->descriptor.begin(), pt->descriptor.end());
-      obs_off.push_back((int32_t)obs_frame.size());
-    }
+  for (auto& sp : _scene_points) {
+    ScenePoint& pt = *sp;
+    if (pt.numFrames() < 3 || pt.refFrameId() < first_id) continue;
+    size_t before = obs_frame.size();
+    for (uint32_t id : pt.f)
+      if (id >= first_id && id <= last_id) obs_frame.push_back(slot_of(id));
+    if (obs_frame.size() > before) pt.was_refined = true;
+    chosen.push_back(&pt);
+    xyz.insert(xyz.end(), pt.X.data(), pt.X.data() + 3);
+    desc[0].insert(desc[0].end(), pt.descriptor.begin(), pt.descriptor.end());
+    for (int l = 1; l < L; ++l) desc[(size_t)l].insert(desc[(size_t)l].end(), pt.coarse_desc[(size_t)l - 1].begin(), pt.coarse_desc[(size_t)l - 1].end());
+    obs_off.push_back((int32_t)obs_frame.size());
   }
-  const int n_sel = (int)selected.size(), nnz = (int)obs_frame.size();
-  if (_options.verbose)
-    printf("Using %d points (%d residual blocks) [id start %u]\n", n_sel, nnz, frame_id_start);
+  const int n_sel = (int)chosen.size(), nnz = (int)obs_frame.size();
+  if (_options.verbose) printf("Using %d points (%d residual blocks) [id start %u]\n", n_sel, nnz, first_id);
 
-  pba_summary summary;
+  SolveOutcome solved;
+  pba_summary& summary = solved.summary;
+  std::vector<pba_iteration_summary>& iters = solved.iters;
   memset(&summary, 0, sizeof(summary));
-  std::vector<pba_iteration_summary> iters;
   if (n_sel > 0 && nnz > 0) {
-    ensureGpu(n_sel, nnz);
-    std::vector<const uint8_t*> imgs(F);
-    for (int f = 0; f < F; ++f) imgs[f] = _frame_buffer[f].image.data();
-    auto check = [&](int rc, const char* what) { if (rc != PBA_OK) throw std::runtime_error(std::string(what) + ": " + pba_last_error()); };
-    check(pba_set_frames_u8_descriptor(_gpu, F, imgs.data(), _desc_type), "pba_set_frames_u8_descriptor");
-    check(pba_set_poses(_gpu, F, cams.data(), 0 /* first camera constant, :809-816 */), "pba_set_poses");
-    check(pba_set_points(_gpu, n_sel, xyz.data(), desc.data(), obs_off.data(), obs_frame.data(), patch_weights.data()), "pba_set_points");
     pba_solver_options opt;
-    pba_default_solver_options(&opt);       // GetSolverOptions, :738-761
-    check(pba_solve(_gpu, &opt, &summary), "pba_solve");
-    check(pba_get_poses(_gpu, cams.data()), "pba_get_poses");
-    check(pba_get_points(_gpu, xyz.data()), "pba_get_points");
+    pba_default_solver_options(&opt);       // GetSolverOptions, src/photobundle.cc:738-761
+    pba_handle* coarser = nullptr;
+    for (int l = L - 1; l >= 0; --l) {      // coarse to fine; a single level is the reference's optimize()
+      pba_handle* h = deviceLevel(l, n_sel, nnz);
+      check_pba(pba_begin_batch(h), "pba_begin_batch");      // uploads are enqueued; every buffer lives until pba_solve returns
+      uploadWindowFrames(l, h);
+      check_pba(pba_set_poses(h, W, cams.data(), slot_of(first_id) /* first camera constant, :809-816 */), "pba_set_poses");
+      check_pba(pba_set_points(h, n_sel, xyz.data(), desc[(size_t)l].data(), obs_off.data(), obs_frame.data(), patch_weights.data()), "pba_set_points");
+      if (coarser) check_pba(pba_copy_state(h, coarser), "pba_copy_state");   // the coarser level's result, on the device
+      check_pba(pba_solve(h, &opt, &summary), "pba_solve");
+      coarser = h;
+    }
+    check_pba(pba_get_results(coarser, cams.data(), xyz.data()), "pba_get_results");
     int32_t n_it = 0;
-    pba_get_iterations(_gpu, nullptr, 0, &n_it);
-    iters.resize(n_it);
-    if (n_it) pba_get_iterations(_gpu, iters.data(), n_it, &n_it);
-    for (int i = 0; i < n_sel; ++i)
-      for (int k = 0; k < 3; ++k) selected[i]->X[k] = xyz[(size_t)i * 3 + k];
-    (void)P;
+    pba_get_iterations(coarser, nullptr, 0, &n_it);
+    iters.resize((size_t)n_it);
+    if (n_it) pba_get_iterations(coarser, iters.data(), n_it, &n_it);
+    for (int k = 0; k < n_sel; ++k)
+      for (int a = 0; a < 3; ++a) chosen[(size_t)k]->X[a] = xyz[(size_t)k * 3 + a];
   } else {
     snprintf(summary.message, sizeof(summary.message), "no residual blocks in the window");
   }
 
-  // put back the refined camera poses (src/photobundle.cc:841-844)
-  for (uint32_t id = frame_id_start; id <= frame_id_end; ++id)
-    _trajectory.atId((int)id) = ParamsToPose(&cams[(size_t)(id - frame_id_start) * 6]).rigidInverse();
+  // refined world poses back into the trajectory (src/photobundle.cc:841-844)
+  for (uint32_t id = first_id; id <= last_id; ++id)
+    _trajectory.atId((int)id) = ParamsToPose(&cams[(size_t)slot_of(id) * 6]).rigidInverse();
 
-  // all points whose reference frame is the window start leave the system (:851, :888-905)
-  ScenePointPointerList points_to_remove = removePointsAtFrame(frame_id_start);
-  if (_options.verbose) printf("removing %zu old points\n", points_to_remove.size());
+  // points anchored at the oldest frame leave the system with it (:851, :888-905)
+  ScenePointPointerList leaving = removePointsAtFrame(first_id);
+  if (_options.verbose) printf("removing %zu old points\n", leaving.size());
+  if (result) fillResult(*result, solved, leaving, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+}
 
-  if (result) {
-    result->poses = _trajectory.poses();
-    const size_t npts = points_to_remove.size();
-    result->refinedPoints.resize(npts);
-    result->originalPoints.resize(npts);
-    for (size_t i = 0; i < npts; ++i) {
-      result->refinedPoints[i] = points_to_remove[i]->X;
-      result->originalPoints[i] = points_to_remove[i]->X_original;
-    }
-    result->initialCost = summary.initial_cost;
-    result->finalCost = summary.final_cost;
-    result->fixedCost = summary.fixed_cost;
-    result->numSuccessfulStep = summary.num_successful_steps;
-    result->totalTime = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    result->numResiduals = summary.num_residuals;
-    result->message = std::string(summary.message);
-    result->iterationSummary.resize(iters.size());
-    for (size_t i = 0; i < iters.size(); ++i) {
-      ceres::IterationSummary& o = result->iterationSummary[i];
-      const pba_iteration_summary& s = iters[i];
-      o.iteration = s.iteration; o.step_is_valid = s.step_is_valid; o.step_is_nonmonotonic = s.step_is_nonmonotonic;
-      o.step_is_successful = s.step_is_successful; o.cost = s.cost; o.cost_change = s.cost_change;
-      o.gradient_max_norm = s.gradient_max_norm; o.gradient_norm = s.gradient_norm; o.step_norm = s.step_norm;
-      o.relative_decrease = s.relative_decrease; o.trust_region_radius = s.trust_region_radius;
-      o.linear_solver_iterations = s.linear_solver_iterations;
-    }
+// Result as the reference fills it (src/photobundle.cc:857-875): the WHOLE trajectory, the points that just left
+// (refined and as initialised), the solver's figures.
+void PhotometricBundleAdjustment::fillResult(Result& out, const SolveOutcome& solved, const ScenePointPointerList& leaving, double seconds) const {
+  const pba_summary& summary = solved.summary;
+  const std::vector<pba_iteration_summary>& iters = solved.iters;
+  out.poses = _trajectory.poses();
+  out.refinedPoints.clear(); out.originalPoints.clear();
+  for (const auto& p : leaving) { out.refinedPoints.push_back(p->X); out.originalPoints.push_back(p->X_original); }
+  out.initialCost = summary.initial_cost; out.finalCost = summary.final_cost; out.fixedCost = summary.fixed_cost;
+  out.numSuccessfulStep = summary.num_successful_steps;
+  out.numResiduals = summary.num_residuals;
+  out.totalTime = seconds;
+  out.message = summary.message;
+  out.iterationSummary.clear();
+  for (const pba_iteration_summary& s : iters) {
+    ceres::IterationSummary o;
+    o.iteration = s.iteration; o.step_is_valid = s.step_is_valid; o.step_is_nonmonotonic = s.step_is_nonmonotonic;
+    o.step_is_successful = s.step_is_successful; o.cost = s.cost; o.cost_change = s.cost_change;
+    o.gradient_max_norm = s.gradient_max_norm; o.gradient_norm = s.gradient_norm; o.step_norm = s.step_norm;
+    o.relative_decrease = s.relative_decrease; o.trust_region_radius = s.trust_region_radius;
+    o.linear_solver_iterations = s.linear_solver_iterations;
+    out.iterationSummary.push_back(o);
   }
 }
 
 auto PhotometricBundleAdjustment::removePointsAtFrame(uint32_t id) -> ScenePointPointerList {
-  ScenePointPointerList keep, remove;
-  keep.reserve(_scene_points.size());
-  for (auto& p : _scene_points) {
-    if (p->refFrameId() <= id) remove.push_back(std::move(p));
-    else keep.push_back(std::move(p));
-  }
-  _scene_points.swap(keep);
-  return remove;
+  auto stays = [id](const UniquePointer<ScenePoint>& p) { return p->refFrameId() > id; };
+  auto split = std::stable_partition(_scene_points.begin(), _scene_points.end(), stays);
+  ScenePointPointerList gone(std::make_move_iterator(split), std::make_move_iterator(_scene_points.end()));
+  _scene_points.erase(split, _scene_points.end());
+  return gone;
+}
+
+// ---------------------------------------------------------------------------- pyramid front
+// The reference's PhotometricBundleAdjustmentPyr (src/photobundle_pyramid.{h,cc}) is an unfinished sketch: one
+// independent optimiser per level, none at level 0, a level loop that starts out of range.
+// Kept: its interface.  Defined here: ONE point set (created at the finest level), every level solves the same
+// window — frames reduced with cv::pyrDown's rule, intrinsics halved per level, descriptors re-read per level —
+// coarse to fine, each level starting from the coarser level's poses and points.
+PhotometricBundleAdjustmentPyr::PhotometricBundleAdjustmentPyr(int num_levels, const Calibration& calib, const ImageSize& size, const Options& options) {
+  if (num_levels < 1) throw std::runtime_error("PhotometricBundleAdjustmentPyr: num_levels < 1");
+  Options o = options;
+  o.numPyramidLevels = num_levels;
+  _ba.reset(new PhotometricBundleAdjustment(calib, size, o));
+}
+PhotometricBundleAdjustmentPyr::~PhotometricBundleAdjustmentPyr() {}
+void PhotometricBundleAdjustmentPyr::addFrame(const uint8_t* image, const float* depth_map, const Mat44& T, Result* result) {
+  _ba->addFrame(image, depth_map, T, result);
 }

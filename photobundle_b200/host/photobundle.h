@@ -40,6 +40,7 @@ class PhotometricBundleAdjustment {
     DescriptorType descriptorType = DescriptorType::Intensity;
     int device = -1;                // CUDA ordinal (-1: current)
     bool gpuFrontEnd = false;       // addFrame's data association and new-point selection on the device (added option)
+    int numPyramidLevels = 1;       // > 1: every window is solved coarse to fine (PhotometricBundleAdjustmentPyr; added option)
     Options() {}
     Options(const utils::ConfigFile& cf);
   };
@@ -89,10 +90,21 @@ class PhotometricBundleAdjustment {
   std::vector<uint16_t> _mask;
   std::vector<float> _saliency_map;
   Mat33 _K_inv;
-  pba_handle* _gpu = nullptr;
-  int _gpu_max_points = 0, _gpu_max_obs = 0;
+  // one pyramid level on the device ([0] = the finest): its own handle, image size and intrinsics; `resident` = the
+  // frame id held by each ring slot (id % slidingWindowSize), -1: none
+  struct DeviceLevel {
+    pba_handle* h = nullptr;
+    ImageSize size;
+    Calibration calib;
+    int levels_down = 0, cap_points = 0, cap_obs = 0;
+    std::vector<long long> resident;
+  };
+  std::vector<DeviceLevel> _dev;
   int _desc_type = 0, _n_channels = 1;   // PBA_DESC_* / channels per pixel of the descriptor
-  void ensureGpu(int n_points, int n_obs);
+  pba_handle* deviceLevel(int level, int n_points, int n_obs);
+  void uploadWindowFrames(int level, pba_handle* h);
+  struct SolveOutcome;                   // the C ABI's summary + iteration trace of the last level solved
+  void fillResult(Result& out, const SolveOutcome& solved, const ScenePointPointerList& leaving, double seconds) const;
 };
 
 #endif

@@ -16,7 +16,7 @@ class Options(C.Structure):
                 ("maskBlockRadius", C.c_int32), ("maxFrameDistance", C.c_int32), ("nonMaxSuppRadius", C.c_int32),
                 ("doGaussianWeighting", C.c_int32), ("verbose", C.c_int32), ("device", C.c_int32), ("descriptorType", C.c_int32), ("gpuFrontEnd", C.c_int32),
                 ("minScore", C.c_double), ("robustThreshold", C.c_double), ("minValidDepth", C.c_double),
-                ("maxValidDepth", C.c_double)]
+                ("maxValidDepth", C.c_double), ("numPyramidLevels", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -108,6 +108,14 @@ class BundleAdjuster:
     def write_poses(self, path: str):
         if lib().pbah_write_poses_kitti(self._h, path.encode()) != 0:
             raise RuntimeError("writePosesKittiFormat failed")
+
+
+def disparity_to_depth(disparity: np.ndarray, Bf: float) -> np.ndarray:
+    """disparityToDepth of the host shim (src/imgproc.cc:280-330 semantics)."""
+    d = np.ascontiguousarray(disparity, dtype=np.float32)
+    out = np.zeros_like(d)
+    lib().pbah_disparity_to_depth(C.c_void_p(d.ctypes.data), d.shape[0], d.shape[1], C.c_float(Bf), C.c_void_p(out.ctypes.data))
+    return out
 
 
 def load_poses_kitti(path: str, cap: int = 100000) -> np.ndarray:

@@ -268,3 +268,58 @@ def test_sixteen_free_cameras_full_reduced_system():
     for a, b in zip(tr, otr):
         assert abs(a["cost"] - b["cost"]) <= 1e-6 * b["cost"]
     assert s["final_cost"] < 0.6 * s["initial_cost"]
+
+
+@pytest.mark.gpu
+def test_set_points_rejects_malformed_visibility(small_win):
+    """One residual block per (point, frame): more observations than frames, a frame listed twice, or a frame index
+    beyond the window are argument errors, not silent memory corruption (the kernels keep a point's observations in
+    per-frame slots)."""
+    w = small_win
+    h = capi.Handle(w.rows, w.cols, w.fx, w.fy, w.cx, w.cy, radius=w.radius, huber=w.huber, max_frames=w.n_frames,
+                    max_points=w.n_points, max_observations=w.n_obs + 8)
+    h.set_frames_u8(w.images)
+    h.set_poses(w.cams_init, w.fixed_frame)
+    off, frm = w.obs_offsets.copy(), w.obs_frame.copy()
+    bad = frm.copy()
+    bad[1] = bad[0]                                   # duplicate frame inside point 0
+    with pytest.raises(capi.PbaError, match="more than once"):
+        h.set_points(w.points_init, w.desc, off, bad, w.weights)
+    bad = frm.copy()
+    bad[0] = w.n_frames                               # out of range
+    with pytest.raises(capi.PbaError, match="outside"):
+        h.set_points(w.points_init, w.desc, off, bad, w.weights)
+    n0 = int(off[1])
+    off2 = np.concatenate([[0], off[1:] + (w.n_frames + 1 - n0)]).astype(np.int32)    # point 0 gets F + 1 observations
+    frm2 = np.concatenate([np.arange(w.n_frames + 1) % w.n_frames, frm[n0:]]).astype(np.int32)
+    with pytest.raises(capi.PbaError, match="observations in a window"):
+        h.set_points(w.points_init, w.desc, off2, frm2, w.weights)
+    h.set_points(w.points_init, w.desc, off, frm, w.weights)       # the handle is still usable
+    assert h.solve()["final_cost"] > 0
+    h.close()
+
+
+@pytest.mark.gpu
+def test_batched_uploads_and_single_frame_replacement(small_win):
+    """pba_begin_batch: uploads only enqueue, the solve consumes them; pba_set_frame_u8_ex replaces one frame of a
+    resident window; pba_get_results = get_poses + get_points.  Same result as the blocking calls."""
+    w = small_win
+    h = capi.Handle.for_window(w)
+    s0 = h.solve()
+    c0, p0 = h.get_poses(), h.get_points()
+    h2 = capi.Handle(w.rows, w.cols, w.fx, w.fy, w.cx, w.cy, radius=w.radius, huber=w.huber, max_frames=w.n_frames,
+                     max_points=w.n_points, max_observations=w.n_obs)
+    garbage = np.ascontiguousarray(w.images[::-1])
+    h2.set_frames_u8(garbage)                         # wrong frames first ...
+    h2.begin_batch()
+    for f in range(w.n_frames):
+        h2.set_frame_u8_ex(f, w.images[f])            # ... replaced one by one, inside a batch
+    h2.set_poses(w.cams_init, w.fixed_frame)
+    h2.set_points(w.points_init, w.desc, w.obs_offsets, w.obs_frame, w.weights)
+    s1 = h2.solve()
+    c1, p1 = h2.get_results()
+    assert s1["num_iterations"] == s0["num_iterations"]
+    assert abs(s1["final_cost"] - s0["final_cost"]) <= 1e-9 * s0["final_cost"]
+    np.testing.assert_allclose(c1, c0, atol=1e-8)
+    np.testing.assert_allclose(p1, p0, atol=1e-6)
+    h.close(); h2.close()
