@@ -202,8 +202,9 @@ int pba_copy_state(pba_handle* dst, pba_handle* src);
 /* Uploads without a host round trip per call.  Between pba_begin_batch() and the next pba_solve() (or pba_end_batch())
  * the pba_set_* calls only ENQUEUE their host->device copies; the caller keeps every buffer it passed alive and
  * unchanged until that pba_solve() / pba_end_batch() returns (at most one pba_set_points per batch).  A sliding window
- * changes one frame per solve: pba_set_frame_u8_ex() replaces the frame in `slot` of a window set earlier - the level-0
- * uint8 image is reduced `levels_down` times on the device (cv::pyrDown rule) and / or expanded into the channels of
+ * changes one frame per solve: pba_set_frame_u8_ex() replaces the frame in ring slot `slot` (on a handle with no window
+ * yet the ring has cfg.max_frames slots and unwritten slots read as black frames, so a caller may feed frames one by
+ * one from the first addFrame on) - the level-0 uint8 image is reduced `levels_down` times on the device (cv::pyrDown rule) and / or expanded into the channels of
  * `descriptor_type`.  pba_get_results() reads poses and points back with one synchronisation.
  * (what the reference does per frame: DescriptorFrame::Create + ring buffer push, src/photobundle.cc:495, :608) */
 int pba_begin_batch(pba_handle* h);
@@ -264,6 +265,15 @@ int pba_comm_unique_id(void* id128);
 int pba_shard_range(int32_t n_points, const int32_t* obs_offsets, int32_t rank, int32_t n_ranks,
                     int32_t* first, int32_t* last);
 int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_ranks);
+/* The same communicator for `n` handles of ONE process, each on its own device (rank = position in `handles`):
+ * no NCCL, no CUDA IPC - peer access is enabled between the devices and the kernels address the peers' exchange
+ * buffers directly.  Every member then receives the same pba_set_* calls, and pba_solve() must be called on all
+ * members CONCURRENTLY, one host thread per handle (the call blocks while its device waits for the peers; a member
+ * whose peers do not show up within 60 s fails with PBA_ERR_STATE).  pba_get_points / pba_get_results gather the
+ * shards from the peers and may be called on any member once every pba_solve() has returned.  Destroy the members
+ * together.  This is how the C++ class drives Options::nGpus devices behind an unchanged addFrame() (the reference
+ * has no counterpart: apps/run_kitti.cc:47 stays as it is). */
+int pba_comm_init_local(pba_handle* const* handles, int32_t n);
 /* How the per-iteration sums travel between the GPUs of a window: PBA_EXCHANGE_NONE (one GPU),
  * PBA_EXCHANGE_PEER (default: every rank stores its pose blocks / reduced-system contribution
  * straight into all peers' memory over NVLink from inside the kernels and the consumers sum the

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "pba_last_error", "pba_version", "pba_default_solver_options", "pba_create", "pba_destroy",
     "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_frames_u8_pyr", "pba_pyrdown_u8", "pba_set_poses", "pba_set_points",
     "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_copy_state", "pba_begin_batch", "pba_end_batch", "pba_set_frame_u8_ex", "pba_get_results", "pba_get_poses", "pba_get_points", "pba_get_iterations",
-    "pba_comm_unique_id", "pba_comm_init", "pba_shard_range", "pba_comm_exchange_kind",
+    "pba_comm_unique_id", "pba_comm_init", "pba_comm_init_local", "pba_shard_range", "pba_comm_exchange_kind",
     "pba_descriptor_channels", "pba_set_frames_u8_descriptor", "pba_get_channel_plane", "pba_prepare_frame_u8",
     "pba_saliency_map", "pba_extract_descriptors", "pba_associate", "pba_select_candidates",
 ]
@@ -329,6 +329,35 @@ class Handle:
         buf = C.create_string_buffer(unique_id, PBA_UNIQUE_ID_BYTES)
         _check(lib().pba_comm_init(self._h, buf, int(rank), int(n_ranks)), "pba_comm_init")
         self.rank, self.n_ranks = rank, n_ranks
+
+    @staticmethod
+    def comm_init_local(handles):
+        """Handles of THIS process, one per device, joined without NCCL / IPC; solve them with solve_all()."""
+        arr = (C.c_void_p * len(handles))(*[h._h for h in handles])
+        _check(lib().pba_comm_init_local(arr, len(handles)), "pba_comm_init_local")
+        for r, h in enumerate(handles):
+            h.rank, h.n_ranks = r, len(handles)
+
+    @staticmethod
+    def solve_all(handles, **kw):
+        """pba_solve on every member concurrently, one thread per handle (ctypes releases the GIL)."""
+        import threading
+        out, err = [None] * len(handles), [None] * len(handles)
+
+        def run(i):
+            try:
+                out[i] = handles[i].solve(**kw)
+            except Exception as e:  # noqa: BLE001
+                err[i] = e
+        ts = [threading.Thread(target=run, args=(i,)) for i in range(len(handles))]
+        for th in ts:
+            th.start()
+        for th in ts:
+            th.join()
+        for e in err:
+            if e is not None:
+                raise e
+        return out
 
     def exchange_kind(self) -> str:
         return {0: "none", 1: "peer-memory", 2: "nccl"}[int(lib().pba_comm_exchange_kind(self._h))]

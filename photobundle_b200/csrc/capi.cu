@@ -16,6 +16,9 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <nccl.h>   // types/enums only: the library is dlopen'ed when a communicator is requested
 
 using namespace pba;
@@ -79,6 +82,25 @@ static int fail(int code, const char* fmt, ...) {
       return fail(PBA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// A communicator whose ranks are handles of ONE process (pba_comm_init_local): the exchange buffers of the peers are
+// addressed directly (cudaDeviceEnablePeerAccess), and the threads that call pba_solve meet at a host barrier before
+// the first kernel that waits on a peer is launched (allocations made while a peer spins could otherwise block).
+struct LocalGroup {
+  std::mutex m;
+  std::condition_variable cv;
+  std::vector<pba_handle*> members;
+  int arrived = 0;
+  unsigned long long generation = 0;
+  bool arrive_and_wait(int seconds) {
+    std::unique_lock<std::mutex> lk(m);
+    const unsigned long long gen = generation;
+    if (++arrived == (int)members.size()) { arrived = 0; ++generation; cv.notify_all(); return true; }
+    const bool ok = cv.wait_for(lk, std::chrono::seconds(seconds), [&] { return generation != gen; });
+    if (!ok) --arrived;
+    return ok;
+  }
+};
+
 struct pba_handle {
   pba_config cfg;
   int device = 0, sm_count = 148;
@@ -135,6 +157,7 @@ struct pba_handle {
   // multi-GPU: points sharded by contiguous block, frames/poses replicated
   int rank = 0, n_ranks = 1;
   ncclComm_t comm = nullptr;
+  std::shared_ptr<struct LocalGroup> group;   // set by pba_comm_init_local: the ranks are handles of this process
   int n_points_total = 0, nnz_total = 0;
   std::vector<int> shard_begin;   // [n_ranks+1] first global point of each rank
   // per-iteration exchange over NVLink peer memory (CUDA IPC), see pba_device.cuh `Xchg`; when it cannot
@@ -170,7 +193,12 @@ static void free_all(pba_handle* h) {
   cudaFree(h->d_desc); cudaFree(h->d_obs_off); cudaFree(h->d_obs_frame); cudaFree(h->d_V); cudaFree(h->d_gp);
   cudaFree(h->d_W); cudaFree(h->d_Xacc); cudaFree(h->d_Ucur);
   for (int q = 0; q < kMaxRanks; ++q)
-    if (h->peer_xchg[q] && h->peer_xchg[q] != h->d_xchg) cudaIpcCloseMemHandle(h->peer_xchg[q]);
+    if (!h->group && h->peer_xchg[q] && h->peer_xchg[q] != h->d_xchg) cudaIpcCloseMemHandle(h->peer_xchg[q]);
+  if (h->group) {   // leave the group: the remaining members must not be solved again (their peers' buffers are gone)
+    std::lock_guard<std::mutex> lk(h->group->m);
+    auto& mem = h->group->members;
+    mem.erase(std::remove(mem.begin(), mem.end(), h), mem.end());
+  }
   cudaFree(h->d_xchg);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   cudaFree(h->d_scale_p); cudaFree(h->d_Vinv); cudaFree(h->d_S); cudaFree(h->d_Vinv2); cudaFree(h->d_ticket); cudaFree(h->d_dbg); cudaFree(h->d_stamps);
@@ -183,6 +211,41 @@ static void free_all(pba_handle* h) {
 }
 
 
+// The exchange buffer of one rank: 16-byte LL cells for exchange 1 (evaluation + P under both hypotheses) and exchange 2
+// (P again after a mis-speculation), double-buffered by epoch parity, one region per source rank; then the arrival
+// flags, the verdict word and the error word.
+struct XchgLayout { size_t x1_n, x2_n, n_cells, bytes; };
+static XchgLayout xchg_layout(int max_frames, int n) {
+  const size_t F = (size_t)max_frames, D = 6 * F;
+  const size_t xa_n = F * kUStride + kEacc + kMaxRanks, nn = D * (D + 1);
+  XchgLayout l;
+  l.x1_n = xa_n + 2 * nn; l.x2_n = nn;
+  l.n_cells = 2 * (size_t)n * (l.x1_n + l.x2_n);
+  l.bytes = sizeof(ulonglong2) * l.n_cells + sizeof(unsigned long long) * ((size_t)n + 2) + 64;
+  return l;
+}
+
+// h->peer_xchg[0..n) are mapped: fill the kernel-side descriptor and switch the handle to the peer-memory exchange
+static int adopt_xchg(pba_handle* h, const XchgLayout& lay) {
+  const int n = h->n_ranks;
+  Xchg& x = h->xc;
+  memset(&x, 0, sizeof(x));
+  x.n_ranks = n; x.rank = h->rank; x.x1_n = (int)lay.x1_n; x.x2_n = (int)lay.x2_n;
+  for (int q = 0; q < n; ++q) {
+    ulonglong2* base = static_cast<ulonglong2*>(h->peer_xchg[q]);
+    x.x1[q] = base;
+    x.x2[q] = base + 2 * n * lay.x1_n;
+    x.fr[q] = reinterpret_cast<unsigned long long*>(base + lay.n_cells);
+  }
+  unsigned long long* fl_own = reinterpret_cast<unsigned long long*>(static_cast<ulonglong2*>(h->d_xchg) + lay.n_cells);
+  x.verdict = fl_own + n;
+  x.error = reinterpret_cast<int*>(fl_own + n + 1);
+  if (!h->d_Vinv2) CUDA_TRY(cudaMalloc(&h->d_Vinv2, sizeof(double) * 2 * (size_t)h->cfg.max_points * 6));
+  h->use_xchg = true;
+  h->epoch_next = 1;
+  return PBA_OK;
+}
+
 // Peer-memory exchange buffers: allocate, export through CUDA IPC, all-gather the handles with NCCL, map
 // every peer.  All ranks agree (all-reduce of a success flag) on whether the exchange is usable; when
 // it is not, the NCCL all-reduce path stays in place.
@@ -191,11 +254,8 @@ static int setup_xchg(pba_handle* h) {
   const int n = h->n_ranks;
   const char* mode = getenv("PBA_MGPU_EXCHANGE");
   int want = !(mode && strcmp(mode, "nccl") == 0);
-  const size_t F = h->cfg.max_frames, D = 6 * F;
-  const size_t xa_n = F * kUStride + kEacc + kMaxRanks, nn = D * (D + 1);
-  const size_t x1_n = xa_n + 2 * nn, x2_n = nn;   // exchange 1: evaluation + P under both hypotheses; exchange 2: P
-  const size_t n_cells = 2 * n * (x1_n + x2_n);   // 16-byte LL cells
-  const size_t bytes = sizeof(ulonglong2) * n_cells + sizeof(unsigned long long) * (n + 2) + 64;
+  const XchgLayout lay = xchg_layout(h->cfg.max_frames, n);
+  const size_t x1_n = lay.x1_n, x2_n = lay.x2_n, n_cells = lay.n_cells, bytes = lay.bytes;
   if (h->d_xchg) { cudaFree(h->d_xchg); h->d_xchg = nullptr; }
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
@@ -239,22 +299,8 @@ static int setup_xchg(pba_handle* h) {
     if (want) fprintf(stderr, "[pba_b200] rank %d: peer-memory exchange unavailable, using NCCL all-reduce\n", h->rank);
     return PBA_OK;
   }
-  Xchg& x = h->xc;
-  memset(&x, 0, sizeof(x));
-  x.n_ranks = n; x.rank = h->rank; x.x1_n = (int)x1_n; x.x2_n = (int)x2_n;
-  for (int q = 0; q < n; ++q) {
-    ulonglong2* base = static_cast<ulonglong2*>(h->peer_xchg[q]);
-    x.x1[q] = base;
-    x.x2[q] = base + 2 * n * x1_n;
-    x.fr[q] = reinterpret_cast<unsigned long long*>(base + n_cells);
-  }
-  unsigned long long* fl_own = reinterpret_cast<unsigned long long*>(static_cast<ulonglong2*>(h->d_xchg) + n_cells);
-  x.verdict = fl_own + n;
-  x.error = reinterpret_cast<int*>(fl_own + n + 1);
-  if (!h->d_Vinv2) CUDA_TRY(cudaMalloc(&h->d_Vinv2, sizeof(double) * 2 * (size_t)h->cfg.max_points * 6));
-  h->use_xchg = true;
-  h->epoch_next = 1;
-  return PBA_OK;
+  (void)x1_n; (void)x2_n; (void)n_cells;
+  return adopt_xchg(h, lay);
 }
 
 // End of an upload call: block until the borrowed host buffers have been consumed - unless the caller has opened a
@@ -1011,6 +1057,18 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   if (timeline && !h->d_dbg) CUDA_TRY(cudaMalloc(&h->d_dbg, sizeof(unsigned long long) * 16 * 1024));
   const int sgrid = h->use_xchg ? schur_grid_x(h->n_points, h->sm_count) : schur_grid(h->n_points, h->sm_count);
   int launches = 0;
+  const bool multi = h->n_ranks > 1 && !h->use_xchg;   // NCCL all-reduce path; the peer-memory exchange needs no host-side calls
+  // one GPU: the whole loop runs on the device (WHILE node); PBA_NO_GRAPH=1 keeps the stream loop
+  const bool use_graph = !multi && !timeline && getenv("PBA_NO_GRAPH") == nullptr;
+  if (use_graph) {
+    rc = ensure_lm_graph(h, lp, sgrid, s->n_free);
+    if (rc) return rc;
+  }
+  if (h->group) {   // ranks of one process: every allocation above is done before any rank launches a kernel that waits on a peer
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!h->group->arrive_and_wait(60))
+      return fail(PBA_ERR_STATE, "pba_solve: the other members of the local communicator did not call pba_solve (one thread per handle, concurrently)");
+  }
   if (h->use_xchg) {   // align the ranks before the clock starts (device-side barrier over peer memory)
     CUDA_TRY(launch_rendezvous(h->xc, s->xepoch, h->stream));
     launches += 1;
@@ -1019,7 +1077,6 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   // iteration 0: evaluate x.  Then per LM iteration: K_B (decide + Schur + solve), K_A
   // (back-substitute + evaluate the candidate).  The state ping-pongs between two structs;
   // kernels turn into no-ops once `done` is set, so iterations are enqueued in groups.
-  const bool multi = h->n_ranks > 1 && !h->use_xchg;   // NCCL all-reduce path; the peer-memory exchange needs no host-side calls
   const size_t xacc_n = (size_t)F * kUStride + kEacc + kMaxRanks;
   int collectives = 0;
   CUDA_TRY(launch_k_step(make_step_params(h, h->d_state), h->cfg.patch_radius, h->stream));
@@ -1031,11 +1088,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   const int group = 4;
   bool done = false;
   int k = 0;
-  // one GPU: the whole loop runs on the device (WHILE node); PBA_NO_GRAPH=1 keeps the stream loop
-  const bool use_graph = !multi && !timeline && getenv("PBA_NO_GRAPH") == nullptr;
   if (use_graph) {
-    rc = ensure_lm_graph(h, lp, sgrid, s->n_free);
-    if (rc) return rc;
     CUDA_TRY(cudaGraphLaunch(h->lm_exec, h->stream));
     CUDA_TRY(cudaMemcpyAsync(s, h->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
@@ -1195,8 +1248,8 @@ int pba_end_batch(pba_handle* h) {
 int pba_set_frame_u8_ex(pba_handle* h, int32_t slot, const uint8_t* image, int32_t src_rows, int32_t src_cols, int32_t levels_down,
                         int32_t descriptor_type) {
   if (!h || !image) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8_ex: null argument");
-  if (!h->have_frames) return fail(PBA_ERR_STATE, "pba_set_frame_u8_ex: replaces one frame of a window that has been set (pba_set_frames_* first)");
-  if (slot < 0 || slot >= h->n_frames) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8_ex: slot %d of %d frames", slot, h->n_frames);
+  const int n_slots = h->have_frames ? h->n_frames : h->cfg.max_frames;   // a cold handle: the ring has max_frames slots
+  if (slot < 0 || slot >= n_slots) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8_ex: slot %d of %d frames", slot, n_slots);
   const int C = pba_descriptor_channels(descriptor_type);
   if (C < 0 || C != h->cfg.n_channels) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8_ex: descriptor type %d does not match the handle's %d channels", descriptor_type, h->cfg.n_channels);
   if (levels_down < 0 || (levels_down > 0 && C != 1)) return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8_ex: pyramid levels are built for the Intensity descriptor only");
@@ -1205,6 +1258,17 @@ int pba_set_frame_u8_ex(pba_handle* h, int32_t slot, const uint8_t* image, int32
   if (r != h->cfg.rows || cc != h->cfg.cols)
     return fail(PBA_ERR_ARGUMENT, "pba_set_frame_u8_ex: %dx%d reduced %d times is %dx%d, handle is %dx%d", src_rows, src_cols, levels_down, r, cc, h->cfg.rows, h->cfg.cols);
   CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->have_frames) {   // no window yet: the slots not written so far read as black frames
+    if (!h->d_u8) {
+      CUDA_TRY(cudaMalloc(&h->d_u8, (size_t)h->cfg.max_frames * h->plane + 64));
+      CUDA_TRY(cudaMemsetAsync(h->d_u8, 0, (size_t)h->cfg.max_frames * h->plane, h->stream));
+    }
+    if (C > 1 && !h->d_f32) {
+      CUDA_TRY(cudaMalloc(&h->d_f32, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane + 64));
+      CUDA_TRY(cudaMemsetAsync(h->d_f32, 0, sizeof(float) * (size_t)h->cfg.max_frames * C * h->plane, h->stream));
+    }
+    h->frames_are_u8 = (C == 1); h->have_frames = true; h->n_frames = h->cfg.max_frames;
+  }
   if (levels_down == 0) {
     int rc = upload_plane_u8(h, slot, image);
     if (rc) return rc;
@@ -1272,12 +1336,24 @@ int pba_get_points(pba_handle* h, double* xyz) {
   double* full = h->d_pts_full;
   CUDA_TRY(cudaMemcpyAsync(full + (size_t)h->shard_begin[h->rank] * 3, h->d_pts, sizeof(double) * (size_t)h->n_points * 3,
                            cudaMemcpyDeviceToDevice, h->stream));
-  NCCL_TRY(g_nccl.GroupStart());
-  for (int r = 0; r < h->n_ranks; ++r) {
-    const size_t cnt = (size_t)(h->shard_begin[r + 1] - h->shard_begin[r]) * 3;
-    if (cnt) NCCL_TRY(g_nccl.Broadcast(full + (size_t)h->shard_begin[r] * 3, full + (size_t)h->shard_begin[r] * 3, cnt, ncclDouble, r, h->comm, h->stream));
+  if (h->group) {   // ranks of this process: read the peers' shards directly (their solves have returned)
+    std::vector<pba_handle*> mem;
+    { std::lock_guard<std::mutex> lk(h->group->m); mem = h->group->members; }
+    if ((int)mem.size() != h->n_ranks) return fail(PBA_ERR_STATE, "pba_get_points: a member of the local communicator has been destroyed");
+    for (int r = 0; r < h->n_ranks; ++r) {
+      const size_t cnt = (size_t)(h->shard_begin[r + 1] - h->shard_begin[r]) * 3;
+      if (!cnt || r == h->rank) continue;
+      if (mem[r]->n_points * 3 != (int)cnt) return fail(PBA_ERR_STATE, "pba_get_points: rank %d holds %d points, %zu expected (pba_set_points on every member first)", r, mem[r]->n_points, cnt / 3);
+      CUDA_TRY(cudaMemcpyPeerAsync(full + (size_t)h->shard_begin[r] * 3, h->device, mem[r]->d_pts, mem[r]->device, sizeof(double) * cnt, h->stream));
+    }
+  } else {
+    NCCL_TRY(g_nccl.GroupStart());
+    for (int r = 0; r < h->n_ranks; ++r) {
+      const size_t cnt = (size_t)(h->shard_begin[r + 1] - h->shard_begin[r]) * 3;
+      if (cnt) NCCL_TRY(g_nccl.Broadcast(full + (size_t)h->shard_begin[r] * 3, full + (size_t)h->shard_begin[r] * 3, cnt, ncclDouble, r, h->comm, h->stream));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
   }
-  NCCL_TRY(g_nccl.GroupEnd());
   CUDA_TRY(cudaMemcpyAsync(xyz, full, sizeof(double) * (size_t)h->n_points_total * 3, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return PBA_OK;
@@ -1317,6 +1393,7 @@ int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_rank
   if (const char* e = load_nccl()) return fail(PBA_ERR_NCCL, "pba_comm_init: %s", e);
   CUDA_TRY(cudaSetDevice(h->device));
   if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+  if (h->group) return fail(PBA_ERR_STATE, "pba_comm_init: the handle belongs to a local communicator (pba_comm_init_local)");
   h->rank = 0; h->n_ranks = 1;
   if (n_ranks > 1) {
     ncclUniqueId id;
@@ -1324,6 +1401,52 @@ int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_rank
     NCCL_TRY(g_nccl.CommInitRank(&h->comm, n_ranks, id, rank));
     h->rank = rank; h->n_ranks = n_ranks;
     int rc = setup_xchg(h);
+    if (rc) return rc;
+  }
+  return PBA_OK;
+}
+
+int pba_comm_init_local(pba_handle* const* handles, int32_t n) {
+  if (!handles || n < 1 || n > kMaxRanks) return fail(PBA_ERR_ARGUMENT, "pba_comm_init_local: %d handles (1..%d)", n, kMaxRanks);
+  for (int i = 0; i < n; ++i) {
+    pba_handle* h = handles[i];
+    if (!h) return fail(PBA_ERR_ARGUMENT, "pba_comm_init_local: handles[%d] is null", i);
+    if (h->have_points) return fail(PBA_ERR_STATE, "pba_comm_init_local: call before pba_set_points (points are sharded at upload)");
+    if (h->comm || h->group || h->n_ranks != 1) return fail(PBA_ERR_STATE, "pba_comm_init_local: handles[%d] already belongs to a communicator", i);
+    if (h->cfg.max_frames != handles[0]->cfg.max_frames) return fail(PBA_ERR_ARGUMENT, "pba_comm_init_local: handles differ in max_frames");
+    for (int j = 0; j < i; ++j)
+      if (handles[j] == h || handles[j]->device == h->device)
+        return fail(PBA_ERR_ARGUMENT, "pba_comm_init_local: handles[%d] and handles[%d] are on the same device %d", j, i, h->device);
+  }
+  if (n == 1) return PBA_OK;
+  for (int i = 0; i < n; ++i) {
+    CUDA_TRY(cudaSetDevice(handles[i]->device));
+    for (int j = 0; j < n; ++j) {
+      if (i == j) continue;
+      int can = 0;
+      CUDA_TRY(cudaDeviceCanAccessPeer(&can, handles[i]->device, handles[j]->device));
+      if (!can) return fail(PBA_ERR_STATE, "pba_comm_init_local: device %d cannot access device %d (use one process per GPU and pba_comm_init)", handles[i]->device, handles[j]->device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(handles[j]->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) return fail(PBA_ERR_CUDA, "pba_comm_init_local: cudaDeviceEnablePeerAccess(%d -> %d): %s", handles[i]->device, handles[j]->device, cudaGetErrorString(e));
+    }
+  }
+  const XchgLayout lay = xchg_layout(handles[0]->cfg.max_frames, n);
+  for (int i = 0; i < n; ++i) {
+    pba_handle* h = handles[i];
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->d_xchg) { cudaFree(h->d_xchg); h->d_xchg = nullptr; }
+    CUDA_TRY(cudaMalloc(&h->d_xchg, lay.bytes));
+    CUDA_TRY(cudaMemset(h->d_xchg, 0, lay.bytes));
+  }
+  auto group = std::make_shared<LocalGroup>();
+  group->members.assign(handles, handles + n);
+  for (int i = 0; i < n; ++i) {
+    pba_handle* h = handles[i];
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->rank = i; h->n_ranks = n; h->group = group;
+    for (int q = 0; q < kMaxRanks; ++q) h->peer_xchg[q] = q < n ? handles[q]->d_xchg : nullptr;
+    int rc = adopt_xchg(h, lay);
     if (rc) return rc;
   }
   return PBA_OK;

@@ -18,7 +18,7 @@ struct pbah_options {
   int32_t maxNumPoints, slidingWindowSize, patchRadius, maskBlockRadius, maxFrameDistance, nonMaxSuppRadius;
   int32_t doGaussianWeighting, verbose, device, descriptorType /* 0 Intensity, 1 IntensityAndGradient, 2 BitPlanes */, gpuFrontEnd;
   double minScore, robustThreshold, minValidDepth, maxValidDepth;
-  int32_t numPyramidLevels, reserved;
+  int32_t numPyramidLevels, nGpus;
 };
 
 extern "C" {
@@ -31,7 +31,7 @@ void pbah_default_options(pbah_options* o) {
   o->maskBlockRadius = d.maskBlockRadius; o->maxFrameDistance = d.maxFrameDistance; o->nonMaxSuppRadius = d.nonMaxSuppRadius;
   o->doGaussianWeighting = d.doGaussianWeighting; o->verbose = d.verbose; o->device = d.device; o->descriptorType = (int32_t)d.descriptorType; o->gpuFrontEnd = d.gpuFrontEnd ? 1 : 0;
   o->minScore = d.minScore; o->robustThreshold = d.robustThreshold; o->minValidDepth = d.minValidDepth; o->maxValidDepth = d.maxValidDepth;
-  o->numPyramidLevels = d.numPyramidLevels; o->reserved = 0;
+  o->numPyramidLevels = d.numPyramidLevels; o->nGpus = d.nGpus;
 }
 
 int pbah_create(int32_t rows, int32_t cols, double fx, double fy, double cx, double cy, double baseline,
@@ -48,6 +48,7 @@ int pbah_create(int32_t rows, int32_t cols, double fx, double fy, double cx, dou
     opt.gpuFrontEnd = o->gpuFrontEnd != 0;
     opt.minScore = o->minScore; opt.robustThreshold = o->robustThreshold; opt.minValidDepth = o->minValidDepth; opt.maxValidDepth = o->maxValidDepth;
     opt.numPyramidLevels = o->numPyramidLevels > 0 ? o->numPyramidLevels : 1;
+    opt.nGpus = o->nGpus > 0 ? o->nGpus : 1;
     pbah_handle* h = new pbah_handle();
     h->ba = new PhotometricBundleAdjustment(Calibration(K, baseline), ImageSize(rows, cols), opt);
     *out = h;

@@ -16,6 +16,8 @@
 #include <limits>
 #include <sstream>
 
+#include <thread>
+
 #include "../../include/pba_b200.h"
 #include "config.h"
 #include "photobundle_pyramid.h"
@@ -356,7 +358,10 @@ PhotometricBundleAdjustment::Options::Options(const utils::ConfigFile& cf)   // 
       maxValidDepth(cf.get<double>("maxValidDepth", 1000.0)),
       nonMaxSuppRadius(cf.get<int>("nonMaxSuppRadius", 1)),
       descriptorType(DescriptorTypeFromString(cf.get<std::string>("descriptorType", "Intensity"))),
-      numPyramidLevels(cf.get<int>("numPyramidLevels", 1)) {}
+      device(cf.get<int>("device", -1)),
+      gpuFrontEnd((bool)cf.get<int>("gpuFrontEnd", 0)),
+      numPyramidLevels(cf.get<int>("numPyramidLevels", 1)),
+      nGpus(cf.get<int>("nGpus", 1)) {}
 
 // ---------------------------------------------------------------------------- ctor / dtor
 PhotometricBundleAdjustment::PhotometricBundleAdjustment(const Calibration& calib, const ImageSize& image_size,
@@ -370,6 +375,7 @@ PhotometricBundleAdjustment::PhotometricBundleAdjustment(const Calibration& cali
                                                                                          : PBA_DESC_BITPLANES;
   _n_channels = pba_descriptor_channels(_desc_type);
   if (_options.numPyramidLevels < 1 || _options.numPyramidLevels > 6) throw std::runtime_error("numPyramidLevels outside [1, 6]");
+  if (_options.nGpus < 1 || _options.nGpus > 8) throw std::runtime_error("nGpus outside [1, 8]");
   if (_options.numPyramidLevels > 1 && _desc_type != PBA_DESC_INTENSITY)
     throw std::runtime_error("pyramid levels are defined for the Intensity descriptor");
   _mask.resize((size_t)_image_size.rows * _image_size.cols);
@@ -388,7 +394,7 @@ PhotometricBundleAdjustment::PhotometricBundleAdjustment(const Calibration& cali
 
 PhotometricBundleAdjustment::~PhotometricBundleAdjustment() {
   for (DeviceLevel& d : _dev)
-    if (d.h) pba_destroy(d.h);
+    for (pba_handle* h : d.ranks) pba_destroy(h);
 }
 
 static void check_pba(int rc, const char* what) {
@@ -399,7 +405,8 @@ static void check_pba(int rc, const char* what) {
 pba_handle* PhotometricBundleAdjustment::deviceLevel(int level, int n_points, int n_obs) {
   DeviceLevel& d = _dev[(size_t)level];
   if (d.h && n_points <= d.cap_points && n_obs <= d.cap_obs) return d.h;
-  if (d.h) { pba_destroy(d.h); d.h = nullptr; }
+  for (pba_handle* h : d.ranks) pba_destroy(h);
+  d.ranks.clear(); d.h = nullptr;
   pba_config cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.rows = d.size.rows; cfg.cols = d.size.cols; cfg.n_channels = _n_channels;
@@ -410,7 +417,16 @@ pba_handle* PhotometricBundleAdjustment::deviceLevel(int level, int n_points, in
   cfg.device = _options.device;
   cfg.fx = d.calib.fx(); cfg.fy = d.calib.fy(); cfg.cx = d.calib.cx(); cfg.cy = d.calib.cy();
   cfg.huber = _options.robustThreshold;
-  check_pba(pba_create(&cfg, &d.h), "pba_create");
+  const int n_gpus = _options.nGpus;
+  if (n_gpus > 1 && cfg.device < 0) cfg.device = 0;
+  for (int r = 0; r < n_gpus; ++r) {      // one handle per device; the points are sharded at pba_set_points
+    pba_handle* h = nullptr;
+    check_pba(pba_create(&cfg, &h), "pba_create");
+    d.ranks.push_back(h);
+    cfg.device += 1;
+  }
+  d.h = d.ranks[0];
+  if (n_gpus > 1) check_pba(pba_comm_init_local(d.ranks.data(), n_gpus), "pba_comm_init_local");
   std::fill(d.resident.begin(), d.resident.end(), (long long)-1);
   return d.h;
 }
@@ -598,23 +614,14 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
 // Frames live in device slots id % slidingWindowSize: a new frame replaces the one that left the window, everything
 // else stays resident (the reference's ring buffer, on the device).  The window-local frame index of the C ABI is
 // that slot.
-void PhotometricBundleAdjustment::uploadWindowFrames(int level, pba_handle* h) {
+void PhotometricBundleAdjustment::uploadWindowFrames(int level) {
   DeviceLevel& d = _dev[(size_t)level];
   const int W = _options.slidingWindowSize, rows = _image_size.rows, cols = _image_size.cols;
-  bool any_resident = false;
-  for (long long id : d.resident) any_resident = any_resident || id >= 0;
-  if (!any_resident) {   // first solve on this handle: the whole window, in slot order
-    std::vector<const uint8_t*> imgs((size_t)W, nullptr);
-    for (const Frame& f : _frame_buffer) imgs[(size_t)(f.id % (uint32_t)W)] = f.image.data();
-    if (level == 0) check_pba(pba_set_frames_u8_descriptor(h, W, imgs.data(), _desc_type), "pba_set_frames_u8_descriptor");
-    else check_pba(pba_set_frames_u8_pyr(h, W, imgs.data(), rows, cols, d.levels_down), "pba_set_frames_u8_pyr");
-    for (const Frame& f : _frame_buffer) d.resident[(size_t)(f.id % (uint32_t)W)] = f.id;
-    return;
-  }
   for (const Frame& f : _frame_buffer) {
     const size_t slot = (size_t)(f.id % (uint32_t)W);
     if (d.resident[slot] == (long long)f.id) continue;
-    check_pba(pba_set_frame_u8_ex(h, (int32_t)slot, f.image.data(), rows, cols, d.levels_down, _desc_type), "pba_set_frame_u8_ex");
+    for (pba_handle* h : d.ranks)   // frames are replicated on every device of the level
+      check_pba(pba_set_frame_u8_ex(h, (int32_t)slot, f.image.data(), rows, cols, d.levels_down, _desc_type), "pba_set_frame_u8_ex");
     d.resident[slot] = f.id;
   }
 }
@@ -664,16 +671,35 @@ void PhotometricBundleAdjustment::optimize(Result* result) {
   if (n_sel > 0 && nnz > 0) {
     pba_solver_options opt;
     pba_default_solver_options(&opt);       // GetSolverOptions, src/photobundle.cc:738-761
+    const DeviceLevel* coarser_level = nullptr;
     pba_handle* coarser = nullptr;
     for (int l = L - 1; l >= 0; --l) {      // coarse to fine; a single level is the reference's optimize()
-      pba_handle* h = deviceLevel(l, n_sel, nnz);
-      check_pba(pba_begin_batch(h), "pba_begin_batch");      // uploads are enqueued; every buffer lives until pba_solve returns
-      uploadWindowFrames(l, h);
-      check_pba(pba_set_poses(h, W, cams.data(), slot_of(first_id) /* first camera constant, :809-816 */), "pba_set_poses");
-      check_pba(pba_set_points(h, n_sel, xyz.data(), desc[(size_t)l].data(), obs_off.data(), obs_frame.data(), patch_weights.data()), "pba_set_points");
-      if (coarser) check_pba(pba_copy_state(h, coarser), "pba_copy_state");   // the coarser level's result, on the device
-      check_pba(pba_solve(h, &opt, &summary), "pba_solve");
-      coarser = h;
+      deviceLevel(l, n_sel, nnz);
+      const DeviceLevel& d = _dev[(size_t)l];
+      const size_t R = d.ranks.size();
+      for (pba_handle* h : d.ranks) check_pba(pba_begin_batch(h), "pba_begin_batch");   // uploads are enqueued; every buffer lives until pba_solve returns
+      uploadWindowFrames(l);
+      for (size_t r = 0; r < R; ++r) {      // every rank receives the whole window and keeps its shard of the points
+        pba_handle* h = d.ranks[r];
+        check_pba(pba_set_poses(h, W, cams.data(), slot_of(first_id) /* first camera constant, :809-816 */), "pba_set_poses");
+        check_pba(pba_set_points(h, n_sel, xyz.data(), desc[(size_t)l].data(), obs_off.data(), obs_frame.data(), patch_weights.data()), "pba_set_points");
+        if (coarser_level) check_pba(pba_copy_state(h, coarser_level->ranks[r]), "pba_copy_state");   // the coarser level's result, on the device
+      }
+      if (R == 1) {
+        check_pba(pba_solve(d.h, &opt, &summary), "pba_solve");
+      } else {                               // one host thread per device: the ranks exchange sums from inside the kernels
+        std::vector<pba_summary> sums(R);
+        std::vector<std::string> errors(R);
+        std::vector<std::thread> workers;
+        for (size_t r = 0; r < R; ++r)
+          workers.emplace_back([&, r] { if (pba_solve(d.ranks[r], &opt, &sums[r]) != PBA_OK) errors[r] = pba_last_error(); });
+        for (std::thread& w : workers) w.join();
+        for (size_t r = 0; r < R; ++r)
+          if (!errors[r].empty()) throw std::runtime_error("pba_solve (device rank " + std::to_string(r) + "): " + errors[r]);
+        summary = sums[0];
+      }
+      coarser_level = &d;
+      coarser = d.h;
     }
     check_pba(pba_get_results(coarser, cams.data(), xyz.data()), "pba_get_results");
     int32_t n_it = 0;

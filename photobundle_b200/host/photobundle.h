@@ -41,6 +41,7 @@ class PhotometricBundleAdjustment {
     int device = -1;                // CUDA ordinal (-1: current)
     bool gpuFrontEnd = false;       // addFrame's data association and new-point selection on the device (added option)
     int numPyramidLevels = 1;       // > 1: every window is solved coarse to fine (PhotometricBundleAdjustmentPyr; added option)
+    int nGpus = 1;                  // > 1: every window's points are sharded over devices device .. device + nGpus - 1 (added option)
     Options() {}
     Options(const utils::ConfigFile& cf);
   };
@@ -93,7 +94,8 @@ class PhotometricBundleAdjustment {
   // one pyramid level on the device ([0] = the finest): its own handle, image size and intrinsics; `resident` = the
   // frame id held by each ring slot (id % slidingWindowSize), -1: none
   struct DeviceLevel {
-    pba_handle* h = nullptr;
+    pba_handle* h = nullptr;           // rank 0 (the only one when nGpus == 1); also the front end's device
+    std::vector<pba_handle*> ranks;    // all nGpus handles of the level, ranks[0] == h
     ImageSize size;
     Calibration calib;
     int levels_down = 0, cap_points = 0, cap_obs = 0;
@@ -102,7 +104,7 @@ class PhotometricBundleAdjustment {
   std::vector<DeviceLevel> _dev;
   int _desc_type = 0, _n_channels = 1;   // PBA_DESC_* / channels per pixel of the descriptor
   pba_handle* deviceLevel(int level, int n_points, int n_obs);
-  void uploadWindowFrames(int level, pba_handle* h);
+  void uploadWindowFrames(int level);
   struct SolveOutcome;                   // the C ABI's summary + iteration trace of the last level solved
   void fillResult(Result& out, const SolveOutcome& solved, const ScenePointPointerList& leaving, double seconds) const;
 };

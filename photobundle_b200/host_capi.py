@@ -16,7 +16,7 @@ class Options(C.Structure):
                 ("maskBlockRadius", C.c_int32), ("maxFrameDistance", C.c_int32), ("nonMaxSuppRadius", C.c_int32),
                 ("doGaussianWeighting", C.c_int32), ("verbose", C.c_int32), ("device", C.c_int32), ("descriptorType", C.c_int32), ("gpuFrontEnd", C.c_int32),
                 ("minScore", C.c_double), ("robustThreshold", C.c_double), ("minValidDepth", C.c_double),
-                ("maxValidDepth", C.c_double), ("numPyramidLevels", C.c_int32), ("reserved", C.c_int32)]
+                ("maxValidDepth", C.c_double), ("numPyramidLevels", C.c_int32), ("nGpus", C.c_int32)]
 
 
 _lib = None

@@ -322,4 +322,15 @@ def test_batched_uploads_and_single_frame_replacement(small_win):
     assert abs(s1["final_cost"] - s0["final_cost"]) <= 1e-9 * s0["final_cost"]
     np.testing.assert_allclose(c1, c0, atol=1e-8)
     np.testing.assert_allclose(p1, p0, atol=1e-6)
-    h.close(); h2.close()
+    # a cold handle fed frame by frame (no pba_set_frames_* at all), as an addFrame()-time upload does
+    h3 = capi.Handle(w.rows, w.cols, w.fx, w.fy, w.cx, w.cy, radius=w.radius, huber=w.huber, max_frames=w.n_frames,
+                     max_points=w.n_points, max_observations=w.n_obs)
+    for f in range(w.n_frames):
+        h3.set_frame_u8_ex(f, w.images[f])
+    h3.set_poses(w.cams_init, w.fixed_frame)
+    h3.set_points(w.points_init, w.desc, w.obs_offsets, w.obs_frame, w.weights)
+    s2 = h3.solve()
+    assert s2["num_iterations"] == s0["num_iterations"] and abs(s2["final_cost"] - s0["final_cost"]) <= 1e-9 * s0["final_cost"]
+    with pytest.raises(capi.PbaError):
+        h3.set_frame_u8_ex(w.n_frames, w.images[0])
+    h.close(); h2.close(); h3.close()

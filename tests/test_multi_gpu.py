@@ -116,3 +116,45 @@ def test_two_gpus_bench_window_repeated_solves():
     assert abs(two["final_cost"] - one["final_cost"]) <= 1e-9 * one["final_cost"]
     np.testing.assert_allclose(np.array(two["cams"]), np.array(one["cams"]), atol=1e-8)
     assert abs(two["second_final_cost"] - two["final_cost"]) <= 1e-12 * two["final_cost"]
+
+
+@pytest.mark.gpu
+def test_local_communicator_two_devices_one_process(small_win):
+    """pba_comm_init_local: two handles of ONE process on two devices (no NCCL, no IPC), pba_solve from one thread per
+    handle, equals the 1-GPU solve; the members agree; a second solve on the same handles works."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    w = small_win
+    one = capi.Handle.for_window(w)
+    s1 = one.solve()
+    c1, p1 = one.get_poses(), one.get_points()
+    acc1 = [t["step_is_successful"] for t in one.get_iterations()]
+    hs = [capi.Handle(w.rows, w.cols, w.fx, w.fy, w.cx, w.cy, radius=w.radius, huber=w.huber, max_frames=w.n_frames,
+                      max_points=w.n_points, max_observations=w.n_obs, device=d) for d in (0, 1)]
+    with pytest.raises(capi.PbaError):
+        capi.Handle.comm_init_local([hs[0], hs[0]])          # the same device twice
+    capi.Handle.comm_init_local(hs)
+    assert [h.exchange_kind() for h in hs] == ["peer-memory", "peer-memory"]
+    for h in hs:
+        h.set_frames_u8(w.images)
+        h.set_poses(w.cams_init, w.fixed_frame)
+        h.set_points(w.points_init, w.desc, w.obs_offsets, w.obs_frame, w.weights)
+        h.save_state()
+    for _ in range(2):
+        ss = capi.Handle.solve_all(hs)
+        assert ss[0]["final_cost"] == ss[1]["final_cost"] and ss[0]["num_iterations"] == ss[1]["num_iterations"]
+        assert [t["step_is_successful"] for t in hs[0].get_iterations()] == acc1
+        assert abs(ss[0]["final_cost"] - s1["final_cost"]) <= 1e-9 * s1["final_cost"]
+        assert ss[0]["num_iterations"] <= ss[0]["num_collectives"] <= 2 * ss[0]["num_iterations"] + 1
+        np.testing.assert_array_equal(hs[0].get_poses(), hs[1].get_poses())
+        np.testing.assert_allclose(hs[0].get_poses(), c1, atol=1e-8)
+        for h in hs:                                          # any member gathers the shards of all
+            np.testing.assert_allclose(h.get_points(), p1, atol=1e-6)
+        for h in hs:
+            h.restore_state()
+    # a member solved alone cannot make progress: it fails after the host barrier's time-out instead of hanging
+    # (not exercised here: the time-out is 60 s)
+    for h in hs:
+        h.close()
+    one.close()
