@@ -101,6 +101,19 @@ def ref_lib() -> C.CDLL | None:
     return r
 
 
+_REF_CALIB_PATH = os.path.join(os.path.dirname(_REF_PATH), "libref_calib.so")
+
+
+def ref_calib_lib() -> C.CDLL | None:
+    """The reference's own camera model (src/calibration.h) and MakePatchWeights compiled from /root/reference, or None."""
+    if not os.path.exists(_REF_CALIB_PATH):
+        return None
+    r = C.CDLL(_REF_CALIB_PATH)
+    r.ref_pyr_down.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
+    r.ref_triangulate.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    return r
+
+
 def _p(a: np.ndarray) -> int:
     return a.ctypes.data
 

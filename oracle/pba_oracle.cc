@@ -915,6 +915,12 @@ void oracle_sample_linear(const float* I, const float* Gx, const float* Gy, int3
   SampleLinear(ps, y, x, out3);
 }
 
+void oracle_project(const double* k4, const double* X, double* uv) {
+  // the expression of descriptor_error() / residual_jacobian() above (Calibration::project, src/calibration.h:33-38)
+  uv[0] = ((X[0] * k4[0]) / X[2]) + k4[2];
+  uv[1] = ((X[1] * k4[1]) / X[2]) + k4[3];
+}
+
 void oracle_patch_weights(int32_t radius, int32_t do_gaussian, double* w) {
   // src/photobundle.cc:617-644 with s_x = s_y = a = 1.
   const int n = (2 * radius + 1) * (2 * radius + 1);

@@ -139,6 +139,8 @@ void oracle_sample_linear(const float* I, const float* Gx, const float* Gy,
                           int32_t rows, int32_t cols, float y, float x, float* out3);
 
 /* src/photobundle.cc:617-644. */
+/* Calibration::project as the residual functor instantiates it (src/calibration.h:33-38): k4 = {fx, fy, cx, cy} */
+void oracle_project(const double* k4, const double* X, double* uv);
 void oracle_patch_weights(int32_t radius, int32_t do_gaussian, double* w);
 
 /* src/photobundle.cc:646-667 with ceres::RotationMatrixToAngleAxis /

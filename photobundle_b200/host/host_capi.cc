@@ -113,6 +113,26 @@ void pbah_disparity_to_depth(const float* disparity, int32_t rows, int32_t cols,
   disparityToDepth(disparity, ImageSize(rows, cols), Bf, depth);
 }
 
+// the camera model and patch weights of the host side, for the tests against the reference's own (oracle/_ref/libref_calib.so)
+void pbah_project(const double* k4, const double* X, double* uv) {
+  Mat33 K = Mat33::Identity();
+  K(0, 0) = k4[0]; K(1, 1) = k4[1]; K(0, 2) = k4[2]; K(1, 2) = k4[3];
+  const Vec2 p = Calibration(K, 0.1).project(Vec3(X[0], X[1], X[2]));
+  uv[0] = p[0]; uv[1] = p[1];
+}
+void pbah_pyr_down(const double* k4, double b, int32_t rows, int32_t cols, double* out7) {
+  Mat33 K = Mat33::Identity();
+  K(0, 0) = k4[0]; K(1, 1) = k4[1]; K(0, 2) = k4[2]; K(1, 2) = k4[3];
+  const Calibration c = Calibration(K, b).pyrDown();
+  const ImageSize s = ImageSize(rows, cols).pyrDown();
+  out7[0] = c.fx(); out7[1] = c.fy(); out7[2] = c.cx(); out7[3] = c.cy(); out7[4] = c.b(); out7[5] = s.rows; out7[6] = s.cols;
+}
+int32_t pbah_patch_weights(int32_t radius, int32_t do_gaussian, double* w) {
+  const std::vector<double> v = MakePatchWeights(radius, do_gaussian != 0);
+  for (size_t i = 0; i < v.size(); ++i) w[i] = v[i];
+  return (int32_t)v.size();
+}
+
 int pbah_write_poses_kitti(pbah_handle* h, const char* filename) {
   return writePosesKittiFormat(filename, h->result.poses) ? 0 : -1;
 }

@@ -209,7 +209,7 @@ static Mat44 ParamsToPose(const double* p) {
 
 // Weights of the patch pixels (behaviour of src/photobundle.cc:617-644): uniform, or an isotropic unit-variance
 // Gaussian normalised to sum 1, row-major over the (2r+1)^2 patch.
-static std::vector<double> MakePatchWeights(int radius, bool do_gaussian) {
+std::vector<double> MakePatchWeights(int radius, bool do_gaussian) {
   const int side = 2 * radius + 1;
   std::vector<double> w((size_t)side * side, 1.0);
   if (!do_gaussian) return w;

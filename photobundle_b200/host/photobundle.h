@@ -109,4 +109,8 @@ class PhotometricBundleAdjustment {
   void fillResult(Result& out, const SolveOutcome& solved, const ScenePointPointerList& leaving, double seconds) const;
 };
 
+// Per-pixel weights of the patch residuals, row-major over (2 radius + 1)^2 (src/photobundle.cc:617-646 with the default
+// s_x = s_y = a = 1): all ones, or a normalised Gaussian.  Exposed for the tests against the reference's own function.
+std::vector<double> MakePatchWeights(int radius, bool do_gaussian);
+
 #endif

@@ -11,6 +11,8 @@ parameters within 1e-5):
 import numpy as np
 import pytest
 
+from gauge import scale_gauge_diff
+
 from oracle import binding as ob
 from photobundle_b200 import capi
 from workloads import synthetic
@@ -132,6 +134,7 @@ def _check_solve(win, pose_tol=1e-5, cost_rtol=1e-4, trans_tol=None, strict_pref
     s = h.solve()
     cams, pts, tr = h.get_poses(), h.get_points(), h.get_iterations()
     h.close()
+    h_trace, o_trace = tr, otr
     assert s["termination_type"] == osum["termination_type"]
     if strict_prefix is None:
         assert [t["step_is_successful"] for t in tr] == [t["step_is_successful"] for t in otr], (s, osum)
@@ -147,6 +150,14 @@ def _check_solve(win, pose_tol=1e-5, cost_rtol=1e-4, trans_tol=None, strict_pref
     assert abs(s["initial_cost"] - osum["initial_cost"]) <= 1e-7 * osum["initial_cost"]
     assert abs(s["final_cost"] - osum["final_cost"]) <= cost_rtol * osum["final_cost"]
     same_path = s["num_iterations"] == osum["num_iterations"]
+    if strict_prefix is not None and same_path and [t["step_is_successful"] for t in h_trace] == [t["step_is_successful"] for t in o_trace]:
+        # the two chaotic tails coincided (what is seen in practice): hold the end point to the tight tolerances, with
+        # the scale gauge taken out explicitly (tests/gauge.py).  Single points with a weakly determined depth keep 1e-3.
+        g = scale_gauge_diff(cams, pts, ocams, opts, win.fixed_frame)
+        assert abs(s["final_cost"] - osum["final_cost"]) <= 1e-5 * osum["final_cost"]
+        assert g["rotations"] <= 1e-5 and g["centres"] <= 1e-4 and abs(g["alpha"] - 1.0) <= 1e-4, g
+        assert g["points"] <= 1e-3, g
+        assert np.percentile(np.abs(pts - opts), 90) <= 1e-4 * max(1.0, np.abs(opts).max())
     if strict_prefix is None or same_path:
         assert np.abs(cams - ocams)[:, :3].max() <= pose_tol, np.abs(cams - ocams).max(0)
         assert np.abs(cams - ocams)[:, 3:].max() <= (trans_tol or pose_tol), np.abs(cams - ocams).max(0)
@@ -202,11 +213,11 @@ def test_lm_max_iterations_and_no_loss(small_win):
     # amplified enough to flip one borderline accept/reject, so the paths are compared at the
     # optimum (north-star tolerances on cost; poses looser, see test_lm_small_ragged) rather than step by step.
     w2 = dataclasses.replace(small_win, huber=0.0)
-    ow = ob.OracleWindow(w2)
+    ow = ob.OracleWindow(w2, num_threads=1)       # fixed summation order on the oracle's side
     ocams, opts, osum, otr = ow.solve(w2.cams_init, w2.points_init)
     h = capi.Handle.for_window(w2)
     s = h.solve()
-    cams, tr = h.get_poses(), h.get_iterations()
+    cams, pts, tr = h.get_poses(), h.get_points(), h.get_iterations()
     h.close()
     assert s["termination_type"] == 0
     n_same = min(len(tr), len(otr), 30)
@@ -215,6 +226,11 @@ def test_lm_max_iterations_and_no_loss(small_win):
         assert abs(a["cost"] - b["cost"]) <= 1e-6 * b["cost"]
     assert abs(s["final_cost"] - osum["final_cost"]) <= 1e-3 * osum["final_cost"]
     assert np.abs(cams - ocams)[:, :3].max() <= 1e-4 and np.abs(cams - ocams)[:, 3:].max() <= 1e-2
+    if [t["step_is_successful"] for t in tr] == [t["step_is_successful"] for t in otr]:
+        # same accept/reject path to the end (what is seen in practice): tight, scale gauge taken out (tests/gauge.py)
+        g = scale_gauge_diff(cams, pts, ocams, opts, w2.fixed_frame)
+        assert abs(s["final_cost"] - osum["final_cost"]) <= 1e-5 * osum["final_cost"]
+        assert g["rotations"] <= 1e-5 and g["centres"] <= 1e-4 and abs(g["alpha"] - 1.0) <= 1e-4 and g["points"] <= 1e-3, g
 
 
 def test_cfg3_full_size(cfg3_win):

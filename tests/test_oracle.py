@@ -247,3 +247,44 @@ def test_scipy_second_opinion():
     # ... and restarted from the oracle's optimum it cannot improve it by more than 1 %.
     res2 = least_squares(fun, x_or, method="trf", x_scale="jac", max_nfev=30, xtol=1e-10, ftol=1e-10)
     assert res2.cost >= 0.99 * s["final_cost"]
+
+
+def test_camera_model_and_patch_weights_match_reference_binary_when_present():
+    """The reference's own Calibration (src/calibration.h: project<T>, project(Vec3), pyrDown), ImageSize::pyrDown
+    (src/types.h:70-73) and MakePatchWeights (src/photobundle.cc:617-646), compiled from where they lie into
+    oracle/_ref/libref_calib.so, against the oracle's restatement AND the host side's own code (compat.h /
+    photobundle.cc, through libpba_host.so): bit for bit."""
+    ref = binding.ref_calib_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_calib.so not built (no /root/reference on this box)")
+    from photobundle_b200 import host_capi
+    host = host_capi.lib()
+    host.pbah_pyr_down.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
+    rng = np.random.default_rng(17)
+    k4 = np.array([718.856, 718.856, 607.1928, 185.2157])                 # config/kitti_stereo.cfg's camera
+    uv_ref, uv_ora, uv_vec, uv_host = (np.zeros(2) for _ in range(4))
+    for _ in range(2000):
+        X = rng.normal(size=3) * np.array([5.0, 2.0, 20.0])
+        if rng.random() < 0.05:
+            X[2] = rng.choice([1e-12, -1e-3, 1e3])
+        ref.ref_project(C.c_void_p(k4.ctypes.data), C.c_void_p(X.ctypes.data), C.c_void_p(uv_ref.ctypes.data))
+        binding.lib().oracle_project(C.c_void_p(k4.ctypes.data), C.c_void_p(X.ctypes.data), C.c_void_p(uv_ora.ctypes.data))
+        assert uv_ref.tobytes() == uv_ora.tobytes()                       # the residual functor's projection
+        ref.ref_project_vec3(C.c_void_p(k4.ctypes.data), C.c_void_p(X.ctypes.data), C.c_void_p(uv_vec.ctypes.data))
+        host.pbah_project(C.c_void_p(k4.ctypes.data), C.c_void_p(X.ctypes.data), C.c_void_p(uv_host.ctypes.data))
+        # addFrame's projection, normHomog(K X) = (1 / p_z) * p: the host divides instead, at most 1 ulp apart
+        np.testing.assert_allclose(uv_host, uv_vec, rtol=4e-16, atol=0)
+    o_ref, o_host = np.zeros(7), np.zeros(7)
+    for rows, cols in ((376, 1241), (375, 1242), (188, 621), (1, 1), (47, 156)):
+        ref.ref_pyr_down(C.c_void_p(k4.ctypes.data), 0.5371657, rows, cols, C.c_void_p(o_ref.ctypes.data))
+        host.pbah_pyr_down(C.c_void_p(k4.ctypes.data), 0.5371657, rows, cols, C.c_void_p(o_host.ctypes.data))
+        assert o_ref.tobytes() == o_host.tobytes()
+        assert list(o_ref[5:]) == [(rows + 1) // 2, (cols + 1) // 2] and o_ref[0] == 0.5 * k4[0] and o_ref[4] == 2 * 0.5371657
+    for radius in (0, 1, 2, 3, 4):
+        for gauss in (0, 1):
+            n = (2 * radius + 1) ** 2
+            w_ref, w_ora, w_host = np.zeros(n), np.zeros(n), np.zeros(n)
+            assert ref.ref_patch_weights(radius, gauss, C.c_void_p(w_ref.ctypes.data)) == n
+            binding.lib().oracle_patch_weights(radius, gauss, C.c_void_p(w_ora.ctypes.data))
+            assert host.pbah_patch_weights(radius, gauss, C.c_void_p(w_host.ctypes.data)) == n
+            assert w_ref.tobytes() == w_ora.tobytes() == w_host.tobytes()
