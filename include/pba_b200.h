@@ -199,6 +199,11 @@ int pba_restore_state(pba_handle* h);
  * trip.  Ordered on dst's stream. */
 int pba_copy_state(pba_handle* dst, pba_handle* src);
 
+/* Diagnostics: how often this handle instantiated its LM-loop graph and how often it re-targeted the instantiated
+ * graph in place (cudaGraphExecKernelNodeSetParams) because only sizes had changed since the previous solve - what a
+ * sliding window does on every frame. */
+int pba_graph_counters(const pba_handle* h, int32_t* builds, int32_t* updates);
+
 /* Uploads without a host round trip per call.  Between pba_begin_batch() and the next pba_solve() (or pba_end_batch())
  * the pba_set_* calls only ENQUEUE their host->device copies; the caller keeps every buffer it passed alive and
  * unchanged until that pba_solve() / pba_end_batch() returns (at most one pba_set_points per batch).  A sliding window

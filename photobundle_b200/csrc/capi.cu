@@ -101,6 +101,8 @@ struct LocalGroup {
   }
 };
 
+constexpr int kSCopies = kSReplicas > 3 ? kSReplicas : 3;
+
 struct pba_handle {
   pba_config cfg;
   int device = 0, sm_count = 148;
@@ -148,6 +150,11 @@ struct pba_handle {
   IterSummary* d_trace = nullptr;
   int trace_cap = 0;
   LmState* h_state = nullptr;  // pinned
+  // pinned landing zone of everything a solve reports, filled by copies enqueued behind the LM loop (one synchronisation):
+  // iteration trace | K_B stamps | exchange error word | cameras | points (this rank's)
+  unsigned char* h_post = nullptr;
+  size_t post_trace = 0, post_stamps = 0, post_err = 0, post_cams = 0, post_pts = 0, post_bytes = 0;
+  bool results_cached = false;   // h_post holds the poses / points of the last solve and nothing has changed them since
   // problem
   int n_frames = 0, fixed_frame = -1, n_points = 0, nnz = 0;
   bool have_frames = false, have_poses = false, have_points = false;
@@ -172,15 +179,19 @@ struct pba_handle {
   cudaGraph_t lm_graph = nullptr;
   cudaGraphExec_t lm_exec = nullptr;
   std::vector<unsigned char> lm_key;   // kernel parameters the instantiated graph was built from
+  std::vector<cudaGraphNode_t> lm_body_nodes;   // the body's four kernel nodes in launch order (parameter updates in place)
+  unsigned long long lm_cond = 0;      // the WHILE node's condition handle
+  int lm_updates = 0, lm_builds = 0;   // how often the instantiated graph was updated in place / rebuilt
 };
 
 static void drop_lm_graph(pba_handle* h) {
   if (h->lm_exec) cudaGraphExecDestroy(h->lm_exec);
   if (h->lm_graph) cudaGraphDestroy(h->lm_graph);
-  h->lm_exec = nullptr; h->lm_graph = nullptr; h->lm_key.clear();
+  h->lm_exec = nullptr; h->lm_graph = nullptr; h->lm_key.clear(); h->lm_body_nodes.clear();
 }
 
 static void free_all(pba_handle* h) {
+  if (getenv("PBA_DEBUG_GRAPH")) fprintf(stderr, "[pba graph] LM loop graph: %d builds, %d in-place parameter updates\n", h->lm_builds, h->lm_updates);
   drop_lm_graph(h);
   cudaFree(h->d_u8); cudaFree(h->d_stage_u8); cudaFree(h->d_f32);
   cudaFree(h->d_scr_a); cudaFree(h->d_scr_b); cudaFree(h->d_new_u8); cudaFree(h->d_new_planes); cudaFree(h->d_sal);
@@ -205,6 +216,7 @@ static void free_all(pba_handle* h) {
   cudaFree(h->d_save_cams); cudaFree(h->d_save_pts); cudaFree(h->d_pyr_scratch); cudaFree(h->d_pts_full);
   cudaFree(h->d_obs_sqnorm); cudaFree(h->d_residuals); cudaFree(h->d_state); cudaFree(h->d_trace);
   if (h->h_state) cudaFreeHost(h->h_state);
+  if (h->h_post) cudaFreeHost(h->h_post);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -392,7 +404,7 @@ int pba_create(const pba_config* cfg, pba_handle** out) {
   CREATE_TRY(cudaMalloc(&h->d_Ucur, sizeof(double) * F * kUStride));
   CREATE_TRY(cudaMalloc(&h->d_scale_p, sizeof(double) * n * 3));
   CREATE_TRY(cudaMalloc(&h->d_Vinv, sizeof(double) * n * 6));
-  CREATE_TRY(cudaMalloc(&h->d_S, sizeof(double) * 3 * reduced_capacity((int)F)));   // x3: the multi-GPU path eliminates under two hypotheses + once more
+  CREATE_TRY(cudaMalloc(&h->d_S, sizeof(double) * kSCopies * reduced_capacity((int)F)));   // multi-GPU: two hypotheses + once more; one GPU: kSReplicas copies
   CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
   CREATE_TRY(cudaMalloc(&h->d_state, 2 * sizeof(LmState)));
   CREATE_TRY(cudaMallocHost(&h->h_state, sizeof(LmState)));
@@ -736,6 +748,7 @@ int pba_select_candidates(pba_handle* h, const float* depth, int32_t n_masked, c
 }
 
 int pba_set_poses(pba_handle* h, int32_t n_frames, const double* cam6, int32_t fixed_frame) {
+  if (h) h->results_cached = false;
   if (!h || !cam6) return fail(PBA_ERR_ARGUMENT, "pba_set_poses: null argument");
   if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(PBA_ERR_CAPACITY, "pba_set_poses: %d frames, capacity %d", n_frames, h->cfg.max_frames);
   if (fixed_frame < -1 || fixed_frame >= n_frames) return fail(PBA_ERR_ARGUMENT, "pba_set_poses: fixed_frame %d", fixed_frame);
@@ -774,6 +787,7 @@ int pba_shard_range(int32_t n_points, const int32_t* obs_offsets, int32_t rank, 
 
 int pba_set_points(pba_handle* h, int32_t n_points, const double* xyz, const double* desc,
                    const int32_t* obs_offsets, const int32_t* obs_frame, const double* weights) {
+  if (h) h->results_cached = false;
   if (!h || !xyz || !desc || !obs_offsets || !obs_frame || !weights) return fail(PBA_ERR_ARGUMENT, "pba_set_points: null argument");
   if (n_points < 0 || n_points > h->cfg.max_points) return fail(PBA_ERR_CAPACITY, "pba_set_points: %d points, capacity %d", n_points, h->cfg.max_points);
   if (obs_offsets[0] != 0) return fail(PBA_ERR_ARGUMENT, "pba_set_points: obs_offsets[0] must be 0");
@@ -955,22 +969,88 @@ static void format_message(const LmState& s, char* out, size_t cap) {
 }
 
 // (Re)build the device-side LM loop when the kernel parameters changed since the last solve.
+// The kernel nodes of a captured linear chain, in launch order.
+static bool chain_in_order(cudaGraph_t g, std::vector<cudaGraphNode_t>& out) {
+  out.clear();
+  size_t n = 0;
+  if (cudaGraphGetRootNodes(g, nullptr, &n) != cudaSuccess || n != 1) return false;
+  cudaGraphNode_t cur;
+  if (cudaGraphGetRootNodes(g, &cur, &n) != cudaSuccess) return false;
+  for (;;) {
+    cudaGraphNodeType ty;
+    if (cudaGraphNodeGetType(cur, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) return false;
+    out.push_back(cur);
+    // (_v2: the body's kernel-to-kernel edges are programmatic, which the plain query refuses to report)
+    size_t nd = 0;
+    if (cudaGraphNodeGetDependentNodes_v2(cur, nullptr, nullptr, &nd) != cudaSuccess) return false;
+    if (nd == 0) return true;
+    if (nd != 1) return false;
+    cudaGraphEdgeData ed;
+    if (cudaGraphNodeGetDependentNodes_v2(cur, &cur, &ed, &nd) != cudaSuccess) return false;
+  }
+}
+
+// Enqueue the body of the LM loop (two iterations: K_B, K_A, K_B, K_A) on the capturing stream.
+static cudaError_t enqueue_lm_body(pba_handle* h, const LmParams& lp0, StepParams* sp, int sgrid, int n_free, int pdl) {
+  cudaError_t e = cudaSuccess;
+  // kernel-to-kernel edges inside the body are programmatic (PDL): the dependent kernel's launch and the part of
+  // its prologue that does not read its predecessor's output overlap with the predecessor's tail (PBA_NO_PDL=1: off)
+  for (int half = 0; half < 2 && e == cudaSuccess; ++half) {
+    LmParams lp = lp0;
+    lp.st_in = h->d_state + half; lp.st_out = h->d_state + (1 - half);
+    lp.dbg = nullptr; lp.cond = h->lm_cond;
+    lp.pdl = half > 0 ? pdl : 0;          // the first kernel of the body follows the loop condition, not a kernel
+    e = launch_schur_solve(lp, sgrid, n_free, h->stream);
+    sp[half].pdl = pdl;
+    if (e == cudaSuccess) e = launch_k_step(sp[half], h->cfg.patch_radius, h->stream);
+  }
+  return e;
+}
+
 static int ensure_lm_graph(pba_handle* h, const LmParams& lp0, int sgrid, int n_free) {
   StepParams sp[2] = {make_step_params(h, h->d_state + 1), make_step_params(h, h->d_state)};
+  const int pdl = getenv("PBA_NO_PDL") == nullptr ? 1 : 0;
   std::vector<unsigned char> key(sizeof(sp) + sizeof(LmParams) + 3 * sizeof(int));
   {
     LmParams k = lp0;
     k.cond = 0; k.st_in = nullptr; k.st_out = nullptr; k.dbg = nullptr;
-    const int extra[3] = {sgrid, n_free, h->cfg.patch_radius + 16 * (getenv("PBA_NO_PDL") == nullptr ? 1 : 0)};
+    const int extra[3] = {sgrid, n_free, h->cfg.patch_radius + 16 * pdl};
     memcpy(key.data(), sp, sizeof(sp));
     memcpy(key.data() + sizeof(sp), &k, sizeof(k));
     memcpy(key.data() + sizeof(sp) + sizeof(k), extra, sizeof(extra));
   }
   if (h->lm_exec && key == h->lm_key) return PBA_OK;
+  // Same loop, other sizes (a sliding window changes its point count with every frame): capture the four launches
+  // again into a scratch graph and move their parameters (arguments, grid, kernel instantiation) into the instantiated
+  // graph's nodes in place; anything the driver refuses falls through to a rebuild.
+  if (h->lm_exec && h->lm_body_nodes.size() == 4 && getenv("PBA_NO_GRAPH_UPDATE") == nullptr) {
+    bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    cudaGraph_t scratch = nullptr;
+    if (ok) {
+      const cudaError_t e = enqueue_lm_body(h, lp0, sp, sgrid, n_free, pdl);
+      const cudaError_t e2 = cudaStreamEndCapture(h->stream, &scratch);
+      ok = e == cudaSuccess && e2 == cudaSuccess && scratch;
+    }
+    std::vector<cudaGraphNode_t> fresh;
+    ok = ok && chain_in_order(scratch, fresh) && fresh.size() == 4;
+    const bool dbg = getenv("PBA_DEBUG_GRAPH") != nullptr;
+    if (dbg && !ok) fprintf(stderr, "[pba graph] update: scratch capture / chain walk failed (%zu nodes)\n", fresh.size());
+    for (int i = 0; i < 4 && ok; ++i) {
+      cudaKernelNodeParams kp;
+      cudaError_t eg = cudaGraphKernelNodeGetParams(fresh[i], &kp);
+      cudaError_t es = eg == cudaSuccess ? cudaGraphExecKernelNodeSetParams(h->lm_exec, h->lm_body_nodes[i], &kp) : eg;
+      ok = es == cudaSuccess;
+      if (dbg && !ok) fprintf(stderr, "[pba graph] update: node %d: get %s / set %s\n", i, cudaGetErrorString(eg), cudaGetErrorString(es));
+    }
+    if (scratch) cudaGraphDestroy(scratch);
+    cudaGetLastError();
+    if (ok) { h->lm_key.swap(key); ++h->lm_updates; return PBA_OK; }
+  }
   drop_lm_graph(h);
   CUDA_TRY(cudaGraphCreate(&h->lm_graph, 0));
   cudaGraphConditionalHandle cond;
   CUDA_TRY(cudaGraphConditionalHandleCreate(&cond, h->lm_graph, 1, cudaGraphCondAssignDefault));
+  h->lm_cond = (unsigned long long)cond;
   cudaGraphNodeParams np = {};
   np.type = cudaGraphNodeTypeConditional;
   np.conditional.handle = cond;
@@ -980,27 +1060,21 @@ static int ensure_lm_graph(pba_handle* h, const LmParams& lp0, int sgrid, int n_
   CUDA_TRY(cudaGraphAddNode(&node, h->lm_graph, nullptr, 0, &np));
   cudaGraph_t body = np.conditional.phGraph_out[0];
   CUDA_TRY(cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-  cudaError_t e = cudaSuccess;
-  // kernel-to-kernel edges inside the body are programmatic (PDL): the dependent kernel's launch and the part of
-  // its prologue that does not read its predecessor's output overlap with the predecessor's tail (PBA_NO_PDL=1: off)
-  const int pdl = getenv("PBA_NO_PDL") == nullptr ? 1 : 0;
-  for (int half = 0; half < 2 && e == cudaSuccess; ++half) {
-    LmParams lp = lp0;
-    lp.st_in = h->d_state + half; lp.st_out = h->d_state + (1 - half);
-    lp.dbg = nullptr; lp.cond = (unsigned long long)cond;
-    lp.pdl = half > 0 ? pdl : 0;          // the first kernel of the body follows the loop condition, not a kernel
-    e = launch_schur_solve(lp, sgrid, n_free, h->stream);
-    sp[half].pdl = pdl;
-    if (e == cudaSuccess) e = launch_k_step(sp[half], h->cfg.patch_radius, h->stream);
-  }
+  const cudaError_t e = enqueue_lm_body(h, lp0, sp, sgrid, n_free, pdl);
   cudaGraph_t captured = nullptr;
   cudaError_t e2 = cudaStreamEndCapture(h->stream, &captured);
   if (e != cudaSuccess || e2 != cudaSuccess) {
     drop_lm_graph(h);
     return fail(PBA_ERR_CUDA, "pba_solve: capturing the LM loop failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
   }
+  if (!chain_in_order(body, h->lm_body_nodes)) {   // no in-place updates then
+    if (getenv("PBA_DEBUG_GRAPH")) fprintf(stderr, "[pba graph] body chain walk failed (%zu nodes)\n", h->lm_body_nodes.size());
+    h->lm_body_nodes.clear();
+  }
+  cudaGetLastError();
   CUDA_TRY(cudaGraphInstantiate(&h->lm_exec, h->lm_graph, 0));
   h->lm_key.swap(key);
+  ++h->lm_builds;
   return PBA_OK;
 }
 
@@ -1022,7 +1096,17 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
     cudaFree(h->d_stamps);
     h->d_stamps = nullptr;
     CUDA_TRY(cudaMalloc(&h->d_stamps, sizeof(unsigned long long) * 2 * (h->trace_cap + 2)));
+    if (h->h_post) { cudaFreeHost(h->h_post); h->h_post = nullptr; }
+    auto up = [](size_t x) { return (x + 63) & ~(size_t)63; };
+    h->post_trace = 0;
+    h->post_stamps = up(sizeof(IterSummary) * h->trace_cap);
+    h->post_err = h->post_stamps + up(sizeof(unsigned long long) * 2 * (h->trace_cap + 2));
+    h->post_cams = h->post_err + 64;
+    h->post_pts = h->post_cams + up(sizeof(double) * 6 * (size_t)h->cfg.max_frames);
+    h->post_bytes = h->post_pts + up(sizeof(double) * 3 * (size_t)h->cfg.max_points);
+    CUDA_TRY(cudaMallocHost(&h->h_post, h->post_bytes));
   }
+  h->results_cached = false;
   CUDA_TRY(cudaMemsetAsync(h->d_stamps, 0, sizeof(unsigned long long) * 2 * (h->trace_cap + 2), h->stream));
   LmState* s = h->h_state;
   memset(s, 0, sizeof(*s));
@@ -1049,7 +1133,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   rc = zero_accumulators(h);
   if (rc) return rc;
   const size_t D = 6 * (size_t)F;
-  CUDA_TRY(cudaMemsetAsync(h->d_S, 0, sizeof(double) * 3 * reduced_capacity(h->cfg.max_frames), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_S, 0, sizeof(double) * kSCopies * reduced_capacity(h->cfg.max_frames), h->stream));
   CUDA_TRY(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
 
   LmParams lp = make_lm_params(h);
@@ -1088,14 +1172,26 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   const int group = 4;
   bool done = false;
   int k = 0;
+  const size_t stamps_bytes = sizeof(unsigned long long) * 2 * (h->trace_cap + 2);
+  bool posted = false;
   if (use_graph) {
+    // everything the host needs from this solve is enqueued behind the loop and waited for ONCE: final state, iteration
+    // trace, K_B stamps, the exchange's error word, and the results themselves (k_publish moves the accepted x into
+    // buffer 0 on the device; sharded points are gathered by pba_get_points instead)
     CUDA_TRY(cudaGraphLaunch(h->lm_exec, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(s, h->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(launch_publish(h->d_state, h->d_cams, h->d_pts, F, h->n_points, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(s, h->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_trace, h->d_trace, sizeof(IterSummary) * h->trace_cap, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_stamps, h->d_stamps, stamps_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (h->use_xchg) CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_err, h->xc.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_cams, h->d_cams, sizeof(double) * 6 * (size_t)F, cudaMemcpyDeviceToHost, h->stream));
+    if (h->n_ranks == 1)
+      CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_pts, h->d_pts, sizeof(double) * 3 * (size_t)h->n_points, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (!s->done) return fail(PBA_ERR_CUDA, "pba_solve: the LM graph returned before the minimizer terminated");
-    launches += 4 * ((s->num_evals + 1) / 2);   // the body (two iterations, four kernels) ran ceil(decisions / 2) times
-    done = true;
+    launches += 4 * ((s->num_evals + 1) / 2) + 1;   // the body (two iterations, four kernels) ran ceil(decisions / 2) times; k_publish
+    done = true; posted = true;
   }
   while (!done) {
     for (int g = 0; g < group; ++g, ++k) {
@@ -1122,7 +1218,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   }
   if (!use_graph) CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   // the accepted x must end up in buffer 0 for pba_get_* and for the next solve
-  if (s->cur != 0) {
+  if (!posted && s->cur != 0) {
     CUDA_TRY(cudaMemcpyAsync(h->d_cams, h->d_cams + (size_t)F * 6, sizeof(double) * F * 6, cudaMemcpyDeviceToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_pts, h->d_pts + (size_t)h->n_points * 3, sizeof(double) * (size_t)h->n_points * 3, cudaMemcpyDeviceToDevice, h->stream));
   }
@@ -1147,9 +1243,15 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
                 (t[16 * i + 2] - t[16 * i + 9]) * 1e-3, t[16 * i + 10] == 1 ? "accepted, radius tripled" : t[16 * i + 10] == 2 ? "rejected" : "second elimination + exchange");
   }
   h->trace.resize(s->n_trace);
-  if (s->n_trace > 0)
-    CUDA_TRY(cudaMemcpyAsync(h->trace.data(), h->d_trace, sizeof(IterSummary) * s->n_trace, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (posted) {
+    if (s->n_trace > 0) memcpy(h->trace.data(), h->h_post + h->post_trace, sizeof(IterSummary) * s->n_trace);
+  } else {
+    if (s->n_trace > 0)
+      CUDA_TRY(cudaMemcpyAsync(h->trace.data(), h->d_trace, sizeof(IterSummary) * s->n_trace, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_stamps, h->d_stamps, stamps_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (h->use_xchg) CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_err, h->xc.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
 
@@ -1162,16 +1264,14 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   summary->kernel_launches = launches; summary->num_collectives = h->use_xchg ? s->n_xchg : collectives;
   summary->device_time_in_seconds = ms * 1e-3;
   {
-    std::vector<unsigned long long> st2(2 * (size_t)(s->num_evals + 1));
-    CUDA_TRY(cudaMemcpy(st2.data(), h->d_stamps, sizeof(unsigned long long) * st2.size(), cudaMemcpyDeviceToHost));
+    const unsigned long long* st2 = reinterpret_cast<const unsigned long long*>(h->h_post + h->post_stamps);
     double kb = 0.0;
     for (int i = 0; i < s->num_evals; ++i)
       if (st2[2 * i] && st2[2 * i + 1] > st2[2 * i]) kb += (double)(st2[2 * i + 1] - st2[2 * i]) * 1e-9;
     summary->kb_device_time_in_seconds = kb;
   }
   if (h->use_xchg) {
-    int xerr = 0;
-    CUDA_TRY(cudaMemcpy(&xerr, h->xc.error, sizeof(int), cudaMemcpyDeviceToHost));
+    const int xerr = *reinterpret_cast<const int*>(h->h_post + h->post_err);
     if (xerr) {
       CUDA_TRY(cudaMemset(h->xc.error, 0, sizeof(int)));
       return fail(PBA_ERR_NCCL, "pba_solve: the peer-memory exchange timed out (a rank did not reach the same LM iteration)");
@@ -1179,6 +1279,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   }
   if (!s->done) { s->msg_code = kMsgMaxIter; s->msg_a = opt.max_num_iterations; summary->termination_type = 1; }
   h->defer_sync = false;   // every upload enqueued before this solve has been consumed
+  h->results_cached = posted;
   format_message(*s, summary->message, sizeof(summary->message));
   summary->total_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
   return PBA_OK;
@@ -1200,6 +1301,7 @@ int pba_save_state(pba_handle* h) {
 }
 
 int pba_restore_state(pba_handle* h) {
+  if (h) h->results_cached = false;
   if (!h) return fail(PBA_ERR_ARGUMENT, "pba_restore_state: null handle");
   if (!h->have_saved) return fail(PBA_ERR_STATE, "pba_restore_state: nothing saved");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -1210,6 +1312,7 @@ int pba_restore_state(pba_handle* h) {
 }
 
 int pba_copy_state(pba_handle* dst, pba_handle* src) {
+  if (dst) dst->results_cached = false;
   if (!dst || !src) return fail(PBA_ERR_ARGUMENT, "pba_copy_state: null handle");
   if (!src->have_poses || !src->have_points || !dst->have_poses || !dst->have_points)
     return fail(PBA_ERR_STATE, "pba_copy_state: both handles need poses and points (the copy replaces their values, not their layout)");
@@ -1308,6 +1411,11 @@ int pba_get_results(pba_handle* h, double* cam6, double* xyz) {
     int rc = pba_get_poses(h, cam6);
     return rc ? rc : pba_get_points(h, xyz);
   }
+  if (h->results_cached) {   // the last pba_solve already brought them to the host together with its summary
+    memcpy(cam6, h->h_post + h->post_cams, sizeof(double) * 6 * (size_t)h->n_frames);
+    memcpy(xyz, h->h_post + h->post_pts, sizeof(double) * 3 * (size_t)h->n_points);
+    return PBA_OK;
+  }
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemcpyAsync(cam6, h->d_cams, sizeof(double) * (size_t)h->n_frames * 6, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaMemcpyAsync(xyz, h->d_pts, sizeof(double) * (size_t)h->n_points * 3, cudaMemcpyDeviceToHost, h->stream));
@@ -1403,6 +1511,12 @@ int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_rank
     int rc = setup_xchg(h);
     if (rc) return rc;
   }
+  return PBA_OK;
+}
+
+int pba_graph_counters(const pba_handle* h, int32_t* builds, int32_t* updates) {
+  if (!h || !builds || !updates) return fail(PBA_ERR_ARGUMENT, "pba_graph_counters: null argument");
+  *builds = h->lm_builds; *updates = h->lm_updates;
   return PBA_OK;
 }
 

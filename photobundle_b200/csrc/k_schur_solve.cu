@@ -165,7 +165,7 @@ constexpr int kMBase = 224;   // thread kMBase keeps the factored diagonal block
 // Writes the step into st and the candidate cameras.  s_cams: both camera buffers [2][kMaxD] (or null).
 // ut_filled: Ut already holds -P (multi-GPU: the rank-ordered sum of every rank's contribution was written there).
 template <int TPW>
-__device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams, bool ut_filled) {
+__device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams, bool ut_filled, int n_rep) {
   const int nf = st.n_free, N = 6 * nf, ld = reduced_ld(N);
   const int cur = st.cur, eb = st.eval_buf, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const double radius = st.radius;
@@ -179,12 +179,28 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
   // Everything this phase reads from global memory is requested FIRST, in one round: the accumulator (-P: a
   // linear copy, all loads of a thread in flight at once) and, after a rejected step, the accepted point's pose
   // blocks; the index arithmetic below runs in the shadow of that round trip.
-  constexpr int kCopyB = 10;
-  const int tot = N * ld;
+  constexpr int kCopyB = 5;                    // double2 per thread per round: 2560 entries per round of 256 threads
+  const int tot = N * ld, tot2 = tot >> 1;     // (ld is even, the copies are 16-byte aligned)
   const bool us_from_xs = xs && st.took_step;
-  double v[kCopyB], uc[2];
+  double2 v[kCopyB];
+  double uc[2];
 #pragma unroll
-  for (int u = 0; u < kCopyB; ++u) v[u] = (!ut_filled && tid + u * nthr < tot) ? __ldcg(lp.S + tid + u * nthr) : 0.0;
+  for (int u = 0; u < kCopyB; ++u) {
+    const bool in = !ut_filled && tid + u * nthr < tot2;
+    v[u] = in ? __ldcg(reinterpret_cast<const double2*>(lp.S) + tid + u * nthr) : make_double2(0.0, 0.0);
+  }
+  if (n_rep > 1) {   // the other copies the CTAs spread their atomics over (same round of loads)
+#pragma unroll
+    for (int u = 0; u < kCopyB; ++u) {
+      double2 w[kSReplicas - 1];
+      const bool in = !ut_filled && tid + u * nthr < tot2;
+#pragma unroll
+      for (int r = 1; r < kSReplicas; ++r)
+        w[r - 1] = in ? __ldcg(reinterpret_cast<const double2*>(lp.S + r * lp.s_cap) + tid + u * nthr) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int r = 1; r < kSReplicas; ++r) { v[u].x += w[r - 1].x; v[u].y += w[r - 1].y; }
+    }
+  }
 #pragma unroll
   for (int u = 0; u < 2; ++u) uc[u] = (!us_from_xs && tid + u * nthr < F * kUStride) ? __ldcg(lp.Ucur + tid + u * nthr) : 0.0;
   // this warp's 8x8 tiles (tr <= tc) of the ABSOLUTE tile grid over Ut — the same assignment in every block step,
@@ -216,16 +232,17 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
 #pragma unroll
   for (int u = 0; u < 2; ++u)
     if (tid + u * nthr < F * kUStride) Us[tid + u * nthr] = us_from_xs ? xs[tid + u * nthr] : uc[u];
-  // the accumulator is re-zeroed on the way, so that the next elimination starts from zero
+  // (the accumulator copies are re-zeroed for the next elimination by the warps that idle during the back-substitution)
 #pragma unroll
   for (int u = 0; u < kCopyB; ++u)
-    if (!ut_filled && tid + u * nthr < tot) { Ut[tid + u * nthr] = -v[u]; lp.S[tid + u * nthr] = 0.0; }
-  for (int e0 = tid + kCopyB * nthr; !ut_filled && e0 < tot; e0 += kCopyB * nthr) {   // wide systems: further rounds
-#pragma unroll
-    for (int u = 0; u < kCopyB; ++u) v[u] = (e0 + u * nthr < tot) ? __ldcg(lp.S + e0 + u * nthr) : 0.0;
-#pragma unroll
-    for (int u = 0; u < kCopyB; ++u)
-      if (e0 + u * nthr < tot) { Ut[e0 + u * nthr] = -v[u]; lp.S[e0 + u * nthr] = 0.0; }
+    if (!ut_filled && tid + u * nthr < tot2) reinterpret_cast<double2*>(Ut)[tid + u * nthr] = make_double2(-v[u].x, -v[u].y);
+  for (int e0 = tid + kCopyB * nthr; !ut_filled && e0 < tot2; e0 += nthr) {   // wide systems: the rest, entry by entry
+    double2 a = make_double2(0.0, 0.0);
+    for (int r = 0; r < n_rep; ++r) {
+      const double2 b = __ldcg(reinterpret_cast<const double2*>(lp.S + r * lp.s_cap) + e0);
+      a.x += b.x; a.y += b.y;
+    }
+    reinterpret_cast<double2*>(Ut)[e0] = make_double2(-a.x, -a.y);
   }
   __syncthreads();
   // + U_s + D_c² on the diagonal blocks, + gs_c on the right-hand-side column: one entry per thread
@@ -348,6 +365,11 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
   // triangle of a block (the chain runs through one multiply-add + one multiply per unknown; everything it reads
   // that does not depend on the unknowns is loaded first), every lane then removes the block's unknowns from
   // the rows above (two rows per lane in flight)
+  if (warp != 0 && !ut_filled) {   // idle until the substitution is done: clear the accumulator copies for the next elimination
+    const double2 z = make_double2(0.0, 0.0);
+    for (int r = 0; r < n_rep; ++r)
+      for (int e0 = tid - 32; e0 < tot2; e0 += nthr - 32) reinterpret_cast<double2*>(lp.S + r * lp.s_cap)[e0] = z;
+  }
   if (warp == 0) {
     for (int i = lane; i < N; i += 32) yv[i] = Ut[i * ld + N];
     __syncwarp();
@@ -648,12 +670,12 @@ __device__ __forceinline__ void take_decision(LmState& s_st, const double* s_xs,
 // Tail of an LM iteration (one CTA): adopt the candidate's pose blocks if the step was taken, solve
 // the reduced camera system, re-zero the accumulators K_A fills next, publish the new state.
 template <int TPW>
-__device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams, bool ut_filled) {
+__device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams, bool ut_filled, int n_rep = 1) {
   const int tid = threadIdx.x;
   if (st.took_step)
     for (int i = tid; i < F * kUStride; i += blockDim.x) lp.Ucur[i] = xs ? xs[i] : __ldcg(lp.Xacc + i);
   __syncthreads();
-  solve_reduced<TPW>(lp, st, sm, F, xs, s_cams, ut_filled);
+  solve_reduced<TPW>(lp, st, sm, F, xs, s_cams, ut_filled, n_rep);
   if (lp.dbg && tid == 0) lp.dbg[3] = gtime();
   for (int i = tid; i < F * kUStride + kEacc + kMaxRanks; i += blockDim.x) lp.Xacc[i] = 0.0;
   if (tid == 0) *lp.ticket = 0u;
@@ -741,7 +763,9 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
 
   const unsigned long long t_dec = lp.dbg ? gtime() : 0ull;
   // ---- (E) eliminate the point blocks -----------------------------------------------------
-  eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, s_st.cur, s_st.radius, s_st.iteration == 1, lp.S, lp.Vinv, blockIdx.x, gridDim.x);
+  const int n_rep = lp.split ? 1 : kSReplicas;   // (split mode: copy 0 is what the all-reduce sums)
+  eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, s_st.cur, s_st.radius, s_st.iteration == 1,
+                      lp.S + (blockIdx.x % n_rep) * lp.s_cap, lp.Vinv, blockIdx.x, gridDim.x);
 
   // ---- (S) the last CTA solves the reduced camera system -------------------------------------
   // bar.sync orders the CTA's atomics before thread 0's cumulative gpu-scope fence + ticket
@@ -765,7 +789,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
       reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
     return;
   }
-  finish_iteration<TPW>(lp, s_st, sm, F, s_xs, s_cams, false);
+  finish_iteration<TPW>(lp, s_st, sm, F, s_xs, s_cams, false, n_rep);
 }
 
 // ---- multi-GPU kernel: speculative elimination, one exchange per LM iteration (pba_device.cuh `Xchg`) -----------
@@ -1073,6 +1097,23 @@ __global__ void k_rendezvous(const Xchg xc, unsigned long long epoch) {
 
 cudaError_t launch_rendezvous(const Xchg& xc, unsigned long long epoch, cudaStream_t stream) {
   k_rendezvous<<<1, 32, 0, stream>>>(xc, epoch);
+  return cudaGetLastError();
+}
+
+// End of a solve: the accepted x must sit in buffer 0 of the cameras / points (what pba_get_* and the next solve read).
+// Decided on the device so that the host can enqueue its result copies behind the loop without a round trip.
+__global__ void k_publish(const LmState* __restrict__ st, double* cams, double* pts, int n_cam, int n_pts) {
+  if (st->cur == 0) return;
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = t0; i < n_cam; i += stride) cams[i] = cams[n_cam + i];
+  for (int i = t0; i < n_pts; i += stride) pts[i] = pts[n_pts + i];
+}
+
+cudaError_t launch_publish(const LmState* st, double* cams, double* pts, int n_frames, int n_points, cudaStream_t stream) {
+  const int n_pts = 3 * n_points;
+  int grid = (n_pts + 255) / 256;
+  grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
+  k_publish<<<grid, 256, 0, stream>>>(st, cams, pts, 6 * n_frames, n_pts);
   return cudaGetLastError();
 }
 

@@ -230,6 +230,11 @@ int schur_grid(int n_points, int sm_count);
 int schur_grid_x(int n_points, int sm_count);   // multi-GPU kernel: two groups of CTAs (one per hypothesis), all resident at once
 cudaError_t launch_schur_solve(const LmParams& lp, int grid, int n_free, cudaStream_t stream);   // lp.xc.n_ranks > 1: the multi-GPU kernel
 cudaError_t launch_solve_only(const LmParams& lp, int n_free, cudaStream_t stream);   // split mode, after the all-reduce of S
+// Copies of the reduced-system accumulator S that the CTAs of the single-GPU K_B spread their atomics over (CTA b adds
+// into copy b % kSReplicas; the solving CTA sums the copies): every entry of S otherwise receives one fp64 atomic from
+// EVERY CTA at about the same time, and same-address atomics are performed one after the other in L2.
+constexpr int kSReplicas = 4;
+cudaError_t launch_publish(const LmState* st, double* cams, double* pts, int n_frames, int n_points, cudaStream_t stream);   // buffer `cur` -> buffer 0
 cudaError_t launch_rendezvous(const Xchg& xc, unsigned long long epoch, cudaStream_t stream);   // device-side barrier across the ranks
 
 // descriptor channels (k_prep.cu): type 1 = IntensityAndGradient (3 planes), 2 = BitPlanes (8 planes)

@@ -350,3 +350,35 @@ def test_batched_uploads_and_single_frame_replacement(small_win):
     with pytest.raises(capi.PbaError):
         h3.set_frame_u8_ex(w.n_frames, w.images[0])
     h.close(); h2.close(); h3.close()
+
+
+def test_loop_graph_is_retargeted_in_place_when_sizes_change(small_win):
+    """A sliding window changes its point count on every frame: the instantiated LM-loop graph (WHILE node, body of four
+    kernels) is re-targeted with cudaGraphExecKernelNodeSetParams instead of being rebuilt, and each solve equals the one
+    a fresh handle gives."""
+    import dataclasses
+
+    def sub(win, n):
+        o = int(win.obs_offsets[n])
+        return dataclasses.replace(win, points_init=win.points_init[:n], points_gt=win.points_gt[:n], desc=win.desc[:n],
+                                   obs_offsets=win.obs_offsets[:n + 1], obs_frame=win.obs_frame[:o])
+    w = small_win
+    wins = [w, sub(w, w.n_points - 7), sub(w, w.n_points // 2), w]
+    ref = []
+    for ww in wins:
+        h = capi.Handle.for_window(ww)
+        s = h.solve()
+        ref.append((s["final_cost"], s["num_iterations"], h.get_poses(), h.get_points()))
+        h.close()
+    h = capi.Handle.for_window(w)
+    for ww, (c, n, poses, pts) in zip(wins, ref):
+        h.set_poses(ww.cams_init, ww.fixed_frame)
+        h.set_points(ww.points_init, ww.desc, ww.obs_offsets, ww.obs_frame, ww.weights)
+        s = h.solve()
+        assert s["num_iterations"] == n and abs(s["final_cost"] - c) <= 1e-9 * c
+        cp, pp = h.get_results()
+        np.testing.assert_allclose(cp, poses, atol=1e-8)
+        np.testing.assert_allclose(pp, pts, atol=1e-6)
+    builds, updates = h.graph_counters()
+    assert builds == 1 and updates == 3, (builds, updates)
+    h.close()
