@@ -395,6 +395,7 @@ def main():
     n_obs_local = h.n_obs_local if world > 1 else win.n_obs
     n_pts_local = win.n_points // world
     exchange_kind = h.exchange_kind()
+    speculates = h.speculates()
     h.close()
 
     # ---- second workload: BASELINE configs[3], 16 frames x 16 000 points x 3 levels, coarse to fine ----------
@@ -418,11 +419,13 @@ def main():
         for _ in range(2):
             cfg4_step()
         barrier()
-        c4_dev, c4_evals, c4_iters, c4_fine, c4_last = 0.0, 0, 0, 0.0, None
+        c4_dev, c4_evals, c4_iters, c4_fine, c4_last, c4_kb, c4_fine_evals = 0.0, 0, 0, 0.0, None, 0.0, 0
         for _ in range(c4_steps):
             out = cfg4_step()
             c4_dev += sum(s["device_time_in_seconds"] for s in out)
             c4_fine += out[-1]["device_time_in_seconds"]
+            c4_kb += out[-1]["kb_device_time_in_seconds"]
+            c4_fine_evals += out[-1]["num_evaluations"]
             c4_evals += sum(s["num_evaluations"] for s in out)
             c4_iters += sum(s["num_iterations"] - 1 for s in out)
             launches += sum(s["kernel_launches"] for s in out)
@@ -437,9 +440,13 @@ def main():
                 "n_observations_per_level": wins[0].n_obs, "n_residuals_per_level": wins[0].n_residuals,
                 "ms_per_solve_all_levels": 1e3 * c4_dev / c4_steps, "ms_per_solve_finest_level": 1e3 * c4_fine / c4_steps,
                 "residuals_per_sec": c4_evals * wins[0].n_residuals / c4_dev, "lm_iters_per_sec": c4_iters / c4_dev,
+                "finest_level_us_per_iteration": {"k_b": 1e6 * c4_kb / max(1, c4_fine_evals - c4_steps),
+                                                  "k_a_incl_launch_gaps": 1e6 * (c4_fine - c4_kb) / max(1, c4_fine_evals),
+                                                  "note": "this rank's own stamps / events (not max over ranks)"},
                 "lm_iterations_per_level": [s["num_iterations"] - 1 for s in c4_last],
                 "final_cost_per_level": [s["final_cost"] for s in c4_last], "steps": c4_steps,
                 "exchanges_per_solve_all_levels": sum(s["num_collectives"] for s in c4_last),
+                "speculation": ("on" if hl[0].speculates() else "off (decision exchanged first: two exchanges per iteration)") if world > 1 else None,
                 "timing": "sum of the three levels' CUDA-event intervals, max over ranks"}
         for hx in hl:
             hx.close()
@@ -482,7 +489,9 @@ def main():
                            f"blocks + cost and the reduced camera system travel in ONE in-kernel exchange ({exchange_kind}); a second "
                            f"one only when neither speculated outcome of the decision held",
             "exchanges_per_solve": xchg / steps if world > 1 else 0,
-            "mis_speculation_rate": (xchg - decisions) / max(1, decisions) if (world > 1 and exchange_kind == "peer-memory") else None,
+            "speculation": ("on: both outcomes of the pending decision are eliminated while the evaluation sums travel" if speculates else
+                            "off: shard too large, decision exchanged first (two exchanges per iteration)") if (world > 1 and exchange_kind == "peer-memory") else None,
+            "mis_speculation_rate": (xchg - decisions) / max(1, decisions) if (world > 1 and exchange_kind == "peer-memory" and speculates) else None,
         },
         "k_a": {"us_per_launch_cold_l2": 1e3 * ka_ms, "us_per_launch_warm_l2": 1e3 * ka_ms_warm,
                 "observations_per_launch": n_obs_local,

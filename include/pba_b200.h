@@ -284,6 +284,12 @@ int pba_comm_init_local(pba_handle* const* handles, int32_t n);
  * straight into all peers' memory over NVLink from inside the kernels and the consumers sum the
  * slots in rank order - no collective call, no extra launch), or PBA_EXCHANGE_NCCL (all-reduce
  * fallback when peer mappings are unavailable or PBA_MGPU_EXCHANGE=nccl). */
+/* With the peer-memory exchange, 1 if K_B eliminates the point blocks under both outcomes of the pending trust-region
+ * decision while the evaluation sums travel (ONE exchange per LM iteration, a second one only when neither outcome
+ * holds); 0 if the shard is large enough that doubling the elimination costs more than a second exchange: then the
+ * decision is exchanged first and every CTA eliminates once (TWO exchanges per iteration).  Valid after
+ * pba_set_points; PBA_MGPU_SPECULATE=0/1 overrides the size rule. */
+int pba_comm_speculates(const pba_handle* h);
 #define PBA_EXCHANGE_NONE 0
 #define PBA_EXCHANGE_PEER 1
 #define PBA_EXCHANGE_NCCL 2

@@ -865,6 +865,15 @@ static StepParams make_step_params(pba_handle* h, const LmState* st) {
   return p;
 }
 
+// Multi-GPU K_B: eliminating under both outcomes of the pending decision costs nothing while each half of the SMs
+// still has at most one batch of points per CTA (32 points); beyond that it doubles the elimination time, and deciding
+// first (one more exchange of ~6 us) is the cheaper iteration.  PBA_MGPU_SPECULATE=0/1 overrides.
+static bool speculate_decision(const pba_handle* h) {
+  if (!h->use_xchg) return false;
+  if (const char* e = getenv("PBA_MGPU_SPECULATE")) return atoi(e) != 0;
+  return h->n_points <= 32 * (h->sm_count / 2);
+}
+
 static LmParams make_lm_params(pba_handle* h) {
   LmParams lp;
   memset(&lp, 0, sizeof(lp));
@@ -873,6 +882,7 @@ static LmParams make_lm_params(pba_handle* h) {
   lp.obs_off = h->d_obs_off; lp.obs_frame = h->d_obs_frame;
   lp.cams = h->d_cams; lp.V = h->d_V; lp.gp = h->d_gp; lp.W = h->d_W;
   lp.Xacc = h->d_Xacc; lp.Ucur = h->d_Ucur; lp.split = (h->n_ranks > 1 && !h->use_xchg) ? 1 : 0;
+  lp.speculate = speculate_decision(h) ? 1 : 0;
   if (h->use_xchg) lp.xc = h->xc;
   lp.scale_p = h->d_scale_p; lp.Vinv = h->d_Vinv; lp.S = h->d_S;
   lp.s_cap = reduced_capacity(h->cfg.max_frames); lp.Vinv2 = h->d_Vinv2;
@@ -1139,7 +1149,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   LmParams lp = make_lm_params(h);
   const bool timeline = getenv("PBA_DEBUG_TIMELINE") != nullptr;
   if (timeline && !h->d_dbg) CUDA_TRY(cudaMalloc(&h->d_dbg, sizeof(unsigned long long) * 16 * 1024));
-  const int sgrid = h->use_xchg ? schur_grid_x(h->n_points, h->sm_count) : schur_grid(h->n_points, h->sm_count);
+  const int sgrid = (h->use_xchg && lp.speculate) ? schur_grid_x(h->n_points, h->sm_count) : schur_grid(h->n_points, h->sm_count);
   int launches = 0;
   const bool multi = h->n_ranks > 1 && !h->use_xchg;   // NCCL all-reduce path; the peer-memory exchange needs no host-side calls
   // one GPU: the whole loop runs on the device (WHILE node); PBA_NO_GRAPH=1 keeps the stream loop
@@ -1492,6 +1502,8 @@ int pba_comm_exchange_kind(const pba_handle* h) {
   if (!h || h->n_ranks <= 1) return PBA_EXCHANGE_NONE;
   return h->use_xchg ? PBA_EXCHANGE_PEER : PBA_EXCHANGE_NCCL;
 }
+
+int pba_comm_speculates(const pba_handle* h) { return (h && speculate_decision(h)) ? 1 : 0; }
 
 int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_ranks) {
   if (!h || !id128) return fail(PBA_ERR_ARGUMENT, "pba_comm_init: null argument");

@@ -763,7 +763,9 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
 
   const unsigned long long t_dec = lp.dbg ? gtime() : 0ull;
   // ---- (E) eliminate the point blocks -----------------------------------------------------
-  const int n_rep = lp.split ? 1 : kSReplicas;   // (split mode: copy 0 is what the all-reduce sums)
+  // (split mode: copy 0 is what the all-reduce sums; wide systems: summing four copies of a 90 x 91 accumulator costs
+  // the solving CTA more than the shorter atomic chains save)
+  const int n_rep = (lp.split || s_st.n_free > 8) ? 1 : kSReplicas;
   eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, s_st.cur, s_st.radius, s_st.iteration == 1,
                       lp.S + (blockIdx.x % n_rep) * lp.s_cap, lp.Vinv, blockIdx.x, gridDim.x);
 
@@ -824,7 +826,10 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
   const unsigned long long t_start = lp.dbg ? gtime() : 0ull;
   // two groups of G = gridDim.x / 2 CTAs: group 0 eliminates under hypothesis A, group 1 under hypothesis R, each
   // over the same blocks of points
-  const int G = gridDim.x >> 1, hyp = blockIdx.x >= G ? 1 : 0, bidx = blockIdx.x - hyp * G;
+  // (lp.speculate == 0: one group, nothing is eliminated before the decision is known - every iteration takes the
+  // "second elimination" path below with all CTAs, at the price of a second exchange)
+  const bool spec = lp.speculate != 0;
+  const int G = spec ? gridDim.x >> 1 : gridDim.x, hyp = (spec && blockIdx.x >= G) ? 1 : 0, bidx = blockIdx.x - hyp * G;
   int pre_o0 = 0, pre_o1 = 0;
   const int per_cta = (lp.n_points + G - 1) / G;
   {
@@ -871,7 +876,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
   const double rad_A = fmin(s_st.max_radius, s_st.radius / fmax(1.0 / 3.0, 1.0 / 3.0));
   const double rad_R = s_st.radius / s_st.decrease_factor;
   const int buf_A = s_st.eval_buf, buf_R = s_st.cur;
-  if (!it0) {
+  if (!it0 && spec) {
     if (hyp == 0) eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, buf_A, rad_A, false, S_A, Vinv_A, bidx, G);
     else eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, buf_R, rad_R, false, S_R, Vinv_R, bidx, G);
   }
@@ -916,7 +921,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
     const size_t slot1 = ((size_t)(e & 1ull) * nr + lp.xc.rank) * lp.xc.x1_n;
     for (int i = tid; i < xn; i += blockDim.x)
       for (int q = 0; q < nr; ++q) ll_store(lp.xc.x1[q] + slot1 + i, s_xs[i], e);
-    if (!it0) {
+    if (!it0 && spec) {
       for (int k0 = tid; k0 < n_ent; k0 += kXB * blockDim.x) {
         double a[kXB], b[kXB];
         int rc[kXB];
@@ -980,8 +985,8 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
       }
       return;
     }
-    const bool hitA = !it0 && s_st.took_step && s_st.radius == rad_A;
-    const bool hitR = !it0 && !s_st.took_step && s_st.radius == rad_R;
+    const bool hitA = spec && !it0 && s_st.took_step && s_st.radius == rad_A;
+    const bool hitR = spec && !it0 && !s_st.took_step && s_st.radius == rad_R;
     if (hitA || hitR) {
       if (tid == 0) st_release_sys(lp.xc.verdict, (e << 3) | (hitA ? kXHitA : kXHitR));
       // -P of the outcome that came true: the rank-ordered sum goes straight into the solver's matrix (entries
@@ -1063,7 +1068,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve_x(const LmPara
       Ut[(rc0 >> 8) * NS + (rc0 & 255)] = -v0;
       if (k1 < n_ent) Ut[(rc1 >> 8) * NS + (rc1 & 255)] = -v1;
     }
-    if (tid == 0) { s_st.xepoch = e + 1; s_st.n_xchg += 2; s_st.n_respec += 1; if (lp.dbg) { lp.dbg[2] = gtime(); lp.dbg[10] = 0; } }
+    if (tid == 0) { s_st.xepoch = e + 1; s_st.n_xchg += 2; s_st.n_respec += spec ? 1 : 0; if (lp.dbg) { lp.dbg[2] = gtime(); lp.dbg[10] = 0; } }
     __syncthreads();
     if (!s_xok && tid == 0) *lp.xc.error = 1;
     if (lp.pdl) pdl_launch_dependents();

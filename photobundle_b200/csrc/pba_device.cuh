@@ -163,6 +163,8 @@ struct LmParams {
   unsigned long long cond;   // non-zero: cudaGraphConditionalHandle of the device-side LM loop, cleared when done
   Xchg xc;                   // multi-GPU exchange over peer memory (xc.n_ranks > 1), else split/NCCL or single GPU
   int pdl;                   // launched with programmatic stream serialization (see pdl_wait)
+  int speculate;             // multi-GPU: eliminate under both outcomes of the pending decision while the evaluation sums travel (one
+                             // exchange per iteration); 0: decide first, then eliminate once with all CTAs (two exchanges) - large shards
 };
 
 // ---- programmatic dependent launch (PDL): the LM loop is a chain K_B -> K_A -> K_B ... of dependent kernels; a
