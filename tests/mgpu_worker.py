@@ -21,6 +21,12 @@ def main():
     kind = sys.argv[1] if len(sys.argv) > 1 else "small"
     if kind == "small":
         win = synthetic.small_window(seed=7)
+    elif kind == "one_point":   # fewer points than ranks: one rank's shard is empty
+        import dataclasses
+        w0 = synthetic.small_window(seed=7)
+        o = int(w0.obs_offsets[1])
+        win = dataclasses.replace(w0, points_init=w0.points_init[:1], points_gt=w0.points_gt[:1], desc=w0.desc[:1],
+                                  obs_offsets=w0.obs_offsets[:2], obs_frame=w0.obs_frame[:o])
     elif kind == "cfg4":      # finest level of BASELINE configs[3]: 16 frames x 16 000 points
         win = synthetic.make_window(n_frames=16, grid=(100, 160))
     else:
@@ -37,7 +43,7 @@ def main():
     s = h.solve()
     cams, pts = h.get_poses(), h.get_points()
     second, second_ms = None, None
-    if kind != "small":      # solve the same window again on the same handle (warm: graph instantiated, L2 primed)
+    if kind not in ("small", "one_point"):      # solve the same window again on the same handle (warm: graph instantiated, L2 primed)
         h.restore_state()
         s2 = h.solve()
         second, second_ms = s2["final_cost"], 1e3 * s2["device_time_in_seconds"]

@@ -160,9 +160,12 @@ def test_run_sequence_driver(seq, tmp_path):
                             str(tmp_path / "refined_poses_2gpu.txt")], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr
         out2 = np.loadtxt(tmp_path / "refined_poses_2gpu.txt")
-        # same trajectory as one GPU: the sums differ in the last bits, every solve stops on a 1e-6 relative cost
-        # tolerance, and the file holds 6 decimals
-        np.testing.assert_allclose(out2, out, atol=5e-5)
+        # same trajectory as one GPU.  A single window agrees to 1e-8 (tests/test_multi_gpu.py); over a sequence the
+        # unordered fp64 atomics can flip a borderline "cost change below 1e-6" test, i.e. one window stops one small
+        # step earlier or later, and the following windows start from there: seen 1e-5 typically, 2e-4 once
+        np.testing.assert_allclose(out2, out, atol=1e-3)
+        T2 = np.tile(np.eye(4), (n, 1, 1)); T2[:, :3, :] = out2.reshape(n, 3, 4)
+        _check_refined(T2, seq)
 
 
 @pytest.mark.gpu

@@ -106,6 +106,20 @@ def test_two_gpus_equal_one_gpu():
 
 
 @pytest.mark.gpu
+def test_two_gpus_empty_shard():
+    """Fewer points than ranks: the rank with the empty shard still takes part in every exchange (zero contribution)
+    instead of leaving its peers to time out."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    one, two = _run_workers(1, "one_point"), _run_workers(2, "one_point")
+    assert two["ranks_agree"] and two["n_pts"] == one["n_pts"] == 1
+    assert two["accepts"] == one["accepts"]
+    assert abs(two["final_cost"] - one["final_cost"]) <= 1e-9 * max(one["final_cost"], 1e-30)
+    np.testing.assert_allclose(np.array(two["cams"]), np.array(one["cams"]), atol=1e-8)
+
+
+@pytest.mark.gpu
 def test_two_gpus_bench_window_repeated_solves():
     """cfg3 window on 2 GPUs, solved twice on the same handle (epochs keep counting across solves)."""
     import torch
