@@ -324,7 +324,7 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
     UB_STAMP(19);
     // trailing update Ut22 -= PᵀP on the tensor pipe (P = the 6 x m panel, rows j0..j0+5): per 8x8 tile two
     // DMMAs (k = 6, the second half-empty).  Tiles straddling the factored part get zeros for rows / columns
-    // < j0 + 6, so whole tiles are stored without predicates; padding rows / columns absorb the overhang.
+    // < j0 + 6; padding rows / columns absorb the overhang.
     {
       const int base = j0 + 6, tb = base >> 3;
       const double* pr = Ut + j0 * ld;
@@ -350,7 +350,9 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
             const double x0 = ra ? -a0[u] : 0.0, x1 = ra ? -a1[u] : 0.0, y0 = cb ? b0[u] : 0.0, y1 = cb ? b1[u] : 0.0;
             dmma884(c[u].x, c[u].y, x0, y0);
             dmma884(c[u].x, c[u].y, x1, y1);
-            *reinterpret_cast<double2*>(Ut + offc[k]) = c[u];
+            // rows above the trailing part received a zero update: not stored, so that the panel rows other warps
+            // are still reading are never written during this phase
+            if (ra) *reinterpret_cast<double2*>(Ut + offc[k]) = c[u];
           }
         }
       }
@@ -730,6 +732,9 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
   }
   for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
     reinterpret_cast<int*>(&s_st)[i] = reinterpret_cast<const int*>(lp.st_in)[i];
+  // (read from the input state, which nothing writes during this kernel: the shared copy's `done` is set by the
+  // deciding lane below while slower warps could still be looking at it)
+  const int was_done = lp.st_in->done;
   if (warp == 0) {
 #pragma unroll
     for (int k = 0; k < (kMaxD + 31) / 32; ++k) {
@@ -741,7 +746,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
   for (int k = 0; k < kXPre; ++k)
     if (tid + k * kSchurThreads < xn) s_xs[tid + k * kSchurThreads] = x_pre[k];
   __syncthreads();
-  if (s_st.done) {
+  if (was_done) {
     if (blockIdx.x == 0) {
       for (int i = tid; i < (int)(sizeof(LmState) / 4); i += blockDim.x)
         reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
