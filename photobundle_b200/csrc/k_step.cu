@@ -173,13 +173,16 @@ constexpr int kRedStride = 6 * kG + 2;   // doubles per lane row of the reductio
 // per warp: geometry [8][20] f64 | reduction transpose [25][6G+2] f64 | patch sums [8][6] f64 |
 //           pose-block accumulators [F][27] f64 | ints [8] int4 | frames [16] i32 |
 //           footprints [8][ROWS][W] f32
-template <int R, bool U8, int WARPS = Geo<U8>::WARPS>
+// USHARE: warps that share one pose-block accumulator (1: private, plain adds; 2: pairs, shared-memory fp64 atomics -
+// what lets 16-frame windows keep 14 warps per CTA and two CTAs per SM)
+template <int R, bool U8, int WARPS = Geo<U8>::WARPS, int USHARE = 1>
 __host__ __device__ constexpr size_t k_step_smem_bytes(int n_frames) {
   // footprints: raw uint8 (ROWS x W bytes) on the Intensity path, fp32 otherwise
   constexpr size_t fp_bytes = (size_t)kStageSlots * Foot<R>::FLOATS * (U8 ? 1 : 4);
   return sizeof(double) * ((size_t)n_frames * (kPoseConst + 6) + WARPS * kEacc + ((Foot<R>::P + 1) & ~1)) +
-         (size_t)WARPS * (sizeof(double) * (kObsBatch * 20 + 25 * kRedStride + 6 * kObsBatch + (size_t)n_frames * kUStride + (n_frames & 1)) +
-                          sizeof(int4) * kObsBatch + sizeof(int) * kMaxFrames + ((fp_bytes + 15) / 16) * 16);
+         (size_t)WARPS * (sizeof(double) * (kObsBatch * 20 + 25 * kRedStride + 6 * kObsBatch) +
+                          sizeof(int4) * kObsBatch + sizeof(int) * kMaxFrames + ((fp_bytes + 15) / 16) * 16) +
+         (size_t)(WARPS / USHARE) * sizeof(double) * ((size_t)n_frames * kUStride + (n_frames & 1));
 }
 
 struct Sums { double s, G11, G12, G22, b1, b2; };
@@ -292,12 +295,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // smem accumulator, W -> HBM, V / g_p -> the caller's register accumulator.
 __device__ __forceinline__ void emit_blocks(double dG11, double dG12, double dG22, double db1, double db2,
                                             const double* __restrict__ g, int f, bool free_cam, int lane, int e1a, int e1b,
-                                            int e2a, int e2b, double* s_U_w, double* __restrict__ outW_o, double& acc_pt) {
+                                            int e2a, int e2b, double* s_U_w, double* __restrict__ outW_o, double& acc_pt,
+                                            const bool shared_u = false) {
   const double* A = g + 2;
   if (lane < 27) {
     if (free_cam) {
       const double v1 = lane < 21 ? quad(A, e1a, e1b, dG11, dG12, dG22) : -(A[e1a] * db1 + A[9 + e1a] * db2);
-      s_U_w[f * kUStride + lane] += v1;   // warp-private: no atomics
+      if (shared_u) atomicAdd(s_U_w + f * kUStride + lane, v1);
+      else s_U_w[f * kUStride + lane] += v1;   // warp-private: no atomics
     }
     const double v2 = lane < 24 ? quad(A, e2a, e2b, dG11, dG12, dG22) : -(A[e2a] * db1 + A[9 + e2a] * db2);
     if (lane < 18) outW_o[lane] = free_cam ? v2 : 0.0;
@@ -325,8 +330,9 @@ __device__ __forceinline__ void block_entries(const double* __restrict__ t, cons
 // NCH: compile-time channel count (1 = Intensity, the north-star descriptor); 0 = runtime count.
 // WARPS: warps per CTA (two CTAs per SM); the default keeps a 4 000-point window in one wave, wide windows
 // (per-warp pose-block accumulators grow with the frame count) use fewer so that two CTAs still fit.
-template <int R, bool U8, int NCH, int WARPS = Geo<U8>::WARPS>
+template <int R, bool U8, int NCH, int WARPS = Geo<U8>::WARPS, int USHARE = 1>
 __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
+  static_assert(WARPS % USHARE == 0, "warps per pose-block accumulator");
   using FT = Foot<R>;
   using FPT = typename std::conditional<U8, uint8_t, float>::type;   // footprint element in shared memory
   constexpr int P = FT::P;
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
   constexpr int kOffU = kOffFp + kFpBytes;                                    // [F][27] f64: this warp's pose blocks
   static_assert(kOffGi % 16 == 0 && kOffFp % 16 == 0 && kOffU % 8 == 0, "per-warp shared-memory layout alignment");
   const int ustride = F * kUStride + (F & 1);
-  const int warp_bytes = kOffU + 8 * ustride;
+  const int warp_bytes = kOffU + (USHARE == 1 ? 8 * ustride : 0);
   unsigned char* s_warp0 = reinterpret_cast<unsigned char*>(s_wts + ((P + 1) & ~1));
   unsigned char* wbase = s_warp0 + warp * warp_bytes;
   double* s_geo_w = reinterpret_cast<double*>(wbase + kOffGeo);
@@ -385,7 +391,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
   int4* s_gi_w = reinterpret_cast<int4*>(wbase + kOffGi);
   int* s_frm_w = reinterpret_cast<int*>(wbase + kOffFrm);
   FPT* s_fp_w = reinterpret_cast<FPT*>(wbase + kOffFp);
-  double* s_U_w = reinterpret_cast<double*>(wbase + kOffU);
+  // pose-block accumulator: at the end of the warp's own region, or (USHARE > 1) one per group of warps behind all regions
+  double* s_U_w = USHARE == 1 ? reinterpret_cast<double*>(wbase + kOffU)
+                              : reinterpret_cast<double*>(s_warp0 + WARPS * warp_bytes) + (warp / USHARE) * ustride;
 
   if (threadIdx.x < 9 * F) pose_consts(cams + 6 * (threadIdx.x / 9), s_pose + (threadIdx.x / 9) * kPoseConst, threadIdx.x % 9);
 #ifdef K_STEP_TRACE
@@ -766,7 +774,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
                 if (prm.obs_sqnorm) prm.obs_sqnorm[o] = q.s;
               }
               emit_blocks(rho1 * q.G11, rho1 * q.G12, rho1 * q.G22, rho1 * q.b1, rho1 * q.b2, g, f, f != prm.fixed_frame, lane,
-                          e1a, e1b, e2a, e2b, s_U_w, outW + (size_t)o * 18, acc_pt);
+                          e1a, e1b, e2a, e2b, s_U_w, outW + (size_t)o * 18, acc_pt, USHARE > 1);
             }
           }
         }
@@ -805,7 +813,10 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
             for (int i = 0; i < kE; ++i) {
               const int f = s_gi_w[i0 + i].x;
               const bool free_cam = f != prm.fixed_frame;
-              if (lane < 27 && free_cam) s_U_w[f * kUStride + lane] += v1[i];   // warp-private: no atomics
+              if (lane < 27 && free_cam) {
+                if (USHARE > 1) atomicAdd(s_U_w + f * kUStride + lane, v1[i]);
+                else s_U_w[f * kUStride + lane] += v1[i];   // warp-private: no atomics
+              }
               if (lane < 18) outW[(size_t)(o0 + ob + i0 + i) * 18 + lane] = free_cam ? v2[i] : 0.0;
               else if (lane < 27) acc_pt += v2[i];
             }
@@ -817,7 +828,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
               const int f = s_gi_w[i].x;
               const double* t = s_tot_w + 6 * i;
               emit_blocks(t[1], t[2], t[3], t[4], t[5], s_geo_w + i * 20, f, f != prm.fixed_frame, lane, e1a, e1b, e2a, e2b,
-                          s_U_w, outW + (size_t)(o0 + ob + i) * 18, acc_pt);
+                          s_U_w, outW + (size_t)(o0 + ob + i) * 18, acc_pt, USHARE > 1);
             }
           }
         }
@@ -851,7 +862,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
   for (int i = threadIdx.x; i < F * kUStride; i += blockDim.x) {
     double acc = 0.0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) acc += reinterpret_cast<const double*>(s_warp0 + w * warp_bytes + kOffU)[i];
+    for (int w = 0; w < WARPS / USHARE; ++w)
+      acc += USHARE == 1 ? reinterpret_cast<const double*>(s_warp0 + w * warp_bytes + kOffU)[i]
+                         : (reinterpret_cast<const double*>(s_warp0 + WARPS * warp_bytes) + w * ustride)[i];
     if (acc != 0.0) atomicAdd(prm.Xacc + i, acc);
   }
   if (threadIdx.x < kEacc) {
@@ -876,18 +889,18 @@ extern "C" void pba_debug_kstep_trace(long long* out, int n) {
 #endif
 
 // ---- host launcher -----------------------------------------------------------------------
-template <int R, bool U8, int NCH, int WARPS = Geo<U8>::WARPS>
+template <int R, bool U8, int NCH, int WARPS = Geo<U8>::WARPS, int USHARE = 1>
 static cudaError_t launch_one(const StepParams& prm, cudaStream_t stream) {
-  const size_t smem = k_step_smem_bytes<R, U8, WARPS>(prm.n_frames);
+  const size_t smem = k_step_smem_bytes<R, U8, WARPS, USHARE>(prm.n_frames);
   static bool configured[64] = {};
   static int sm_count[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k_step<R, U8, NCH, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_step<R, U8, NCH, WARPS, USHARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
     // two CTAs per SM need the large shared-memory carve-out
-    cudaFuncSetAttribute(k_step<R, U8, NCH, WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_step<R, U8, NCH, WARPS, USHARE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     configured[dev & 63] = true;
   }
@@ -902,9 +915,9 @@ static cudaError_t launch_one(const StepParams& prm, cudaStream_t stream) {
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_step<R, U8, NCH, WARPS>, prm);
+    return cudaLaunchKernelEx(&cfg, k_step<R, U8, NCH, WARPS, USHARE>, prm);
   }
-  k_step<R, U8, NCH, WARPS><<<grid, WARPS * 32, smem, stream>>>(prm);
+  k_step<R, U8, NCH, WARPS, USHARE><<<grid, WARPS * 32, smem, stream>>>(prm);
   return cudaGetLastError();
 }
 
@@ -915,7 +928,13 @@ static cudaError_t launch_r(const StepParams& prm, cudaStream_t stream) {
     // two CTAs per SM: 228 KB of shared memory, 1 KB reserved per CTA
     constexpr size_t kPerCta = (233472 - 2 * 1024) / 2;
     if constexpr (R == 2)
-      if (k_step_smem_bytes<R, true>(prm.n_frames) > kPerCta) return launch_one<R, true, 1, 11>(prm, stream);
+      if (k_step_smem_bytes<R, true>(prm.n_frames) > kPerCta) {
+        // wide windows: the per-warp pose-block accumulators ([F][27] doubles) no longer fit twice 14 warps; pairs of
+        // warps share one (shared-memory atomics) so that the geometry of the single-wave case is kept
+        if (getenv("PBA_KA_WIDE_11") == nullptr && k_step_smem_bytes<R, true, 14, 2>(prm.n_frames) <= kPerCta)
+          return launch_one<R, true, 1, 14, 2>(prm, stream);
+        return launch_one<R, true, 1, 11>(prm, stream);
+      }
     return launch_one<R, true, 1>(prm, stream);
   }
   if (prm.fr.n_channels == 1) return launch_one<R, false, 1>(prm, stream);
