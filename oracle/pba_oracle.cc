@@ -437,10 +437,17 @@ int set_threads(const oracle_problem* pb) {
 
 double cost_only(const View& vw, const double* cams, const double* points) {
   const oracle_problem& pb = *vw.pb;
-  double total = 0.0;
   const int nt = set_threads(&pb);
-#pragma omp parallel for schedule(static) reduction(+ : total) num_threads(nt)
+  // per-thread partial sums combined in thread order: the same thread count always gives the same bits (an OpenMP
+  // reduction clause combines in arrival order)
+  std::vector<double> part((size_t)nt * 8, 0.0);
+#pragma omp parallel for schedule(static) num_threads(nt)
   for (int p = 0; p < pb.n_points; ++p) {
+#ifdef _OPENMP
+    double& total = part[(size_t)omp_get_thread_num() * 8];
+#else
+    double& total = part[0];
+#endif
     double r[512];
     std::vector<double> big;
     double* rr = r;
@@ -459,6 +466,8 @@ double cost_only(const View& vw, const double* cams, const double* points) {
       }
     }
   }
+  double total = 0.0;
+  for (int k = 0; k < nt; ++k) total += part[(size_t)k * 8];
   return total;
 }
 
@@ -707,9 +716,16 @@ bool compute_step(const oracle_problem& pb, Workspace& ws, double radius, double
   }
   ws.step_p.assign((size_t)n * 3, 0.0);
   // Back-substitution and model cost change  -s^T g_s - 0.5 s^T H_s s.
-  double sg = 0.0, sHs = 0.0;
-#pragma omp parallel for schedule(static) reduction(+ : sg, sHs) num_threads(nt)
+  std::vector<double> part((size_t)nt * 8, 0.0);   // {s.g, s'Hs} per thread, combined in thread order (deterministic)
+#pragma omp parallel for schedule(static) num_threads(nt)
   for (int p = 0; p < n; ++p) {
+#ifdef _OPENMP
+    double& sg = part[(size_t)omp_get_thread_num() * 8];
+    double& sHs = part[(size_t)omp_get_thread_num() * 8 + 1];
+#else
+    double& sg = part[0];
+    double& sHs = part[1];
+#endif
     const double* sp = ws.scale_p.data() + 3 * p;
     double t[3];
     for (int a = 0; a < 3; ++a) t[a] = sp[a] * ws.gp[(size_t)p * 3 + a];
@@ -746,6 +762,8 @@ bool compute_step(const oracle_problem& pb, Workspace& ws, double radius, double
           sHs += 2.0 * ws.step_c[f * 6 + a] * (sc[a] * ws.W[(size_t)o * 18 + a * 3 + b] * sp[b]) * sv[b];
     }
   }
+  double sg = 0.0, sHs = 0.0;
+  for (int k = 0; k < nt; ++k) { sg += part[(size_t)k * 8]; sHs += part[(size_t)k * 8 + 1]; }
   for (int f = 0; f < F; ++f) {
     if (ws.free_index[f] < 0) continue;
     const double* sc = ws.scale_c.data() + 6 * f;

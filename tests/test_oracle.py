@@ -288,3 +288,17 @@ def test_camera_model_and_patch_weights_match_reference_binary_when_present():
             binding.lib().oracle_patch_weights(radius, gauss, C.c_void_p(w_ora.ctypes.data))
             assert host.pbah_patch_weights(radius, gauss, C.c_void_p(w_host.ctypes.data)) == n
             assert w_ref.tobytes() == w_ora.tobytes() == w_host.tobytes()
+
+
+def test_oracle_is_deterministic_for_a_fixed_thread_count():
+    """Per-thread partial sums are combined in thread order (no OpenMP reduction clauses on the path): two solves with
+    the same thread count give the same bits, whatever the scheduling."""
+    from workloads import synthetic
+    win = synthetic.small_window(seed=11, ragged=True, n_frames=8, grid=(10, 14))
+    for nt in (1, 3, 4):
+        runs = []
+        for _ in range(3):
+            ow = binding.OracleWindow(win, num_threads=nt)
+            cams, pts, summ, tr = ow.solve(win.cams_init, win.points_init)
+            runs.append((cams.tobytes(), pts.tobytes(), summ["final_cost"], len(tr)))
+        assert runs[0] == runs[1] == runs[2], nt
