@@ -199,6 +199,12 @@ int pba_restore_state(pba_handle* h);
  * trip.  Ordered on dst's stream. */
 int pba_copy_state(pba_handle* dst, pba_handle* src);
 
+/* Page-locked host memory for buffers that are passed to pba_set_* / pba_associate / ... on every frame: copies from
+ * (and to) such buffers run at the full rate of the host link, pageable memory goes through the driver's staging
+ * buffers at a third of it.  Optional - every entry point accepts ordinary memory.  NULL on failure. */
+void* pba_host_alloc(size_t bytes);
+void pba_host_free(void* p);
+
 /* Diagnostics: how often this handle instantiated its LM-loop graph and how often it re-targeted the instantiated
  * graph in place (cudaGraphExecKernelNodeSetParams) because only sizes had changed since the previous solve - what a
  * sliding window does on every frame. */
@@ -256,7 +262,9 @@ int pba_associate(pba_handle* h, int32_t n, const double* xyz, const float* ref_
  * are strict local maxima of the saliency map over (2 nms_radius + 1)^2 (IsLocalMax_, src/imgproc.h:175-212)
  * and not masked by a (2 mask_radius + 1)^2 block around a re-observed point.  Returned in scan order
  * (row-major); *n_out may exceed capacity (then only the first `capacity` of an arbitrary order were
- * stored and the call should be repeated with more room). */
+ * stored and the call should be repeated with more room).  `depth` may be NULL: then no depth test is made on the
+ * device (the depth map, 4 bytes per pixel, does not cross the host link) and the caller drops the candidates whose
+ * depth is out of range - the same set in the same order, since the test is per pixel. */
 int pba_select_candidates(pba_handle* h, const float* depth, int32_t n_masked, const int32_t* masked_row_col,
                           int32_t mask_radius, int32_t nms_radius, int32_t border, double min_depth, double max_depth,
                           int32_t capacity, int32_t* cand_row_col, float* cand_saliency, int32_t* n_out);

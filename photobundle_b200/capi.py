@@ -21,7 +21,7 @@ PBA_UNIQUE_ID_BYTES = 128
 EXPORTED_SYMBOLS = [
     "pba_last_error", "pba_version", "pba_default_solver_options", "pba_create", "pba_destroy",
     "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_frames_u8_pyr", "pba_pyrdown_u8", "pba_set_poses", "pba_set_points",
-    "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_copy_state", "pba_graph_counters", "pba_begin_batch", "pba_end_batch", "pba_set_frame_u8_ex", "pba_get_results", "pba_get_poses", "pba_get_points", "pba_get_iterations",
+    "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_copy_state", "pba_host_alloc", "pba_host_free", "pba_graph_counters", "pba_begin_batch", "pba_end_batch", "pba_set_frame_u8_ex", "pba_get_results", "pba_get_poses", "pba_get_points", "pba_get_iterations",
     "pba_comm_unique_id", "pba_comm_init", "pba_comm_init_local", "pba_comm_speculates", "pba_shard_range", "pba_comm_exchange_kind",
     "pba_descriptor_channels", "pba_set_frames_u8_descriptor", "pba_get_channel_plane", "pba_prepare_frame_u8",
     "pba_saliency_map", "pba_extract_descriptors", "pba_associate", "pba_select_candidates",

@@ -699,7 +699,7 @@ int pba_associate(pba_handle* h, int32_t n, const double* xyz, const float* ref_
 int pba_select_candidates(pba_handle* h, const float* depth, int32_t n_masked, const int32_t* masked_row_col,
                           int32_t mask_radius, int32_t nms_radius, int32_t border, double min_depth, double max_depth,
                           int32_t capacity, int32_t* cand_row_col, float* cand_saliency, int32_t* n_out) {
-  if (!h || !depth || !n_out || (n_masked > 0 && !masked_row_col) || (capacity > 0 && (!cand_row_col || !cand_saliency)))
+  if (!h || !n_out || (n_masked > 0 && !masked_row_col) || (capacity > 0 && (!cand_row_col || !cand_saliency)))
     return fail(PBA_ERR_ARGUMENT, "pba_select_candidates: null argument");
   if (h->new_active <= 0) return fail(PBA_ERR_STATE, "pba_select_candidates: call pba_prepare_frame_u8 first");
   if (n_masked < 0 || capacity < 0 || mask_radius < 0 || nms_radius < 0 || border < nms_radius || border < mask_radius)
@@ -722,10 +722,10 @@ int pba_select_candidates(pba_handle* h, const float* depth, int32_t n_masked, c
     CUDA_TRY(cudaMalloc(&h->d_masked_rc, sizeof(int) * 2 * ((size_t)n_masked + n_masked / 2 + 64)));
     h->masked_cap = n_masked + n_masked / 2 + 64;
   }
-  CUDA_TRY(cudaMemcpyAsync(h->d_depth, depth, sizeof(float) * dense, cudaMemcpyHostToDevice, h->stream));
+  if (depth) CUDA_TRY(cudaMemcpyAsync(h->d_depth, depth, sizeof(float) * dense, cudaMemcpyHostToDevice, h->stream));
   if (n_masked > 0) CUDA_TRY(cudaMemcpyAsync(h->d_masked_rc, masked_row_col, sizeof(int) * 2 * (size_t)n_masked, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(launch_saliency(h->d_new_planes, h->new_active, h->cfg.rows, h->cfg.cols, h->pitch, h->plane, h->d_sal, h->stream));
-  CUDA_TRY(launch_candidates(h->d_sal, h->d_mask, h->d_depth, h->cfg.rows, h->cfg.cols, border, nms_radius, n_masked, h->d_masked_rc,
+  CUDA_TRY(launch_candidates(h->d_sal, h->d_mask, depth ? h->d_depth : nullptr, h->cfg.rows, h->cfg.cols, border, nms_radius, n_masked, h->d_masked_rc,
                              mask_radius, min_depth, max_depth, capacity, h->d_count, h->d_cand_rc, h->d_cand_sal, h->stream));
   int count = 0;
   CUDA_TRY(cudaMemcpyAsync(&count, h->d_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -737,11 +737,18 @@ int pba_select_candidates(pba_handle* h, const float* depth, int32_t n_masked, c
     std::vector<float> sal(m);
     CUDA_TRY(cudaMemcpy(rc.data(), h->d_cand_rc, sizeof(int) * 2 * (size_t)m, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(sal.data(), h->d_cand_sal, sizeof(float) * (size_t)m, cudaMemcpyDeviceToHost));
-    // the compaction order is arbitrary: back into scan order (row-major), which is what addFrame produces
-    std::vector<int> idx(m);
-    for (int i = 0; i < m; ++i) idx[i] = i;
-    const int cols = h->cfg.cols;
-    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return (long long)rc[2 * a] * cols + rc[2 * a + 1] < (long long)rc[2 * b] * cols + rc[2 * b + 1]; });
+    // the compaction order is arbitrary: back into scan order (row-major), which is what addFrame produces - a counting
+    // sort by row, then the few candidates of each row by column
+    const int rows = h->cfg.rows;
+    std::vector<int> start((size_t)rows + 1, 0), idx(m);
+    for (int i = 0; i < m; ++i) ++start[(size_t)rc[2 * i] + 1];
+    for (int r = 0; r < rows; ++r) start[(size_t)r + 1] += start[r];
+    {
+      std::vector<int> fill(start.begin(), start.end() - 1);
+      for (int i = 0; i < m; ++i) idx[fill[rc[2 * i]]++] = i;
+    }
+    for (int r = 0; r < rows; ++r)
+      std::sort(idx.begin() + start[r], idx.begin() + start[(size_t)r + 1], [&](int a, int b) { return rc[2 * a + 1] < rc[2 * b + 1]; });
     for (int i = 0; i < m; ++i) { cand_row_col[2 * i] = rc[2 * idx[i]]; cand_row_col[2 * i + 1] = rc[2 * idx[i] + 1]; cand_saliency[i] = sal[idx[i]]; }
   }
   return PBA_OK;
@@ -1525,6 +1532,13 @@ int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_rank
   }
   return PBA_OK;
 }
+
+void* pba_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void pba_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int pba_graph_counters(const pba_handle* h, int32_t* builds, int32_t* updates) {
   if (!h || !builds || !updates) return fail(PBA_ERR_ARGUMENT, "pba_graph_counters: null argument");

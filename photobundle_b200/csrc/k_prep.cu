@@ -257,8 +257,10 @@ __global__ void __launch_bounds__(256) k_candidates(const float* __restrict__ sa
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int max_rows = rows - border - 1, max_cols = cols - border - 1;
   if (y < border || y >= max_rows || x < border || x >= max_cols) return;
-  const float z = depth[(size_t)y * cols + x];
-  if (!((double)z >= min_depth && (double)z <= max_depth)) return;
+  if (depth) {   // (no depth map on the device: the caller applies the depth test to what comes back)
+    const float z = depth[(size_t)y * cols + x];
+    if (!((double)z >= min_depth && (double)z <= max_depth)) return;
+  }
   const float v = sal[(size_t)y * cols + x];
   if (nms > 0) {
     if (!mask[(size_t)y * cols + x] || v < 0.0f) return;

@@ -397,6 +397,16 @@ PhotometricBundleAdjustment::~PhotometricBundleAdjustment() {
     for (pba_handle* h : d.ranks) pba_destroy(h);
 }
 
+void* PhotometricBundleAdjustment::Pinned::need(size_t n) {
+  if (n <= bytes) return p;
+  pba_host_free(p);
+  bytes = n + n / 2 + 4096;
+  p = pba_host_alloc(bytes);
+  if (!p) { bytes = 0; throw std::runtime_error("pba_host_alloc failed"); }
+  return p;
+}
+PhotometricBundleAdjustment::Pinned::~Pinned() { pba_host_free(p); }
+
 static void check_pba(int rc, const char* what) {
   if (rc != PBA_OK) throw std::runtime_error(std::string(what) + ": " + pba_last_error());
 }
@@ -443,7 +453,26 @@ static void ExtractPatch(double* dst, const uint8_t* I, int rows, int cols, int 
   }
 }
 
+// PBA_HOST_TIMING=1: wall-clock phases of addFrame / optimize on stderr (developer aid, scripts/seq_timing.py)
+namespace {
+struct PhaseClock {
+  const bool on = getenv("PBA_HOST_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  std::string line;
+  void mark(const char* what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    char buf[64];
+    snprintf(buf, sizeof(buf), " %s %.0f us", what, 1e6 * std::chrono::duration<double>(n - t).count());
+    line += buf;
+    t = n;
+  }
+  void flush(const char* who) { if (on) fprintf(stderr, "[pba host] %s:%s\n", who, line.c_str()); }
+};
+}  // namespace
+
 void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_ptr, const Mat44& T, Result* result) {
+  PhaseClock clk;
   _trajectory.push_back(T, (int)_frame_id);
   const Mat44 T_w = _trajectory.back(), T_c = T_w.rigidInverse();
   const int rows = _image_size.rows, cols = _image_size.cols;
@@ -459,6 +488,7 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
   frame.image.assign(I_ptr, I_ptr + (size_t)rows * cols);
   if (multi || on_gpu) check_pba(pba_prepare_frame_u8(deviceLevel(0, 0, 0), I_ptr, _desc_type), "pba_prepare_frame_u8");
   pba_handle* const gpu0 = _dev[0].h;
+  clk.mark("copy+prepare");
 
   // ---- (1) which live points are seen again in this frame (src/photobundle.cc:508-542): project with the INITIAL
   // pose, compare the stored 5x5 patch with the one around the projection (ZNCC), block the neighbourhood of a hit
@@ -468,22 +498,26 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
   auto is_live = [&](const ScenePoint& p) { return (int)_frame_id - (int)p.lastFrameId() <= _options.maxFrameDistance; };
   if (on_gpu) {
     std::vector<ScenePoint*> live;
-    std::vector<double> xyz;
-    std::vector<float> patches, norms;
-    for (auto& sp : _scene_points) {
-      if (!is_live(*sp)) continue;
-      live.push_back(sp.get());
-      xyz.insert(xyz.end(), sp->X.data(), sp->X.data() + 3);
-      patches.insert(patches.end(), sp->patch.data, sp->patch.data + ZnccPatch::kLen);
-      norms.push_back(sp->patch.norm);
-    }
+    live.reserve(_scene_points.size());
+    for (auto& sp : _scene_points)
+      if (is_live(*sp)) live.push_back(sp.get());
     n_tested = (int)live.size();
-    std::vector<float> score(live.size());
-    std::vector<int32_t> rc(2 * live.size());
+    const size_t nl = live.size();
+    // gathered straight into page-locked memory: 128 bytes per live point cross the link every frame
+    double* xyz = static_cast<double*>(_pin_xyz.need(sizeof(double) * 3 * nl));
+    float* patches = static_cast<float*>(_pin_patch.need(sizeof(float) * ZnccPatch::kLen * nl));
+    float* norms = static_cast<float*>(_pin_norm.need(sizeof(float) * nl));
+    float* score = static_cast<float*>(_pin_score.need(sizeof(float) * nl));
+    int32_t* rc = static_cast<int32_t*>(_pin_rc.need(sizeof(int32_t) * 2 * nl));
+    for (size_t k = 0; k < nl; ++k) {
+      const ScenePoint& sp = *live[k];
+      for (int a = 0; a < 3; ++a) xyz[3 * k + a] = sp.X[a];
+      std::copy(sp.patch.data, sp.patch.data + ZnccPatch::kLen, patches + (size_t)ZnccPatch::kLen * k);
+      norms[k] = sp.patch.norm;
+    }
     double K_rowmajor[9];
     for (int k = 0; k < 9; ++k) K_rowmajor[k] = _calib.K()(k / 3, k % 3);
-    check_pba(pba_associate(gpu0, (int32_t)live.size(), xyz.data(), patches.data(), norms.data(), T_c.m, K_rowmajor, border, score.data(), rc.data()),
-              "pba_associate");
+    check_pba(pba_associate(gpu0, (int32_t)nl, xyz, patches, norms, T_c.m, K_rowmajor, border, score, rc), "pba_associate");
     for (size_t k = 0; k < live.size(); ++k) {
       if (!(score[k] > _options.minScore)) continue;   // points outside the band carry -2
       ++n_reobserved;
@@ -508,6 +542,7 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
     }
   }
 
+  clk.mark("associate");
   // ---- (2) new points (src/photobundle.cc:545-575): unmasked strict local maxima of the saliency map (sum over the
   // channels of |Ix| + |Iy|, central differences, zero on the image border) that carry a valid depth
   ScenePointPointerList fresh;
@@ -530,13 +565,27 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
     std::vector<float> cand_sal;
     for (int attempt = 0; attempt < 2; ++attempt) {
       cand_rc.resize(2 * (size_t)room); cand_sal.resize((size_t)room);
-      check_pba(pba_select_candidates(gpu0, Z_ptr, (int32_t)(hit_rc.size() / 2), hit_rc.data(), mask_radius, _options.nonMaxSuppRadius, border,
+      check_pba(pba_select_candidates(gpu0, nullptr /* depth test below: the map stays on the host */, (int32_t)(hit_rc.size() / 2), hit_rc.data(), mask_radius, _options.nonMaxSuppRadius, border,
                                       _options.minValidDepth, _options.maxValidDepth, room, cand_rc.data(), cand_sal.data(), &n_cand),
                 "pba_select_candidates");
       if (n_cand <= room) break;
       room = n_cand;                             // rare: more candidates than room; once more with enough
     }
-    for (int k = 0; k < n_cand; ++k) lift(cand_rc[2 * k], cand_rc[2 * k + 1], Z_ptr[(size_t)cand_rc[2 * k] * cols + cand_rc[2 * k + 1]], cand_sal[k]);
+    // keep the maxNumPoints most salient BEFORE building scene points (step (3) below, on indices: std::nth_element's
+    // permutation depends only on the comparison results, so the survivors and their order are those of the host path)
+    std::vector<int> keep;
+    keep.reserve((size_t)n_cand);
+    for (int k = 0; k < n_cand; ++k) {             // the depth test of src/photobundle.cc:552-553, in scan order
+      const float z = Z_ptr[(size_t)cand_rc[2 * (size_t)k] * cols + cand_rc[2 * (size_t)k + 1]];
+      if ((double)z >= _options.minValidDepth && (double)z <= _options.maxValidDepth) keep.push_back(k);
+    }
+    if ((int)keep.size() > _options.maxNumPoints) {
+      std::nth_element(keep.begin(), keep.begin() + _options.maxNumPoints, keep.end(),
+                       [&](int a, int b) { return cand_sal[(size_t)a] > cand_sal[(size_t)b]; });
+      keep.resize((size_t)_options.maxNumPoints);
+    }
+    fresh.reserve(keep.size());
+    for (int k : keep) lift(cand_rc[2 * (size_t)k], cand_rc[2 * (size_t)k + 1], Z_ptr[(size_t)cand_rc[2 * (size_t)k] * cols + cand_rc[2 * (size_t)k + 1]], cand_sal[(size_t)k]);
   } else {
     if (multi) {
       check_pba(pba_saliency_map(gpu0, _saliency_map.data()), "pba_saliency_map");
@@ -564,6 +613,7 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
         if (z >= _options.minValidDepth && z <= _options.maxValidDepth && beats_neighbours(y, x)) lift(y, x, z, _saliency_map[(size_t)y * cols + x]);
       }
   }
+  clk.mark("candidates");
   // ---- (3) keep the maxNumPoints most salient (src/photobundle.cc:578-585; std::nth_element, so which of several
   // equally salient points survives is the standard library's choice, as in the reference)
   if (fresh.size() > (size_t)_options.maxNumPoints) {
@@ -574,6 +624,7 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
   }
   if (_options.verbose)
     printf("updated %d [%0.2f%%] max %d new %d\n", n_reobserved, 100.0 * n_reobserved / _scene_points.size(), n_tested, (int)fresh.size());
+  clk.mark("top-n");
   // ---- (4) reference descriptors of the new points (src/photobundle.cc:597-606), every pyramid level
   if (multi) {
     const int n_new = (int)fresh.size();
@@ -606,7 +657,9 @@ void PhotometricBundleAdjustment::addFrame(const uint8_t* I_ptr, const float* Z_
   // ring buffer of slidingWindowSize frames (boost::circular_buffer in the reference, :608); a full window is solved
   if ((int)_frame_buffer.size() == _options.slidingWindowSize) _frame_buffer.pop_front();
   _frame_buffer.push_back(std::move(frame));
-  if ((int)_frame_buffer.size() == _options.slidingWindowSize) optimize(result);
+  clk.mark("descriptors");
+  if ((int)_frame_buffer.size() == _options.slidingWindowSize) { optimize(result); clk.mark("optimize"); }
+  clk.flush("addFrame");
   ++_frame_id;
 }
 
@@ -632,6 +685,7 @@ struct PhotometricBundleAdjustment::SolveOutcome {
 };
 
 void PhotometricBundleAdjustment::optimize(Result* result) {
+  PhaseClock clk;
   const auto t0 = std::chrono::steady_clock::now();
   const uint32_t first_id = _frame_buffer.front().id, last_id = _frame_buffer.back().id;
   const int W = _options.slidingWindowSize, L = _options.numPyramidLevels;
@@ -648,6 +702,11 @@ void PhotometricBundleAdjustment::optimize(Result* result) {
   std::vector<double> xyz;
   std::vector<std::vector<double>> desc((size_t)L);
   std::vector<int32_t> obs_off(1, 0), obs_frame;
+  {   // one allocation each instead of growth by doubling (a 10 000-point window packs 2 MB of descriptors)
+    const size_t n_all = _scene_points.size(), dd = n_all ? _scene_points[0]->descriptor.size() : 0;
+    chosen.reserve(n_all); xyz.reserve(3 * n_all); obs_off.reserve(n_all + 1); obs_frame.reserve(n_all * (size_t)std::min(W, 8));
+    for (int l = 0; l < L; ++l) desc[(size_t)l].reserve(n_all * dd);
+  }
   for (auto& sp : _scene_points) {
     ScenePoint& pt = *sp;
     if (pt.numFrames() < 3 || pt.refFrameId() < first_id) continue;
@@ -664,6 +723,7 @@ void PhotometricBundleAdjustment::optimize(Result* result) {
   const int n_sel = (int)chosen.size(), nnz = (int)obs_frame.size();
   if (_options.verbose) printf("Using %d points (%d residual blocks) [id start %u]\n", n_sel, nnz, first_id);
 
+  clk.mark("pack");
   SolveOutcome solved;
   pba_summary& summary = solved.summary;
   std::vector<pba_iteration_summary>& iters = solved.iters;
@@ -701,6 +761,7 @@ void PhotometricBundleAdjustment::optimize(Result* result) {
       coarser_level = &d;
       coarser = d.h;
     }
+    clk.mark("upload+solve");
     check_pba(pba_get_results(coarser, cams.data(), xyz.data()), "pba_get_results");
     int32_t n_it = 0;
     pba_get_iterations(coarser, nullptr, 0, &n_it);
@@ -719,7 +780,10 @@ void PhotometricBundleAdjustment::optimize(Result* result) {
   // points anchored at the oldest frame leave the system with it (:851, :888-905)
   ScenePointPointerList leaving = removePointsAtFrame(first_id);
   if (_options.verbose) printf("removing %zu old points\n", leaving.size());
+  clk.mark("write-back+evict");
   if (result) fillResult(*result, solved, leaving, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  clk.mark("result");
+  clk.flush("optimize");
 }
 
 // Result as the reference fills it (src/photobundle.cc:857-875): the WHOLE trajectory, the points that just left

@@ -102,6 +102,13 @@ class PhotometricBundleAdjustment {
     std::vector<long long> resident;
   };
   std::vector<DeviceLevel> _dev;
+  // grow-only page-locked staging for what addFrame sends to / receives from the device every frame (pba_host_alloc)
+  struct Pinned {
+    void* p = nullptr; size_t bytes = 0;
+    void* need(size_t n);
+    ~Pinned();
+  };
+  Pinned _pin_xyz, _pin_patch, _pin_norm, _pin_score, _pin_rc;
   int _desc_type = 0, _n_channels = 1;   // PBA_DESC_* / channels per pixel of the descriptor
   pba_handle* deviceLevel(int level, int n_points, int n_obs);
   void uploadWindowFrames(int level);
