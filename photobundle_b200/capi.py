@@ -231,10 +231,10 @@ class Handle:
     def select_candidates(self, depth, masked_rc, mask_radius: int, nms_radius: int, border: int, min_depth: float, max_depth: float,
                           capacity: int = 1 << 20):
         """New-point candidates of addFrame on the frame of prepare_frame_u8: (row_col [m, 2] in scan order, saliency [m])."""
-        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        depth = None if depth is None else np.ascontiguousarray(depth, dtype=np.float32)   # None: no depth test on the device
         masked = np.ascontiguousarray(masked_rc, dtype=np.int32).reshape(-1, 2)
         rc, sal, n_out = np.zeros((capacity, 2), dtype=np.int32), np.zeros(capacity, dtype=np.float32), C.c_int32()
-        _check(lib().pba_select_candidates(self._h, _ptr(depth), masked.shape[0], _ptr(masked), int(mask_radius), int(nms_radius), int(border),
+        _check(lib().pba_select_candidates(self._h, None if depth is None else _ptr(depth), masked.shape[0], _ptr(masked), int(mask_radius), int(nms_radius), int(border),
                                            C.c_double(min_depth), C.c_double(max_depth), capacity, _ptr(rc), _ptr(sal), C.byref(n_out)),
                "pba_select_candidates")
         assert n_out.value <= capacity

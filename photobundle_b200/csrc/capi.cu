@@ -874,11 +874,13 @@ static StepParams make_step_params(pba_handle* h, const LmState* st) {
 
 // Multi-GPU K_B: eliminating under both outcomes of the pending decision costs nothing while each half of the SMs
 // still has at most one batch of points per CTA (32 points); beyond that it doubles the elimination time, and deciding
-// first (one more exchange of ~6 us) is the cheaper iteration.  PBA_MGPU_SPECULATE=0/1 overrides.
+// first (one more exchange of ~6 us) is the cheaper iteration.  Wide windows (more than 8 frames) never speculate: the
+// message would carry two 90 x 91 systems to every peer (measured at 8 GPUs, 16 frames: K_B 122 us against 88 us).
+// PBA_MGPU_SPECULATE=0/1 overrides.
 static bool speculate_decision(const pba_handle* h) {
   if (!h->use_xchg) return false;
   if (const char* e = getenv("PBA_MGPU_SPECULATE")) return atoi(e) != 0;
-  return h->n_points <= 32 * (h->sm_count / 2);
+  return h->n_points <= 32 * (h->sm_count / 2) && h->n_frames <= 8;
 }
 
 static LmParams make_lm_params(pba_handle* h) {

@@ -287,6 +287,13 @@ def test_device_front_end_kernels_match_reference_restatement(seq):
     assert len(new) > 50
     assert [tuple(x) for x in cand_rc] == [(p["y"], p["x"]) for p in new]          # scan order, same pixels
     assert np.array_equal(cand_sal, np.array([p["saliency"] for p in new], dtype=np.float32))
+    # depth = NULL: no depth map crosses the link, the caller gates what comes back - same set, same order
+    Zh = Z.copy()
+    Zh[::7, ::5] = 0.0                                                    # invalid depths scattered over the frame
+    with_depth, _ = h.select_candidates(Zh, np.array(hits, dtype=np.int32), 1, 1, B, 0.01, 1000.0)
+    no_depth, _ = h.select_candidates(None, np.array(hits, dtype=np.int32), 1, 1, B, 0.01, 1000.0)
+    z_at = Zh[no_depth[:, 0], no_depth[:, 1]]
+    assert len(with_depth) < len(no_depth) and np.array_equal(no_depth[(z_at >= 0.01) & (z_at <= 1000.0)], with_depth)
     # and the re-observed set the restatement recorded is the one the kernel's scores select
     assert sorted(hits) == sorted({(r, c) for (r, c) in hits})
     h.close()
