@@ -413,9 +413,36 @@ def main():
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     n_obs_local = h.n_obs_local if world > 1 else win.n_obs
-    n_pts_local = win.n_points // world
+    n_pts_local = getattr(h, "n_points_local", win.n_points) if world > 1 else win.n_points
     exchange_kind = h.exchange_kind()
     speculates = h.speculates()
+    sharded = h.sharded()
+    # the library does not shard a window that fits one K_A wave (pba_comm_sharded); the north-star's sharded layout is
+    # measured beside it by forcing it
+    forced = None
+    if world > 1 and not sharded:
+        os.environ["PBA_MGPU_REPLICATE"] = "0"
+        h.set_poses(win.cams_init, win.fixed_frame)
+        h.set_points(win.points_init, win.desc, win.obs_offsets, win.obs_frame, win.weights)
+        h.save_state()
+        f_dev, f_x = 0.0, 0
+        for k in range(nwarm + steps):
+            h.restore_state()
+            flush.fill_(k & 0xff)
+            torch.cuda.synchronize()
+            barrier()
+            s = h.solve()
+            if k >= nwarm:
+                f_dev += s["device_time_in_seconds"]
+                f_x += s["num_collectives"]
+        del os.environ["PBA_MGPU_REPLICATE"]
+        if dist is not None:
+            tt = torch.tensor([f_dev], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            f_dev = float(tt[0])
+        forced = {"ms_per_step": 1e3 * f_dev / steps, "value": evals * win.n_residuals / f_dev if f_dev > 0 else None,
+                  "exchanges_per_solve": f_x / steps, "what": "the same window FORCED into point shards over the ranks "
+                  "(PBA_MGPU_REPLICATE=0): one in-kernel exchange per LM iteration over NVLink peer memory"}
     h.close()
 
     # ---- second workload: BASELINE configs[3], 16 frames x 16 000 points x 3 levels, coarse to fine ----------
@@ -505,9 +532,13 @@ def main():
             "timing": "sum of per-step CUDA-event intervals recorded by the library on its own stream; "
                       "L2 flushed (256 MiB write) between steps outside the intervals",
             "parallelism": "1 window on 1 GPU" if world == 1 else
+                           (f"1 window on {world} GPUs, NOT sharded: all of its points fit one wave of K_A on one GPU, so sharding cannot "
+                            f"shorten an LM iteration and every exchange costs more than it saves; every rank solves the whole window "
+                            f"(pba_comm_sharded = 0), the forced-sharding figure is under run.sharded_anyway") if not sharded else
                            f"1 window, points sharded over {world} GPUs (frames/poses replicated); per LM iteration the pose "
                            f"blocks + cost and the reduced camera system travel in ONE in-kernel exchange ({exchange_kind}); a second "
                            f"one only when neither speculated outcome of the decision held",
+            "sharded_anyway": forced,
             "exchanges_per_solve": xchg / steps if world > 1 else 0,
             "speculation": ("on: both outcomes of the pending decision are eliminated while the evaluation sums travel" if speculates else
                             "off: shard too large, decision exchanged first (two exchanges per iteration)") if (world > 1 and exchange_kind == "peer-memory") else None,

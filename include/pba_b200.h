@@ -292,6 +292,14 @@ int pba_comm_init_local(pba_handle* const* handles, int32_t n);
  * straight into all peers' memory over NVLink from inside the kernels and the consumers sum the
  * slots in rank order - no collective call, no extra launch), or PBA_EXCHANGE_NCCL (all-reduce
  * fallback when peer mappings are unavailable or PBA_MGPU_EXCHANGE=nccl). */
+/* 1 if the window passed to the last pba_set_points is sharded over the communicator's ranks, 0 if every rank holds
+ * (and solves) the whole window.  A window whose points all fit into one wave of K_A on one GPU (<= 28 warps x SM
+ * count = 4 144 points on a B200) is NOT sharded: sharding cannot shorten its LM iteration - K_A is that single wave's
+ * latency, the reduced solve is replicated anyway - and every exchange over NVLink costs more than it saves (measured:
+ * 8 x 4 000 points, 0.69 ms on one GPU, 0.82 / 0.84 / 0.93 ms sharded over 2 / 4 / 8).  Every rank then runs the
+ * single-GPU path on the full window; the ranks' results agree to rounding (fp64 atomics are unordered), no exchange
+ * takes place and pba_summary.num_collectives is 0.  PBA_MGPU_REPLICATE=0 / 1 forces sharding / replication. */
+int pba_comm_sharded(const pba_handle* h);
 /* With the peer-memory exchange, 1 if K_B eliminates the point blocks under both outcomes of the pending trust-region
  * decision while the evaluation sums travel (ONE exchange per LM iteration, a second one only when neither outcome
  * holds); 0 if the shard is large enough that doubling the elimination costs more than a second exchange: then the

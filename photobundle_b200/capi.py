@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "pba_last_error", "pba_version", "pba_default_solver_options", "pba_create", "pba_destroy",
     "pba_set_frames_u8", "pba_set_frames_f32", "pba_set_frame_u8", "pba_set_frames_u8_pyr", "pba_pyrdown_u8", "pba_set_poses", "pba_set_points",
     "pba_eval", "pba_eval_timed", "pba_solve", "pba_save_state", "pba_restore_state", "pba_copy_state", "pba_host_alloc", "pba_host_free", "pba_graph_counters", "pba_begin_batch", "pba_end_batch", "pba_set_frame_u8_ex", "pba_get_results", "pba_get_poses", "pba_get_points", "pba_get_iterations",
-    "pba_comm_unique_id", "pba_comm_init", "pba_comm_init_local", "pba_comm_speculates", "pba_shard_range", "pba_comm_exchange_kind",
+    "pba_comm_unique_id", "pba_comm_init", "pba_comm_init_local", "pba_comm_speculates", "pba_comm_sharded", "pba_shard_range", "pba_comm_exchange_kind",
     "pba_descriptor_channels", "pba_set_frames_u8_descriptor", "pba_get_channel_plane", "pba_prepare_frame_u8",
     "pba_saliency_map", "pba_extract_descriptors", "pba_associate", "pba_select_candidates",
 ]
@@ -260,8 +260,11 @@ class Handle:
         self.n_points = n
         self.n_obs = int(obs_offsets[-1])
         nr, rk = getattr(self, "n_ranks", 1), getattr(self, "rank", 0)
+        if nr > 1 and not self.sharded():     # window too small to shard: every rank holds all of it
+            nr, rk = 1, 0
         a, b = shard_range(obs_offsets, rk, nr)
         self.n_obs_local = int(obs_offsets[b] - obs_offsets[a])
+        self.n_points_local = int(b - a)
 
     def eval(self, want_residuals: bool = True) -> dict:
         F, n, nnz = self.n_frames, self.n_points, self.n_obs
@@ -364,6 +367,9 @@ class Handle:
             if e is not None:
                 raise e
         return out
+
+    def sharded(self) -> bool:
+        return bool(lib().pba_comm_sharded(self._h))
 
     def speculates(self) -> bool:
         return bool(lib().pba_comm_speculates(self._h))

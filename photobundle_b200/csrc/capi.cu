@@ -163,6 +163,13 @@ struct pba_handle {
   std::vector<IterSummary> trace;
   // multi-GPU: points sharded by contiguous block, frames/poses replicated
   int rank = 0, n_ranks = 1;
+  // A window whose points all fit into ONE wave of K_A on one GPU is not sharded even when a communicator exists:
+  // sharding cannot shorten its iteration (K_A is that one wave's latency, the reduced solve is replicated anyway) and
+  // every exchange costs more than it saves - each rank then solves the whole window (`replicated`).  eff_ranks /
+  // eff_xchg are what the solve path looks at: the communicator's values, or 1 / false for a replicated window.
+  bool replicated = false;
+  int eff_ranks = 1;
+  bool eff_xchg = false;
   ncclComm_t comm = nullptr;
   std::shared_ptr<struct LocalGroup> group;   // set by pba_comm_init_local: the ranks are handles of this process
   int n_points_total = 0, nnz_total = 0;
@@ -792,6 +799,13 @@ int pba_shard_range(int32_t n_points, const int32_t* obs_offsets, int32_t rank, 
   return PBA_OK;
 }
 
+// K_A keeps one point per warp, 14 warps per CTA, two CTAs per SM: up to that many points are ONE wave on one GPU.
+// PBA_MGPU_REPLICATE=0 / 1 forces sharding / replication.
+static bool replicate_window(const pba_handle* h, int n_points) {
+  if (const char* e = getenv("PBA_MGPU_REPLICATE")) return atoi(e) != 0;
+  return n_points <= 2 * 14 * h->sm_count;
+}
+
 int pba_set_points(pba_handle* h, int32_t n_points, const double* xyz, const double* desc,
                    const int32_t* obs_offsets, const int32_t* obs_frame, const double* weights) {
   if (h) h->results_cached = false;
@@ -819,9 +833,13 @@ int pba_set_points(pba_handle* h, int32_t n_points, const double* xyz, const dou
     }
   }
   CUDA_TRY(cudaSetDevice(h->device));
-  // this rank's shard (the whole window on one GPU)
-  shard_split(n_points, obs_offsets, h->n_ranks, h->shard_begin);
-  const int p0 = h->shard_begin[h->rank], p1 = h->shard_begin[h->rank + 1];
+  // this rank's shard (the whole window on one GPU, or when the window is too small to gain from sharding)
+  h->replicated = h->n_ranks > 1 && replicate_window(h, n_points);
+  h->eff_ranks = h->replicated ? 1 : h->n_ranks;
+  h->eff_xchg = h->use_xchg && !h->replicated;
+  const int my_rank = h->replicated ? 0 : h->rank;
+  shard_split(n_points, obs_offsets, h->eff_ranks, h->shard_begin);
+  const int p0 = h->shard_begin[my_rank], p1 = h->shard_begin[my_rank + 1];
   const int n_loc = p1 - p0, o_base = obs_offsets[p0], nnz_loc = obs_offsets[p1] - o_base;
   if (!h->p_desc) {   // pinned staging, sized for the handle's capacity
     CUDA_TRY(cudaMallocHost(&h->p_desc, sizeof(float) * (size_t)h->cfg.max_points * h->CP));
@@ -878,7 +896,7 @@ static StepParams make_step_params(pba_handle* h, const LmState* st) {
 // message would carry two 90 x 91 systems to every peer (measured at 8 GPUs, 16 frames: K_B 122 us against 88 us).
 // PBA_MGPU_SPECULATE=0/1 overrides.
 static bool speculate_decision(const pba_handle* h) {
-  if (!h->use_xchg) return false;
+  if (!h->eff_xchg) return false;
   if (const char* e = getenv("PBA_MGPU_SPECULATE")) return atoi(e) != 0;
   return h->n_points <= 32 * (h->sm_count / 2) && h->n_frames <= 8;
 }
@@ -890,9 +908,9 @@ static LmParams make_lm_params(pba_handle* h) {
   lp.n_frames = h->n_frames; lp.n_points = h->n_points; lp.nnz = h->nnz;
   lp.obs_off = h->d_obs_off; lp.obs_frame = h->d_obs_frame;
   lp.cams = h->d_cams; lp.V = h->d_V; lp.gp = h->d_gp; lp.W = h->d_W;
-  lp.Xacc = h->d_Xacc; lp.Ucur = h->d_Ucur; lp.split = (h->n_ranks > 1 && !h->use_xchg) ? 1 : 0;
+  lp.Xacc = h->d_Xacc; lp.Ucur = h->d_Ucur; lp.split = (h->eff_ranks > 1 && !h->eff_xchg) ? 1 : 0;
   lp.speculate = speculate_decision(h) ? 1 : 0;
-  if (h->use_xchg) lp.xc = h->xc;
+  if (h->eff_xchg) lp.xc = h->xc;
   lp.scale_p = h->d_scale_p; lp.Vinv = h->d_Vinv; lp.S = h->d_S;
   lp.s_cap = reduced_capacity(h->cfg.max_frames); lp.Vinv2 = h->d_Vinv2;
   return lp;
@@ -1142,7 +1160,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   for (int f = 0; f < F; ++f)
     if (h->frame_used[f] && f != h->fixed_frame) s->free_index[f] = s->n_free++;
   s->cur = 0; s->eval_buf = 0; s->decrease_factor = 2.0; s->radius = opt.initial_trust_region_radius;
-  if (h->use_xchg) {   // every rank advances by the same amount per solve: flags never need a reset
+  if (h->eff_xchg) {   // every rank advances by the same amount per solve: flags never need a reset
     s->xepoch = h->epoch_next;
     h->epoch_next += (unsigned long long)opt.max_num_iterations + 16ull;
   }
@@ -1158,21 +1176,21 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   LmParams lp = make_lm_params(h);
   const bool timeline = getenv("PBA_DEBUG_TIMELINE") != nullptr;
   if (timeline && !h->d_dbg) CUDA_TRY(cudaMalloc(&h->d_dbg, sizeof(unsigned long long) * 16 * 1024));
-  const int sgrid = (h->use_xchg && lp.speculate) ? schur_grid_x(h->n_points, h->sm_count) : schur_grid(h->n_points, h->sm_count);
+  const int sgrid = (h->eff_xchg && lp.speculate) ? schur_grid_x(h->n_points, h->sm_count) : schur_grid(h->n_points, h->sm_count);
   int launches = 0;
-  const bool multi = h->n_ranks > 1 && !h->use_xchg;   // NCCL all-reduce path; the peer-memory exchange needs no host-side calls
+  const bool multi = h->eff_ranks > 1 && !h->eff_xchg;   // NCCL all-reduce path; the peer-memory exchange needs no host-side calls
   // one GPU: the whole loop runs on the device (WHILE node); PBA_NO_GRAPH=1 keeps the stream loop
   const bool use_graph = !multi && !timeline && getenv("PBA_NO_GRAPH") == nullptr;
   if (use_graph) {
     rc = ensure_lm_graph(h, lp, sgrid, s->n_free);
     if (rc) return rc;
   }
-  if (h->group) {   // ranks of one process: every allocation above is done before any rank launches a kernel that waits on a peer
+  if (h->group && h->eff_xchg) {   // ranks of one process: every allocation above is done before any rank launches a kernel that waits on a peer
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (!h->group->arrive_and_wait(60))
       return fail(PBA_ERR_STATE, "pba_solve: the other members of the local communicator did not call pba_solve (one thread per handle, concurrently)");
   }
-  if (h->use_xchg) {   // align the ranks before the clock starts (device-side barrier over peer memory)
+  if (h->eff_xchg) {   // align the ranks before the clock starts (device-side barrier over peer memory)
     CUDA_TRY(launch_rendezvous(h->xc, s->xepoch, h->stream));
     launches += 1;
   }
@@ -1203,9 +1221,9 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
     CUDA_TRY(cudaMemcpyAsync(s, h->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_trace, h->d_trace, sizeof(IterSummary) * h->trace_cap, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_stamps, h->d_stamps, stamps_bytes, cudaMemcpyDeviceToHost, h->stream));
-    if (h->use_xchg) CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_err, h->xc.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h->eff_xchg) CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_err, h->xc.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_cams, h->d_cams, sizeof(double) * 6 * (size_t)F, cudaMemcpyDeviceToHost, h->stream));
-    if (h->n_ranks == 1)
+    if (h->eff_ranks == 1)
       CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_pts, h->d_pts, sizeof(double) * 3 * (size_t)h->n_points, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (!s->done) return fail(PBA_ERR_CUDA, "pba_solve: the LM graph returned before the minimizer terminated");
@@ -1255,7 +1273,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
         fprintf(stderr, "[pba timeline] K_B %2d eliminate (last CTA): setup %5.2f us  points %5.2f us  warp merge %5.2f us  atomics+ticket %5.2f us\n", i,
                 (t[16 * i + 12] - t[16 * i + 1]) * 1e-3, (t[16 * i + 13] - t[16 * i + 12]) * 1e-3, (t[16 * i + 14] - t[16 * i + 13]) * 1e-3,
                 (t[16 * i + 2] - t[16 * i + 14]) * 1e-3);
-    if (h->use_xchg)
+    if (h->eff_xchg)
       for (int i = 0; i < std::min(k, 14); ++i)
         fprintf(stderr, "[pba timeline] rank %d K_B %2d exchange: eliminate (both hypotheses) %5.2f us  push %5.2f us  sum+decide %5.2f us  sum P %5.2f us  -> %s\n", h->rank, i,
                 (t[16 * i + 1] - t[16 * i]) * 1e-3, (t[16 * i + 8] - t[16 * i + 1]) * 1e-3, (t[16 * i + 9] - t[16 * i + 8]) * 1e-3,
@@ -1268,7 +1286,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
     if (s->n_trace > 0)
       CUDA_TRY(cudaMemcpyAsync(h->trace.data(), h->d_trace, sizeof(IterSummary) * s->n_trace, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_stamps, h->d_stamps, stamps_bytes, cudaMemcpyDeviceToHost, h->stream));
-    if (h->use_xchg) CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_err, h->xc.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h->eff_xchg) CUDA_TRY(cudaMemcpyAsync(h->h_post + h->post_err, h->xc.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
   float ms = 0.f;
@@ -1280,7 +1298,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
   summary->num_residual_blocks = h->nnz_total; summary->num_residuals = h->nnz_total * h->CP;
   summary->num_iterations = s->n_trace; summary->termination_type = s->termination_type;
   summary->num_evaluations = s->num_evals;
-  summary->kernel_launches = launches; summary->num_collectives = h->use_xchg ? s->n_xchg : collectives;
+  summary->kernel_launches = launches; summary->num_collectives = h->eff_xchg ? s->n_xchg : collectives;
   summary->device_time_in_seconds = ms * 1e-3;
   {
     const unsigned long long* st2 = reinterpret_cast<const unsigned long long*>(h->h_post + h->post_stamps);
@@ -1289,7 +1307,7 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
       if (st2[2 * i] && st2[2 * i + 1] > st2[2 * i]) kb += (double)(st2[2 * i + 1] - st2[2 * i]) * 1e-9;
     summary->kb_device_time_in_seconds = kb;
   }
-  if (h->use_xchg) {
+  if (h->eff_xchg) {
     const int xerr = *reinterpret_cast<const int*>(h->h_post + h->post_err);
     if (xerr) {
       CUDA_TRY(cudaMemset(h->xc.error, 0, sizeof(int)));
@@ -1426,7 +1444,7 @@ int pba_set_frame_u8_ex(pba_handle* h, int32_t slot, const uint8_t* image, int32
 int pba_get_results(pba_handle* h, double* cam6, double* xyz) {
   if (!h || !cam6 || !xyz) return fail(PBA_ERR_ARGUMENT, "pba_get_results: null argument");
   if (!h->have_poses || !h->have_points) return fail(PBA_ERR_STATE, "pba_get_results: poses/points not set");
-  if (h->n_ranks > 1) {   // sharded points: gather (pba_get_points), poses are replicated
+  if (h->eff_ranks > 1) {   // sharded points: gather (pba_get_points), poses are replicated
     int rc = pba_get_poses(h, cam6);
     return rc ? rc : pba_get_points(h, xyz);
   }
@@ -1454,7 +1472,7 @@ int pba_get_points(pba_handle* h, double* xyz) {
   if (!h || !xyz) return fail(PBA_ERR_ARGUMENT, "pba_get_points: null argument");
   if (!h->have_points) return fail(PBA_ERR_STATE, "pba_get_points: points not set");
   CUDA_TRY(cudaSetDevice(h->device));
-  if (h->n_ranks == 1) {
+  if (h->eff_ranks == 1) {
     CUDA_TRY(cudaMemcpy(xyz, h->d_pts, sizeof(double) * (size_t)h->n_points * 3, cudaMemcpyDeviceToHost));
     return PBA_OK;
   }
@@ -1466,8 +1484,8 @@ int pba_get_points(pba_handle* h, double* xyz) {
   if (h->group) {   // ranks of this process: read the peers' shards directly (their solves have returned)
     std::vector<pba_handle*> mem;
     { std::lock_guard<std::mutex> lk(h->group->m); mem = h->group->members; }
-    if ((int)mem.size() != h->n_ranks) return fail(PBA_ERR_STATE, "pba_get_points: a member of the local communicator has been destroyed");
-    for (int r = 0; r < h->n_ranks; ++r) {
+    if ((int)mem.size() != h->eff_ranks) return fail(PBA_ERR_STATE, "pba_get_points: a member of the local communicator has been destroyed");
+    for (int r = 0; r < h->eff_ranks; ++r) {
       const size_t cnt = (size_t)(h->shard_begin[r + 1] - h->shard_begin[r]) * 3;
       if (!cnt || r == h->rank) continue;
       if (mem[r]->n_points * 3 != (int)cnt) return fail(PBA_ERR_STATE, "pba_get_points: rank %d holds %d points, %zu expected (pba_set_points on every member first)", r, mem[r]->n_points, cnt / 3);
@@ -1475,7 +1493,7 @@ int pba_get_points(pba_handle* h, double* xyz) {
     }
   } else {
     NCCL_TRY(g_nccl.GroupStart());
-    for (int r = 0; r < h->n_ranks; ++r) {
+    for (int r = 0; r < h->eff_ranks; ++r) {
       const size_t cnt = (size_t)(h->shard_begin[r + 1] - h->shard_begin[r]) * 3;
       if (cnt) NCCL_TRY(g_nccl.Broadcast(full + (size_t)h->shard_begin[r] * 3, full + (size_t)h->shard_begin[r] * 3, cnt, ncclDouble, r, h->comm, h->stream));
     }
@@ -1512,6 +1530,8 @@ int pba_comm_exchange_kind(const pba_handle* h) {
   return h->use_xchg ? PBA_EXCHANGE_PEER : PBA_EXCHANGE_NCCL;
 }
 
+int pba_comm_sharded(const pba_handle* h) { return (h && h->have_points && h->eff_ranks > 1) ? 1 : 0; }
+
 int pba_comm_speculates(const pba_handle* h) { return (h && speculate_decision(h)) ? 1 : 0; }
 
 int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_ranks) {
@@ -1532,6 +1552,7 @@ int pba_comm_init(pba_handle* h, const void* id128, int32_t rank, int32_t n_rank
     int rc = setup_xchg(h);
     if (rc) return rc;
   }
+  h->replicated = false; h->eff_ranks = h->n_ranks; h->eff_xchg = h->use_xchg;   // until pba_set_points has seen the window
   return PBA_OK;
 }
 
@@ -1590,6 +1611,7 @@ int pba_comm_init_local(pba_handle* const* handles, int32_t n) {
     for (int q = 0; q < kMaxRanks; ++q) h->peer_xchg[q] = q < n ? handles[q]->d_xchg : nullptr;
     int rc = adopt_xchg(h, lay);
     if (rc) return rc;
+    h->replicated = false; h->eff_ranks = n; h->eff_xchg = true;
   }
   return PBA_OK;
 }

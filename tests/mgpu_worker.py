@@ -53,7 +53,7 @@ def main():
     if rank == 0:
         print("MGPU_RESULT " + json.dumps(dict(
             world=world, second_final_cost=second, second_device_ms=second_ms, final_cost=s["final_cost"], initial_cost=s["initial_cost"], iters=s["num_iterations"],
-            collectives=s["num_collectives"], exchange=h.exchange_kind(), launches=s["kernel_launches"], device_ms=1e3 * s["device_time_in_seconds"],
+            collectives=s["num_collectives"], exchange=h.exchange_kind(), sharded=h.sharded(), launches=s["kernel_launches"], device_ms=1e3 * s["device_time_in_seconds"],
             cams=cams.tolist(), pts_head=pts[:5].tolist(), pts_tail=pts[-5:].tolist(), n_pts=int(pts.shape[0]),
             accepts=[t["step_is_successful"] for t in tr],
             ranks_agree=all(np.array_equal(np.array(g["cams"]), cams) and g["cost"] == s["final_cost"] for g in gathered))))

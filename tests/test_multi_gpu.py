@@ -67,11 +67,13 @@ def test_sharded_blocks_sum_to_global_gloo():
     assert q.get(timeout=5) <= 1e-13
 
 
-def _run_workers(n, kind, exchange=None):
+def _run_workers(n, kind, exchange=None, replicate=False):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(29700 + n), os.path.join(ROOT, "tests", "mgpu_worker.py"), kind]
     env = dict(os.environ)
     env.pop("PBA_MGPU_EXCHANGE", None)
+    # the windows of these tests fit one K_A wave, which the library would not shard (pba_comm_sharded): force it
+    env["PBA_MGPU_REPLICATE"] = "1" if replicate else "0"
     if exchange:
         env["PBA_MGPU_EXCHANGE"] = exchange
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
@@ -106,6 +108,31 @@ def test_two_gpus_equal_one_gpu():
 
 
 @pytest.mark.gpu
+def test_two_gpus_small_window_is_not_sharded():
+    """Default policy: a window that fits one wave of K_A is solved whole by every rank - no exchange at all, and the
+    result is the single-GPU one (to rounding: fp64 atomics are unordered)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    one = _run_workers(1, "small")
+    env_backup = os.environ.pop("PBA_MGPU_REPLICATE", None)
+    try:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+               "--master-port", "29733", os.path.join(ROOT, "tests", "mgpu_worker.py"), "small"]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    finally:
+        if env_backup is not None:
+            os.environ["PBA_MGPU_REPLICATE"] = env_backup
+    assert r.returncode == 0, r.stderr[-2000:]
+    two = json.loads([l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1][len("MGPU_RESULT "):])
+    assert two["sharded"] is False and two["collectives"] == 0
+    assert two["accepts"] == one["accepts"] and two["n_pts"] == one["n_pts"]
+    assert abs(two["final_cost"] - one["final_cost"]) <= 1e-9 * one["final_cost"]
+    np.testing.assert_allclose(np.array(two["cams"]), np.array(one["cams"]), atol=1e-8)
+    np.testing.assert_allclose(np.array(two["pts_tail"]), np.array(one["pts_tail"]), atol=1e-6)
+
+
+@pytest.mark.gpu
 def test_two_gpus_empty_shard():
     """Fewer points than ranks: the rank with the empty shard still takes part in every exchange (zero contribution)
     instead of leaving its peers to time out."""
@@ -133,7 +160,7 @@ def test_two_gpus_bench_window_repeated_solves():
 
 
 @pytest.mark.gpu
-def test_local_communicator_two_devices_one_process(small_win):
+def test_local_communicator_two_devices_one_process(small_win, monkeypatch):
     """pba_comm_init_local: two handles of ONE process on two devices (no NCCL, no IPC), pba_solve from one thread per
     handle, equals the 1-GPU solve; the members agree; a second solve on the same handles works."""
     import torch
@@ -144,6 +171,7 @@ def test_local_communicator_two_devices_one_process(small_win):
     s1 = one.solve()
     c1, p1 = one.get_poses(), one.get_points()
     acc1 = [t["step_is_successful"] for t in one.get_iterations()]
+    monkeypatch.setenv("PBA_MGPU_REPLICATE", "0")            # a window this small would not be sharded by default
     hs = [capi.Handle(w.rows, w.cols, w.fx, w.fy, w.cx, w.cy, radius=w.radius, huber=w.huber, max_frames=w.n_frames,
                       max_points=w.n_points, max_observations=w.n_obs, device=d) for d in (0, 1)]
     with pytest.raises(capi.PbaError):
@@ -155,6 +183,7 @@ def test_local_communicator_two_devices_one_process(small_win):
         h.set_poses(w.cams_init, w.fixed_frame)
         h.set_points(w.points_init, w.desc, w.obs_offsets, w.obs_frame, w.weights)
         h.save_state()
+    assert all(h.sharded() for h in hs)
     for _ in range(2):
         ss = capi.Handle.solve_all(hs)
         assert ss[0]["final_cost"] == ss[1]["final_cost"] and ss[0]["num_iterations"] == ss[1]["num_iterations"]
