@@ -101,7 +101,7 @@ struct LocalGroup {
   }
 };
 
-constexpr int kSCopies = kSReplicas > 3 ? kSReplicas : 3;
+constexpr int kSCopies = 2 * kSReplicas > 3 ? 2 * kSReplicas : 3;   // one GPU: two alternating sets of kSReplicas copies; multi-GPU: three accumulators
 
 struct pba_handle {
   pba_config cfg;

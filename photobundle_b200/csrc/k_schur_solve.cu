@@ -165,7 +165,8 @@ constexpr int kMBase = 224;   // thread kMBase keeps the factored diagonal block
 // Writes the step into st and the candidate cameras.  s_cams: both camera buffers [2][kMaxD] (or null).
 // ut_filled: Ut already holds -P (multi-GPU: the rank-ordered sum of every rank's contribution was written there).
 template <int TPW>
-__device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams, bool ut_filled, int n_rep) {
+__device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams, bool ut_filled, int n_rep,
+                              size_t s_off) {
   const int nf = st.n_free, N = 6 * nf, ld = reduced_ld(N);
   const int cur = st.cur, eb = st.eval_buf, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const double radius = st.radius;
@@ -187,7 +188,7 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
 #pragma unroll
   for (int u = 0; u < kCopyB; ++u) {
     const bool in = !ut_filled && tid + u * nthr < tot2;
-    v[u] = in ? __ldcg(reinterpret_cast<const double2*>(lp.S) + tid + u * nthr) : make_double2(0.0, 0.0);
+    v[u] = in ? __ldcg(reinterpret_cast<const double2*>(lp.S + s_off) + tid + u * nthr) : make_double2(0.0, 0.0);
   }
   if (n_rep > 1) {   // the other copies the CTAs spread their atomics over (same round of loads)
 #pragma unroll
@@ -196,7 +197,7 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
       const bool in = !ut_filled && tid + u * nthr < tot2;
 #pragma unroll
       for (int r = 1; r < kSReplicas; ++r)
-        w[r - 1] = in ? __ldcg(reinterpret_cast<const double2*>(lp.S + r * lp.s_cap) + tid + u * nthr) : make_double2(0.0, 0.0);
+        w[r - 1] = in ? __ldcg(reinterpret_cast<const double2*>(lp.S + s_off + r * lp.s_cap) + tid + u * nthr) : make_double2(0.0, 0.0);
 #pragma unroll
       for (int r = 1; r < kSReplicas; ++r) { v[u].x += w[r - 1].x; v[u].y += w[r - 1].y; }
     }
@@ -239,7 +240,7 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
   for (int e0 = tid + kCopyB * nthr; !ut_filled && e0 < tot2; e0 += nthr) {   // wide systems: the rest, entry by entry
     double2 a = make_double2(0.0, 0.0);
     for (int r = 0; r < n_rep; ++r) {
-      const double2 b = __ldcg(reinterpret_cast<const double2*>(lp.S + r * lp.s_cap) + e0);
+      const double2 b = __ldcg(reinterpret_cast<const double2*>(lp.S + s_off + r * lp.s_cap) + e0);
       a.x += b.x; a.y += b.y;
     }
     reinterpret_cast<double2*>(Ut)[e0] = make_double2(-a.x, -a.y);
@@ -367,10 +368,12 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
   // triangle of a block (the chain runs through one multiply-add + one multiply per unknown; everything it reads
   // that does not depend on the unknowns is loaded first), every lane then removes the block's unknowns from
   // the rows above (two rows per lane in flight)
-  if (warp != 0 && !ut_filled) {   // idle until the substitution is done: clear the accumulator copies for the next elimination
+  // the accumulator this solve consumed must be zero again before it is used next: with the alternating sets of the
+  // single-GPU kernel (n_rep > 1) the CTAs of the NEXT launch clear it, off this CTA's critical path; otherwise the
+  // warps that idle during the substitution do
+  if (warp != 0 && !ut_filled && n_rep == 1) {
     const double2 z = make_double2(0.0, 0.0);
-    for (int r = 0; r < n_rep; ++r)
-      for (int e0 = tid - 32; e0 < tot2; e0 += nthr - 32) reinterpret_cast<double2*>(lp.S + r * lp.s_cap)[e0] = z;
+    for (int e0 = tid - 32; e0 < tot2; e0 += nthr - 32) reinterpret_cast<double2*>(lp.S + s_off)[e0] = z;
   }
   if (warp == 0) {
     for (int i = lane; i < N; i += 32) yv[i] = Ut[i * ld + N];
@@ -672,12 +675,13 @@ __device__ __forceinline__ void take_decision(LmState& s_st, const double* s_xs,
 // Tail of an LM iteration (one CTA): adopt the candidate's pose blocks if the step was taken, solve
 // the reduced camera system, re-zero the accumulators K_A fills next, publish the new state.
 template <int TPW>
-__device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams, bool ut_filled, int n_rep = 1) {
+__device__ void finish_iteration(const LmParams& lp, LmState& st, double* sm, int F, const double* xs, const double* s_cams, bool ut_filled, int n_rep = 1,
+                                 size_t s_off = 0) {
   const int tid = threadIdx.x;
   if (st.took_step)
     for (int i = tid; i < F * kUStride; i += blockDim.x) lp.Ucur[i] = xs ? xs[i] : __ldcg(lp.Xacc + i);
   __syncthreads();
-  solve_reduced<TPW>(lp, st, sm, F, xs, s_cams, ut_filled, n_rep);
+  solve_reduced<TPW>(lp, st, sm, F, xs, s_cams, ut_filled, n_rep, s_off);
   if (lp.dbg && tid == 0) lp.dbg[3] = gtime();
   for (int i = tid; i < F * kUStride + kEacc + kMaxRanks; i += blockDim.x) lp.Xacc[i] = 0.0;
   if (tid == 0) *lp.ticket = 0u;
@@ -768,11 +772,23 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
 
   const unsigned long long t_dec = lp.dbg ? gtime() : 0ull;
   // ---- (E) eliminate the point blocks -----------------------------------------------------
-  // (split mode: copy 0 is what the all-reduce sums; wide systems: summing four copies of a 90 x 91 accumulator costs
-  // the solving CTA more than the shorter atomic chains save)
+  // The accumulator S: kSReplicas copies the CTAs spread their atomics over, in two SETS that alternate from launch to
+  // launch - this launch adds into (and its solving CTA reads) set `par`, and clears its slice of the other set, which
+  // the previous launch consumed: nobody clears anything on the solving CTA's critical path.  (Split mode: one copy, the
+  // all-reduce sums it; wide systems: one copy - summing four 90 x 91 accumulators costs the solving CTA more than the
+  // shorter atomic chains save - and the solving CTA clears it.)
   const int n_rep = (lp.split || s_st.n_free > 8) ? 1 : kSReplicas;
+  const size_t s_off = n_rep > 1 ? (size_t)(s_st.num_evals & 1) * kSReplicas * lp.s_cap : 0;
+  if (n_rep > 1) {
+    double2* other = reinterpret_cast<double2*>(lp.S + (size_t)((s_st.num_evals & 1) ^ 1) * kSReplicas * lp.s_cap);
+    const int N0 = 6 * s_st.n_free, tot2 = (N0 * reduced_ld(N0)) >> 1;
+    const double2 z = make_double2(0.0, 0.0);
+    for (int r = 0; r < kSReplicas; ++r)
+      for (int e0 = blockIdx.x * kSchurThreads + tid; e0 < tot2; e0 += gridDim.x * kSchurThreads)
+        other[(size_t)r * (lp.s_cap >> 1) + e0] = z;
+  }
   eliminate<LPP, TPW>(lp, s_st, sm, pre_o0, pre_o1, s_st.cur, s_st.radius, s_st.iteration == 1,
-                      lp.S + (blockIdx.x % n_rep) * lp.s_cap, lp.Vinv, blockIdx.x, gridDim.x);
+                      lp.S + s_off + (blockIdx.x % n_rep) * lp.s_cap, lp.Vinv, blockIdx.x, gridDim.x);
 
   // ---- (S) the last CTA solves the reduced camera system -------------------------------------
   // bar.sync orders the CTA's atomics before thread 0's cumulative gpu-scope fence + ticket
@@ -796,7 +812,7 @@ __global__ void __launch_bounds__(kSchurThreads, 1) k_schur_solve(const LmParams
       reinterpret_cast<int*>(lp.st_out)[i] = reinterpret_cast<const int*>(&s_st)[i];
     return;
   }
-  finish_iteration<TPW>(lp, s_st, sm, F, s_xs, s_cams, false, n_rep);
+  finish_iteration<TPW>(lp, s_st, sm, F, s_xs, s_cams, false, n_rep, s_off);
 }
 
 // ---- multi-GPU kernel: speculative elimination, one exchange per LM iteration (pba_device.cuh `Xchg`) -----------
