@@ -237,13 +237,25 @@ __device__ void solve_reduced(const LmParams& lp, LmState& st, double* sm, int F
 #pragma unroll
   for (int u = 0; u < kCopyB; ++u)
     if (!ut_filled && tid + u * nthr < tot2) reinterpret_cast<double2*>(Ut)[tid + u * nthr] = make_double2(-v[u].x, -v[u].y);
-  for (int e0 = tid + kCopyB * nthr; !ut_filled && e0 < tot2; e0 += nthr) {   // wide systems: the rest, entry by entry
-    double2 a = make_double2(0.0, 0.0);
-    for (int r = 0; r < n_rep; ++r) {
-      const double2 b = __ldcg(reinterpret_cast<const double2*>(lp.S + s_off + r * lp.s_cap) + e0);
-      a.x += b.x; a.y += b.y;
+  // wide systems: the rest in further rounds, again with all loads of a round in flight together (one load at a time
+  // made this loop 9 of the 11 us that assembling a 90 x 91 system took)
+  constexpr int kTailB = 6;
+  for (int e0 = tid + kCopyB * nthr; !ut_filled && e0 < tot2; e0 += kTailB * nthr) {
+    double2 a[kTailB];
+#pragma unroll
+    for (int u = 0; u < kTailB; ++u)
+      a[u] = e0 + u * nthr < tot2 ? __ldcg(reinterpret_cast<const double2*>(lp.S + s_off) + e0 + u * nthr) : make_double2(0.0, 0.0);
+    for (int r = 1; r < n_rep; ++r) {
+#pragma unroll
+      for (int u = 0; u < kTailB; ++u) {
+        const double2 b = e0 + u * nthr < tot2 ? __ldcg(reinterpret_cast<const double2*>(lp.S + s_off + r * lp.s_cap) + e0 + u * nthr)
+                                                : make_double2(0.0, 0.0);
+        a[u].x += b.x; a[u].y += b.y;
+      }
     }
-    reinterpret_cast<double2*>(Ut)[e0] = make_double2(-a.x, -a.y);
+#pragma unroll
+    for (int u = 0; u < kTailB; ++u)
+      if (e0 + u * nthr < tot2) reinterpret_cast<double2*>(Ut)[e0 + u * nthr] = make_double2(-a[u].x, -a[u].y);
   }
   __syncthreads();
   // + U_s + D_c² on the diagonal blocks, + gs_c on the right-hand-side column: one entry per thread
