@@ -139,3 +139,25 @@ def test_no_fixed_camera_uses_tile_path(small_ragged_win):
     assert [t["step_is_successful"] for t in tr[:n]] == [t["step_is_successful"] for t in otr[:n]]
     for a, b in zip(tr[:n], otr[:n]):
         assert abs(a["cost"] - b["cost"]) <= 1e-6 * b["cost"]
+
+
+@pytest.mark.gpu
+def test_cfg4_shape_through_the_host_class():
+    """BASELINE configs[3]'s shape - a 16-frame window, ~16 000 points, 3 pyramid levels - driven through the C++ class
+    the way apps/run_kitti.cc drives it (addFrame per frame; PhotometricBundleAdjustmentPyr semantics, levels handed
+    over on the device): every full window is solved coarse to fine and the trajectory improves."""
+    from photobundle_b200 import host_capi
+    from test_host import _check_refined
+    seq = synthetic.make_sequence(n_frames=18, rows=240, cols=320, intrinsics=(400.0, 400.0, 159.7, 120.2), seed=9)
+    rows, cols = seq.images.shape[1:]
+    n = seq.images.shape[0]
+    ba = host_capi.BundleAdjuster(rows, cols, *seq.K4, slidingWindowSize=16, maxNumPoints=1024, verbose=0, minScore=0.65,
+                                  numPyramidLevels=3, gpuFrontEnd=1)
+    ran = [ba.add_frame(seq.images[i], seq.depths[i], seq.T_rel_init[i]) for i in range(n)]
+    assert ran == [False] * 15 + [True] * (n - 15)
+    res = ba.result()
+    ba.close()
+    assert res["poses"].shape == (n, 4, 4) and np.isfinite(res["poses"]).all()
+    assert res["numResiduals"] > 25 * 16000                  # (619 550 when written: ~25 000 residual blocks of 5x5)
+    assert res["finalCost"] < res["initialCost"] and res["numSuccessfulStep"] >= 1
+    _check_refined(res["poses"], seq)
