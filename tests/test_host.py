@@ -66,6 +66,14 @@ def test_kitti_pose_io_roundtrip(tmp_path):
     if os.path.exists(p):
         T = host_capi.load_poses_kitti(p)
         assert T.shape == (4541, 4, 4) and np.allclose(T[0], np.eye(4)) and np.allclose(T[:, 3], [0, 0, 0, 1])
+    # the same file's head as a committed fixture (tests/golden/make_kitti_pose_golden.py), so that the GPU box checks
+    # the reference's own data too
+    g = os.path.join(ROOT, "tests", "golden", "kitti_init_poor_00_head.txt")
+    Tg = host_capi.load_poses_kitti(g)
+    want = np.loadtxt(g)
+    assert Tg.shape == (12, 4, 4) and np.array_equal(Tg[:, :3, :].reshape(12, 12), want)
+    assert np.array_equal(Tg[0], np.eye(4)) and np.array_equal(Tg[:, 3], np.tile([0, 0, 0, 1.0], (12, 1)))
+    assert int(open(os.path.join(ROOT, "tests", "golden", "kitti_init_poor_00_meta.txt")).read()) == 4541
     fn = tmp_path / "poses.txt"
     rng = np.random.default_rng(0)
     rows = rng.normal(size=(7, 12))
@@ -166,6 +174,32 @@ def test_run_sequence_driver(seq, tmp_path):
         np.testing.assert_allclose(out2, out, atol=1e-3)
         T2 = np.tile(np.eye(4), (n, 1, 1)); T2[:, :3, :] = out2.reshape(n, 3, 4)
         _check_refined(T2, seq)
+
+
+@pytest.mark.gpu
+def test_run_sequence_with_the_reference_configuration(seq, tmp_path):
+    """The reference's own config/kitti_stereo.cfg (fixture tests/golden/kitti_stereo.cfg: maxNumPoints 4096,
+    slidingWindowSize 5, patchRadius 1, minScore 0.65, robustThreshold 0.05; the dataset / stereo keys are not ours and
+    are ignored) drives the sliding-window application: utils::ConfigFile semantics + the 3x3-patch kernels."""
+    rows, cols = seq.images.shape[1:]
+    n = seq.images.shape[0]
+    with open(tmp_path / "seq.bin", "wb") as f:
+        f.write(np.array([rows, cols, n], dtype=np.int32).tobytes())
+        f.write(np.array(list(seq.K4) + [0.5], dtype=np.float64).tobytes())
+        for i in range(n):
+            f.write(seq.images[i].tobytes())
+            f.write(seq.depths[i].tobytes())
+    np.savetxt(tmp_path / "init.txt", seq.T_rel_init[:, :3, :].reshape(n, 12), fmt="%.12f")
+    cfg = open(os.path.join(ROOT, "tests", "golden", "kitti_stereo.cfg")).read()
+    assert "patchRadius = 1" in cfg and "slidingWindowSize = 5" in cfg
+    (tmp_path / "ref.cfg").write_text(cfg + "\nverbose = 0\n")
+    exe = os.path.join(ROOT, "photobundle_b200", "run_sequence")
+    r = subprocess.run([exe, str(tmp_path / "seq.bin"), str(tmp_path / "init.txt"), str(tmp_path / "ref.cfg"),
+                        str(tmp_path / "refined_poses.txt")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    out = np.loadtxt(tmp_path / "refined_poses.txt")
+    T = np.tile(np.eye(4), (n, 1, 1)); T[:, :3, :] = out.reshape(n, 3, 4)
+    _check_refined(T, seq)
 
 
 @pytest.mark.gpu
