@@ -180,7 +180,7 @@ __host__ __device__ constexpr size_t k_step_smem_bytes(int n_frames) {
   // footprints: raw uint8 (ROWS x W bytes) on the Intensity path, fp32 otherwise
   constexpr size_t fp_bytes = (size_t)kStageSlots * Foot<R>::FLOATS * (U8 ? 1 : 4);
   return sizeof(double) * ((size_t)n_frames * (kPoseConst + 6) + WARPS * kEacc + ((Foot<R>::P + 1) & ~1)) +
-         (size_t)WARPS * (sizeof(double) * (kObsBatch * 20 + 25 * kRedStride + 6 * kObsBatch) +
+         (size_t)WARPS * (sizeof(double) * (kObsBatch * 20 + (R == 1 ? 27 : 25) * kRedStride + 6 * kObsBatch) +
                           sizeof(int4) * kObsBatch + sizeof(int) * kMaxFrames + ((fp_bytes + 15) / 16) * 16) +
          (size_t)(WARPS / USHARE) * sizeof(double) * ((size_t)n_frames * kUStride + (n_frames & 1));
 }
@@ -338,6 +338,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
   constexpr int P = FT::P;
   constexpr int PR = (P + 31) / 32;             // pixel rounds per lane
   constexpr bool kQuad = (NCH == 1 && PR == 1); // ILP-4 fast path available
+  // 3x3 patches on the uint8 path (the reference's own KITTI configuration, config/kitti_stereo.cfg:22): a patch fills 9
+  // of 32 lanes, so three observations are sampled side by side (lane / 9) and a group covers 6 observations
+  constexpr bool kPack3 = (R == 1 && U8 && NCH == 1 && kG == 2);
   constexpr bool kAsyncStage = (NCH == 1);      // footprints staged with cp.async ahead of (G2)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int F = prm.n_frames;
@@ -375,7 +378,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
   constexpr int kFpBytes = ((kStageSlots * FT::FLOATS * (int)sizeof(FPT) + 15) / 16) * 16;
   constexpr int kOffGeo = 0;                                                  // [8][20] f64
   constexpr int kOffRed = kOffGeo + 8 * kObsBatch * 20;                       // [25][6G+2] f64
-  constexpr int kOffTot = kOffRed + 8 * 25 * kRedStride;                      // [8][6] f64: patch sums of the batch's observations
+  constexpr int kOffTot = kOffRed + 8 * (R == 1 ? 27 : 25) * kRedStride;   // (27 rows: three 3x3 patches side by side)
+  //                      // [8][6] f64: patch sums of the batch's observations
   constexpr int kOffGi = kOffTot + 8 * 6 * kObsBatch;                         // [8] int4
   constexpr int kOffFrm = kOffGi + 16 * kObsBatch;                            // [16] i32
   constexpr int kOffFp = kOffFrm + 4 * kMaxFrames;                            // [8][ROWS][W] footprints
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
       if (lane < nobs) frm_l = __ldg(prm.obs_frame + o0 + lane);
       X0 = pts_cur[3 * p]; X1 = pts_cur[3 * p + 1]; X2 = pts_cur[3 * p + 2];
 #pragma unroll
-      for (int r = 0; r < PR; ++r) p0c[r] = (double)__ldg(prm.desc + (size_t)p * CP + min(lane + 32 * r, P - 1));
+      for (int r = 0; r < PR; ++r) p0c[r] = (double)__ldg(prm.desc + (size_t)p * CP + (kPack3 ? lane % 9 : min(lane + 32 * r, P - 1)));
     }
     if (need_barrier) { KTRACE(12); __syncthreads(); need_barrier = false; }
     if (!valid) break;
@@ -608,10 +612,12 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
       double pdx[PR], pdy[PR], wj[PR];
 #pragma unroll
       for (int r = 0; r < PR; ++r) {
-        const int j = min(lane_l + 32 * r, P - 1);      // lanes beyond the patch re-do pixel P-1 with weight 0
+        // lanes beyond the patch re-do pixel P-1 with weight 0; 3x3 patches (kPack3): lane -> pixel lane % 9 of one of
+        // THREE observations sampled side by side, lanes 27..31 carry weight 0
+        const int j = kPack3 ? lane_l % 9 : min(lane_l + 32 * r, P - 1);
         const int py = j / FT::SIDE, pxo = j - py * FT::SIDE;
         pdx[r] = (double)(pxo - R); pdy[r] = (double)(py - R);
-        wj[r] = (lane_l + 32 * r < P) ? s_wts[j] : 0.0;
+        wj[r] = (kPack3 ? lane_l < 27 : lane_l + 32 * r < P) ? s_wts[j] : 0.0;
       }
       // lane l < 21 <-> upper-triangle entry (a, b) of the 6x6 pose block, rows of length 6, 5, ... 1
       int e1a = 0, e1b = 0, e2a = 0, e2b = 0;
@@ -667,6 +673,52 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_step(const StepParams prm) {
         KTRACE(4);
         // ---- (S)+(R): four observations at a time when every one of them is interior -------
         for (int qb = 0; qb < ns_obs; qb += kG) {
+          if constexpr (kPack3) {
+            const int n6 = min(6, ns_obs - qb);
+            if ((((fastmask >> (sb + qb)) & ((1u << n6) - 1u)) == ((1u << n6) - 1u))) {
+              const int sub = min(lane / 9, 2), jpx = lane - 9 * (lane / 9);
+              double v6[2][6];
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const int oi = 3 * i + sub;                          // observation of the group this lane samples
+                const int ii = sb + qb + min(oi, n6 - 1);            // out-of-range slots redo the last one
+                const int4 gi = s_gi_w[ii];
+                const double* g = s_geo_w + ii * 20;
+                float I1, gx, gy;
+                sample_fast_u8<R>(s_fp_w + (ii - sb) * FT::FLOATS, gi.y, gi.z, g[0], g[1], pdx[0], pdy[0], I1, gx, gy);
+                const double rr = __dmul_rn(wj[0], __dsub_rn(p0c[0], (double)I1));   // photobundle.cc:720
+                if (want_res && lane < 27 && oi < n6) prm.residuals[(size_t)(o0 + ob + ii) * CP + jpx] = rr;
+                const double hx = wj[0] * (double)gx, hy = wj[0] * (double)gy;
+                v6[i][0] = rr * rr; v6[i][1] = hx * hx; v6[i][2] = hx * hy; v6[i][3] = hy * hy; v6[i][4] = rr * hx; v6[i][5] = rr * hy;
+              }
+              // transpose-reduce: row = lane (27 rows of 12 sums); total (observation 3i + s, sum k) = sum over the 9
+              // pixel rows of sub-observation s of column 6i + k
+              if (lane < 27) {
+                double2* row = reinterpret_cast<double2*>(s_red_w + lane * kRedStride);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                  for (int k = 0; k < 3; ++k) row[i * 3 + k] = make_double2(v6[i][2 * k], v6[i][2 * k + 1]);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int T = lane + 32 * h2;                        // 36 totals: observation T / 6, sum T % 6
+                if (T < 6 * n6) {
+                  const int oi = T / 6, k = T - 6 * oi, i = oi / 3, s = oi - 3 * i;
+                  const double* col = s_red_w + (9 * s) * kRedStride + 6 * i + k;
+                  double tot = 0.0;
+#pragma unroll
+                  for (int l = 0; l < 9; ++l) tot += col[l * kRedStride];
+                  s_tot_w[(sb + qb) * 6 + T] = tot;
+                }
+              }
+              defmask |= ((1u << n6) - 1u) << (sb + qb);
+              __syncwarp();
+              qb += 6 - kG;                                          // (the loop adds kG)
+              continue;
+            }
+          }
           const int nq = min(kG, ns_obs - qb);
           const bool all_fast = kQuad && (((fastmask >> (sb + qb)) & ((1u << nq) - 1u)) == ((1u << nq) - 1u));
           if (kQuad && all_fast) {
