@@ -357,6 +357,9 @@ def test_loop_graph_is_retargeted_in_place_when_sizes_change(small_win):
     kernels) is re-targeted with cudaGraphExecKernelNodeSetParams instead of being rebuilt, and each solve equals the one
     a fresh handle gives."""
     import dataclasses
+    import os
+    if os.environ.get("PBA_NO_GRAPH"):
+        pytest.skip("PBA_NO_GRAPH=1: the stream-launched loop has no graph to re-target")
 
     def sub(win, n):
         o = int(win.obs_offsets[n])
