@@ -332,7 +332,7 @@ def main():
     # batched windows (auxiliary): B independent windows solved concurrently, one handle + stream + host
     # thread each — a single 8x4k window is latency-bound and leaves most of the GPU idle
     batched = None
-    if world == 1:
+    if True:   # at N GPUs: B windows per GPU, no communication at all (what a multi-GPU box is good for with windows this small)
         import threading as _th
         B = 4
         hs = [capi.Handle.for_window(win, device=local_rank) for _ in range(B)]
@@ -347,6 +347,7 @@ def main():
                 ev += hs[i].solve()["num_evaluations"]
             res[i] = ev
         torch.cuda.synchronize()
+        barrier()
         tb = time.perf_counter()
         ths = [_th.Thread(target=_work, args=(i,)) for i in range(B)]
         for t in ths:
@@ -355,8 +356,17 @@ def main():
             t.join()
         torch.cuda.synchronize()
         tb = time.perf_counter() - tb
-        batched = {"windows_in_flight": B, "residuals_per_sec": sum(res) * win.n_residuals / tb,
-                   "solves_per_sec": B * steps / tb, "timing": "host wall clock around all threads"}
+        ev_all = float(sum(res))
+        if dist is not None:
+            tt = torch.tensor([tb], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            te = torch.tensor([ev_all], device="cuda", dtype=torch.float64)
+            dist.all_reduce(te, op=dist.ReduceOp.SUM)
+            tb, ev_all = float(tt[0]), float(te[0])
+        batched = {"windows_in_flight": B * world, "residuals_per_sec": ev_all * win.n_residuals / tb,
+                   "solves_per_sec": B * world * steps / tb,
+                   "what": f"{B} independent windows per GPU on {world} GPU(s), one handle + stream + host thread each, no communication",
+                   "timing": "host wall clock around all threads, max over ranks"}
         launches += sum(res) * 2
         for hb in hs:
             hb.close()
