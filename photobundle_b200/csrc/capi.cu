@@ -1185,6 +1185,11 @@ int pba_solve(pba_handle* h, const pba_solver_options* opt_in, pba_summary* summ
     rc = ensure_lm_graph(h, lp, sgrid, s->n_free);
     if (rc) return rc;
   }
+  if (h->group && h->eff_xchg) {
+    std::lock_guard<std::mutex> lk(h->group->m);
+    if ((int)h->group->members.size() != h->n_ranks)
+      return fail(PBA_ERR_STATE, "pba_solve: a member of the local communicator has been destroyed (its exchange buffer is gone)");
+  }
   if (h->group && h->eff_xchg) {   // ranks of one process: every allocation above is done before any rank launches a kernel that waits on a peer
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (!h->group->arrive_and_wait(60))
