@@ -114,6 +114,18 @@ def ref_calib_lib() -> C.CDLL | None:
     return r
 
 
+_REF_IMGPROC_PATH = os.path.join(os.path.dirname(_REF_PATH), "libref_imgproc.so")
+
+
+def ref_imgproc_lib() -> C.CDLL | None:
+    """The reference's own imgradient / disparityToDepth (src/imgproc.cc) compiled from /root/reference, or None."""
+    if not os.path.exists(_REF_IMGPROC_PATH):
+        return None
+    r = C.CDLL(_REF_IMGPROC_PATH)
+    r.ref_disparity_to_depth.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
+    return r
+
+
 def _p(a: np.ndarray) -> int:
     return a.ctypes.data
 

@@ -302,3 +302,37 @@ def test_oracle_is_deterministic_for_a_fixed_thread_count():
             cams, pts, summ, tr = ow.solve(win.cams_init, win.points_init)
             runs.append((cams.tobytes(), pts.tobytes(), summ["final_cost"], len(tr)))
         assert runs[0] == runs[1] == runs[2], nt
+
+
+def test_imgradient_and_disparity_match_reference_binary_when_present():
+    """The reference's own imgradient (src/imgproc.cc:26-106) and disparityToDepth (:274-322), compiled from where they
+    lie into oracle/_ref/libref_imgproc.so.  The gradient the oracle restates - and K_A forms on the fly from uint8
+    footprints - equals it bit for bit (uint8 and float sources, odd sizes).  disparityToDepth: the host side's version
+    uses an exact reciprocal and one invalid mark where the reference's SSE body uses _mm_rcp_ps (~12 bits) and its scalar
+    tail another mark: same valid set, values within the reciprocal's error, invalid pixels negative in both."""
+    ref = binding.ref_imgproc_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_imgproc.so not built (no /root/reference on this box)")
+    rng = np.random.default_rng(23)
+    for rows, cols in ((9, 13), (376, 1241), (31, 64)):
+        I8 = rng.integers(0, 256, size=(rows, cols), dtype=np.uint8)
+        If = I8.astype(np.float32)
+        gx_r, gy_r, gx_o, gy_o = (np.full((rows, cols), 7.0, dtype=np.float32) for _ in range(4))
+        ref.ref_imgradient_u8(C.c_void_p(I8.ctypes.data), rows, cols, C.c_void_p(gx_r.ctypes.data), C.c_void_p(gy_r.ctypes.data))
+        binding.lib().oracle_imgradient(C.c_void_p(If.ctypes.data), rows, cols, C.c_void_p(gx_o.ctypes.data), C.c_void_p(gy_o.ctypes.data))
+        assert gx_r.tobytes() == gx_o.tobytes() and gy_r.tobytes() == gy_o.tobytes()
+        Fn = rng.uniform(0, 255, size=(rows, cols)).astype(np.float32)      # non-integer channel values (descriptor planes)
+        ref.ref_imgradient_f32(C.c_void_p(Fn.ctypes.data), rows, cols, C.c_void_p(gx_r.ctypes.data), C.c_void_p(gy_r.ctypes.data))
+        binding.lib().oracle_imgradient(C.c_void_p(Fn.ctypes.data), rows, cols, C.c_void_p(gx_o.ctypes.data), C.c_void_p(gy_o.ctypes.data))
+        assert gx_r.tobytes() == gx_o.tobytes() and gy_r.tobytes() == gy_o.tobytes()
+    from photobundle_b200 import host_capi
+    for rows, cols in ((376, 1241), (16, 16), (5, 7)):
+        d = rng.uniform(-1.0, 90.0, size=(rows, cols)).astype(np.float32)
+        d[rng.random(d.shape) < 0.1] = 0.0
+        z_ref = np.zeros_like(d)
+        ref.ref_disparity_to_depth(C.c_void_p(d.ctypes.data), rows, cols, C.c_float(386.1), C.c_void_p(z_ref.ctypes.data))
+        z = host_capi.disparity_to_depth(d, 386.1)
+        valid = d > 0.01
+        assert np.array_equal(z_ref > 0, valid) and np.array_equal(z > 0, valid)
+        np.testing.assert_allclose(z[valid], z_ref[valid], rtol=4e-4)
+        assert (z_ref[~valid] < 0).all() and (z[~valid] == np.float32(-0.1)).all()
