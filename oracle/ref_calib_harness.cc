@@ -20,6 +20,20 @@ Calibration make(const double* k4, double b) {
 #ifdef REF_PATCH_WEIGHTS_INC
 #include REF_PATCH_WEIGHTS_INC
 #endif
+// interp2 + interpolateFixedPatch (src/photobundle.cc:258-310, templates of that file cut out the same way): the bilinear
+// lookup of the data association (ZnccPatch_::set) - ZnccPatch_ itself is left out because its sums go through Eigen's
+// own reductions, which no shim reproduces.
+#ifdef REF_INTERP2_INC
+#include REF_INTERP2_INC
+namespace {
+struct ImgU8 {   // the Image concept interp2 needs; operator() returns uint8_t like Image_<uint8_t>
+  const uint8_t* p; int r, c;
+  int rows() const { return r; }
+  int cols() const { return c; }
+  uint8_t operator()(int y, int x) const { return p[(long)y * c + x]; }
+};
+}  // namespace
+#endif
 
 extern "C" {
 
@@ -44,6 +58,21 @@ void ref_triangulate(const double* k4, double b, const double* uvd, double* xyz)
   const Vec_<double, 3> p = make(k4, b).triangulate(uvd);
   xyz[0] = p[0]; xyz[1] = p[1]; xyz[2] = p[2];
 }
+
+#ifdef REF_INTERP2_INC
+float ref_interp2_u8(const uint8_t* I, int32_t rows, int32_t cols, float x, float y) {
+  ImgU8 im{I, rows, cols};
+  return interp2(im, x, y);
+}
+// the 5x5 patch ZnccPatch_<2, float>::set reads (before its mean is removed), uv in double as addFrame passes it
+void ref_interp_patch5_u8(const uint8_t* I, int32_t rows, int32_t cols, double u, double v, float* out25) {
+  ImgU8 im{I, rows, cols};
+  Vec_<float, 25> dst;
+  const double uv[2] = {u, v};
+  interpolateFixedPatch<2>(dst, im, uv, 0.0f, 0.0f);
+  for (int k = 0; k < 25; ++k) out25[k] = dst[k];
+}
+#endif
 
 #ifdef REF_PATCH_WEIGHTS_INC
 int32_t ref_patch_weights(int32_t radius, int32_t do_gaussian, double* w) {

@@ -127,6 +127,9 @@ void pbah_pyr_down(const double* k4, double b, int32_t rows, int32_t cols, doubl
   const ImageSize s = ImageSize(rows, cols).pyrDown();
   out7[0] = c.fx(); out7[1] = c.fy(); out7[2] = c.cx(); out7[3] = c.cy(); out7[4] = c.b(); out7[5] = s.rows; out7[6] = s.cols;
 }
+void pbah_interp_patch5_u8(const uint8_t* I, int32_t rows, int32_t cols, double u, double v, float* out25) {
+  InterpPatch5(I, rows, cols, u, v, out25);
+}
 int32_t pbah_patch_weights(int32_t radius, int32_t do_gaussian, double* w) {
   const std::vector<double> v = MakePatchWeights(radius, do_gaussian != 0);
   for (size_t i = 0; i < v.size(); ++i) w[i] = v[i];

@@ -244,6 +244,12 @@ static inline float interp2_u8(const uint8_t* I, int rows, int cols, float xf, f
   return fillval;
 }
 
+// The raw 5x5 lookup ZnccPatch::set starts from, for the test against the reference's own interp2 / interpolateFixedPatch.
+void InterpPatch5(const uint8_t* I, int rows, int cols, double px, double py, float* out25) {
+  const float x = (float)px, y = (float)py;
+  for (int k = 0; k < 25; ++k) out25[k] = interp2_u8(I, rows, cols, (k % 5 - 2) + x, (k / 5 - 2) + y);
+}
+
 // Mean-free 5x5 patch and its norm for the zero-normalised cross correlation of the data association
 // (ZnccPatch_<2, float>, src/photobundle.cc:315-361).
 struct ZnccPatch {

@@ -119,5 +119,8 @@ class PhotometricBundleAdjustment {
 // Per-pixel weights of the patch residuals, row-major over (2 radius + 1)^2 (src/photobundle.cc:617-646 with the default
 // s_x = s_y = a = 1): all ones, or a normalised Gaussian.  Exposed for the tests against the reference's own function.
 std::vector<double> MakePatchWeights(int radius, bool do_gaussian);
+// The 5x5 bilinear lookup of the data association before its mean is removed (interp2 + interpolateFixedPatch<2>,
+// src/photobundle.cc:258-310), exposed for the same reason.
+void InterpPatch5(const uint8_t* I, int rows, int cols, double px, double py, float* out25);
 
 #endif

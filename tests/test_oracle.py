@@ -336,3 +336,26 @@ def test_imgradient_and_disparity_match_reference_binary_when_present():
         assert np.array_equal(z_ref > 0, valid) and np.array_equal(z > 0, valid)
         np.testing.assert_allclose(z[valid], z_ref[valid], rtol=4e-4)
         assert (z_ref[~valid] < 0).all() and (z[~valid] == np.float32(-0.1)).all()
+
+
+def test_association_lookup_matches_reference_binary_when_present():
+    """interp2 / interpolateFixedPatch<2> of the reference (src/photobundle.cc:258-310, compiled from where they lie into
+    oracle/_ref/libref_calib.so): the 5x5 bilinear lookup ZnccPatch_::set starts from equals the host's (and through
+    tests/test_host.py the device's) bit for bit, inside the image, on its last row / column and outside."""
+    ref = binding.ref_calib_lib()
+    if ref is None or not hasattr(ref, "ref_interp_patch5_u8"):
+        pytest.skip("oracle/_ref/libref_calib.so not built (no /root/reference on this box)")
+    from photobundle_b200 import host_capi
+    host = host_capi.lib()
+    ref.ref_interp_patch5_u8.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p]
+    host.pbah_interp_patch5_u8.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p]
+    rng = np.random.default_rng(29)
+    rows, cols = 23, 37
+    I = rng.integers(0, 256, size=(rows, cols), dtype=np.uint8)
+    a, b = np.zeros(25, dtype=np.float32), np.zeros(25, dtype=np.float32)
+    pts = [(rng.uniform(-4, cols + 3), rng.uniform(-4, rows + 3)) for _ in range(3000)]
+    pts += [(cols - 3.0, 5.25), (7.5, rows - 3.0), (cols - 3.0, rows - 3.0), (cols - 1.0, rows - 1.0), (2.0, 2.0), (0.0, 0.0), (-0.5, 3.0)]
+    for u, v in pts:
+        ref.ref_interp_patch5_u8(C.c_void_p(I.ctypes.data), rows, cols, u, v, C.c_void_p(a.ctypes.data))
+        host.pbah_interp_patch5_u8(C.c_void_p(I.ctypes.data), rows, cols, u, v, C.c_void_p(b.ctypes.data))
+        assert a.tobytes() == b.tobytes(), (u, v, a, b)
