@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <cstddef>
 #include <cstring>
+#include <cassert>
 #include <type_traits>
 #include <smmintrin.h>
 #include "opencv2/core/core.hpp"   // ref_shim: names only
@@ -14,7 +15,26 @@
 #include REF_IMGRADIENT_INC
 #include REF_DISPARITY_INC          // is_aligned + disparityToDepth(const float*, ...) of src/imgproc.cc:274-322
 
+namespace {
+template <class T> struct Plane {   // the Image / Mask concept of IsLocalMax_ (src/imgproc.h:175-212)
+  typedef T Scalar;
+  const T* p; int r, c;
+  int rows() const { return r; }
+  int cols() const { return c; }
+  T operator()(int y, int x) const { return p[(long)y * c + x]; }
+};
+}  // namespace
+
 extern "C" {
+// IsLocalMax_ for every pixel at least `radius` away from the border (elsewhere 0)
+void ref_local_maxima(const float* sal, const uint8_t* mask, int32_t rows, int32_t cols, int32_t radius, uint8_t* out) {
+  Plane<float> S{sal, rows, cols};
+  Plane<uint8_t> M{mask, rows, cols};
+  IsLocalMax_<Plane<float>, Plane<uint8_t> > is_max(S, M, radius);
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < cols; ++x)
+      out[(long)y * cols + x] = (y >= radius && y < rows - radius && x >= radius && x < cols - radius) ? (is_max(y, x) ? 1 : 0) : 0;
+}
 void ref_imgradient_u8(const uint8_t* I, int32_t rows, int32_t cols, float* gx, float* gy) {
   imgradient(I, ImageSize(rows, cols), gx, gy);
 }

@@ -48,6 +48,26 @@ class Zncc:
         return f32(dot / d) if float(d) > 1e-6 else f32(-1.0)
 
 
+def local_maxima(S, mask, n):
+    """IsLocalMax_ (src/imgproc.h:175-212) for every pixel: unmasked, not below 0, and strictly above all neighbours of the
+    (2n+1)^2 window (a tie loses); radius 0 accepts everything.  Pixels whose window leaves the image compare against +inf
+    (the callers never ask for them)."""
+    rows, cols = S.shape
+    out = np.ones((rows, cols), dtype=bool)
+    if n > 0:
+        out &= mask & ~(S < 0)
+        for r in range(-n, n + 1):
+            for c in range(-n, n + 1):
+                if r == 0 and c == 0:
+                    continue
+                sh = np.full((rows, cols), np.inf, dtype=f32)
+                ys = slice(max(0, -r), rows - max(0, r)); yd = slice(max(0, r), rows - max(0, -r))
+                xs = slice(max(0, -c), cols - max(0, c)); xd = slice(max(0, c), cols - max(0, -c))
+                sh[ys, xs] = S[yd, xd]
+                out &= ~(sh >= S)
+    return out
+
+
 def extract_patch(I, x, y, radius):
     rows, cols = I.shape
     mc, mr = cols - radius - 1, rows - radius - 1
@@ -97,17 +117,7 @@ class RefFrontEnd:
         cand = np.zeros((rows, cols), dtype=bool)
         cand[B:max_rows, B:max_cols] = True
         cand &= (Z >= o["minValidDepth"]) & (Z <= o["maxValidDepth"])
-        if n > 0:
-            cand &= mask & ~(S < 0)
-            for r in range(-n, n + 1):
-                for c in range(-n, n + 1):
-                    if r == 0 and c == 0:
-                        continue
-                    sh = np.full((rows, cols), np.inf, dtype=f32)
-                    ys = slice(max(0, -r), rows - max(0, r)); yd = slice(max(0, r), rows - max(0, -r))
-                    xs = slice(max(0, -c), cols - max(0, c)); xd = slice(max(0, c), cols - max(0, -c))
-                    sh[ys, xs] = S[yd, xd]
-                    cand &= ~(sh >= S)
+        cand &= local_maxima(S, mask, n)
         new = []
         for y, x in zip(*np.nonzero(cand)):
             z = float(Z[y, x])

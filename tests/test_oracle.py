@@ -359,3 +359,25 @@ def test_association_lookup_matches_reference_binary_when_present():
         ref.ref_interp_patch5_u8(C.c_void_p(I.ctypes.data), rows, cols, u, v, C.c_void_p(a.ctypes.data))
         host.pbah_interp_patch5_u8(C.c_void_p(I.ctypes.data), rows, cols, u, v, C.c_void_p(b.ctypes.data))
         assert a.tobytes() == b.tobytes(), (u, v, a, b)
+
+
+def test_local_maximum_rule_matches_reference_binary_when_present():
+    """IsLocalMax_ (src/imgproc.h:175-212, compiled from where it lies) against the restatement the device's
+    pba_select_candidates is tested with (tests/ref_addframe.py::local_maxima): ties lose, masked pixels lose, radius 0
+    accepts everything."""
+    ref = binding.ref_imgproc_lib()
+    if ref is None or not hasattr(ref, "ref_local_maxima"):
+        pytest.skip("oracle/_ref/libref_imgproc.so not built (no /root/reference on this box)")
+    from ref_addframe import local_maxima        # (tests/ is on sys.path: conftest lives there)
+    rng = np.random.default_rng(31)
+    for radius in (0, 1, 2):
+        rows, cols = 41, 57
+        S = rng.integers(0, 6, size=(rows, cols)).astype(np.float32)          # few levels: plenty of ties
+        S[rng.random(S.shape) < 0.05] *= 7.5
+        mask = (rng.random(S.shape) > 0.2).astype(np.uint8)
+        out = np.zeros((rows, cols), dtype=np.uint8)
+        ref.ref_local_maxima(C.c_void_p(S.ctypes.data), C.c_void_p(mask.ctypes.data), rows, cols, radius, C.c_void_p(out.ctypes.data))
+        mine = local_maxima(S, mask.astype(bool), radius)
+        inner = (slice(radius, rows - radius), slice(radius, cols - radius))
+        assert np.array_equal(out[inner].astype(bool), mine[inner])
+        assert out[inner].sum() > (20 if radius else 100)
