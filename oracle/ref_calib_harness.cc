@@ -20,6 +20,19 @@ Calibration make(const double* k4, double b) {
 #ifdef REF_PATCH_WEIGHTS_INC
 #include REF_PATCH_WEIGHTS_INC
 #endif
+// ExtractPatch (src/photobundle.cc:466-479): the reference descriptor of a new point, clamped at the image border
+#ifdef REF_EXTRACT_PATCH_INC
+#include <algorithm>
+#include REF_EXTRACT_PATCH_INC
+namespace {
+struct ImgF32 {   // a channel as DescriptorFrame keeps it (Image_<float>)
+  const float* p; int r, c;
+  int rows() const { return r; }
+  int cols() const { return c; }
+  float operator()(int y, int x) const { return p[(long)y * c + x]; }
+};
+}  // namespace
+#endif
 // interp2 + interpolateFixedPatch (src/photobundle.cc:258-310, templates of that file cut out the same way): the bilinear
 // lookup of the data association (ZnccPatch_::set) - ZnccPatch_ itself is left out because its sums go through Eigen's
 // own reductions, which no shim reproduces.
@@ -71,6 +84,15 @@ void ref_interp_patch5_u8(const uint8_t* I, int32_t rows, int32_t cols, double u
   const double uv[2] = {u, v};
   interpolateFixedPatch<2>(dst, im, uv, 0.0f, 0.0f);
   for (int k = 0; k < 25; ++k) out25[k] = dst[k];
+}
+#endif
+
+#ifdef REF_EXTRACT_PATCH_INC
+void ref_extract_patch_f32(const float* I, int32_t rows, int32_t cols, int32_t x, int32_t y, int32_t radius, double* dst) {
+  ImgF32 im{I, rows, cols};
+  Vec_<int, 2> uv;
+  uv[0] = x; uv[1] = y;
+  ExtractPatch(dst, im, uv, radius);
 }
 #endif
 

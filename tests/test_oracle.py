@@ -381,3 +381,26 @@ def test_local_maximum_rule_matches_reference_binary_when_present():
         inner = (slice(radius, rows - radius), slice(radius, cols - radius))
         assert np.array_equal(out[inner].astype(bool), mine[inner])
         assert out[inner].sum() > (20 if radius else 100)
+
+
+def test_extract_patch_matches_reference_binary_when_present():
+    """ExtractPatch (src/photobundle.cc:466-479, compiled from where it lies): the reference descriptor of a new point -
+    integer pixel, clamped so that the whole patch stays inside the image - against the oracle's restatement (which the
+    device's pba_extract_descriptors equals bit for bit, tests/test_descriptors.py)."""
+    ref = binding.ref_calib_lib()
+    if ref is None or not hasattr(ref, "ref_extract_patch_f32"):
+        pytest.skip("oracle/_ref/libref_calib.so not built (no /root/reference on this box)")
+    rng = np.random.default_rng(37)
+    rows, cols = 19, 27
+    plane = rng.uniform(0, 255, size=(rows, cols)).astype(np.float32)
+    for radius in (1, 2, 3):
+        P = (2 * radius + 1) ** 2
+        xy = np.stack([rng.integers(-3, cols + 3, size=200), rng.integers(-3, rows + 3, size=200)], axis=1).astype(np.int32)
+        xy = np.concatenate([xy, np.array([[0, 0], [cols - 1, rows - 1], [radius, radius], [cols - radius - 1, rows - radius - 1]], dtype=np.int32)])
+        mine = np.zeros((xy.shape[0], P))
+        binding.lib().oracle_extract_patches(C.c_void_p(plane.ctypes.data), 1, rows, cols, radius, xy.shape[0], C.c_void_p(xy.ctypes.data),
+                                             C.c_void_p(mine.ctypes.data))
+        theirs = np.zeros(P)
+        for k, (x, y) in enumerate(xy):
+            ref.ref_extract_patch_f32(C.c_void_p(plane.ctypes.data), rows, cols, int(x), int(y), radius, C.c_void_p(theirs.ctypes.data))
+            assert theirs.tobytes() == mine[k].tobytes(), (radius, x, y)
