@@ -126,6 +126,19 @@ def ref_imgproc_lib() -> C.CDLL | None:
     return r
 
 
+_REF_FUNCTOR_PATH = os.path.join(os.path.dirname(_REF_PATH), "libref_functor.so")
+
+
+def ref_functor_lib() -> C.CDLL | None:
+    """The reference's residual functor body (src/photobundle.cc:696-727) over its own sampler and camera model, or None."""
+    if not os.path.exists(_REF_FUNCTOR_PATH):
+        return None
+    r = C.CDLL(_REF_FUNCTOR_PATH)
+    r.ref_residual_block.restype = C.c_int32
+    r.ref_residual_block.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
+    return r
+
+
 def _p(a: np.ndarray) -> int:
     return a.ctypes.data
 

@@ -404,3 +404,35 @@ def test_extract_patch_matches_reference_binary_when_present():
         for k, (x, y) in enumerate(xy):
             ref.ref_extract_patch_f32(C.c_void_p(plane.ctypes.data), rows, cols, int(x), int(y), radius, C.c_void_p(theirs.ctypes.data))
             assert theirs.tobytes() == mine[k].tobytes(), (radius, x, y)
+
+
+def test_residual_functor_matches_reference_binary_when_present():
+    """The reference's own residual functor - the body of DescriptorError::operator()<double> (src/photobundle.cc:696-727)
+    over its own SampleWithDerivative and Calibration::project, compiled from where they lie into
+    oracle/_ref/libref_functor.so (only ceres::AngleAxisRotatePoint is restated: Ceres is absent) - against the oracle's
+    residual block on every observation of a ragged window, interior and border, 1 and 3 channels: bit for bit."""
+    ref = binding.ref_functor_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_functor.so not built (no /root/reference on this box)")
+    for win, planes in ((synthetic.small_window(seed=11, ragged=True, n_frames=8, grid=(10, 14)), None),
+                        (synthetic.small_window(seed=3, radius=1, ragged=True, n_frames=6), None)):
+        ow = binding.OracleWindow(win, num_threads=1, planes=planes)
+        F, Cn, rows, cols = ow.planes.shape
+        k4 = np.array([win.fx, win.fy, win.cx, win.cy])
+        rng = np.random.default_rng(41)
+        n_checked = 0
+        for p in range(win.n_points):
+            for o in range(int(win.obs_offsets[p]), int(win.obs_offsets[p + 1])):
+                f = int(win.obs_frame[o])
+                cam = win.cams_init[f] + (rng.normal(size=6) * 1e-3 if o % 3 else 0.0)
+                X = win.points_init[p] * (1.0 if o % 5 else 1.6)          # some projections land near / beyond the border
+                r_o, _, _ = ow.residual_block(f, cam, X, ow.desc[p], mode=2)
+                r_r = np.zeros(ow.CP)
+                cam = np.ascontiguousarray(cam, dtype=np.float64); X = np.ascontiguousarray(X, dtype=np.float64)
+                ok = ref.ref_residual_block(C.c_void_p(ow.planes[f].ctypes.data), C.c_void_p(ow.gx[f].ctypes.data), C.c_void_p(ow.gy[f].ctypes.data),
+                                            Cn, rows, cols, C.c_void_p(k4.ctypes.data), win.radius, C.c_void_p(ow.desc[p].ctypes.data),
+                                            C.c_void_p(ow.weights.ctypes.data), C.c_void_p(cam.ctypes.data), C.c_void_p(X.ctypes.data),
+                                            C.c_void_p(r_r.ctypes.data))
+                assert ok == 1 and r_r.tobytes() == r_o.tobytes(), (p, o, np.abs(r_r - r_o).max())
+                n_checked += 1
+        assert n_checked > 300
