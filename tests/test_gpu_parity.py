@@ -385,3 +385,34 @@ def test_loop_graph_is_retargeted_in_place_when_sizes_change(small_win):
     builds, updates = h.graph_counters()
     assert builds == 1 and updates == 3, (builds, updates)
     h.close()
+
+
+def test_k1_residuals_against_the_reference_functor(small_ragged_win):
+    """K_A's residuals against the REFERENCE's own functor body (oracle/_ref/libref_functor.so: DescriptorError::operator()
+    <double> of src/photobundle.cc:696-727 over the reference's sampler and camera model, compiled from where they lie; only
+    AngleAxisRotatePoint is restated) - without the oracle in between.  Same bar as against the oracle: bit-exact for
+    >= 99.9 % of the samples (device vs glibc sin / cos can differ by an ulp), the rest within 1e-4 grey levels."""
+    import ctypes as C
+    ref = ob.ref_functor_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_functor.so not built")
+    w = small_ragged_win
+    h = capi.Handle.for_window(w)
+    ev = h.eval(want_residuals=True)
+    h.close()
+    ow = ob.OracleWindow(w, num_threads=1)           # only for the channel planes and their gradients
+    F, Cn, rows, cols = ow.planes.shape
+    k4 = np.array([w.fx, w.fy, w.cx, w.cy])
+    want = np.zeros_like(ev["residuals"])
+    for p in range(w.n_points):
+        X = np.ascontiguousarray(w.points_init[p], dtype=np.float64)
+        for o in range(int(w.obs_offsets[p]), int(w.obs_offsets[p + 1])):
+            f = int(w.obs_frame[o])
+            cam = np.ascontiguousarray(w.cams_init[f], dtype=np.float64)
+            assert ref.ref_residual_block(C.c_void_p(ow.planes[f].ctypes.data), C.c_void_p(ow.gx[f].ctypes.data), C.c_void_p(ow.gy[f].ctypes.data),
+                                          Cn, rows, cols, C.c_void_p(k4.ctypes.data), w.radius, C.c_void_p(ow.desc[p].ctypes.data),
+                                          C.c_void_p(ow.weights.ctypes.data), C.c_void_p(cam.ctypes.data), C.c_void_p(X.ctypes.data),
+                                          C.c_void_p(want[o].ctypes.data)) == 1
+    same = (ev["residuals"] == want)
+    assert same.mean() >= 0.999, same.mean()
+    assert np.abs(ev["residuals"] - want).max() <= 1e-4
