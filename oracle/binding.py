@@ -136,6 +136,8 @@ def ref_functor_lib() -> C.CDLL | None:
     r = C.CDLL(_REF_FUNCTOR_PATH)
     r.ref_residual_block.restype = C.c_int32
     r.ref_residual_block.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
+    r.ref_residual_block_jet.restype = C.c_int32
+    r.ref_residual_block_jet.argtypes = [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
     return r
 
 

@@ -9,6 +9,7 @@
 namespace ceres {
 template <typename T>
 inline void AngleAxisRotatePoint(const T angle_axis[3], const T pt[3], T result[3]) {
+  using std::sqrt; using std::cos; using std::sin;   // doubles; Jets find ceres::sqrt / cos / sin by ADL
   const T theta2 = angle_axis[0] * angle_axis[0] + angle_axis[1] * angle_axis[1] + angle_axis[2] * angle_axis[2];
   if (theta2 > T(std::numeric_limits<double>::epsilon())) {
     const T theta = sqrt(theta2);

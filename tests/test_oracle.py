@@ -436,3 +436,34 @@ def test_residual_functor_matches_reference_binary_when_present():
                 assert ok == 1 and r_r.tobytes() == r_o.tobytes(), (p, o, np.abs(r_r - r_o).max())
                 n_checked += 1
         assert n_checked > 300
+
+
+def test_residual_jacobian_matches_reference_functor_with_jets_when_present():
+    """The same reference functor body instantiated with ceres::Jet<double, 9> as AutoDiffCostFunction<.., 6, 3> seeds it
+    (reference sampler chain rule src/jet_extras.h; Jet algebra and AngleAxisRotatePoint restated from Ceres' published
+    definitions) against the oracle's autodiff residual block: residuals and all nine Jacobian columns bit for bit."""
+    ref = binding.ref_functor_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_functor.so not built (no /root/reference on this box)")
+    win = synthetic.small_window(seed=11, ragged=True, n_frames=8, grid=(10, 14))
+    ow = binding.OracleWindow(win, num_threads=1)
+    F, Cn, rows, cols = ow.planes.shape
+    k4 = np.array([win.fx, win.fy, win.cx, win.cy])
+    rng = np.random.default_rng(43)
+    n_checked = 0
+    for p in range(0, win.n_points, 2):
+        for o in range(int(win.obs_offsets[p]), int(win.obs_offsets[p + 1])):
+            f = int(win.obs_frame[o])
+            cam = np.ascontiguousarray(win.cams_init[f] + rng.normal(size=6) * 1e-3, dtype=np.float64)
+            X = np.ascontiguousarray(win.points_init[p] * (1.0 if o % 7 else 1.5), dtype=np.float64)
+            r_o, Jc, Jp = ow.residual_block(f, cam, X, ow.desc[p], mode=1)
+            r_r, J = np.zeros(ow.CP), np.zeros((ow.CP, 9))
+            ok = ref.ref_residual_block_jet(C.c_void_p(ow.planes[f].ctypes.data), C.c_void_p(ow.gx[f].ctypes.data), C.c_void_p(ow.gy[f].ctypes.data),
+                                            Cn, rows, cols, C.c_void_p(k4.ctypes.data), win.radius, C.c_void_p(ow.desc[p].ctypes.data),
+                                            C.c_void_p(ow.weights.ctypes.data), C.c_void_p(cam.ctypes.data), C.c_void_p(X.ctypes.data),
+                                            C.c_void_p(r_r.ctypes.data), C.c_void_p(J.ctypes.data))
+            assert ok == 1 and r_r.tobytes() == r_o.tobytes()
+            assert np.ascontiguousarray(J[:, :6]).tobytes() == Jc.tobytes() and np.ascontiguousarray(J[:, 6:]).tobytes() == Jp.tobytes(), \
+                (p, o, np.abs(J[:, :6] - Jc).max(), np.abs(J[:, 6:] - Jp).max())
+            n_checked += 1
+    assert n_checked > 150
