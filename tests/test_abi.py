@@ -58,6 +58,28 @@ def test_default_solver_options_are_the_reference_ones():
     assert o.max_num_consecutive_invalid_steps == 5 and o.jacobi_scaling == 1
 
 
+def test_default_solver_options_against_the_reference_source_text():
+    """The values GetSolverOptions sets (src/photobundle.cc:738-761), read from the reference's own source text when the
+    tree is present: max_num_iterations and the three tolerances are what pba_default_solver_options returns; the solver /
+    strategy it names (SPARSE_SCHUR, TRUST_REGION, LEVENBERG_MARQUARDT) are what K_B implements; the loss threshold the
+    residual blocks get comes from Options::robustThreshold (:797)."""
+    import re
+    src_path = "/root/reference/src/photobundle.cc"
+    if not os.path.exists(src_path):
+        pytest.skip("reference tree not present (GPU box)")
+    src = open(src_path).read()
+    body = src[src.index("GetSolverOptions(int num_threads"):src.index("void PhotometricBundleAdjustment::optimize(Result* result)")]
+    o = capi.SolverOptions()
+    capi.lib().pba_default_solver_options(C.byref(o))
+    assert int(re.search(r"options\.max_num_iterations\s*=\s*(\d+);", body).group(1)) == o.max_num_iterations
+    tol = float(re.search(r"double tol = ([0-9.e+-]+)\)", body).group(1))
+    for name in ("function_tolerance", "gradient_tolerance", "parameter_tolerance"):
+        assert re.search(r"options\.%s\s*=\s*tol;" % name, body) and getattr(o, name) == tol
+    for token in ("ceres::SPARSE_SCHUR", "ceres::TRUST_REGION", "ceres::LEVENBERG_MARQUARDT"):
+        assert token in body
+    assert "huber_t = _options.robustThreshold" in src and "huber_t > 0.0 ? new ceres::HuberLoss(huber_t) : nullptr" in src
+
+
 def test_argument_errors_are_reported():
     L = capi.lib()
     h = C.c_void_p()
