@@ -34,6 +34,13 @@ def lib():
     return _lib
 
 
+def default_options() -> "Options":
+    """PhotometricBundleAdjustment::Options as its default constructor leaves it."""
+    o = Options()
+    lib().pbah_default_options(C.byref(o))
+    return o
+
+
 class BundleAdjuster:
     """Mirror of `PhotometricBundleAdjustment photoba(calib, size, options); photoba.addFrame(...)`."""
 

@@ -355,3 +355,34 @@ def test_pyramid_class_coarse_to_fine():
     # (the two runs refine differently, so later frames associate slightly different point sets)
     assert np.isfinite(res[2]["poses"]).all() and abs(res[2]["numResiduals"] - res[1]["numResiduals"]) <= 0.05 * res[1]["numResiduals"]
     assert res[2]["finalCost"] <= 1.10 * res[1]["finalCost"]
+
+
+def test_options_defaults_against_the_reference_header_and_ctor():
+    """PhotometricBundleAdjustment::Options: the in-class defaults of src/photobundle.h:29-67 and the fall-back values of
+    the ConfigFile constructor (src/photobundle.cc:86-103), read from the reference's own source text when the tree is
+    present, against the host class's defaults (pbah_default_options) and its ConfigFile constructor (host source)."""
+    import re
+    hdr_path, src_path = "/root/reference/src/photobundle.h", "/root/reference/src/photobundle.cc"
+    if not os.path.exists(hdr_path):
+        pytest.skip("reference tree not present (GPU box)")
+    hdr = open(hdr_path).read()
+    hdr = hdr[hdr.index("struct Options"):hdr.index("struct Result")]
+    want = {m.group(2): m.group(3) for m in re.finditer(r"^\s+(int|bool|double) (\w+) = ([-\w.]+);", hdr, re.M)}
+    assert len(want) >= 13
+    o = host_capi.default_options()
+    for name, text in want.items():
+        if name == "numThreads":
+            continue                       # not an option of the device path (ignored)
+        have = getattr(o, name)
+        ref = {"true": 1, "false": 0}.get(text, None)
+        ref = float(text) if ref is None else ref
+        assert float(have) == ref, (name, have, text)
+    # the ConfigFile constructor's fall-backs: cf.get<T>("key", default)
+    ref_cc = open(src_path).read()
+    mine = open(os.path.join(ROOT, "photobundle_b200", "host", "photobundle.cc")).read()
+    pat = re.compile(r'(\w+)\(\s*(?:\(bool\))?\s*cf\.get<(\w+(?:::\w+)?)>\("(\w+)",\s*([^)]+)\)')
+    ref_defaults = {m.group(3): m.group(4).strip() for m in pat.finditer(ref_cc)}
+    my_defaults = {m.group(3): m.group(4).strip() for m in pat.finditer(mine)}
+    assert len(ref_defaults) >= 13
+    for key, val in ref_defaults.items():
+        assert key in my_defaults and my_defaults[key] == val, (key, val, my_defaults.get(key))
